@@ -1,0 +1,157 @@
+/*
+ * xitorch_b200 -- C ABI of the B200-native (sm_100a) Krylov hot path of xitorch.
+ *
+ * The reference (xitorch @ ad9eec1) is pure Python and has no FFI; its plug-in
+ * surface for this path is
+ *   B1  the `method=` callables of linalg.symeig / linalg.solve
+ *         xitorch/linalg/symeig.py:275-280   fcn(A, neig, mode, M, **opts) -> (evals, evecs)
+ *         xitorch/linalg/solve.py:144-153    fcn(A, B, E, M, **opts)       -> X
+ *   B2  the dense operator the methods call
+ *         xitorch/_core/linop.py:692-702     MatrixLinearOperator._mv/_mm/_rmv/_rmm = torch.matmul
+ * Every entry point below is what a binding for one of those would call; each cites the
+ * reference function it replaces.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - all pointers except `*_out` / `xt_*_args` themselves are DEVICE pointers of torch CUDA tensors
+ *   - the library never allocates, frees or retains device memory: the caller passes a workspace
+ *     (size from xt_*_workspace_bytes) and owns every buffer
+ *   - work is enqueued on `stream` (a cudaStream_t); solver entry points synchronise that stream
+ *     only to read their convergence flag, matvec never synchronises
+ *   - return value: XT_OK, or a negative xt_status; xt_last_error() gives the message
+ *     (thread-local).  Non-convergence is NOT an error: converged_out = 0 and the best iterate
+ *     is returned, the caller emits the ConvergenceWarning (reference convention,
+ *     xitorch/_impls/linalg/solve.py:182-186)
+ *   - dense matrices are row-major with a row stride `ld*` (elements) and a batch stride
+ *     (elements, 0 = the same matrix for every batch item); vectors/blocks are (n, ncols)
+ *     row-major -- torch's natural layout for a (*, n, ncols) tensor
+ *   - dtype = storage type of A (and M); vectors, scalars and results are
+ *     float for XT_F32 / XT_BF16 and double for XT_F64
+ *   - re-entrant; no global state except the per-device SM-count cache
+ */
+#ifndef XITORCH_B200_H
+#define XITORCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { XT_F32 = 0, XT_BF16 = 1, XT_F64 = 2 } xt_dtype;
+
+typedef enum {
+  XT_OK = 0,
+  XT_ERR_INVALID = -1,     /* bad argument / unsupported shape or alignment */
+  XT_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+  XT_ERR_WORKSPACE = -3,   /* workspace too small */
+  XT_ERR_BREAKDOWN = -4    /* numerical breakdown that cannot be recovered (e.g. non-finite input) */
+} xt_status;
+
+int xt_version(void);
+const char* xt_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense block matvec   Y_b = A_b X_b  [ - Z_b diag(E_b) ]        b = 0..nbatch-1
+ * replaces MatrixLinearOperator._mm/_mv (xitorch/_core/linop.py:692-696) and the shifted operator
+ * x -> A x - (M x) E of _setup_linear_problem (xitorch/_impls/linalg/solve.py:590-595; pass Z = M X,
+ * or Z = NULL for Z = X).
+ *   A: (nbatch, nrows, ncolsA) row-major, row stride lda;   X: (nbatch, ncolsA, k), row stride ldx
+ *   Y: (nbatch, nrows, k), row stride ldy;                  E: (nbatch, k) or NULL
+ *   k >= 1 (handled in column groups of <= 16).  `impl`: 0 = auto, 1 = force the TMA kernel,
+ *   2 = force the plain-load kernel (used by the tests to cross-check the two).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;
+  int32_t nbatch, nrows, ncolsA, k;
+  const void* A; int64_t lda, a_bstride;
+  const void* X; int64_t ldx, x_bstride;
+  void* Y;       int64_t ldy, y_bstride;
+  const void* E; int64_t e_bstride;
+  const void* Z; int64_t ldz, z_bstride;
+  int32_t impl;
+  void* stream;
+} xt_matvec_args;
+
+int xt_block_matvec(const xt_matvec_args* args);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear solvers  A X - M X diag(E) = B   (all columns and batch items in lock-step, global stop
+ * test ||r||_2(col) < max(rtol ||b||, atol), best iterate returned) -- replace
+ *   cg        xitorch/_impls/linalg/solve.py:69-190
+ *   bicgstab  xitorch/_impls/linalg/solve.py:192-324
+ *   gmres     xitorch/_impls/linalg/solve.py:326-433   (E/M unsupported, as in the reference)
+ * The operator must already be the one to iterate on: the posdef probe / normal-equation
+ * switch of _setup_linear_problem (solve.py:605-643) is host logic done by the caller.
+ *   A, M: (nbatch, n, n);  B, X: (nbatch, n, ncols), row strides ldb/ldx;  E: (nbatch, ncols)|NULL
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;
+  int32_t n, nbatch, ncols;
+  const void* A; int64_t lda, a_bstride;
+  const void* M; int64_t ldm, m_bstride;      /* NULL = identity */
+  const void* E; int64_t e_bstride;           /* NULL = no shift */
+  const void* B; int64_t ldb, b_bstride;
+  void* X;       int64_t ldx, x_bstride;      /* out */
+  double rtol, atol, eps;
+  int32_t max_niter;
+  int32_t resid_calc_every;                   /* 0 = never recompute the true residual */
+  int32_t check_every;                        /* host polls the device convergence flag every this many iterations (>=1) */
+  int32_t* niter_out;                         /* host, may be NULL */
+  int32_t* converged_out;                     /* host, may be NULL */
+  double* best_resid_out;                     /* host, may be NULL: max column residual norm of the returned iterate */
+  int64_t* napply_out;                        /* host, may be NULL: number of block operator applications */
+  void* workspace; size_t workspace_bytes;
+  void* stream;
+} xt_solve_args;
+
+size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, int32_t nbatch,
+                                int32_t ncols, int32_t max_niter, int32_t has_M);
+int xt_cg(const xt_solve_args* args);
+int xt_bicgstab(const xt_solve_args* args);
+int xt_gmres(const xt_solve_args* args);
+
+/* ---------------------------------------------------------------------------------------------
+ * Extreme eigenpairs of a dense Hermitian operator by block Rayleigh-Ritz on a growing Krylov
+ * subspace -- replaces davidson (xitorch/_impls/linalg/symeig.py:100-227) incl. tallqr
+ * (xitorch/_utils/tensor.py:8-19); expansion = 0 appends the orthonormalised Ritz residuals
+ * (the reference's Davidson step, symeig.py:207-220), expansion = 1 appends the orthonormalised
+ * A*(last block) (block Lanczos with full reorthogonalisation: the same Krylov space, method
+ * "lanczos" of BASELINE.json).  Stop: max |A X - X Lambda| < min_eps (symeig.py:188,200);
+ * the best pair by that measure is returned (symeig.py:196-199).
+ *   A: (nbatch, n, n) (batch items are solved one after another);
+ *   V0: (nbatch, n, neig) start block, any full-rank block (it is orthonormalised here)
+ *   evals: (nbatch, neig) ascending;  evecs: (nbatch, n, neig), row stride ldv
+ *   max_basis: thick-restart cap on the subspace dimension (multiple of neig, >= 3*neig)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;
+  int32_t n, nbatch, neig;
+  int32_t mode;                               /* 0 = lowest, 1 = uppest */
+  int32_t expansion;                          /* 0 = davidson (residuals), 1 = lanczos (A * last block) */
+  const void* A; int64_t lda, a_bstride;
+  const void* V0; int64_t ldv0, v0_bstride;
+  void* evals;   int64_t evals_bstride;
+  void* evecs;   int64_t ldv, evecs_bstride;
+  int32_t max_niter, max_basis, check_every;
+  double min_eps;
+  int32_t* niter_out;                         /* host, may be NULL: iterations of the last batch item */
+  int32_t* converged_out;                     /* host, may be NULL: 1 iff every batch item met min_eps */
+  double* best_resid_out;                     /* host, may be NULL: max over batch of the returned max|R| */
+  int64_t* napply_out;                        /* host, may be NULL: block operator applications (all items) */
+  void* workspace; size_t workspace_bytes;
+  void* stream;
+} xt_symeig_args;
+
+size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis);
+int xt_symeig_krylov(const xt_symeig_args* args);
+
+/* small dense symmetric eigensolver used for the projected problem (device, one CTA):
+ * T (m x m, row-major fp64, destroyed) -> w (m, ascending), S (m x m row-major, columns = eigenvectors).
+ * Exposed for the parity tests.  */
+int xt_small_eigh(double* T, int32_t m, double* w, double* S, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XITORCH_B200_H */

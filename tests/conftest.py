@@ -1,0 +1,37 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "krylov_golden.pt")
+    return torch.load(path, weights_only=False)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_extension():
+    # the product fails loudly without its CUDA extension; build it (nvcc cross-compiles on CPU boxes)
+    from xitorch_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from xitorch_b200.csrc.build import build
+        build()

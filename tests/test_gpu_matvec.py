@@ -1,0 +1,110 @@
+"""GPU parity of the dense block matvec (C ABI `xt_block_matvec`) against torch fp64 matmul."""
+import pytest
+import torch
+
+from xitorch_b200 import _dense
+import xitorch_b200 as xt
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref(A, X, E=None, Z=None):
+    y = A.double() @ X.double()
+    if E is not None:
+        y = y - (X.double() if Z is None else Z.double()) * E.double().unsqueeze(-2)
+    return y
+
+
+def _tol(dtype):
+    return {torch.float32: 2e-6, torch.bfloat16: 2e-6, torch.float64: 1e-13}[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("n,k", [(64, 1), (100, 3), (256, 8), (1000, 2), (1024, 16), (2048, 5), (4100, 8)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_matvec_square(dtype, n, k, impl):
+    g = torch.Generator().manual_seed(n * 31 + k)
+    A = torch.randn(n, n, generator=g).to(dtype)
+    X = torch.randn(n, k, generator=g)
+    vdt = torch.float64 if dtype == torch.float64 else torch.float32
+    es = A.element_size()
+    if impl == 1 and (n * es) % 16 != 0:
+        pytest.skip("row stride not 16-byte aligned: TMA path not applicable")
+    y = _dense.block_matvec(A.to(DEV), X.to(vdt).to(DEV), impl=impl)
+    ref = _ref(A, X.to(vdt))
+    scale = (A.double().abs() @ X.double().abs()).max().item()
+    err = (y.double().cpu() - ref).abs().max().item()
+    assert y.dtype == vdt and tuple(y.shape) == (n, k)
+    assert err <= _tol(dtype) * scale, (err, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_matvec_rect_batched_shift(dtype):
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(3, 200, 200, generator=g).to(dtype)
+    X = torch.randn(3, 200, 4, generator=g).to(dtype)
+    E = torch.randn(3, 4, generator=g).to(dtype)
+    Z = torch.randn(3, 200, 4, generator=g).to(dtype)
+    for impl in (1, 2):
+        y = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), Z=Z.to(DEV), impl=impl)
+        assert (y.double().cpu() - _ref(A, X, E, Z)).abs().max().item() <= _tol(dtype) * 200
+        y = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), impl=impl)
+        assert (y.double().cpu() - _ref(A, X, E)).abs().max().item() <= _tol(dtype) * 200
+    # broadcast A over a batch of X, rectangular A, adjoint
+    A2 = torch.randn(96, 160, generator=g).to(dtype)
+    X2 = torch.randn(2, 5, 160, 3, generator=g).to(dtype)
+    y = _dense.block_matvec(A2.to(DEV), X2.to(DEV))
+    assert tuple(y.shape) == (2, 5, 96, 3)
+    assert (y.double().cpu() - A2.double() @ X2.double()).abs().max().item() <= _tol(dtype) * 200
+    X3 = torch.randn(96, 2, generator=g).to(dtype)
+    y = _dense.block_matvec(A2.to(DEV), X3.to(DEV), adjoint=True)
+    assert (y.double().cpu() - A2.double().t() @ X3.double()).abs().max().item() <= _tol(dtype) * 200
+
+
+def test_matvec_many_columns_and_tiles():
+    # k > 16 (column groups), more tiles than SMs (persistent loop), ragged last tile
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(20000, 520, generator=g)
+    X = torch.randn(520, 37, generator=g)
+    y = _dense.block_matvec(A.to(DEV), X.to(DEV))
+    ref = A.double() @ X.double()
+    assert (y.double().cpu() - ref).abs().max().item() <= 2e-6 * (A.abs().double() @ X.abs().double()).max().item()
+
+
+def test_linop_mm_uses_kernel_and_matches():
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(512, 512, generator=g, dtype=torch.float64)
+    A = (A + A.t()) / 2
+    op = xt.LinearOperator.m(A.to(DEV), is_hermitian=True)
+    x = torch.randn(512, 7, generator=g, dtype=torch.float64).to(DEV)
+    with torch.no_grad():
+        y = op.mm(x)
+        yv = op.mv(x[:, 0])
+        yr = op.rmm(x)
+    assert torch.allclose(y.cpu(), A @ x.cpu(), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(yv.cpu(), A @ x[:, 0].cpu(), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(yr.cpu(), y.cpu())
+    # with autograd on, the differentiable library path is taken and gives the same numbers
+    Ag = A.to(DEV).requires_grad_()
+    y2 = xt.LinearOperator.m(Ag, is_hermitian=True).mm(x)
+    assert y2.requires_grad and torch.allclose(y2.detach(), y, rtol=1e-12, atol=1e-12)
+
+
+def test_full_size_linearity_property():
+    # BASELINE size (N=16384, k=8): size-independent checks -- linearity and a row-sum identity
+    n, k = 16384, 8
+    g = torch.Generator(device=DEV).manual_seed(1)
+    A = torch.randn(n, n, device=DEV, generator=g)
+    X = torch.randn(n, k, device=DEV, generator=g)
+    W = torch.randn(n, k, device=DEV, generator=g)
+    y1 = _dense.block_matvec(A, X)
+    y2 = _dense.block_matvec(A, W)
+    y12 = _dense.block_matvec(A, X + 2 * W)
+    assert (y12 - (y1 + 2 * y2)).abs().max().item() <= 5e-4 * y12.abs().max().item()
+    ones = torch.ones(n, 1, device=DEV)
+    rs = _dense.block_matvec(A, ones)[:, 0]
+    assert torch.allclose(rs.double(), A.double().sum(dim=1), rtol=1e-4, atol=1e-2)
+    # and the two kernels agree on a row sample
+    yp = _dense.block_matvec(A[:256].contiguous(), X, impl=2)
+    assert (yp - y1[:256]).abs().max().item() <= 2e-4 * y1.abs().max().item()

@@ -1,0 +1,87 @@
+"""
+Host wrapper of the dense block-matvec kernel (`xt_block_matvec`): the accelerated body of
+`MatrixLinearOperator._mm/_mv/_rmm/_rmv` (reference: torch.matmul,
+/root/reference/xitorch/_core/linop.py:692-702).  Batch broadcasting follows torch.matmul.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from xitorch_b200 import _lib
+
+_SUPPORTED = (torch.float32, torch.bfloat16, torch.float64)
+
+
+def supports(mat: torch.Tensor, x: torch.Tensor) -> bool:
+    return (mat.is_cuda and x.is_cuda and mat.dtype in _SUPPORTED and not x.is_complex()
+            and mat.dim() >= 2 and x.dim() >= 2 and x.shape[-1] >= 1 and mat.shape[-1] >= 1 and mat.shape[-2] >= 1)
+
+
+def flatten_batch(mat: torch.Tensor, batch: Tuple[int, ...]):
+    """(mat3d, a_bstride) such that item b of the flattened broadcast batch reads mat3d at b * a_bstride."""
+    p, q = mat.shape[-2:]
+    nb = 1
+    for s in batch:
+        nb *= s
+    ba = tuple(mat.shape[:-2])
+    nba = 1
+    for s in ba:
+        nba *= s
+    if nba == 1:
+        m2 = mat.reshape(p, q)
+        if m2.stride(-1) != 1:
+            m2 = m2.contiguous()
+        return m2, 0, m2.stride(0)
+    if tuple([1] * (len(batch) - len(ba)) + list(ba)) != tuple(batch):
+        mat = mat.expand(*batch, p, q)
+    m3 = mat.reshape(nb, p, q)
+    if m3.stride(-1) != 1:
+        m3 = m3.contiguous()
+    return m3, m3.stride(0), m3.stride(1)
+
+
+def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
+                 E: Optional[torch.Tensor] = None, Z: Optional[torch.Tensor] = None,
+                 impl: int = 0) -> torch.Tensor:
+    """``mat @ x`` (or ``mat^T @ x``), optionally ``- Z * E`` with ``E (*B, k)``, ``Z (*B, p, k)`` (default x)."""
+    _lib.require_cuda(mat, "the dense block matvec")
+    if adjoint:
+        mat = mat.transpose(-2, -1).contiguous()     # materialised, like the reference's `.H` for dense operators
+    p, q = mat.shape[-2:]
+    if x.shape[-2] != q:
+        raise RuntimeError("block_matvec: shape mismatch %s @ %s" % (tuple(mat.shape), tuple(x.shape)))
+    k = x.shape[-1]
+    vdt = _lib.vec_dtype(mat.dtype)
+    out_dtype = x.dtype
+    batch = tuple(torch.broadcast_shapes(mat.shape[:-2], x.shape[:-2]))
+    nb = 1
+    for s in batch:
+        nb *= s
+    if nb == 0:
+        return torch.empty((*batch, p, k), dtype=out_dtype, device=x.device)
+    m3, a_bstride, lda = flatten_batch(mat, batch)
+    if m3.data_ptr() % 16 != 0:
+        m3 = m3.clone()
+    xx = x.to(vdt).expand(*batch, q, k).reshape(nb, q, k).contiguous()
+    y = torch.empty((nb, p, k), dtype=vdt, device=x.device)
+    a = _lib.MatvecArgs()
+    a.dtype = _lib.dtype_code(mat.dtype)
+    a.nbatch, a.nrows, a.ncolsA, a.k = nb, p, q, k
+    a.A, a.lda, a.a_bstride = m3.data_ptr(), lda, a_bstride
+    a.X, a.ldx, a.x_bstride = xx.data_ptr(), k, q * k
+    a.Y, a.ldy, a.y_bstride = y.data_ptr(), k, p * k
+    keep = [m3, xx, y]
+    if E is not None:
+        ee = E.to(vdt).expand(*batch, k).reshape(nb, k).contiguous()
+        a.E, a.e_bstride = ee.data_ptr(), k
+        keep.append(ee)
+        if Z is not None:
+            zz = Z.to(vdt).expand(*batch, p, k).reshape(nb, p, k).contiguous()
+            a.Z, a.ldz, a.z_bstride = zz.data_ptr(), k, p * k
+            keep.append(zz)
+    a.impl = impl
+    a.stream = _lib.stream_ptr(x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().xt_block_matvec(a), "block_matvec")
+    y = y.reshape(*batch, p, k)
+    return y if out_dtype == vdt else y.to(out_dtype)

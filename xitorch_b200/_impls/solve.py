@@ -1,0 +1,312 @@
+"""
+Method implementations behind `xitorch_b200.linalg.solve` (plug-in layer L3 of SURVEY.md 1).
+
+`cg`, `bicgstab`, `gmres` keep the reference signatures and option names
+(/root/reference/xitorch/_impls/linalg/solve.py:69-80, 192-204, 326-334) but run on the B200 through the
+C ABI (`xt_cg`, `xt_bicgstab`, `xt_gmres`): one fused block-matvec kernel per operator application with
+the iteration's dot products in its epilogue, device-side convergence control.  They need a CUDA
+operator; there is NO CPU fallback (a CPU operator raises RuntimeError).
+
+Host logic kept here (the part of `_setup_linear_problem`, solve.py:560-643, that is not arithmetic):
+batch broadcasting, the zero-RHS shortcut, the Hermitian / posdef decision and the normal-equation
+switch.  The reference's posdef *probe* (power iterations, solve.py:617-634) compares two vector norms
+(`-mostneg_eival <= offset` with both sides >= 0) and therefore always yields posdef=True for finite
+operators; it is elided (saves up to 20 operator applications, same decision).
+"""
+import ctypes as C
+import math
+import warnings
+from typing import Optional, Sequence
+
+import torch
+
+from xitorch_b200 import _lib
+from xitorch_b200._utils import ConvergenceWarning, bcast_dims, normalize_bcast_dims
+from xitorch_b200.linop import LinearOperator, MatrixLinearOperator
+
+__all__ = ["exactsolve", "custom_exactsolve", "cg", "bicgstab", "gmres", "get_batchdims"]
+
+
+def get_batchdims(A, B, E, M):
+    """broadcast batch shape of the solution (solve.py:540-549)."""
+    dims = [A.shape[:-2], B.shape[:-2]]
+    if E is not None:
+        dims.append(E.shape[:-1])
+        if M is not None:
+            dims.append(M.shape[:-2])
+    return bcast_dims(*dims)
+
+
+# ----------------------------------------------------------------------------- exact (dense) path
+def exactsolve(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor], M: Optional[LinearOperator]):
+    """Direct dense solve (row f2 of SURVEY.md 8f; reference solve.py:481-537): LU of the full matrix, one
+    shifted matrix per column when E is given, Cholesky whitening when M is given."""
+    Amat = A.fullmatrix()
+    if E is None:
+        return torch.linalg.solve(Amat, B)
+    if M is None:
+        return _solve_shifted(Amat, B, E)
+    L = torch.linalg.cholesky(M.fullmatrix())
+    Linv = torch.inverse(L)
+    LinvT = Linv.transpose(-2, -1).conj()
+    A2 = torch.matmul(Linv, A.mm(LinvT))
+    X2 = _solve_shifted(A2, torch.matmul(Linv, B), E)
+    return torch.matmul(LinvT, X2)
+
+
+def _solve_shifted(Amat, B, E):
+    n = Amat.shape[-1]
+    BA, BB, BE = normalize_bcast_dims(Amat.shape[:-2], B.shape[:-2], E.shape[:-1])
+    Ec = E.reshape(1, *BE, E.shape[-1]).transpose(0, -1)                  # (ncols, *BE, 1)
+    Bc = B.reshape(1, *BB, *B.shape[-2:]).transpose(0, -1)                # (ncols, *BB, n, 1)
+    eye = torch.eye(n, dtype=Amat.dtype, device=Amat.device)
+    AE = Amat.reshape(*BA, n, n) - Ec.unsqueeze(-1) * eye                 # (ncols, *BAE, n, n)
+    try:
+        r = torch.linalg.solve(AE, Bc)
+    except torch._C._LinAlgError:
+        eps = torch.finfo(Amat.dtype).eps
+        bump = 10 * eps * AE.reshape(*AE.shape[:-2], -1).max(dim=-1)[0][..., None, None]
+        r = torch.linalg.solve(AE + eye * bump, Bc)
+    return r.transpose(0, -1).squeeze(0)
+
+
+def custom_exactsolve(A, B, E=None, M=None, **options):
+    return exactsolve(A, B, E, M)
+
+
+# ----------------------------------------------------------------------------- Krylov methods (CUDA only)
+def _dense_of(op: LinearOperator, what: str) -> torch.Tensor:
+    if isinstance(op, MatrixLinearOperator):
+        return op.mat
+    # composite / matrix-free operators: materialise (rows f3 of SURVEY.md 8f are not fused yet)
+    if op.shape[-1] > 16384:
+        raise RuntimeError("xitorch_b200: %s is matrix-free with n=%d; only dense (or materialisable) operators "
+                           "are supported by the fused Krylov kernels" % (what, op.shape[-1]))
+    with torch.no_grad():
+        return op.fullmatrix()
+
+
+def _default_check_every(n: int, nbatch: int, esize: int) -> int:
+    t_iter = max(nbatch * n * n * esize / 6.0e12, 8e-6)     # one pass over A at ~6 TB/s, >= launch floor
+    return max(1, min(64, int(4e-4 / t_iter)))
+
+
+def _flatten(t: torch.Tensor, batch: Sequence[int], tail: Sequence[int], dtype) -> torch.Tensor:
+    nb = 1
+    for s in batch:
+        nb *= s
+    return t.to(dtype).expand(*batch, *tail).reshape(nb, *tail).contiguous()
+
+
+def _mat3(mat: torch.Tensor, batch: Sequence[int]):
+    from xitorch_b200._dense import flatten_batch
+    m3, bstride, ld = flatten_batch(mat, tuple(batch))
+    if m3.data_ptr() % 16 != 0:
+        m3 = m3.clone()
+    return m3, bstride, ld
+
+
+def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, need_hermit: bool,
+                max_niter: int, rtol: float, atol: float, eps: float, resid_calc_every: int,
+                check_every: Optional[int], info: Optional[dict]):
+    _lib.require_cuda(B, "linalg.solve(method=%r)" % name)
+    n, ncols = A.shape[-1], B.shape[-1]
+    batch = get_batchdims(A, B, E, M)
+    Amat = _dense_of(A, "A")
+    _lib.require_cuda(Amat, "linalg.solve(method=%r)" % name)
+    if Amat.is_complex() or B.is_complex():
+        raise RuntimeError("xitorch_b200: complex operators are not supported by the fused Krylov kernels")
+    vdt = _lib.vec_dtype(Amat.dtype)
+    out_dtype = B.dtype if B.dtype in (torch.float32, torch.float64) else vdt
+
+    # zero right-hand side -> zeros (solve.py:116-119)
+    if torch.allclose(B, B * 0, rtol=rtol, atol=atol):
+        return torch.zeros((*batch, n, ncols), dtype=out_dtype, device=B.device)
+
+    Mmat = None
+    if E is not None and M is not None:
+        Mmat = _dense_of(M, "M").to(Amat.dtype)
+
+    hermit = A.is_hermitian and (M is None or E is None or M.is_hermitian)
+    if need_hermit and not hermit:
+        posdef = False
+    if posdef is None:
+        posdef = True          # what the reference's probe always concludes (see module docstring)
+
+    Bv = B
+    if not posdef:
+        # normal equations (solve.py:637-643):  (A-EM)^H (A-EM) x = (A-EM)^H b, built densely per column
+        if E is not None:
+            Ec = E.reshape(*([1] * (len(batch) - E.dim() + 1)), *E.shape) if E.dim() - 1 < len(batch) else E
+            eye = torch.eye(n, dtype=Amat.dtype, device=Amat.device) if Mmat is None else Mmat
+            Afull = Amat.expand(*batch, n, n).unsqueeze(-3) - \
+                Ec.to(Amat.dtype).expand(*batch, ncols)[..., None, None] * eye.expand(*batch, n, n).unsqueeze(-3)
+            # (*batch, ncols, n, n): every column becomes its own batch item with one right-hand side
+            AT = Afull.transpose(-2, -1)
+            Amat = torch.matmul(AT, Afull)
+            Bcol = B.expand(*batch, n, ncols).transpose(-2, -1).unsqueeze(-1).to(Amat.dtype)   # (*batch, ncols, n, 1)
+            Bv = torch.matmul(AT, Bcol)
+            x = _call(name, Amat, None, None, Bv, (*batch, ncols), n, 1, vdt, max_niter, rtol, atol, eps,
+                      resid_calc_every, check_every, info)
+            return x.squeeze(-1).transpose(-2, -1).to(out_dtype)
+        AT = Amat.transpose(-2, -1)
+        Bv = torch.matmul(AT.to(vdt), B.to(vdt))
+        Amat = torch.matmul(AT, Amat)
+    x = _call(name, Amat, Mmat, E, Bv, batch, n, ncols, vdt, max_niter, rtol, atol, eps, resid_calc_every,
+              check_every, info)
+    return x.to(out_dtype)
+
+
+def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, eps, resid_calc_every,
+          check_every, info):
+    L = _lib.lib()
+    nb = 1
+    for s in batch:
+        nb *= s
+    A3, a_bs, lda = _mat3(Amat, batch)
+    Bf = _flatten(B, batch, (n, ncols), vdt)
+    X = torch.empty((nb, n, ncols), dtype=vdt, device=Bf.device)
+    keep = [A3, Bf, X]
+    g = _lib.SolveArgs()
+    g.dtype = _lib.dtype_code(Amat.dtype)
+    g.n, g.nbatch, g.ncols = n, nb, ncols
+    g.A, g.lda, g.a_bstride = A3.data_ptr(), lda, a_bs
+    if Mmat is not None:
+        M3, m_bs, ldm = _mat3(Mmat, batch)
+        keep.append(M3)
+        g.M, g.ldm, g.m_bstride = M3.data_ptr(), ldm, m_bs
+    if E is not None:
+        Ef = _flatten(E, batch, (ncols,), vdt)
+        keep.append(Ef)
+        g.E, g.e_bstride = Ef.data_ptr(), ncols
+    g.B, g.ldb, g.b_bstride = Bf.data_ptr(), ncols, n * ncols
+    g.X, g.ldx, g.x_bstride = X.data_ptr(), ncols, n * ncols
+    g.rtol, g.atol, g.eps = float(rtol), float(atol), float(eps)
+    g.max_niter = int(max_niter)
+    g.resid_calc_every = int(resid_calc_every)
+    g.check_every = int(check_every) if check_every else _default_check_every(n, nb, Amat.element_size())
+    niter, conv, best, napply = C.c_int32(0), C.c_int32(0), C.c_double(0.0), C.c_int64(0)
+    g.niter_out, g.converged_out = C.pointer(niter), C.pointer(conv)
+    g.best_resid_out, g.napply_out = C.pointer(best), C.pointer(napply)
+    wsb = L.xt_solve_workspace_bytes(name.encode(), g.dtype, n, nb, ncols, g.max_niter, 1 if Mmat is not None else 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=Bf.device)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
+    g.stream = _lib.stream_ptr(Bf.device)
+    with torch.cuda.device(Bf.device):
+        _lib.check(getattr(L, "xt_" + name)(g), name)
+    if info is not None:
+        info.update(niter=niter.value, converged=bool(conv.value), best_resid=best.value, napply=napply.value)
+    if not conv.value:
+        warnings.warn(ConvergenceWarning(
+            "Convergence is not achieved after %d iterations. Max norm of best resid: %.3e"
+            % (max_niter, best.value)))
+    return X.reshape(*batch, n, ncols)
+
+
+def _no_precond(**kw):
+    for k, v in kw.items():
+        if v is not None:
+            raise RuntimeError("xitorch_b200: option %s is not supported by the fused kernels yet "
+                               "(SURVEY.md 8f row f4)" % k)
+
+
+def cg(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: Optional[LinearOperator] = None,
+       posdef: Optional[bool] = None, precond: Optional[LinearOperator] = None,
+       max_niter: Optional[int] = None, rtol: float = 1e-6, atol: float = 1e-8, eps: float = 1e-12,
+       resid_calc_every: int = 10, verbose: bool = False, check_every: Optional[int] = None,
+       info: Optional[dict] = None, **unused) -> torch.Tensor:
+    r"""
+    Conjugate gradient on the B200 (fused matvec + p.Ap kernel per iteration).
+
+    Keyword arguments
+    -----------------
+    posdef: bool or None
+        Whether :math:`\mathbf{AX-MXE}` is positive definite for all columns and batches.
+        ``False`` (or a non-Hermitian operator) switches to the normal equations. ``None`` means True.
+    precond: LinearOperator or None
+        Not supported by the fused kernel yet (must be None).
+    max_niter: int or None
+        Maximum number of iterations. If None, ``int(1.5 * A.shape[-1])``.
+    rtol, atol: float
+        Stop when every column satisfies ``||r|| < max(rtol * ||b||, atol)``.
+    eps: float
+        Replacement for exactly-zero denominators.
+    resid_calc_every: int
+        Recompute the true residual ``B - A x`` every this many iterations (0: never).
+    verbose: bool
+        Ignored (convergence control lives on the device).
+    check_every: int or None
+        Host polls the device convergence flag every this many iterations (None: chosen from the size).
+    info: dict or None
+        If given, receives ``niter``, ``converged``, ``best_resid``, ``napply``.
+    """
+    _no_precond(precond=precond)
+    if max_niter is None:
+        max_niter = int(1.5 * A.shape[-1])
+    return _run_krylov("cg", A, B, E, M, posdef, True, max_niter, rtol, atol, eps, resid_calc_every,
+                       check_every, info)
+
+
+def bicgstab(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None,
+             M: Optional[LinearOperator] = None, posdef: Optional[bool] = None,
+             precond_l: Optional[LinearOperator] = None, precond_r: Optional[LinearOperator] = None,
+             max_niter: Optional[int] = None, rtol: float = 1e-6, atol: float = 1e-8, eps: float = 1e-12,
+             verbose: bool = False, resid_calc_every: int = 10, check_every: Optional[int] = None,
+             info: Optional[dict] = None, **unused) -> torch.Tensor:
+    r"""
+    Stabilised bi-conjugate gradient on the B200 (two fused matvec kernels per iteration carrying
+    ``r0hat.v`` and ``t.s, t.t``).
+
+    Keyword arguments
+    -----------------
+    posdef: bool or None
+        ``False`` switches to the normal equations; ``None`` means True.
+    precond_l, precond_r: LinearOperator or None
+        Not supported by the fused kernel yet (must be None).
+    max_niter: int or None
+        Maximum number of iterations. If None, ``int(1.5 * A.shape[-1])``.
+    rtol, atol: float
+        Stop when every column satisfies ``||r|| < max(rtol * ||b||, atol)``.
+    eps: float
+        Replacement for exactly-zero denominators.
+    verbose: bool
+        Ignored.
+    resid_calc_every: int
+        Recompute the true residual every this many iterations (0: never).
+    check_every, info:
+        As in :func:`cg`.
+    """
+    _no_precond(precond_l=precond_l, precond_r=precond_r)
+    if max_niter is None:
+        max_niter = int(1.5 * A.shape[-1])
+    return _run_krylov("bicgstab", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, resid_calc_every,
+                       check_every, info)
+
+
+def gmres(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: Optional[LinearOperator] = None,
+          posdef: Optional[bool] = None, max_niter: Optional[int] = None, rtol: float = 1e-6,
+          atol: float = 1e-8, eps: float = 1e-12, check_every: Optional[int] = None,
+          info: Optional[dict] = None, **unused) -> torch.Tensor:
+    r"""
+    Unrestarted GMRES on the B200 (fused matvec, block classical Gram-Schmidt twice, Givens
+    least squares on the device).
+
+    Keyword arguments
+    -----------------
+    posdef: bool or None
+        ``False`` switches to the normal equations; ``None`` means True.
+    max_niter: int or None
+        Maximum number of iterations (= Krylov dimension). If None, ``min(A.shape[-1], 256)``.
+    rtol, atol: float
+        Stop when every column satisfies ``||r|| < max(rtol * ||b||, atol)``.
+    eps: float
+        Replacement for exactly-zero denominators.
+    check_every, info:
+        As in :func:`cg`.
+    """
+    if E is not None:
+        raise RuntimeError("gmres does not support E (neither does the reference method: "
+                           "xitorch/_impls/linalg/solve.py:386-398)")
+    if max_niter is None:
+        max_niter = min(int(A.shape[-1]), 256)
+    return _run_krylov("gmres", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, 0, check_every, info)

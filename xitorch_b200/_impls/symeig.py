@@ -1,0 +1,199 @@
+"""
+Method implementations behind `xitorch_b200.linalg.symeig` (plug-in layer L3 of SURVEY.md 1).
+
+`davidson` keeps the reference signature and option names
+(/root/reference/xitorch/_impls/linalg/symeig.py:100-109); `lanczos` is the new block-Lanczos method of
+BASELINE.json (config 5) entering through the same `method=` plug-in point.  Both run on the B200 through
+`xt_symeig_krylov` (csrc/symeig.cu) and need a CUDA operator -- there is NO CPU fallback.
+`exacteig` is the dense `eigh` path (row f2 of SURVEY.md 8f).
+"""
+import ctypes as C
+import warnings
+from typing import Optional
+
+import torch
+
+from xitorch_b200 import _lib
+from xitorch_b200._utils import ConvergenceWarning, bcast_dims
+from xitorch_b200.linop import LinearOperator
+from xitorch_b200._impls.solve import _dense_of, _mat3
+
+__all__ = ["exacteig", "custom_exacteig", "davidson", "lanczos"]
+
+
+def _take(evals, evecs, neig, mode):
+    if mode == "lowest":
+        return evals[..., :neig], evecs[..., :neig]
+    return evals[..., -neig:], evecs[..., -neig:]
+
+
+def exacteig(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]):
+    """full dense eigendecomposition then truncation (reference symeig.py:11-44); the generalized
+    problem is whitened with the Cholesky factor of M."""
+    Amat = A.fullmatrix()
+    if M is None:
+        evals, evecs = torch.linalg.eigh(Amat)
+        return _take(evals, evecs, neig, mode)
+    L = torch.linalg.cholesky(M.fullmatrix())
+    Linv = torch.inverse(L)
+    LinvT = Linv.transpose(-2, -1).conj()
+    evals, q = torch.linalg.eigh(torch.matmul(Linv, torch.matmul(Amat, LinvT)))
+    evals, q = _take(evals, q, neig, mode)
+    return evals, torch.matmul(LinvT, q)
+
+
+def custom_exacteig(A, neig, mode, M=None, **options):
+    return exacteig(A, neig, mode, M)
+
+
+def _default_max_basis(n: int, neig: int) -> int:
+    mb = max(16 * neig, 64)
+    mb = min(mb, 512, n)
+    return max((mb // neig) * neig, 2 * neig)
+
+
+def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator], expansion: int,
+            max_niter: int, nguess: Optional[int], v_init: str, min_eps: float, max_basis: Optional[int],
+            check_every: Optional[int], info: Optional[dict], name: str):
+    if nguess is not None and nguess != neig:
+        raise RuntimeError("xitorch_b200.%s: nguess must equal neig (got %d vs %d)" % (name, nguess, neig))
+    if mode not in ("lowest", "uppest"):
+        raise RuntimeError("Unknown mode: %s" % mode)
+    n = A.shape[-1]
+    Amat = _dense_of(A, "A")
+    _lib.require_cuda(Amat, "linalg.symeig(method=%r)" % name)
+    if Amat.is_complex():
+        raise RuntimeError("xitorch_b200.%s: complex operators are not supported (the reference davidson is "
+                           "real-only as well, SURVEY.md 3.6)" % name)
+    if Amat.dtype == torch.bfloat16:
+        raise RuntimeError("xitorch_b200.%s: bf16 operators are not supported for eigenproblems" % name)
+    dev = Amat.device
+    LinvT = None
+    if M is not None:
+        # generalized problem A x = lambda M x  ->  (L^-1 A L^-T) y = lambda y,  x = L^-T y   (library GEMMs)
+        Mmat = _dense_of(M, "M").to(Amat.dtype)
+        L = torch.linalg.cholesky(Mmat)
+        Linv = torch.inverse(L)
+        LinvT = Linv.transpose(-2, -1)
+        Amat = torch.matmul(Linv, torch.matmul(Amat, LinvT))
+        Amat = 0.5 * (Amat + Amat.transpose(-2, -1))
+    batch = tuple(Amat.shape[:-2])
+    nb = 1
+    for s in batch:
+        nb *= s
+    vdt = Amat.dtype
+
+    # start block (the reference reseeds the GLOBAL RNG with 12421, symeig.py:236; a local generator with
+    # the same seed is used here so callers' random streams are left alone)
+    kind = v_init.lower()
+    if kind == "eye":
+        V0 = torch.eye(n, neig, dtype=vdt, device=dev).expand(nb, n, neig).contiguous()
+    elif kind in ("randn", "rand", "random"):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(12421)
+        fn = torch.randn if kind == "randn" else torch.rand
+        V0 = fn((nb, n, neig), dtype=vdt, device=dev, generator=gen)
+    else:
+        raise ValueError("Unknown v_init type: %s" % v_init)
+
+    if max_basis is None:
+        max_basis = _default_max_basis(n, neig)
+    A3, a_bs, lda = _mat3(Amat, batch)
+    evals = torch.empty((nb, neig), dtype=vdt, device=dev)
+    evecs = torch.empty((nb, n, neig), dtype=vdt, device=dev)
+    L_ = _lib.lib()
+    g = _lib.SymeigArgs()
+    g.dtype = _lib.dtype_code(vdt)
+    g.n, g.nbatch, g.neig = n, nb, neig
+    g.mode = 0 if mode == "lowest" else 1
+    g.expansion = expansion
+    g.A, g.lda, g.a_bstride = A3.data_ptr(), lda, (a_bs if nb > 1 else 0)
+    g.V0, g.ldv0, g.v0_bstride = V0.data_ptr(), neig, n * neig
+    g.evals, g.evals_bstride = evals.data_ptr(), neig
+    g.evecs, g.ldv, g.evecs_bstride = evecs.data_ptr(), neig, n * neig
+    g.max_niter, g.max_basis = int(max_niter), int(max_basis)
+    if check_every is None:
+        t_iter = max(n * n * Amat.element_size() / 6.0e12, 3e-5)
+        check_every = max(1, min(16, int(3e-4 / t_iter)))
+    g.check_every = int(check_every)
+    g.min_eps = float(min_eps)
+    niter, conv, best, napply = C.c_int32(0), C.c_int32(0), C.c_double(0.0), C.c_int64(0)
+    g.niter_out, g.converged_out = C.pointer(niter), C.pointer(conv)
+    g.best_resid_out, g.napply_out = C.pointer(best), C.pointer(napply)
+    wsb = L_.xt_symeig_workspace_bytes(g.dtype, n, neig, g.max_basis)
+    if wsb == 0:
+        raise RuntimeError("xitorch_b200.%s: n=%d is too small for neig=%d (need n >= 2*neig)" % (name, n, neig))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
+    g.stream = _lib.stream_ptr(dev)
+    with torch.cuda.device(dev):
+        _lib.check(L_.xt_symeig_krylov(g), name)
+    if info is not None:
+        info.update(niter=niter.value, converged=bool(conv.value), best_resid=best.value, napply=napply.value,
+                    max_basis=int(max_basis))
+    evals = evals.reshape(*batch, neig)
+    evecs = evecs.reshape(*batch, n, neig)
+    if LinvT is not None:
+        evecs = torch.matmul(LinvT, evecs)
+    return evals, evecs
+
+
+def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
+             max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
+             max_addition: Optional[int] = None, min_eps: float = 1e-6, verbose: bool = False,
+             max_basis: Optional[int] = None, check_every: Optional[int] = None,
+             info: Optional[dict] = None, **unused):
+    """
+    Block Davidson (Rayleigh-Ritz on span{V0, r0, r1, ...}) on the B200.
+
+    Arguments
+    ---------
+    max_niter: int
+        Maximum number of iterations (subspace expansions)
+    nguess: int or None
+        Size of the start block; must be ``neig`` (or None)
+    v_init: str
+        Mode of the initial guess (``"randn"``, ``"rand"``, ``"eye"``)
+    max_addition: int or None
+        Accepted for compatibility and unused, exactly as in the reference (always ``neig``)
+    min_eps: float
+        Stop when the largest entry of the residual ``|A X - X E|`` is below this value
+    verbose: bool
+        Ignored (convergence control lives on the device)
+    max_basis: int or None
+        Thick-restart cap on the subspace dimension (None: ``max(16 * neig, 64)``, at most 512 and n)
+    check_every: int or None
+        Host polls the device convergence flag every this many iterations
+    info: dict or None
+        If given, receives ``niter``, ``converged``, ``best_resid``, ``napply``, ``max_basis``
+    """
+    return _krylov(A, neig, mode, M, 0, max_niter, nguess, v_init, min_eps, max_basis, check_every, info,
+                   "davidson")
+
+
+def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
+            max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
+            min_eps: float = 1e-6, verbose: bool = False, max_basis: Optional[int] = None,
+            check_every: Optional[int] = None, info: Optional[dict] = None, **unused):
+    """
+    Block Lanczos with full reorthogonalisation and Rayleigh-Ritz extraction on the B200: the same
+    Krylov space as ``davidson`` (which has no preconditioner), expanded with the orthonormalised
+    ``A @ (last block)`` instead of the Ritz residuals.
+
+    Arguments
+    ---------
+    max_niter: int
+        Maximum number of iterations (subspace expansions)
+    nguess: int or None
+        Size of the start block; must be ``neig`` (or None)
+    v_init: str
+        Mode of the initial guess (``"randn"``, ``"rand"``, ``"eye"``)
+    min_eps: float
+        Stop when the largest entry of the residual ``|A X - X E|`` is below this value
+    verbose: bool
+        Ignored
+    max_basis, check_every, info:
+        As in :func:`davidson`
+    """
+    return _krylov(A, neig, mode, M, 1, max_niter, nguess, v_init, min_eps, max_basis, check_every, info,
+                   "lanczos")

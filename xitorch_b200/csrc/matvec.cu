@@ -1,0 +1,601 @@
+// Dense block matvec  Y = A X [- Z diag(E)]  for row-major A (fp32 / bf16 / fp64), k <= 16 columns,
+// with optional fused per-tile dot products -- the kernel behind MatrixLinearOperator.mm
+// (reference: xitorch/_core/linop.py:692-696 = torch.matmul) and behind every Krylov iteration.
+//
+// HBM-bound: A is read exactly once.  Design (B200 / sm_100a):
+//   * one persistent CTA per SM, each owning tiles of TH <= 128 consecutive rows chosen so that
+//     #tiles ~= #SMs (or >> #SMs) -- see mv_tiling()
+//   * warp 0 (one elected lane) streams A through TMA: 3-D tensor map (cols, rows, batch), boxes of
+//     8 rows x 128 B with SWIZZLE_128B, L2 evict-first hint, multi-stage mbarrier ring
+//   * warp 1 stages the matching chunk of X into the same stage (plain coalesced loads; arbitrary
+//     strides, zero padding) -- this is the hook where solver prologues get fused
+//   * warps 2..9 (256 threads) consume: thread <-> (row, k-slice); 16-byte conflict-free LDS of its
+//     row (swizzle-aware), X chunk broadcast from shared memory, packed FFMA2 accumulation with
+//     per-stage blocked summation; k-slices are reduced through shared memory at tile end
+//   * epilogue per row: shift term, store Y, fused partial dots (warp-shuffle + smem reduction,
+//     one deterministic partial per tile, fp64)
+// A second, plain-load kernel (one warp per row) covers shapes the TMA path cannot take
+// (row stride not a multiple of 16 B) and cross-checks the TMA kernel in the tests.
+#include "matvec.cuh"
+
+#include <cstdarg>
+#include <mutex>
+
+namespace xt {
+
+// ============================================================================ host utilities
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+MvTiling mv_tiling(int nbatch, int nrows) {
+  MvTiling t;
+  const int64_t total = (int64_t)nbatch * nrows;
+  const int G = num_sms();
+  // rows per tile so that one wave of G CTAs covers everything, rounded up to the TMA box height
+  int64_t th = (total + (int64_t)G * MV_BOX_ROWS - 1) / ((int64_t)G * MV_BOX_ROWS) * MV_BOX_ROWS;
+  if (th > MV_TILE_ROWS) th = MV_TILE_ROWS;
+  if (th > ((nrows + MV_BOX_ROWS - 1) / MV_BOX_ROWS) * MV_BOX_ROWS)
+    th = ((nrows + MV_BOX_ROWS - 1) / MV_BOX_ROWS) * MV_BOX_ROWS;
+  if (th < MV_BOX_ROWS) th = MV_BOX_ROWS;
+  t.tile_rows = (int)th;
+  t.tiles_per_batch = (nrows + t.tile_rows - 1) / t.tile_rows;
+  t.ntiles = t.tiles_per_batch * nbatch;
+  t.grid = t.ntiles < G ? t.ntiles : G;
+  return t;
+}
+
+// ---------------------------------------------------------------------------- tensor map creation
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static size_t dtype_size(int dt) { return dt == XT_F32 ? 4 : (dt == XT_BF16 ? 2 : 8); }
+
+bool mv_tma_ok(const MvArgs& a) {
+  const size_t es = dtype_size(a.dtype);
+  if (reinterpret_cast<uintptr_t>(a.A) % 16) return false;
+  if ((a.lda * es) % 16) return false;
+  if (a.nbatch > 1 && a.a_bstride != 0 && (a.a_bstride * es) % 16) return false;
+  if (a.lda < a.ncolsA) return false;
+  if (get_encode_fn() == nullptr) return false;
+  return true;
+}
+
+static int make_tmap(const MvArgs& a, CUtensorMap* tm, bool* batched) {
+  const size_t es = dtype_size(a.dtype);
+  const bool b3 = (a.nbatch > 1 && a.a_bstride != 0);
+  *batched = b3;
+  CUtensorMapDataType dt = a.dtype == XT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : (a.dtype == XT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64);
+  cuuint64_t dims[3] = {(cuuint64_t)a.ncolsA, (cuuint64_t)a.nrows, (cuuint64_t)(b3 ? a.nbatch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)(a.lda * es),
+                           (cuuint64_t)((b3 ? a.a_bstride : (int64_t)a.nrows * a.lda) * es)};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)MV_BOX_ROWS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(tm, dt, 3, const_cast<void*>(a.A), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (ncols=%d nrows=%d lda=%lld)", (int)r, a.ncolsA,
+                   a.nrows, (long long)a.lda);
+    return XT_ERR_CUDA;
+  }
+  return XT_OK;
+}
+
+// ============================================================================ device code
+struct MvDev {
+  int nbatch, nrows, ncolsA, kvalid;
+  int tile_rows, tiles_per_batch, ntiles;
+  int rows_pad;     // power of two >= tile_rows, in {16,32,64,128}
+  int nstages;
+  int a_batched;
+  const void* X; int64_t ldx, x_bstride;
+  void* Y; int64_t ldy, y_bstride;
+  const void* E; int64_t e_bstride;
+  const void* Z; int64_t ldz, z_bstride;
+  const void* U; int64_t ldu, u_bstride;
+  double* dot_out;
+  const int* done_flag;
+};
+
+template <typename TA> struct ElemTraits;
+template <> struct ElemTraits<float> {
+  static constexpr int EPV = 4;  // elements per 16-byte vector
+  __device__ static __forceinline__ void unpack(const float4& v, float (&a)[4]) {
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+  }
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+  static constexpr int EPV = 8;
+  __device__ static __forceinline__ void unpack(const float4& v, float (&a)[8]) {
+    const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[2 * i] = __uint_as_float(w[i] << 16);
+      a[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct ElemTraits<double> {
+  static constexpr int EPV = 2;
+  __device__ static __forceinline__ void unpack(const float4& v, double (&a)[2]) {
+    a[0] = __hiloint2double(__float_as_int(v.y), __float_as_int(v.x));
+    a[1] = __hiloint2double(__float_as_int(v.w), __float_as_int(v.z));
+  }
+};
+
+// K values of one X row from shared memory (explicit ld.shared, widest loads)
+template <int K, typename TV> __device__ __forceinline__ void load_xrow(uint32_t addr, TV (&x)[K]) {
+  constexpr int BYTES = K * (int)sizeof(TV);
+  if constexpr (BYTES % 16 == 0) {
+    float4* x4 = reinterpret_cast<float4*>(x);
+#pragma unroll
+    for (int i = 0; i < BYTES / 16; ++i) x4[i] = lds128(addr + 16 * i);
+  } else if constexpr (BYTES == 8) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    *reinterpret_cast<float2*>(x) = v;
+  } else {
+    static_assert(BYTES == 4, "unexpected X row size");
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    *reinterpret_cast<float*>(x) = v;
+  }
+}
+
+template <int K> __device__ __forceinline__ void fma_row(float a, const float (&x)[K], float (&acc)[K]) {
+  if constexpr (K % 2 == 0) {
+    const float2 aa = make_float2(a, a);
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i) {
+      float2 r = __ffma2_rn(aa, make_float2(x[2 * i], x[2 * i + 1]), make_float2(acc[2 * i], acc[2 * i + 1]));
+      acc[2 * i] = r.x;
+      acc[2 * i + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = fmaf(a, x[i], acc[i]);
+  }
+}
+template <int K> __device__ __forceinline__ void fma_row(double a, const double (&x)[K], double (&acc)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = fma(a, x[i], acc[i]);
+}
+
+constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 128 B
+
+template <typename TA, typename TV, int K>
+__global__ void __launch_bounds__(MV_THREADS, 1)
+mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
+  using Tr = ElemTraits<TA>;
+  constexpr int EPV = Tr::EPV;
+  constexpr int BOXC = 128 / (int)sizeof(TA);   // columns per box
+  constexpr int KC = 2 * BOXC;                  // columns per stage
+  constexpr int XBYTES = KC * K * (int)sizeof(TV);
+  constexpr int STAGE_BYTES = MV_STAGE_A_BYTES + XBYTES;
+
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;
+  uint8_t* stage_base = smem;
+  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);                 // [MV_CONSUMERS][K]
+  double* dscr = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(red) + MV_CONSUMERS * K * sizeof(TV));  // [8][2][K]
+  uint64_t* full = reinterpret_cast<uint64_t*>(dscr + 8 * 2 * K);
+  uint64_t* empty = full + NS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.ncolsA + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 2);                    // TMA lane (expect_tx) + X-staging warp
+      mbar_init(&empty[s], MV_CONSUMERS / 32);   // one arrival per consumer warp
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_batch;
+        const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+        const int rows = min(p.tile_rows, p.nrows - row0);
+        const int ngroups = (rows + MV_BOX_ROWS - 1) / MV_BOX_ROWS;
+        const int bA = p.a_batched ? b : 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int kc = ch * KC;
+          const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(ngroups * nb * 1024));
+          for (int g = 0; g < ngroups; ++g)
+            for (int bx = 0; bx < nb; ++bx)
+              tma_load_3d(dst + (g * 2 + bx) * 1024, &tmA, &full[s], kc + bx * BOXC, row0 + g * MV_BOX_ROWS, bA, pol);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ X staging warp
+    const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const TV* Xb = Xg + (int64_t)b * p.x_bstride;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int kc = ch * KC;
+        mbar_wait(&empty[s], ph ^ 1);
+        TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+#pragma unroll 4
+        for (int idx = lane; idx < KC * K; idx += 32) {
+          const int c = idx / K, v = idx - c * K;
+          TV val = TV(0);
+          if (kc + c < p.ncolsA && v < p.kvalid) val = Xb[(int64_t)(kc + c) * p.ldx + v];
+          xs[idx] = val;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumers
+    const int tc = threadIdx.x - 64;
+    const int r = tc & (p.rows_pad - 1);
+    const int q = tc / p.rows_pad;
+    const int ksplit = MV_CONSUMERS / p.rows_pad;
+    const int nvec = 16 / ksplit;
+    const int cw = warp - 2;
+    const uint32_t a_row_off = (uint32_t)((r >> 3) * 2048 + (r & 7) * 128);
+    const uint32_t sw = (uint32_t)(r & 7);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+      const int rows = min(p.tile_rows, p.nrows - row0);
+      const bool active = r < rows;
+      TV acc[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) acc[i] = TV(0);
+
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int kc = ch * KC;
+        mbar_wait(&full[s], ph);
+        if (active) {
+          const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES) + a_row_off;
+          const uint32_t xs = smem_u32(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+          TV loc[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) loc[i] = TV(0);
+#pragma unroll 2
+          for (int v = 0; v < nvec; ++v) {
+            const int gv = q * nvec + v;
+            const int bx = gv >> 3;
+            if (kc + bx * BOXC < p.ncolsA) {
+              const float4 raw = lds128(a_s + bx * 1024 + (((uint32_t)(gv & 7) ^ sw) << 4));
+              TV a[EPV];
+              Tr::unpack(raw, a);
+              const uint32_t xr = xs + (uint32_t)(gv * EPV * K * (int)sizeof(TV));
+#pragma unroll
+              for (int j = 0; j < EPV; ++j) {
+                TV x[K];
+                load_xrow<K, TV>(xr + (uint32_t)(j * K * (int)sizeof(TV)), x);
+                fma_row<K>(a[j], x, loc);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) acc[i] += loc[i];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+
+      // ---- reduce the k-slices, then the per-row epilogue (threads with q == 0)
+      if (q > 0) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) red[(size_t)tc * K + i] = acc[i];
+      }
+      named_bar_sync(1, MV_CONSUMERS);
+      double d0[K], d1[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
+      if (q == 0 && active) {
+        for (int qq = 1; qq < ksplit; ++qq) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) acc[i] += red[(size_t)(qq * p.rows_pad + r) * K + i];
+        }
+        const int64_t row = row0 + r;
+        if (p.E != nullptr) {
+          const TV* Eb = reinterpret_cast<const TV*>(p.E) + (int64_t)b * p.e_bstride;
+          const TV* Zr = (p.Z != nullptr)
+                             ? reinterpret_cast<const TV*>(p.Z) + (int64_t)b * p.z_bstride + row * p.ldz
+                             : reinterpret_cast<const TV*>(p.X) + (int64_t)b * p.x_bstride + row * p.ldx;
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            if (i < p.kvalid) acc[i] -= Eb[i] * Zr[i];
+        }
+        TV* Yr = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride + row * p.ldy;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          if (i < p.kvalid) Yr[i] = acc[i];
+        if (p.dot_out != nullptr) {
+          const TV* Ur = (p.U != nullptr)
+                             ? reinterpret_cast<const TV*>(p.U) + (int64_t)b * p.u_bstride + row * p.ldu
+                             : nullptr;
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            if (i < p.kvalid) {
+              d1[i] = (double)acc[i] * (double)acc[i];
+              if (Ur != nullptr) d0[i] = (double)Ur[i] * (double)acc[i];
+            }
+          }
+        }
+      }
+      if (p.dot_out != nullptr) {
+        // rows of this tile live in the q == 0 threads: tc < rows_pad  <=> consumer warps 0..rows_pad/32-1
+        // (rows_pad = 16 shares warp 0 with q = 1 whose d's are zero)
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          d0[i] = warp_sum(d0[i]);
+          d1[i] = warp_sum(d1[i]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            dscr[(cw * 2 + 0) * K + i] = d0[i];
+            dscr[(cw * 2 + 1) * K + i] = d1[i];
+          }
+        }
+      }
+      named_bar_sync(1, MV_CONSUMERS);   // red[] / dscr[] hand-over
+      if (p.dot_out != nullptr && tc < 2 * K) {
+        const int which = tc / K, i = tc - which * K;
+        double sum = 0.0;
+        for (int w = 0; w < MV_CONSUMERS / 32; ++w) sum += dscr[(w * 2 + which) * K + i];
+        p.dot_out[((size_t)tile * 2 + which) * MV_MAXK + i] = sum;
+      }
+      // the next tile's first red[]/dscr[] writes happen after its whole K sweep and a barrier: no hazard with
+      // the reads above except dscr (written after the next first barrier) -> safe as well.
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- plain-load kernel
+// one CTA per tile (same tiling => same dot layout), one warp per row, lanes stride the columns.
+template <typename TA, typename TV>
+__global__ void __launch_bounds__(256)
+mv_plain_kernel(const TA* __restrict__ A, int64_t lda, int64_t a_bstride, const MvDev p) {
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  __shared__ double dscr[8][2][MV_MAXK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int b = tile / p.tiles_per_batch;
+    const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+    const int rows = min(p.tile_rows, p.nrows - row0);
+    const TA* Ab = A + (int64_t)b * a_bstride;
+    const TV* Xb = reinterpret_cast<const TV*>(p.X) + (int64_t)b * p.x_bstride;
+    double d0[MV_MAXK], d1[MV_MAXK];
+#pragma unroll
+    for (int i = 0; i < MV_MAXK; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
+    for (int rr = warp; rr < rows; rr += 8) {
+      const int64_t row = row0 + rr;
+      const TA* Ar = Ab + row * lda;
+      TV acc[MV_MAXK];
+#pragma unroll
+      for (int i = 0; i < MV_MAXK; ++i) acc[i] = TV(0);
+      for (int c = lane; c < p.ncolsA; c += 32) {
+        const TV a = (TV)Ar[c];
+        const TV* xr = Xb + (int64_t)c * p.ldx;
+#pragma unroll
+        for (int i = 0; i < MV_MAXK; ++i)
+          if (i < p.kvalid) acc[i] += a * xr[i];
+      }
+#pragma unroll
+      for (int i = 0; i < MV_MAXK; ++i) acc[i] = warp_sum(acc[i]);
+      if (lane == 0) {
+        if (p.E != nullptr) {
+          const TV* Eb = reinterpret_cast<const TV*>(p.E) + (int64_t)b * p.e_bstride;
+          const TV* Zr = (p.Z != nullptr)
+                             ? reinterpret_cast<const TV*>(p.Z) + (int64_t)b * p.z_bstride + row * p.ldz
+                             : Xb + row * p.ldx;
+          for (int i = 0; i < p.kvalid; ++i) acc[i] -= Eb[i] * Zr[i];
+        }
+        TV* Yr = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride + row * p.ldy;
+        const TV* Ur = (p.U != nullptr)
+                           ? reinterpret_cast<const TV*>(p.U) + (int64_t)b * p.u_bstride + row * p.ldu
+                           : nullptr;
+#pragma unroll
+        for (int i = 0; i < MV_MAXK; ++i) {
+          if (i < p.kvalid) {
+            Yr[i] = acc[i];
+            d1[i] += (double)acc[i] * (double)acc[i];
+            if (Ur != nullptr) d0[i] += (double)Ur[i] * (double)acc[i];
+          }
+        }
+      }
+    }
+    if (p.dot_out != nullptr) {
+      __syncthreads();
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < MV_MAXK; ++i) { dscr[warp][0][i] = d0[i]; dscr[warp][1][i] = d1[i]; }
+      }
+      __syncthreads();
+      if (threadIdx.x < 2 * MV_MAXK) {
+        const int which = threadIdx.x / MV_MAXK, i = threadIdx.x % MV_MAXK;
+        double sum = 0.0;
+        for (int w = 0; w < 8; ++w) sum += dscr[w][which][i];
+        p.dot_out[((size_t)tile * 2 + which) * MV_MAXK + i] = sum;
+      }
+    }
+  }
+}
+
+// ============================================================================ launch
+template <typename TA, typename TV, int K>
+static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);
+  constexpr int KC = 2 * BOXC;
+  constexpr int XBYTES = KC * K * (int)sizeof(TV);
+  constexpr int STAGE_BYTES = MV_STAGE_A_BYTES + XBYTES;
+  const size_t fixed = MV_CONSUMERS * K * sizeof(TV) + 8 * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
+  if (ns > 6) ns = 6;
+  if (ns < 2) {
+    set_last_error("matvec: not enough shared memory for 2 stages");
+    return XT_ERR_INVALID;
+  }
+  const size_t smem = (size_t)ns * STAGE_BYTES + fixed;
+  MvDev dev = dev0;
+  dev.nstages = ns;
+  CUtensorMap tm;
+  bool batched = false;
+  int rc = make_tmap(a, &tm, &batched);
+  if (rc != XT_OK) return rc;
+  dev.a_batched = batched ? 1 : 0;
+  auto kern = mv_tma_kernel<TA, TV, K>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  kern<<<til.grid, MV_THREADS, smem, st>>>(tm, dev);
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
+template <typename TA, typename TV>
+static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
+  if (a.k <= 1) return launch_tma_k<TA, TV, 1>(a, dev, til, st);
+  if (a.k <= 2) return launch_tma_k<TA, TV, 2>(a, dev, til, st);
+  if (a.k <= 4) return launch_tma_k<TA, TV, 4>(a, dev, til, st);
+  if (a.k <= 8) return launch_tma_k<TA, TV, 8>(a, dev, til, st);
+  return launch_tma_k<TA, TV, 16>(a, dev, til, st);
+}
+
+template <typename TA, typename TV>
+static int launch_plain(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
+  int grid = til.ntiles < 8 * num_sms() ? til.ntiles : 8 * num_sms();
+  mv_plain_kernel<TA, TV><<<grid, 256, 0, st>>>(reinterpret_cast<const TA*>(a.A), a.lda, a.a_bstride, dev);
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
+int mv_launch(const MvArgs& a, cudaStream_t st) {
+  XT_REQUIRE(a.k >= 1 && a.k <= MV_MAXK, "matvec: k=%d outside 1..%d", a.k, MV_MAXK);
+  XT_REQUIRE(a.nbatch >= 1 && a.nrows >= 1 && a.ncolsA >= 1, "matvec: empty problem (%d,%d,%d)", a.nbatch, a.nrows,
+             a.ncolsA);
+  XT_REQUIRE(a.A && a.X && a.Y, "matvec: null pointer");
+  XT_REQUIRE(a.E == nullptr || a.Z != nullptr || a.nrows == a.ncolsA, "matvec: shift with Z = X needs a square A");
+  const MvTiling til = mv_tiling(a.nbatch, a.nrows);
+  MvDev d;
+  d.nbatch = a.nbatch; d.nrows = a.nrows; d.ncolsA = a.ncolsA; d.kvalid = a.k;
+  d.tile_rows = til.tile_rows; d.tiles_per_batch = til.tiles_per_batch; d.ntiles = til.ntiles;
+  int rp = 16;
+  while (rp < til.tile_rows) rp <<= 1;
+  d.rows_pad = rp;
+  d.nstages = 0; d.a_batched = 0;
+  d.X = a.X; d.ldx = a.ldx; d.x_bstride = a.x_bstride;
+  d.Y = a.Y; d.ldy = a.ldy; d.y_bstride = a.y_bstride;
+  d.E = a.E; d.e_bstride = a.e_bstride;
+  d.Z = a.Z; d.ldz = a.ldz; d.z_bstride = a.z_bstride;
+  d.U = a.U; d.ldu = a.ldu; d.u_bstride = a.u_bstride;
+  d.dot_out = a.dot_out;
+  d.done_flag = a.done_flag;
+
+  bool use_tma = (a.impl == 1) || (a.impl == 0 && mv_tma_ok(a));
+  if (a.impl == 1 && !mv_tma_ok(a)) {
+    set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
+    return XT_ERR_INVALID;
+  }
+  switch (a.dtype) {
+    case XT_F32:
+      return use_tma ? launch_tma<float, float>(a, d, til, st) : launch_plain<float, float>(a, d, til, st);
+    case XT_BF16:
+      return use_tma ? launch_tma<__nv_bfloat16, float>(a, d, til, st)
+                     : launch_plain<__nv_bfloat16, float>(a, d, til, st);
+    case XT_F64:
+      return use_tma ? launch_tma<double, double>(a, d, til, st) : launch_plain<double, double>(a, d, til, st);
+    default:
+      set_last_error("matvec: unknown dtype %d", a.dtype);
+      return XT_ERR_INVALID;
+  }
+}
+
+}  // namespace xt
+
+// ============================================================================ C ABI
+extern "C" {
+
+int xt_version(void) { return 100; }
+const char* xt_last_error(void) { return xt::last_error(); }
+
+int xt_block_matvec(const xt_matvec_args* g) {
+  if (g == nullptr) return XT_ERR_INVALID;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
+  const size_t vs = (g->dtype == XT_F64) ? 8 : 4;
+  // column groups of <= 16: one pass over A per group
+  for (int c0 = 0; c0 < g->k; c0 += xt::MV_MAXK) {
+    xt::MvArgs a;
+    a.dtype = g->dtype;
+    a.nbatch = g->nbatch; a.nrows = g->nrows; a.ncolsA = g->ncolsA;
+    a.k = (g->k - c0 < xt::MV_MAXK) ? (g->k - c0) : xt::MV_MAXK;
+    a.A = g->A; a.lda = g->lda; a.a_bstride = g->a_bstride;
+    a.X = static_cast<const char*>(g->X) + c0 * vs; a.ldx = g->ldx; a.x_bstride = g->x_bstride;
+    a.Y = static_cast<char*>(g->Y) + c0 * vs; a.ldy = g->ldy; a.y_bstride = g->y_bstride;
+    a.E = g->E ? static_cast<const char*>(g->E) + c0 * vs : nullptr; a.e_bstride = g->e_bstride;
+    a.Z = g->Z ? static_cast<const char*>(g->Z) + c0 * vs : nullptr; a.ldz = g->ldz; a.z_bstride = g->z_bstride;
+    a.U = nullptr; a.ldu = 0; a.u_bstride = 0; a.dot_out = nullptr;
+    a.impl = g->impl;
+    a.done_flag = nullptr;
+    int rc = xt::mv_launch(a, st);
+    if (rc != XT_OK) return rc;
+  }
+  return XT_OK;
+}
+
+}  // extern "C"

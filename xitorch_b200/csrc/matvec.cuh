@@ -1,0 +1,47 @@
+// Internal interface of the dense block matvec (shared by the solver drivers).
+#pragma once
+#include "common.cuh"
+
+namespace xt {
+
+constexpr int MV_MAXK = 16;          // columns handled by one pass over A
+constexpr int MV_TILE_ROWS = 128;    // max rows of a CTA tile
+constexpr int MV_BOX_ROWS = 8;       // rows of one TMA box (= one 128B-swizzle atom: 8 x 128 B)
+constexpr int MV_CONSUMERS = 256;    // consumer threads (8 warps)
+constexpr int MV_THREADS = MV_CONSUMERS + 64;   // + TMA warp + X-staging warp
+
+// Work decomposition of one block matvec launch (identical for both kernels, so that the
+// per-tile partial dot products have one layout).
+struct MvTiling {
+  int tile_rows;        // TH: multiple of 8, <= 128
+  int tiles_per_batch;
+  int ntiles;
+  int grid;
+};
+MvTiling mv_tiling(int nbatch, int nrows);
+
+// Y_b = A_b X_b [- Z_b diag(E_b)], plus optional fused per-tile partial dot products
+//   dot_out[tile][0][c] = sum_rows U[row][c] * Y[row][c]      (if U != nullptr)
+//   dot_out[tile][1][c] = sum_rows Y[row][c]^2
+// stored as double, layout [ntiles][2][MV_MAXK].
+struct MvArgs {
+  int dtype;                                   // xt_dtype of A
+  int nbatch, nrows, ncolsA, k;                // k <= MV_MAXK
+  const void* A; int64_t lda, a_bstride;
+  const void* X; int64_t ldx, x_bstride;
+  void* Y; int64_t ldy, y_bstride;
+  const void* E; int64_t e_bstride;            // optional shift (nbatch, k)
+  const void* Z; int64_t ldz, z_bstride;       // optional Z (defaults to X when E is given)
+  const void* U; int64_t ldu, u_bstride;       // optional dot operand
+  double* dot_out;                             // optional (needs U or self-dot), see above
+  int impl;                                    // 0 auto, 1 TMA, 2 plain
+  const int* done_flag;                        // optional device flag: kernel exits immediately when *done_flag != 0
+};
+
+// enqueue on `stream`; returns xt_status
+int mv_launch(const MvArgs& a, cudaStream_t stream);
+
+// true when the TMA kernel can take these arguments (alignment / stride rules)
+bool mv_tma_ok(const MvArgs& a);
+
+}  // namespace xt

@@ -1,0 +1,138 @@
+// Shared pieces of the linear-solver drivers (solve.cu, gmres.cu).
+#pragma once
+#include "matvec.cuh"
+
+#include <cstring>
+#include <cmath>
+
+namespace xt {
+
+constexpr int SV_THREADS = 512;
+constexpr int SV_MAXCS = 8;     // column slots per thread  => ncols <= 32 * 8
+
+// device-resident control block of one solve
+struct SolveCtl {
+  int done;            // 1 once the stop test passed
+  int converged;
+  int niter;           // iteration at which the stop test passed (or last executed)
+  int improved_iter;   // iteration whose iterate is the best so far and still has to be copied to best_x
+  int last_iter;       // last iteration whose residual norms were evaluated
+  unsigned int counter;
+  double best_resid;
+};
+
+template <typename TV> struct SolveState {
+  int n, nbatch, ncols;
+  int tiles_per_batch;
+  TV *x, *r, *p, *q, *s, *rhat, *bestx;   // contiguous (nbatch, n, ncols); q = A p (cg) / v (bicgstab); s,t bicgstab
+  TV *t;
+  const TV* B; int64_t ldb, b_bstride;
+  double* dots;          // [ngroups][ntiles][2][16]
+  int64_t dots_gstride;  // ntiles*2*16
+  double *rz;            // cg: r.z ; bicgstab: rho            [nbatch*ncols]
+  double *alpha, *omega; // bicgstab scalars                    [nbatch*ncols]
+  double *rhonew;        //                                     [nbatch*ncols]
+  double *stop;          // [nbatch*ncols]
+  double *cta_max; int* cta_bad;   // [nbatch]
+  SolveCtl* ctl;
+  double eps;
+};
+
+__device__ __forceinline__ double safedenom(double v, double eps) { return v == 0.0 ? eps : v; }
+
+// per-column block reduction of up to NR quantities; result in smem res[NR][ncols] (double)
+template <int NR>
+__device__ __forceinline__ void col_reduce(const double (&part)[NR][SV_MAXCS], int ncols, int tx, int ty, int TX,
+                                           int TY, double* scr /* [TY][NR][TX] */, double* res /* [NR][ncols] */) {
+  for (int cs = 0; cs * TX < ncols; ++cs) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NR; ++k) scr[(ty * NR + k) * TX + tx] = part[k][cs];
+    __syncthreads();
+    const int c = cs * TX + tx;
+    if (ty < NR && c < ncols) {
+      double sum = 0.0;
+      for (int y = 0; y < TY; ++y) sum += scr[(y * NR + ty) * TX + tx];
+      res[ty * ncols + c] = sum;
+    }
+  }
+  __syncthreads();
+}
+
+// sum of the fused matvec dot partials of batch item b, column c
+template <typename TV>
+__device__ __forceinline__ double tile_dot(const SolveState<TV>& S, int b, int c, int which) {
+  const double* base = S.dots + (int64_t)(c / MV_MAXK) * S.dots_gstride;
+  double sum = 0.0;
+  for (int t = 0; t < S.tiles_per_batch; ++t)
+    sum += base[((size_t)(b * S.tiles_per_batch + t) * 2 + which) * MV_MAXK + (c % MV_MAXK)];
+  return sum;
+}
+
+struct Geo {
+  int tx, ty, TX, TY;
+};
+__device__ __forceinline__ Geo geo(int ncols) {
+  Geo g;
+  int TX = 1;
+  while (TX < ncols && TX < 32) TX <<= 1;
+  g.TX = TX;
+  g.TY = SV_THREADS / TX;
+  g.tx = threadIdx.x % TX;
+  g.ty = threadIdx.x / TX;
+  return g;
+}
+
+struct OpDesc {
+  int dtype, n, nbatch, ncols;
+  const void* A; int64_t lda, a_bstride;
+  const void* M; int64_t ldm, m_bstride;
+  const void* E; int64_t e_bstride;
+};
+
+// Y = A X - (M X) E  (+ fused dots with U on the A pass); `mx` is scratch for M X
+template <typename TV>
+static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const TV* U, double* dots, int64_t dots_gstride,
+                    const int* done_flag, cudaStream_t st, int64_t* napply) {
+  const int64_t len = (int64_t)op.n * op.ncols;
+  for (int c0 = 0, gi = 0; c0 < op.ncols; c0 += MV_MAXK, ++gi) {
+    const int kg = (op.ncols - c0 < MV_MAXK) ? (op.ncols - c0) : MV_MAXK;
+    MvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dtype = op.dtype;
+    a.nbatch = op.nbatch; a.nrows = op.n; a.ncolsA = op.n; a.k = kg;
+    a.X = X + c0; a.ldx = op.ncols; a.x_bstride = len;
+    a.done_flag = done_flag;
+    if (op.E != nullptr && op.M != nullptr) {
+      a.A = op.M; a.lda = op.ldm; a.a_bstride = op.m_bstride;
+      a.Y = mx + c0; a.ldy = op.ncols; a.y_bstride = len;
+      int rc = mv_launch(a, st);
+      if (rc != XT_OK) return rc;
+    }
+    a.A = op.A; a.lda = op.lda; a.a_bstride = op.a_bstride;
+    a.Y = Y + c0; a.ldy = op.ncols; a.y_bstride = len;
+    if (op.E != nullptr) {
+      a.E = static_cast<const TV*>(op.E) + c0; a.e_bstride = op.e_bstride;
+      if (op.M != nullptr) { a.Z = mx + c0; a.ldz = op.ncols; a.z_bstride = len; }
+    }
+    if (dots != nullptr) {
+      a.U = U ? U + c0 : nullptr; a.ldu = op.ncols; a.u_bstride = len;
+      a.dot_out = dots + gi * dots_gstride;
+    }
+    int rc = mv_launch(a, st);
+    if (rc != XT_OK) return rc;
+  }
+  if (napply) ++(*napply);
+  return XT_OK;
+}
+
+static inline int poll_done(SolveCtl* ctl, cudaStream_t st, int* done) {
+  int h = 0;
+  XT_CUDA_OK(cudaMemcpyAsync(&h, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XT_CUDA_OK(cudaStreamSynchronize(st));
+  *done = h;
+  return XT_OK;
+}
+
+
+}  // namespace xt

@@ -1,0 +1,464 @@
+"""
+Operator interface (boundary B2 of SURVEY.md 8b).
+
+Host-side mirror of the reference's `xitorch.LinearOperator` contract
+(/root/reference/xitorch/_core/linop.py:15-552) and of its dense implementation
+`MatrixLinearOperator` (linop.py:676-708) -- same method names, shape rules and
+error behaviour, written from scratch:
+
+  * a subclass must implement `_mv`; `_mm/_rmv/_rmm/_fullmatrix/_getparamnames` are optional
+    (linop.py:36-51); forgetting `super().__init__` raises RuntimeError on first use (:550-552)
+  * `mv/mm/rmv/rmm` validate the contracted dimension -> RuntimeError (:232,255,294,322)
+  * `mm` falls back to batched `_mv` (:259-274); `rmv` falls back to the autograd adjoint trick
+    (:524-543); Hermitian operators route `rmv/rmm` to `mv/mm` (:298,326)
+  * `LinearOperator.m(mat, is_hermitian)` builds the dense operator, checking symmetry (:59-107)
+  * `.H`, `.matmul`, `+ - *` (:377-447); `fullmatrix()` never caches
+  * parameters are exposed by name (`_getparamnames`) so the autograd boundary can swap them
+    (`getlinopparams` / `uselinopparams`, :200-212).
+
+The dense operator is the accelerated one: on a CUDA device with autograd off (the state inside
+`torch.autograd.Function.forward`, where the Krylov loops run) `MatrixLinearOperator.mm/mv/rmm/rmv`
+launch the hand-written sm_100a block-matvec kernel through the C ABI
+(`xt_block_matvec_*`, include/xitorch_b200.h).  When autograd needs a graph (backward's
+`A.mm(x)` under `enable_grad`) the differentiable library GEMM is used instead.
+"""
+import warnings
+from contextlib import contextmanager
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from xitorch_b200 import _utils
+from xitorch_b200 import debug as _debug
+
+__all__ = ["LinearOperator", "MatrixLinearOperator"]
+
+
+def _indent(s: str, n: int) -> str:
+    pad = " " * n
+    return ("\n" + pad).join(s.split("\n"))
+
+
+class LinearOperator(object):
+    """Base class of (batched) linear operators of shape ``(*B, p, q)``."""
+
+    _impl_flags_ready = False
+    _has = {}
+
+    def __new__(cls, *args, **kwargs):
+        if not cls.__dict__.get("_impl_flags_ready", False):
+            cls._has = {name: getattr(cls, name) is not getattr(LinearOperator, name)
+                        for name in ("_mv", "_mm", "_rmv", "_rmm", "_fullmatrix", "_getparamnames")}
+            cls._impl_flags_ready = True
+            if not cls._has["_mv"]:
+                raise RuntimeError("LinearOperator must have at least _mv(self) method implemented")
+        return super(LinearOperator, cls).__new__(cls)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def m(cls, mat: torch.Tensor, is_hermitian: Optional[bool] = None):
+        """Dense-matrix operator. ``is_hermitian=None`` checks ``mat == mat^H`` (one full pass);
+        ``True`` on a non-symmetric matrix raises RuntimeError."""
+        if is_hermitian is None:
+            if mat.shape[-2] != mat.shape[-1]:
+                is_hermitian = False
+            else:
+                is_hermitian = bool(torch.allclose(mat, mat.transpose(-2, -1).conj()))
+        elif is_hermitian:
+            if not torch.allclose(mat, mat.transpose(-2, -1).conj()):
+                raise RuntimeError("The linear operator is indicated to be hermitian, but the matrix is not")
+        return MatrixLinearOperator(mat, is_hermitian)
+
+    def __init__(self, shape: Sequence[int], is_hermitian: bool = False,
+                 dtype: Optional[torch.dtype] = None, device: Optional[torch.device] = None,
+                 _suppress_hermit_warning: bool = False) -> None:
+        if len(shape) < 2:
+            raise RuntimeError("The shape must have at least 2 dimensions")
+        if is_hermitian and shape[-1] != shape[-2]:
+            raise RuntimeError("The object is indicated as Hermitian, but the shape is not square")
+        self._shape = tuple(shape)
+        self._batchshape = list(shape[:-2])
+        self._is_hermitian = bool(is_hermitian)
+        self._dtype = dtype if dtype is not None else torch.float32
+        self._device = device if device is not None else torch.device("cpu")
+        self._linop_ready = True
+        if (not _suppress_hermit_warning) and self._is_hermitian and \
+                (self._has.get("_rmv") or self._has.get("_rmm")):
+            warnings.warn("The LinearOperator is Hermitian with implemented rmv or rmm. "
+                          "We will use the mv and mm methods instead", stacklevel=2)
+
+    def _require_init(self):
+        if not getattr(self, "_linop_ready", False):
+            raise RuntimeError("super().__init__ must be executed in the __init__ of a LinearOperator subclass")
+
+    def __repr__(self) -> str:
+        return "LinearOperator (%s) with shape %s, dtype = %s, device = %s" % \
+            (self.__class__.__name__, tuple(self.shape), self.dtype, self.device)
+
+    # ------------------------------------------------------------------ to be implemented
+    def _mv(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _mm(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _rmv(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _rmm(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _fullmatrix(self) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _getparamnames(self, prefix: str = "") -> List[str]:
+        return []
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def getparamnames(self, methodname: str, prefix: str = "") -> List[str]:
+        if methodname in ("mv", "rmv", "mm", "rmm", "fullmatrix"):
+            return self._getparamnames(prefix=prefix)
+        raise KeyError("getparamnames for method %s is not implemented" % methodname)
+
+    def _unique_param_names(self) -> List[str]:
+        names, seen = [], set()
+        for nm in self._getparamnames(prefix=""):
+            t = _utils.get_attr(self, nm)
+            if id(t) not in seen:
+                seen.add(id(t))
+                names.append(nm)
+        return names
+
+    def getlinopparams(self) -> List[torch.Tensor]:
+        """unique tensors that `mm` depends on (the reference's getuniqueparams("mm"))."""
+        return [_utils.get_attr(self, nm) for nm in self._unique_param_names()]
+
+    @contextmanager
+    def uselinopparams(self, *params):
+        """temporarily substitute the operator's parameters (restored on exit, even on error)."""
+        allnames = self._getparamnames(prefix="")
+        uniq = self._unique_param_names()
+        if len(params) != len(uniq):
+            raise RuntimeError("uselinopparams expects %d tensors, got %d" % (len(uniq), len(params)))
+        originals = [(nm, _utils.get_attr(self, nm)) for nm in allnames]
+        by_id = {id(_utils.get_attr(self, nm)): p for nm, p in zip(uniq, params)}
+        try:
+            for nm, orig in originals:
+                _utils.set_attr(self, nm, by_id[id(orig)])
+            yield self
+        finally:
+            for nm, orig in originals:
+                _utils.set_attr(self, nm, orig)
+
+    # ------------------------------------------------------------------ public operations
+    def mv(self, x: torch.Tensor) -> torch.Tensor:
+        """``A x`` for ``x`` of shape ``(..., q)`` -> ``(..., p)``."""
+        self._require_init()
+        if x.shape[-1] != self.shape[-1]:
+            raise RuntimeError("Cannot operate .mv on shape %s. Expected (...,%d)" %
+                               (str(tuple(x.shape)), self.shape[-1]))
+        return self._mv(x)
+
+    def _cols_as_batch(self, x: torch.Tensor, fcn) -> torch.Tensor:
+        # (..., q, r) -> r leading batch of vectors (r, ..., q), apply, and move back
+        xb = list(x.shape[:-2])
+        if len(xb) < len(self._batchshape):
+            xb = [1] * (len(self._batchshape) - len(xb)) + xb
+        x1 = x.reshape(1, *xb, *x.shape[-2:]).transpose(0, -1).squeeze(-1)
+        y = fcn(x1)
+        return y.unsqueeze(-1).transpose(0, -1).squeeze(0)
+
+    def mm(self, x: torch.Tensor) -> torch.Tensor:
+        """``A X`` for ``X`` of shape ``(..., q, r)`` -> ``(..., p, r)``."""
+        self._require_init()
+        if x.shape[-2] != self.shape[-1]:
+            raise RuntimeError("Cannot operate .mm on shape %s. Expected (...,%d,*)" %
+                               (str(tuple(x.shape)), self.shape[-1]))
+        if self._has["_mm"]:
+            return self._mm(x)
+        return self._cols_as_batch(x, self._mv)
+
+    def rmv(self, x: torch.Tensor) -> torch.Tensor:
+        """``A^H x`` for ``x`` of shape ``(..., p)`` -> ``(..., q)``."""
+        self._require_init()
+        if x.shape[-1] != self.shape[-2]:
+            raise RuntimeError("Cannot operate .rmv on shape %s. Expected (...,%d)" %
+                               (str(tuple(x.shape)), self.shape[-2]))
+        if self._is_hermitian:
+            return self._mv(x)
+        if not self._has["_rmv"]:
+            return self._adjoint_rmv(x)
+        return self._rmv(x)
+
+    def rmm(self, x: torch.Tensor) -> torch.Tensor:
+        """``A^H X`` for ``X`` of shape ``(..., p, r)`` -> ``(..., q, r)``."""
+        self._require_init()
+        if x.shape[-2] != self.shape[-2]:
+            raise RuntimeError("Cannot operate .rmm on shape %s. Expected (...,%d,*)" %
+                               (str(tuple(x.shape)), self.shape[-2]))
+        if self._is_hermitian:
+            return self.mm(x)
+        if self._has["_rmm"]:
+            return self._rmm(x)
+        return self._cols_as_batch(x, self._rmv if self._has["_rmv"] else self.rmv)
+
+    def _adjoint_rmv(self, xt: torch.Tensor) -> torch.Tensor:
+        # A^H x through autograd: d/dv <A v, x> (the reference's adjoint trick, linop.py:524-543)
+        bx = _utils.bcast_dims(xt.shape[:-1], self.shape[:-2])
+        with torch.enable_grad():
+            probe = torch.zeros((*bx, self.shape[-1]), dtype=xt.dtype, device=xt.device).requires_grad_()
+            out = self._mv(probe)
+        (res,) = torch.autograd.grad(out, (probe,), grad_outputs=(xt.conj(),),
+                                     create_graph=torch.is_grad_enabled())
+        return res.conj()
+
+    def fullmatrix(self) -> torch.Tensor:
+        if self._has["_fullmatrix"]:
+            return self._fullmatrix()
+        self._require_init()
+        eye = torch.eye(self._shape[-1], dtype=self._dtype, device=self._device)
+        return self.mm(eye)
+
+    def scipy_linalg_op(self):
+        from scipy.sparse.linalg import LinearOperator as spLinearOperator
+        tt = lambda v: torch.as_tensor(v, dtype=self.dtype, device=self.device)   # noqa: E731
+        nn = lambda t: t.detach().cpu().numpy()                                   # noqa: E731
+        return spLinearOperator(shape=self.shape,
+                                matvec=lambda v: nn(self.mv(tt(v))), rmatvec=lambda v: nn(self.rmv(tt(v))),
+                                matmat=lambda v: nn(self.mm(tt(v))), rmatmat=lambda v: nn(self.rmm(tt(v))))
+
+    def check(self, warn: Optional[bool] = None) -> None:
+        """cheap self-consistency check (shape of mv/mm, adjoint identity, Hermiticity)."""
+        if warn is None:
+            warn = _debug.is_debug_enabled()
+        p, q = self.shape[-2:]
+        x = torch.rand(q, dtype=self.dtype, device=self.device)
+        y = self.mv(x)
+        if list(y.shape) != [*self._batchshape, p]:
+            raise RuntimeError("mv returned shape %s, expected %s" % (tuple(y.shape), (*self._batchshape, p)))
+        X = torch.rand(q, 2, dtype=self.dtype, device=self.device)
+        Y = self.mm(X)
+        if list(Y.shape) != [*self._batchshape, p, 2]:
+            raise RuntimeError("mm returned shape %s" % (tuple(Y.shape),))
+        if not torch.allclose(Y[..., 0], self.mv(X[..., 0]), rtol=1e-4, atol=1e-6):
+            raise RuntimeError("mm and mv are inconsistent")
+        z = torch.rand(p, dtype=self.dtype, device=self.device)
+        lhs = (self.rmv(z).conj() * x).sum(-1)
+        rhs = (z.conj() * self.mv(x)).sum(-1)
+        if not torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-6):
+            msg = "rmv is not the adjoint of mv"
+            if self._is_hermitian:
+                msg = "The linear operator is marked Hermitian but <A^H z, x> != <z, A x>"
+            raise RuntimeError(msg)
+
+    # ------------------------------------------------------------------ algebra
+    @property
+    def H(self):
+        if self._is_hermitian:
+            return self
+        if isinstance(self, MatrixLinearOperator):
+            return LinearOperator.m(self.fullmatrix().transpose(-2, -1).conj())
+        return AdjointLinearOperator(self)
+
+    def matmul(self, b: "LinearOperator", is_hermitian: bool = False):
+        if self.shape[-1] != b.shape[-2]:
+            raise RuntimeError("Mismatch shape of matmul operation: %s and %s" % (self.shape, b.shape))
+        if isinstance(self, MatrixLinearOperator) and isinstance(b, MatrixLinearOperator):
+            return LinearOperator.m(self.fullmatrix() @ b.fullmatrix(), is_hermitian=is_hermitian)
+        return MatmulLinearOperator(self, b, is_hermitian=is_hermitian)
+
+    def _addsub(self, b, sign):
+        assert isinstance(b, LinearOperator), "Only addition with another LinearOperator is supported"
+        if tuple(self.shape[-2:]) != tuple(b.shape[-2:]):
+            raise RuntimeError("Mismatch shape of add operation: %s and %s" % (self.shape, b.shape))
+        if isinstance(self, MatrixLinearOperator) and isinstance(b, MatrixLinearOperator):
+            return LinearOperator.m(self.fullmatrix() + sign * b.fullmatrix())
+        return AddLinearOperator(self, b, sign)
+
+    def __add__(self, b):
+        return self._addsub(b, 1)
+
+    def __sub__(self, b):
+        return self._addsub(b, -1)
+
+    def __rsub__(self, b):
+        return b.__sub__(self)
+
+    def __mul__(self, f: Union[int, float]):
+        if not isinstance(f, (int, float)):
+            raise TypeError("LinearOperator multiplication only supports integer or floating point")
+        if isinstance(self, MatrixLinearOperator):
+            return LinearOperator.m(self.fullmatrix() * f)
+        return MulLinearOperator(self, f)
+
+    __rmul__ = __mul__
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dtype(self) -> torch.dtype:
+        return self._dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @property
+    def shape(self) -> Sequence[int]:
+        return self._shape
+
+    @property
+    def is_hermitian(self) -> bool:
+        return self._is_hermitian
+
+    @property
+    def is_mv_implemented(self) -> bool:
+        return True
+
+    @property
+    def is_mm_implemented(self) -> bool:
+        return self._has["_mm"]
+
+    @property
+    def is_rmv_implemented(self) -> bool:
+        return self._has["_rmv"]
+
+    @property
+    def is_rmm_implemented(self) -> bool:
+        return self._has["_rmm"]
+
+    @property
+    def is_fullmatrix_implemented(self) -> bool:
+        return self._has["_fullmatrix"]
+
+    @property
+    def is_getparamnames_implemented(self) -> bool:
+        return self._has["_getparamnames"]
+
+
+# ---------------------------------------------------------------------- composites
+class AdjointLinearOperator(LinearOperator):
+    def __init__(self, obj: LinearOperator):
+        super().__init__(shape=(*obj.shape[:-2], obj.shape[-1], obj.shape[-2]),
+                         is_hermitian=obj.is_hermitian, dtype=obj.dtype, device=obj.device,
+                         _suppress_hermit_warning=True)
+        self.obj = obj
+
+    def __repr__(self):
+        return "AdjointLinearOperator with shape %s of:\n - %s" % (tuple(self.shape), _indent(repr(self.obj), 3))
+
+    def _mv(self, x):
+        return self.obj.rmv(x)
+
+    def _rmv(self, x):
+        return self.obj.mv(x)
+
+    def _getparamnames(self, prefix=""):
+        return self.obj._getparamnames(prefix=prefix + "obj.")
+
+    @property
+    def H(self):
+        return self.obj
+
+
+class MatmulLinearOperator(LinearOperator):
+    def __init__(self, a: LinearOperator, b: LinearOperator, is_hermitian: bool = False):
+        super().__init__(shape=(*_utils.bcast_dims(a.shape[:-2], b.shape[:-2]), a.shape[-2], b.shape[-1]),
+                         is_hermitian=is_hermitian, dtype=a.dtype, device=a.device,
+                         _suppress_hermit_warning=True)
+        self.a, self.b = a, b
+
+    def __repr__(self):
+        return "MatmulLinearOperator with shape %s of:\n * %s\n * %s" % \
+            (tuple(self.shape), _indent(repr(self.a), 3), _indent(repr(self.b), 3))
+
+    def _mv(self, x):
+        return self.a.mv(self.b.mv(x))
+
+    def _rmv(self, x):
+        return self.b.rmv(self.a.rmv(x))
+
+    def _getparamnames(self, prefix=""):
+        return self.a._getparamnames(prefix=prefix + "a.") + self.b._getparamnames(prefix=prefix + "b.")
+
+
+class AddLinearOperator(LinearOperator):
+    def __init__(self, a: LinearOperator, b: LinearOperator, mul: int = 1):
+        assert mul in (1, -1)
+        super().__init__(shape=(*_utils.bcast_dims(a.shape[:-2], b.shape[:-2]), a.shape[-2], b.shape[-1]),
+                         is_hermitian=a.is_hermitian and b.is_hermitian, dtype=a.dtype, device=a.device,
+                         _suppress_hermit_warning=True)
+        self.a, self.b, self.mul = a, b, mul
+
+    def __repr__(self):
+        return "AddLinearOperator with shape %s of:\n * %s\n * %s" % \
+            (tuple(self.shape), _indent(repr(self.a), 3), _indent(repr(self.b), 3))
+
+    def _mv(self, x):
+        return self.a.mv(x) + self.mul * self.b.mv(x)
+
+    def _rmv(self, x):
+        return self.a.rmv(x) + self.mul * self.b.rmv(x)
+
+    def _getparamnames(self, prefix=""):
+        return self.a._getparamnames(prefix=prefix + "a.") + self.b._getparamnames(prefix=prefix + "b.")
+
+
+class MulLinearOperator(LinearOperator):
+    def __init__(self, a: LinearOperator, f: Union[int, float]):
+        super().__init__(shape=a.shape, is_hermitian=a.is_hermitian, dtype=a.dtype, device=a.device,
+                         _suppress_hermit_warning=True)
+        self.a, self.f = a, f
+
+    def __repr__(self):
+        return "MulLinearOperator with shape %s of: \n * %s\n * %s" % \
+            (tuple(self.shape), _indent(repr(self.a), 3), _indent(repr(self.f), 3))
+
+    def _mv(self, x):
+        return self.a.mv(x) * self.f
+
+    def _rmv(self, x):
+        return self.a.rmv(x) * self.f
+
+    def _getparamnames(self, prefix=""):
+        return self.a._getparamnames(prefix=prefix + "a.")
+
+
+# ---------------------------------------------------------------------- the dense (accelerated) operator
+class MatrixLinearOperator(LinearOperator):
+    """Dense operator with public attribute ``mat`` and parameter name ``"mat"``."""
+
+    def __init__(self, mat: torch.Tensor, is_hermitian: bool) -> None:
+        super().__init__(shape=mat.shape, is_hermitian=is_hermitian, dtype=mat.dtype, device=mat.device,
+                         _suppress_hermit_warning=True)
+        self.mat = mat
+
+    def __repr__(self):
+        return "MatrixLinearOperator with shape %s:\n   %s" % (tuple(self.shape), _indent(repr(self.mat), 3))
+
+    def _apply(self, x: torch.Tensor, adjoint: bool) -> torch.Tensor:
+        mat = self.mat
+        needs_graph = torch.is_grad_enabled() and (mat.requires_grad or x.requires_grad)
+        if mat.is_cuda and not needs_graph and not mat.is_complex():
+            from xitorch_b200 import _dense
+            if _dense.supports(mat, x):
+                return _dense.block_matvec(mat, x, adjoint=adjoint)
+        m = mat.transpose(-2, -1).conj() if adjoint else mat
+        return torch.matmul(m, x)
+
+    def _mv(self, x):
+        return self._apply(x.unsqueeze(-1), False).squeeze(-1)
+
+    def _mm(self, x):
+        return self._apply(x, False)
+
+    def _rmv(self, x):
+        return self._apply(x.unsqueeze(-1), True).squeeze(-1)
+
+    def _rmm(self, x):
+        return self._apply(x, True)
+
+    def _fullmatrix(self):
+        return self.mat
+
+    def _getparamnames(self, prefix=""):
+        return [prefix + "mat"]
