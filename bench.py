@@ -1,0 +1,314 @@
+"""
+bench.py -- the headline benchmark of BASELINE.json:
+  "Davidson iters/sec & HBM GB/s for symeig neig=8 on N=16384 dense LinOp"
+
+    python bench.py --gpus 1 --steps K --warmup W                 # our arm (B200, CUDA kernels via the C ABI)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference algorithm on the host CPU cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # N independent problems, one per GPU (weak scaling)
+
+A "step" is one complete `symeig(A, neig=8, mode="lowest", method="davidson", min_eps=1e-4)` solve of the
+BASELINE configs[1] problem (make_herm, N=16384, fp32); an "iteration" is one subspace
+expansion (one block matvec over A + Rayleigh-Ritz + residual + orthogonalisation).
+  value    = Davidson iterations / second with A resident in HBM (whole job, all ranks)
+  e2e      = the same through the public API from PINNED HOST buffers: H2D of A every step + solve + D2H of
+             the eigenpairs, all inside the timed region
+  roofline = the dominant kernel (block matvec, reads A once: 4*N^2 B per launch) timed in situ with CUDA
+             events on its launch stream (xt_profile_*), against the measured HBM peak
+  cpu_baseline = the oracle (bit-identical restatement of the reference's davidson, torch-CPU, all host
+             threads) on the same matrix
+A (1 GiB) is larger than L2 (126 MB), so every pass streams from HBM.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "davidson_iters_per_sec_symeig_neig8_N16384"
+UNIT = "iters/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def _physical_gpu_index(local: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the path (the oracle is a bit-identical restatement of
+    xitorch/_impls/linalg/symeig.py:100-227 on the same ATen calls), all host threads."""
+    if rank != 0:
+        return
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    A = oracle.make_herm(args.n, args.neig, torch.float32, seed=args.seed)
+    iters = 0
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle.davidson(A, args.neig, "lowest", min_eps=args.min_eps)
+    steps = max(1, min(args.steps, 5))        # bounded sample: each solve is ~0.3-1 s of CPU work
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, info = oracle.davidson(A, args.neig, "lowest", min_eps=args.min_eps, return_info=True)
+        iters += info["niter"]
+    dt = time.perf_counter() - t0
+    val = iters / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: symeig davidson neig=%d N=%d fp32 make_herm min_eps=%g" %
+                   (args.neig, args.n, args.min_eps), "a_read_gbs": iters * 4.0 * args.n * args.n / dt / 1e9},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d full solves (%d iterations) of the same N=%d matrix, torch-CPU %d threads"
+                                   % (steps, iters, args.n, cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--neig", type=int, default=8)
+    ap.add_argument("--min-eps", dest="min_eps", type=float, default=1e-4)
+    ap.add_argument("--method", default="davidson")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=7, help="make_herm seed (7: the reference's own fp32 davidson survives on it)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import oracle
+    import xitorch_b200 as xt
+    from xitorch_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    _lib.lib()
+
+    # one independent problem per rank (weak scaling, no data-path collective)
+    A_host = oracle.make_herm(args.n, args.neig, torch.float32, seed=args.seed + 1000 * rank).pin_memory()
+    A = A_host.to(dev, non_blocking=True)
+    op = xt.LinearOperator.m(A, is_hermitian=True)
+
+    def solve(o):
+        info = {}
+        ev, vec = xt.linalg.symeig(o, neig=args.neig, mode="lowest", method=args.method, min_eps=args.min_eps,
+                                   info=info)
+        return ev, vec, info
+
+    for _ in range(warmup):
+        ev, vec, info = solve(op)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput
+    sampler = ClockSampler(_physical_gpu_index(local))
+    barrier()
+    sampler.start()
+    _lib.profile_reset(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 0
+    all_conv = True
+    e0.record()
+    for _ in range(args.steps):
+        ev, vec, info = solve(op)
+        iters += info["niter"]
+        all_conv = all_conv and info["converged"]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    mv_ms, n_mv, n_launch = _lib.profile_read()
+    _lib.profile_reset(False)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    it = torch.tensor([float(iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    ms_max, iters_all = t.item(), it.item()
+    value = iters_all / (ms_max * 1e-3)
+
+    # parity spot check of what was timed (rank 0): fp64 Rayleigh quotients / residual of the returned pairs
+    Ad = A.double()
+    X = vec.double()
+    resid = (Ad @ X - X * ev.double()).abs().max().item()
+    rq = (X * (Ad @ X)).sum(0)
+    eig_rel = ((rq - ev.double()).abs() / rq.abs()).max().item()
+    del Ad
+
+    # ------------------------------------------------------------------ end to end from pinned host memory
+    ev_host = torch.empty((args.neig,), dtype=torch.float32).pin_memory()
+    vec_host = torch.empty((args.n, args.neig), dtype=torch.float32).pin_memory()
+    A2 = torch.empty_like(A)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    for _ in range(1):
+        A2.copy_(A_host, non_blocking=True)
+        solve(xt.LinearOperator.m(A2, is_hermitian=True))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(e2e_steps):
+        A2.copy_(A_host, non_blocking=True)                         # H2D of this step's input
+        ev2, vec2, info2 = solve(xt.LinearOperator.m(A2, is_hermitian=True))
+        ev_host.copy_(ev2, non_blocking=True)                       # D2H of this step's result
+        vec_host.copy_(vec2, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_iters += info2["niter"]
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    ie = torch.tensor([float(e2e_iters)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ie, op=dist.ReduceOp.SUM)
+    e2e_value = ie.item() / te.item()
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        bytes_per_launch = 4.0 * args.n * args.n
+        avg_ms = mv_ms / max(n_mv, 1)
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "C2: symeig %s neig=%d N=%d fp32 make_herm min_eps=%g, one independent problem per GPU"
+                            % (args.method, args.neig, args.n, args.min_eps),
+                "iters_per_step": iters / args.steps, "converged": bool(all_conv),
+                "l2": "inputs larger than L2 (A = %.2f GiB per pass)" % (bytes_per_launch / 2 ** 30),
+                "eig_rel_err_vs_fp64_rayleigh": eig_rel, "max_abs_residual": resid,
+                "hbm_gbs_whole_iteration": iters * bytes_per_launch / (ms * 1e-3) / 1e9,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "mv_tma_kernel<float,float,%d>" % args.neig,
+                         "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches": n_mv,
+                         "share_of_step": mv_ms / ms if ms > 0 else None, "peak_source": peak_src},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_launch),
+                    "d2h_bytes_per_step": 4 * (args.neig + args.n * args.neig), "steps": e2e_steps,
+                    "ms_per_step": te.item() / e2e_steps * 1e3},
+            "gpu_launches": int(n_launch),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            Acpu = A_host.clone()
+            oracle.davidson(Acpu, args.neig, "lowest", min_eps=args.min_eps)
+            reps, cit = 3, 0
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                evo, _, io = oracle.davidson(Acpu, args.neig, "lowest", min_eps=args.min_eps, return_info=True)
+                cit += io["niter"]
+            cdt = time.perf_counter() - t0
+            out["cpu_baseline"] = {
+                "value": cit / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d full solves (%d iterations) of the same matrix, oracle davidson fp32 min_eps=%g, "
+                          "torch-CPU %d threads, A-read %.1f GB/s" % (reps, cit, args.min_eps, cores,
+                                                                      cit * bytes_per_launch / cdt / 1e9)}
+            out["config"]["eig_rel_err_vs_oracle"] = ((ev.cpu().double() - evo.double()).abs()
+                                                      / evo.double().abs()).max().item()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,13 @@ typedef enum {
 int xt_version(void);
 const char* xt_last_error(void);
 
+/* Launch accounting and in-situ timing of the dominant kernel (used by bench.py for the roofline):
+ * xt_profile_reset(enable) zeroes the counters; with enable != 0 every block-matvec launch is bracketed
+ * by CUDA events on its stream.  xt_profile_read synchronises on the last event and returns the summed
+ * matvec kernel time (ms), the number of matvec launches and the number of ALL kernel launches. */
+void xt_profile_reset(int enable);
+int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_launches);
+
 /* ---------------------------------------------------------------------------------------------
  * Dense block matvec   Y_b = A_b X_b  [ - Z_b diag(E_b) ]        b = 0..nbatch-1
  * replaces MatrixLinearOperator._mm/_mv (xitorch/_core/linop.py:692-696) and the shifted operator

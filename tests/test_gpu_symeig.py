@@ -1,0 +1,152 @@
+"""GPU parity of davidson / lanczos (public API -> C ABI `xt_symeig_krylov`) against the committed reference
+outputs, the CPU oracle and fp64 eigvalsh.  Tolerance: eigenvalues within 1e-5 relative (north_star)."""
+import ctypes
+
+import pytest
+import torch
+
+import oracle
+import xitorch_b200 as xt
+from xitorch_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+EIG_RTOL = 1e-5
+
+
+def _check_pairs(A, evals, evecs, ref_evals, min_eps):
+    A64 = A.double()
+    ev = evals.double().cpu()
+    X = evecs.double().cpu()
+    rel = ((ev - ref_evals.double()).abs() / ref_evals.double().abs()).max().item()
+    assert rel <= EIG_RTOL, (rel, ev, ref_evals)
+    resid = (A64 @ X - X * ev.unsqueeze(-2)).abs().max().item()
+    assert resid <= 20 * min_eps + 1e-12, resid
+    gram = X.transpose(-2, -1) @ X
+    assert (gram - torch.eye(gram.shape[-1], dtype=torch.float64)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("method", ["davidson", "lanczos"])
+def test_golden_davidson_cases(golden, method):
+    for case in golden["davidson"]:
+        n, neig, mode, dtype = case["n"], case["neig"], case["mode"], case["dtype"]
+        if case["A"] is not None:
+            A = case["A"]
+        else:
+            A = oracle.make_herm(n, neig, torch.float64, seed=case["seed"]).to(dtype)
+        info = {}
+        evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, mode=mode,
+                                        method=method, min_eps=case["min_eps"], info=info)
+        assert evals.dtype == dtype and tuple(evals.shape) == (*case["batch"], neig)
+        assert info["converged"], (case["n"], mode, info)
+        _check_pairs(A, evals, evecs, case["evals"], case["min_eps"])                # vs the reference's davidson
+        _check_pairs(A, evals, evecs, case["evals_exact_f64"], case["min_eps"])      # vs fp64 eigvalsh
+        if case["evecs_abs"] is not None and dtype == torch.float64:
+            assert (evecs.abs().cpu() - case["evecs_abs"]).abs().max().item() <= 1e-5
+        # same Krylov space => about the same number of expansions as the reference algorithm (rounding at the
+        # threshold shifts the stopping iteration by a few)
+        assert abs(info["niter"] - case["oracle_niter"]) <= max(3, case["oracle_niter"] // 8), (info, case["oracle_niter"])
+
+
+def test_generalized_problem(golden):
+    c = golden["davidson_M"]
+    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(c["A"].to(DEV), True), neig=c["neig"],
+                                    M=xt.LinearOperator.m(c["M"].to(DEV), True), method="davidson",
+                                    min_eps=c["min_eps"])
+    assert ((evals.cpu() - c["evals"]).abs() / c["evals"].abs()).max().item() <= EIG_RTOL
+    X = evecs.cpu()
+    assert (c["A"] @ X - c["M"] @ X * evals.cpu().unsqueeze(-2)).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("method", ["davidson", "lanczos"])
+def test_fp32_2048_vs_oracle_fp64(method):
+    """fp32 operator at N=2048: the reference's own fp32 davidson only survives min_eps >= 1e-4
+    (SURVEY.md 8a A3); ours is compared with the oracle run in fp64 on the same fp32 matrix."""
+    n, neig = 2048, 8
+    A = oracle.make_herm(n, neig, torch.float32)
+    ev_o, _ = oracle.davidson(A.double(), neig, "lowest", min_eps=1e-9)
+    info = {}
+    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, method=method,
+                                    min_eps=1e-4, info=info)
+    assert info["converged"], info
+    _check_pairs(A, evals, evecs, ev_o, 1e-4)
+
+
+def test_thick_restart_slow_spectrum():
+    """slow-converging shifted GOE matrix with a small restart cap: exercises the thick restart; the
+    converged pairs must still match fp64 eigvalsh."""
+    n, neig = 1024, 4
+    A = oracle.make_slow_herm(n, torch.float64)
+    ref = torch.linalg.eigvalsh(A)[:neig]
+    info = {}
+    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, method="davidson",
+                                    min_eps=1e-7, max_basis=32, max_niter=2000, info=info)
+    assert info["converged"], info
+    _check_pairs(A, evals, evecs, ref, 1e-7)
+    assert info["niter"] > 32 // neig          # i.e. at least one restart happened
+
+
+def test_uppest_and_batch():
+    A = torch.stack([oracle.make_herm(200, 4, torch.float64, seed=s) for s in (1, 2, 3)])
+    ref = torch.linalg.eigvalsh(A)[..., -3:]
+    evals, evecs = xt.linalg.usymeig(xt.LinearOperator.m(A.to(DEV), True), neig=3, method="davidson", min_eps=1e-8)
+    assert tuple(evals.shape) == (3, 3) and tuple(evecs.shape) == (3, 200, 3)
+    assert ((evals.cpu() - ref).abs() / ref.abs()).max().item() <= EIG_RTOL
+
+
+def test_small_eigh_kernel():
+    L = _lib.lib()
+    for m in (8, 33, 104, 128):
+        g = torch.Generator().manual_seed(m)
+        T = torch.randn(m, m, generator=g, dtype=torch.float64)
+        T = (T + T.t()) / 2
+        Td = T.clone().to(DEV)
+        w = torch.zeros(3 * m + 8, dtype=torch.float64, device=DEV)
+        S = torch.zeros(2 * m * m, dtype=torch.float64, device=DEV)
+        rc = L.xt_small_eigh(ctypes.c_void_p(Td.data_ptr()), m, ctypes.c_void_p(w.data_ptr()),
+                             ctypes.c_void_p(S.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        wr, _ = torch.linalg.eigh(T)
+        wv = w[:m].cpu()
+        Sv = S[:m * m].reshape(m, m).cpu()
+        assert (wv - wr).abs().max().item() <= 1e-12 * max(1.0, wr.abs().max().item())
+        assert (T @ Sv - Sv * wv).abs().max().item() <= 1e-11
+        assert (Sv.t() @ Sv - torch.eye(m, dtype=torch.float64)).abs().max().item() <= 1e-12
+
+
+def test_symeig_backward_with_krylov_adjoint():
+    """symeig backward re-enters `solve(A, -B, E=evals)` with the CUDA cg (symeig.py:365-367)."""
+    n, neig = 128, 3
+    A0 = oracle.make_herm(n, neig, torch.float64, seed=4)
+    A = A0.to(DEV).requires_grad_()
+    bck = {"method": "cg", "rtol": 1e-11, "atol": 1e-14, "posdef": True}
+    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A, True), neig=neig, method="davidson", min_eps=1e-9,
+                                    bck_options=bck)
+    loss = evals.sum() + (evecs.abs() ** 4).sum()
+    (gA,) = torch.autograd.grad(loss, (A,))
+    Ar = A0.clone().requires_grad_()
+    ev, vec = torch.linalg.eigh((Ar + Ar.t()) / 2)
+    lr = ev[:neig].sum() + (vec[:, :neig].abs() ** 4).sum()
+    (gr,) = torch.autograd.grad(lr, (Ar,))
+    gsym = (gA + gA.t()).cpu() / 2
+    assert torch.allclose(gsym, gr, rtol=1e-5, atol=1e-7), (gsym - gr).abs().max()
+
+
+def test_full_size_residual_property():
+    """BASELINE configs[1] at full size (N=16384, neig=8, fp32): size-independent checks -- residual
+    identity ||A x - lambda x||, orthonormality, and the known structure of make_herm (eigenvalues near 1..8)."""
+    n, neig = 16384, 8
+    A = oracle.make_herm(n, neig, torch.float32).to(DEV)
+    info = {}
+    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A, True), neig=neig, method="davidson", min_eps=1e-4,
+                                    info=info)
+    assert info["converged"], info
+    R = A.double() @ evecs.double() - evecs.double() * evals.double()
+    assert R.abs().max().item() <= 5e-4
+    G = evecs.double().t() @ evecs.double()
+    assert (G - torch.eye(neig, dtype=torch.float64, device=DEV)).abs().max().item() <= 1e-4
+    # Rayleigh quotients in fp64 agree with the returned eigenvalues to 1e-5 relative
+    rq = (evecs.double() * (A.double() @ evecs.double())).sum(0)
+    assert ((rq - evals.double()).abs() / rq.abs()).max().item() <= EIG_RTOL
+    assert ((evals.cpu() - (1 + torch.arange(neig))).abs() < 0.05).all()

@@ -20,7 +20,7 @@ _DTYPES = {torch.float32: XT_F32, torch.bfloat16: XT_BF16, torch.float64: XT_F64
 
 # every symbol include/xitorch_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "xt_version", "xt_last_error", "xt_block_matvec",
+    "xt_version", "xt_last_error", "xt_profile_reset", "xt_profile_read", "xt_block_matvec",
     "xt_solve_workspace_bytes", "xt_cg", "xt_bicgstab", "xt_gmres",
     "xt_symeig_workspace_bytes", "xt_symeig_krylov", "xt_small_eigh",
 ]
@@ -93,6 +93,10 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.xt_version.restype = C.c_int
         L.xt_last_error.restype = C.c_char_p
+        L.xt_profile_reset.argtypes = [C.c_int]
+        L.xt_profile_reset.restype = None
+        L.xt_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.xt_profile_read.restype = C.c_int
         L.xt_block_matvec.argtypes = [C.POINTER(MatvecArgs)]
         L.xt_block_matvec.restype = C.c_int
         for name in ("xt_cg", "xt_bicgstab", "xt_gmres"):
@@ -138,3 +142,14 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
         raise RuntimeError(
             "xitorch_b200: %s needs CUDA tensors; this package has no CPU path for the Krylov "
             "methods (got a tensor on %s)" % (what, t.device))
+
+
+def profile_reset(enable: bool = True) -> None:
+    lib().xt_profile_reset(1 if enable else 0)
+
+
+def profile_read():
+    """(matvec_ms, matvec_launches, total_launches) since the last profile_reset."""
+    ms, nmv, ntot = C.c_double(0.0), C.c_int64(0), C.c_int64(0)
+    check(lib().xt_profile_read(C.byref(ms), C.byref(nmv), C.byref(ntot)), "profile_read")
+    return ms.value, nmv.value, ntot.value

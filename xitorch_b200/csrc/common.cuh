@@ -33,6 +33,12 @@ void set_last_error(const char* fmt, ...);
 
 int num_sms();  // SM count of the current device (cached)
 
+// launch accounting / in-situ kernel timing (xt_profile_* in the C ABI)
+void note_launch(int n = 1);                        // every kernel launch site calls this
+void prof_mv_begin(cudaStream_t st);                // CUDA events around each block-matvec launch when enabled
+void prof_mv_end(cudaStream_t st);
+#define XT_LAUNCHED() xt::note_launch(1)
+
 template <typename T> struct VecOf { using type = float; };
 template <> struct VecOf<double> { using type = double; };
 

@@ -301,7 +301,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   }
   XT_REQUIRE(smem_step <= 200 * 1024 && smem_fin <= 200 * 1024,
              "gmres: max_niter*ncols = %d*%d too large for the on-chip Hessenberg state", maxk, g->ncols);
-  gm_init_kernel<TV><<<g->nbatch, SV_THREADS, smem_init, st>>>(S, g->rtol, g->atol);
+  gm_init_kernel<TV><<<g->nbatch, SV_THREADS, smem_init, st>>>(S, g->rtol, g->atol); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
@@ -309,7 +309,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   for (int k = 0; k < maxk; ++k) {
     int rc = apply_op<TV>(op, S.Q + (int64_t)k * len, S.w, mx, nullptr, nullptr, 0, done_flag, st, &napply);
     if (rc != XT_OK) return rc;
-    gm_step_kernel<TV><<<g->nbatch, SV_THREADS, smem_step, st>>>(S, k);
+    gm_step_kernel<TV><<<g->nbatch, SV_THREADS, smem_step, st>>>(S, k); XT_LAUNCHED();
     XT_CUDA_OK(cudaGetLastError());
     if ((k + 1) % ce == 0 || k + 1 == maxk) {
       int done = 0;
@@ -318,7 +318,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
       if (done) break;
     }
   }
-  gm_final_kernel<TV><<<g->nbatch, SV_THREADS, smem_fin, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride);
+  gm_final_kernel<TV><<<g->nbatch, SV_THREADS, smem_fin, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   SolveCtl h;
   XT_CUDA_OK(cudaMemcpyAsync(&h, S.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));

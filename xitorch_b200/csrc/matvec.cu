@@ -6,7 +6,7 @@
 //   * one persistent CTA per SM, each owning tiles of TH <= 128 consecutive rows chosen so that
 //     #tiles ~= #SMs (or >> #SMs) -- see mv_tiling()
 //   * warp 0 (one elected lane) streams A through TMA: 3-D tensor map (cols, rows, batch), boxes of
-//     8 rows x 128 B with SWIZZLE_128B, L2 evict-first hint, multi-stage mbarrier ring
+//     tile_rows x 128 B with SWIZZLE_128B (two per stage), L2 evict-first hint, multi-stage mbarrier ring
 //   * warp 1 stages the matching chunk of X into the same stage (plain coalesced loads; arbitrary
 //     strides, zero padding) -- this is the hook where solver prologues get fused
 //   * warps 2..9 (256 threads) consume: thread <-> (row, k-slice); 16-byte conflict-free LDS of its
@@ -20,6 +20,7 @@
 
 #include <cstdarg>
 #include <mutex>
+#include <vector>
 
 namespace xt {
 
@@ -32,6 +33,26 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------- launch accounting / profiling
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;     // pairs (begin, end)
+  int64_t launches = 0, mv_launches = 0;
+};
+static ProfState g_prof;
+void note_launch(int n) { g_prof.launches += n; }
+void prof_mv_begin(cudaStream_t st) {
+  ++g_prof.mv_launches;
+  if (!g_prof.on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof.ev.push_back(e); }
+}
+void prof_mv_end(cudaStream_t st) {
+  if (!g_prof.on || (g_prof.ev.size() & 1) == 0) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof.ev.push_back(e); }
+}
 
 int num_sms() {
   static int cached[64] = {0};
@@ -92,7 +113,7 @@ bool mv_tma_ok(const MvArgs& a) {
   return true;
 }
 
-static int make_tmap(const MvArgs& a, CUtensorMap* tm, bool* batched) {
+static int make_tmap(const MvArgs& a, int box_rows, CUtensorMap* tm, bool* batched) {
   const size_t es = dtype_size(a.dtype);
   const bool b3 = (a.nbatch > 1 && a.a_bstride != 0);
   *batched = b3;
@@ -101,7 +122,7 @@ static int make_tmap(const MvArgs& a, CUtensorMap* tm, bool* batched) {
   cuuint64_t dims[3] = {(cuuint64_t)a.ncolsA, (cuuint64_t)a.nrows, (cuuint64_t)(b3 ? a.nbatch : 1)};
   cuuint64_t strides[2] = {(cuuint64_t)(a.lda * es),
                            (cuuint64_t)((b3 ? a.a_bstride : (int64_t)a.nrows * a.lda) * es)};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)MV_BOX_ROWS, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = get_encode_fn()(tm, dt, 3, const_cast<void*>(a.A), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -204,7 +225,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   constexpr int BOXC = 128 / (int)sizeof(TA);   // columns per box
   constexpr int KC = 2 * BOXC;                  // columns per stage
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
-  constexpr int STAGE_BYTES = MV_STAGE_A_BYTES + XBYTES;
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;   // swizzle atoms need 1024-B aligned stages
 
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
 
@@ -239,45 +260,52 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_batch;
         const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
-        const int rows = min(p.tile_rows, p.nrows - row0);
-        const int ngroups = (rows + MV_BOX_ROWS - 1) / MV_BOX_ROWS;
         const int bA = p.a_batched ? b : 0;
         for (int ch = 0; ch < nchunks; ++ch) {
           const int kc = ch * KC;
           const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(ngroups * nb * 1024));
-          for (int g = 0; g < ngroups; ++g)
-            for (int bx = 0; bx < nb; ++bx)
-              tma_load_3d(dst + (g * 2 + bx) * 1024, &tmA, &full[s], kc + bx * BOXC, row0 + g * MV_BOX_ROWS, bA, pol);
+          // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128));
+          for (int bx = 0; bx < nb; ++bx)
+            tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), &tmA, &full[s], kc + bx * BOXC, row0, bA, pol);
           if (++s == NS) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ X staging warp
+    // All loads of a chunk are issued back to back (KC*K/32 independent loads per lane) and one chunk
+    // ahead of the shared-memory slot becoming free, so their L2 latency overlaps the wait.
     const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    constexpr int NPL = KC * K / 32;
+    TV vals[NPL];
+    auto load_chunk = [&](int tile, int ch) {
       const int b = tile / p.tiles_per_batch;
       const TV* Xb = Xg + (int64_t)b * p.x_bstride;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int kc = ch * KC;
-        mbar_wait(&empty[s], ph ^ 1);
-        TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
-#pragma unroll 4
-        for (int idx = lane; idx < KC * K; idx += 32) {
-          const int c = idx / K, v = idx - c * K;
-          TV val = TV(0);
-          if (kc + c < p.ncolsA && v < p.kvalid) val = Xb[(int64_t)(kc + c) * p.ldx + v];
-          xs[idx] = val;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
-        if (++s == NS) { s = 0; ph ^= 1; }
+      const int kc = ch * KC;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int idx = lane + 32 * i;
+        const int c = idx / K, v = idx - c * K;
+        vals[i] = (kc + c < p.ncolsA && v < p.kvalid) ? Xb[(int64_t)(kc + c) * p.ldx + v] : TV(0);
       }
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    int tile = blockIdx.x, ch = 0;
+    if (tile < p.ntiles) load_chunk(tile, 0);
+    while (tile < p.ntiles) {
+      mbar_wait(&empty[s], ph ^ 1);
+      TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      if (++s == NS) { s = 0; ph ^= 1; }
+      if (++ch == nchunks) { ch = 0; tile += gridDim.x; }
+      if (tile < p.ntiles) load_chunk(tile, ch);
     }
   } else {
     // ------------------------------------------------------------------ consumers
@@ -287,7 +315,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     const int ksplit = MV_CONSUMERS / p.rows_pad;
     const int nvec = 16 / ksplit;
     const int cw = warp - 2;
-    const uint32_t a_row_off = (uint32_t)((r >> 3) * 2048 + (r & 7) * 128);
+    const uint32_t a_row_off = (uint32_t)(r * 128);
     const uint32_t sw = (uint32_t)(r & 7);
     int s = 0;
     uint32_t ph = 0;
@@ -314,7 +342,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
             const int gv = q * nvec + v;
             const int bx = gv >> 3;
             if (kc + bx * BOXC < p.ncolsA) {
-              const float4 raw = lds128(a_s + bx * 1024 + (((uint32_t)(gv & 7) ^ sw) << 4));
+              const float4 raw = lds128(a_s + bx * (MV_TILE_ROWS * 128) + (((uint32_t)(gv & 7) ^ sw) << 4));
               TV a[EPV];
               Tr::unpack(raw, a);
               const uint32_t xr = xs + (uint32_t)(gv * EPV * K * (int)sizeof(TV));
@@ -481,7 +509,7 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
-  constexpr int STAGE_BYTES = MV_STAGE_A_BYTES + XBYTES;
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
   const size_t fixed = MV_CONSUMERS * K * sizeof(TV) + 8 * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
   int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
   if (ns > 6) ns = 6;
@@ -494,7 +522,7 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   dev.nstages = ns;
   CUtensorMap tm;
   bool batched = false;
-  int rc = make_tmap(a, &tm, &batched);
+  int rc = make_tmap(a, til.tile_rows, &tm, &batched);
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
   auto kern = mv_tma_kernel<TA, TV, K>;
@@ -503,7 +531,10 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
     XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  prof_mv_begin(st);
   kern<<<til.grid, MV_THREADS, smem, st>>>(tm, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }
@@ -520,7 +551,10 @@ static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cu
 template <typename TA, typename TV>
 static int launch_plain(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
   int grid = til.ntiles < 8 * num_sms() ? til.ntiles : 8 * num_sms();
+  prof_mv_begin(st);
   mv_plain_kernel<TA, TV><<<grid, 256, 0, st>>>(reinterpret_cast<const TA*>(a.A), a.lda, a.a_bstride, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }
@@ -572,6 +606,31 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
 extern "C" {
 
 int xt_version(void) { return 100; }
+
+void xt_profile_reset(int enable) {
+  for (cudaEvent_t e : xt::g_prof.ev) cudaEventDestroy(e);
+  xt::g_prof.ev.clear();
+  xt::g_prof.on = enable != 0;
+  xt::g_prof.launches = 0;
+  xt::g_prof.mv_launches = 0;
+}
+
+int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_launches) {
+  double ms = 0.0;
+  const size_t np = xt::g_prof.ev.size() / 2;
+  if (np > 0) {
+    XT_CUDA_OK(cudaEventSynchronize(xt::g_prof.ev[2 * np - 1]));
+    for (size_t i = 0; i < np; ++i) {
+      float t = 0.f;
+      XT_CUDA_OK(cudaEventElapsedTime(&t, xt::g_prof.ev[2 * i], xt::g_prof.ev[2 * i + 1]));
+      ms += t;
+    }
+  }
+  if (matvec_ms) *matvec_ms = ms;
+  if (matvec_launches) *matvec_launches = xt::g_prof.mv_launches;
+  if (total_launches) *total_launches = xt::g_prof.launches;
+  return XT_OK;
+}
 const char* xt_last_error(void) { return xt::last_error(); }
 
 int xt_block_matvec(const xt_matvec_args* g) {

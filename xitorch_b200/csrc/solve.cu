@@ -390,7 +390,7 @@ template <typename TV> static size_t step_smem(int ncols) {
 }
 
 template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>& S, int64_t napply, cudaStream_t st) {
-  solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride);
+  solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   SolveCtl h;
   XT_CUDA_OK(cudaMemcpyAsync(&h, S.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -413,7 +413,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
             g->E, g->e_bstride};
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
-  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0);
+  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
@@ -423,12 +423,12 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
     if (rc != XT_OK) return rc;
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 0);
+      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 0); XT_LAUNCHED();
     } else {
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1);
+      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1); XT_LAUNCHED();
       rc = apply_op<TV>(op, S.x, S.q, mx, nullptr, nullptr, 0, done_flag, st, &napply);
       if (rc != XT_OK) return rc;
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2);
+      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
     if (k % ce == 0 || k == g->max_niter) {
@@ -452,26 +452,26 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
             g->E, g->e_bstride};
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
-  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1);
+  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
   const int* done_flag = &S.ctl->done;
   for (int k = 1; k <= g->max_niter; ++k) {
-    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1);
+    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1); XT_LAUNCHED();
     rc = apply_op<TV>(op, S.p, S.q, mx, S.rhat, S.dots, S.dots_gstride, done_flag, st, &napply);   // v = A p, rhat.v
     if (rc != XT_OK) return rc;
-    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2);
+    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
     rc = apply_op<TV>(op, S.s, S.t, mx, S.s, S.dots, S.dots_gstride, done_flag, st, &napply);      // t = A s, t.s, t.t
     if (rc != XT_OK) return rc;
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 3);
+      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 3); XT_LAUNCHED();
     } else {
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 4);
+      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 4); XT_LAUNCHED();
       rc = apply_op<TV>(op, S.x, S.t, mx, nullptr, nullptr, 0, done_flag, st, &napply);
       if (rc != XT_OK) return rc;
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 5);
+      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 5); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
     if (k % ce == 0 || k == g->max_niter) {

@@ -538,15 +538,15 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
-    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl);
+    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
     gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
-                                                       g->ldv0, n, k, Rblk);
+                                                       g->ldv0, n, k, Rblk); XT_LAUNCHED();
     for (int pass = 0; pass < 2; ++pass) {
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
       subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, 0, pass == 0 ? Rblk : V, nullptr, Zbuf, nullptr,
-                                                            W.G, W.ctl);
-      orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, 0, Zbuf, W.C2, W.G, V, W.ctl);
+                                                            W.G, W.ctl); XT_LAUNCHED();
+      orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, 0, Zbuf, W.C2, W.G, V, W.ctl); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
 
@@ -571,13 +571,13 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       // 2. C = V^T W  (new block column of T)
       XT_CUDA_OK(cudaMemsetAsync(W.C, 0, sizeof(double) * (size_t)m * k, st));
       subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, W.C, nullptr,
-                                                            W.ctl);
+                                                            W.ctl); XT_LAUNCHED();
       // 3. Rayleigh-Ritz on T
       rr_kernel<<<1, EIG_THREADS, eig_smem, st>>>(W.T, mb, W.C, m, k, W.Tw, W.S, W.w, W.order, W.Sk, W.theta, g->mode,
-                                                  1, W.ctl);
+                                                  1, W.ctl); XT_LAUNCHED();
       // 4. Ritz vectors, residual, bookkeeping
       ritz_kernel<TV><<<grid_rows, SE_THREADS, (size_t)m * k * sizeof(double), st>>>(
-          V, AV, n, k, m, W.Sk, W.theta, Xslots, W.evals_slots, Rblk, W.ctl, iter, (float)g->min_eps);
+          V, AV, n, k, m, W.Sk, W.theta, Xslots, W.evals_slots, Rblk, W.ctl, iter, (float)g->min_eps); XT_LAUNCHED();
       XT_CUDA_OK(cudaGetLastError());
       if (iter >= g->max_niter) break;
       if (m + k > n) break;                      // the basis cannot grow any further (symeig.py:202-203)
@@ -590,27 +590,29 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       // 5. expansion block, orthogonalised against V
       XT_CUDA_OK(cudaMemsetAsync(W.C2, 0, sizeof(double) * (size_t)m * k, st));
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
-      if (g->expansion == 1)
+      if (g->expansion == 1) {
         subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, AV + j * blk, W.C, Zbuf, W.C2, W.G, W.ctl);
-      else
+      } else {
         subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Rblk, nullptr, Zbuf, W.C2, W.G, W.ctl);
+      }
+      XT_LAUNCHED();
       if (m + k > mb) {
         // thick restart: finish the new block against the OLD basis first, then compress V / AV / T
-        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Zbuf, W.C2, W.G, Rblk, W.ctl);
+        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Zbuf, W.C2, W.G, Rblk, W.ctl); XT_LAUNCHED();
         const int first = (g->mode == 0) ? 0 : (m - keep);
         const int64_t tot = (int64_t)n * keep;
         const int rg = (int)((tot + SE_THREADS - 1) / SE_THREADS);
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl);
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl);
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(AV, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.w, W.order, first, keep, W.ctl);
+        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.w, W.order, first, keep, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, Rblk, (size_t)blk * sizeof(TV),
                                    cudaMemcpyDeviceToDevice, st));
         m = keep + k;
       } else {
         orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Zbuf, W.C2, W.G, V + (int64_t)(m / k) * blk,
-                                                                  W.ctl);
+                                                                  W.ctl); XT_LAUNCHED();
         m += k;
       }
       XT_CUDA_OK(cudaGetLastError());
@@ -618,7 +620,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     // ---- output
     output_kernel<TV><<<grid_rows, 256, 0, st>>>(Xslots, W.evals_slots, n, k,
                                                  static_cast<TV*>(g->evecs) + (int64_t)b * g->evecs_bstride, g->ldv,
-                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, W.ctl);
+                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, W.ctl); XT_LAUNCHED();
     EigCtl h;
     XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
     XT_CUDA_OK(cudaStreamSynchronize(st));
@@ -669,7 +671,7 @@ int xt_small_eigh(double* T, int32_t m, double* w, double* S, void* stream) {
   double* wraw = w + m;
   int* order = reinterpret_cast<int*>(w + 2 * m);
   const size_t smem = (size_t)(2 * (m / 2 + 2)) * sizeof(double) + (size_t)(m + 2) * sizeof(int) + 64;
-  xt::small_eigh_kernel<<<1, xt::EIG_THREADS, smem, st>>>(T, m, w, S, Sraw, wraw, order);
+  xt::small_eigh_kernel<<<1, xt::EIG_THREADS, smem, st>>>(T, m, w, S, Sraw, wraw, order); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }

@@ -208,9 +208,9 @@ class LinearOperator(object):
         with torch.enable_grad():
             probe = torch.zeros((*bx, self.shape[-1]), dtype=xt.dtype, device=xt.device).requires_grad_()
             out = self._mv(probe)
-        (res,) = torch.autograd.grad(out, (probe,), grad_outputs=(xt.conj(),),
+        (res,) = torch.autograd.grad(out, (probe,), grad_outputs=(xt.contiguous().expand_as(out),),
                                      create_graph=torch.is_grad_enabled())
-        return res.conj()
+        return res
 
     def fullmatrix(self) -> torch.Tensor:
         if self._has["_fullmatrix"]:
