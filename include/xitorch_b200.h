@@ -153,10 +153,12 @@ typedef struct {
 size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis);
 int xt_symeig_krylov(const xt_symeig_args* args);
 
-/* small dense symmetric eigensolver used for the projected problem (device, one CTA):
- * T (m x m, row-major fp64, destroyed) -> w (m, ascending), S (m x m row-major, columns = eigenvectors).
- * Exposed for the parity tests.  */
-int xt_small_eigh(double* T, int32_t m, double* w, double* S, void* stream);
+/* small dense symmetric eigensolver used for the projected problem (device, one CTA; replaces torch.linalg.eigh
+ * at xitorch/_impls/linalg/symeig.py:174): the nev lowest (mode 0) or highest (mode 1) eigenpairs of the m x m
+ * row-major fp64 matrix T -> w_out[nev] ascending, S_out (m x nev row-major, orthonormal columns).
+ * scratch: >= m*(m|1) doubles.  Exposed for the parity tests. */
+int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out,
+                  double* scratch, void* stream);
 
 #ifdef __cplusplus
 }

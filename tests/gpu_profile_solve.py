@@ -1,0 +1,13 @@
+"""one davidson solve (C2) for profiling under ncu (not a pytest file)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, oracle
+import xitorch_b200 as xt
+n, neig = 16384, 8
+A = oracle.make_herm(n, neig, torch.float32, seed=7).cuda()
+op = xt.LinearOperator.m(A, is_hermitian=True)
+for _ in range(int(os.environ.get("REPS", "2"))):
+    info = {}
+    ev, vec = xt.linalg.symeig(op, neig=neig, method=os.environ.get("METHOD", "davidson"), min_eps=1e-4, info=info)
+torch.cuda.synchronize()
+print(info, ev.cpu().numpy())

@@ -94,25 +94,58 @@ def test_uppest_and_batch():
     assert ((evals.cpu() - ref).abs() / ref.abs()).max().item() <= EIG_RTOL
 
 
-def test_small_eigh_kernel():
+def _small_eigh(T, nev, mode):
     L = _lib.lib()
-    for m in (8, 33, 104, 128):
-        g = torch.Generator().manual_seed(m)
-        T = torch.randn(m, m, generator=g, dtype=torch.float64)
+    m = T.shape[0]
+    Td = T.contiguous().to(DEV)
+    w = torch.zeros(nev, dtype=torch.float64, device=DEV)
+    S = torch.zeros(m, nev, dtype=torch.float64, device=DEV)
+    scratch = torch.zeros(m * (m | 1) + 8, dtype=torch.float64, device=DEV)
+    vp = ctypes.c_void_p
+    rc = L.xt_small_eigh(vp(Td.data_ptr()), m, nev, mode, vp(w.data_ptr()), vp(S.data_ptr()), vp(scratch.data_ptr()),
+                         vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L.xt_last_error()
+    torch.cuda.synchronize()
+    return w.cpu(), S.cpu()
+
+
+@pytest.mark.parametrize("m", [2, 3, 8, 33, 104, 128, 160, 200])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_small_eigh_kernel_random(m, mode):
+    g = torch.Generator().manual_seed(m)
+    T = torch.randn(m, m, generator=g, dtype=torch.float64)
+    T = (T + T.t()) / 2
+    nev = min(8, m)
+    w, S = _small_eigh(T, nev, mode)
+    wr = torch.linalg.eigvalsh(T)
+    wr = wr[:nev] if mode == 0 else wr[-nev:]
+    scale = max(1.0, wr.abs().max().item())
+    assert (w - wr).abs().max().item() <= 1e-12 * scale * m
+    assert (T @ S - S * w).abs().max().item() <= 1e-11 * scale * m
+    assert (S.t() @ S - torch.eye(nev, dtype=torch.float64)).abs().max().item() <= 1e-12
+
+
+def test_small_eigh_kernel_special_cases():
+    g = torch.Generator().manual_seed(0)
+    m = 96
+    Q, _ = torch.linalg.qr(torch.randn(m, m, generator=g, dtype=torch.float64))
+    # degenerate and tightly clustered spectra, a diagonal matrix, a block-tridiagonal matrix, many pairs (restart)
+    spectra = [torch.cat([torch.tensor([1., 1., 1., 2., 2.], dtype=torch.float64), torch.linspace(3, 30, m - 5, dtype=torch.float64)]),
+               torch.cat([1 + 1e-9 * torch.arange(4, dtype=torch.float64), torch.linspace(2, 5, m - 4, dtype=torch.float64)])]
+    mats = [(Q * w) @ Q.t() for w in spectra]
+    mats.append(torch.diag(torch.arange(m, 0, -1, dtype=torch.float64)))
+    bt = torch.diag(torch.arange(1.0, m + 1, dtype=torch.float64))
+    bt = bt + torch.diag(torch.full((m - 8,), 0.1, dtype=torch.float64), 8) + torch.diag(torch.full((m - 8,), 0.1, dtype=torch.float64), -8)
+    mats.append(bt)
+    for T in mats:
         T = (T + T.t()) / 2
-        Td = T.clone().to(DEV)
-        w = torch.zeros(3 * m + 8, dtype=torch.float64, device=DEV)
-        S = torch.zeros(2 * m * m, dtype=torch.float64, device=DEV)
-        rc = L.xt_small_eigh(ctypes.c_void_p(Td.data_ptr()), m, ctypes.c_void_p(w.data_ptr()),
-                             ctypes.c_void_p(S.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0
-        torch.cuda.synchronize()
-        wr, _ = torch.linalg.eigh(T)
-        wv = w[:m].cpu()
-        Sv = S[:m * m].reshape(m, m).cpu()
-        assert (wv - wr).abs().max().item() <= 1e-12 * max(1.0, wr.abs().max().item())
-        assert (T @ Sv - Sv * wv).abs().max().item() <= 1e-11
-        assert (Sv.t() @ Sv - torch.eye(m, dtype=torch.float64)).abs().max().item() <= 1e-12
+        for nev, mode in ((8, 0), (8, 1), (48, 0), (48, 1)):
+            w, S = _small_eigh(T, nev, mode)
+            wr = torch.linalg.eigvalsh(T)
+            wr = wr[:nev] if mode == 0 else wr[-nev:]
+            assert (w - wr).abs().max().item() <= 1e-11 * m
+            assert (T @ S - S * w).abs().max().item() <= 1e-10 * m
+            assert (S.t() @ S - torch.eye(nev, dtype=torch.float64)).abs().max().item() <= 1e-11
 
 
 def test_symeig_backward_with_krylov_adjoint():

@@ -110,7 +110,8 @@ def lib():
         L.xt_symeig_workspace_bytes.restype = C.c_size_t
         L.xt_symeig_krylov.argtypes = [C.POINTER(SymeigArgs)]
         L.xt_symeig_krylov.restype = C.c_int
-        L.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
         L.xt_small_eigh.restype = C.c_int
         _lib = L
     return _lib

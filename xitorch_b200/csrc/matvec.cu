@@ -139,7 +139,7 @@ static int make_tmap(const MvArgs& a, int box_rows, CUtensorMap* tm, bool* batch
 struct MvDev {
   int nbatch, nrows, ncolsA, kvalid;
   int tile_rows, tiles_per_batch, ntiles;
-  int rows_pad;     // power of two >= tile_rows, in {16,32,64,128}
+  int rows_pad;     // tile_rows rounded up to a multiple of 16
   int nstages;
   int a_batched;
   const void* X; int64_t ldx, x_bstride;
@@ -217,8 +217,8 @@ template <int K> __device__ __forceinline__ void fma_row(double a, const double 
 
 constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 128 B
 
-template <typename TA, typename TV, int K>
-__global__ void __launch_bounds__(MV_THREADS, 1)
+template <typename TA, typename TV, int K, int NC>
+__global__ void __launch_bounds__(NC + 64, 1)
 mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   using Tr = ElemTraits<TA>;
   constexpr int EPV = Tr::EPV;
@@ -233,9 +233,9 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.nstages;
   uint8_t* stage_base = smem;
-  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);                 // [MV_CONSUMERS][K]
-  double* dscr = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(red) + MV_CONSUMERS * K * sizeof(TV));  // [8][2][K]
-  uint64_t* full = reinterpret_cast<uint64_t*>(dscr + 8 * 2 * K);
+  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);                 // [NC][K]
+  double* dscr = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(red) + NC * K * sizeof(TV));  // [NC/32][2][K]
+  uint64_t* full = reinterpret_cast<uint64_t*>(dscr + (NC / 32) * 2 * K);
   uint64_t* empty = full + NS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,7 +244,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 2);                    // TMA lane (expect_tx) + X-staging warp
-      mbar_init(&empty[s], MV_CONSUMERS / 32);   // one arrival per consumer warp
+      mbar_init(&empty[s], NC / 32);   // one arrival per consumer warp
     }
     fence_mbar_init();
     prefetch_tmap(&tmA);
@@ -309,10 +309,13 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     }
   } else {
     // ------------------------------------------------------------------ consumers
+    // thread <-> (row r, k-slice q): rows_pad = tile_rows rounded up to 16, ksplit = largest power of two with
+    // ksplit * rows_pad <= NC; threads with q >= ksplit idle (whole warps, never partial quarter-warps)
     const int tc = threadIdx.x - 64;
-    const int r = tc & (p.rows_pad - 1);
+    const int r = tc % p.rows_pad;
     const int q = tc / p.rows_pad;
-    const int ksplit = MV_CONSUMERS / p.rows_pad;
+    int ksplit = 16;
+    while (ksplit * p.rows_pad > NC) ksplit >>= 1;
     const int nvec = 16 / ksplit;
     const int cw = warp - 2;
     const uint32_t a_row_off = (uint32_t)(r * 128);
@@ -323,7 +326,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       const int b = tile / p.tiles_per_batch;
       const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
       const int rows = min(p.tile_rows, p.nrows - row0);
-      const bool active = r < rows;
+      const bool active = (r < rows) && (q < ksplit);
       TV acc[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) acc[i] = TV(0);
@@ -363,11 +366,11 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       }
 
       // ---- reduce the k-slices, then the per-row epilogue (threads with q == 0)
-      if (q > 0) {
+      if (q > 0 && q < ksplit) {
 #pragma unroll
         for (int i = 0; i < K; ++i) red[(size_t)tc * K + i] = acc[i];
       }
-      named_bar_sync(1, MV_CONSUMERS);
+      named_bar_sync(1, NC);
       double d0[K], d1[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
@@ -419,11 +422,11 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
           }
         }
       }
-      named_bar_sync(1, MV_CONSUMERS);   // red[] / dscr[] hand-over
+      named_bar_sync(1, NC);   // red[] / dscr[] hand-over
       if (p.dot_out != nullptr && tc < 2 * K) {
         const int which = tc / K, i = tc - which * K;
         double sum = 0.0;
-        for (int w = 0; w < MV_CONSUMERS / 32; ++w) sum += dscr[(w * 2 + which) * K + i];
+        for (int w = 0; w < NC / 32; ++w) sum += dscr[(w * 2 + which) * K + i];
         p.dot_out[((size_t)tile * 2 + which) * MV_MAXK + i] = sum;
       }
       // the next tile's first red[]/dscr[] writes happen after its whole K sweep and a barrier: no hazard with
@@ -504,13 +507,13 @@ mv_plain_kernel(const TA* __restrict__ A, int64_t lda, int64_t a_bstride, const 
 }
 
 // ============================================================================ launch
-template <typename TA, typename TV, int K>
+template <typename TA, typename TV, int K, int NC>
 static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
   constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
-  const size_t fixed = MV_CONSUMERS * K * sizeof(TV) + 8 * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
+  const size_t fixed = NC * K * sizeof(TV) + (NC / 32) * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
   int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
   if (ns > 6) ns = 6;
   if (ns < 2) {
@@ -525,14 +528,14 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
-  auto kern = mv_tma_kernel<TA, TV, K>;
+  auto kern = mv_tma_kernel<TA, TV, K, NC>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   prof_mv_begin(st);
-  kern<<<til.grid, MV_THREADS, smem, st>>>(tm, dev);
+  kern<<<til.grid, NC + 64, smem, st>>>(tm, dev);
   prof_mv_end(st);
   XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
@@ -541,11 +544,12 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
 
 template <typename TA, typename TV>
 static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
-  if (a.k <= 1) return launch_tma_k<TA, TV, 1>(a, dev, til, st);
-  if (a.k <= 2) return launch_tma_k<TA, TV, 2>(a, dev, til, st);
-  if (a.k <= 4) return launch_tma_k<TA, TV, 4>(a, dev, til, st);
-  if (a.k <= 8) return launch_tma_k<TA, TV, 8>(a, dev, til, st);
-  return launch_tma_k<TA, TV, 16>(a, dev, til, st);
+  // 512 consumer threads (16 warps) where the register budget allows it, 256 for the widest blocks
+  if (a.k <= 1) return launch_tma_k<TA, TV, 1, 512>(a, dev, til, st);
+  if (a.k <= 2) return launch_tma_k<TA, TV, 2, 512>(a, dev, til, st);
+  if (a.k <= 4) return launch_tma_k<TA, TV, 4, 512>(a, dev, til, st);
+  if (a.k <= 8) return launch_tma_k<TA, TV, 8, 512>(a, dev, til, st);
+  return launch_tma_k<TA, TV, 16, 256>(a, dev, til, st);
 }
 
 template <typename TA, typename TV>
@@ -569,9 +573,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   MvDev d;
   d.nbatch = a.nbatch; d.nrows = a.nrows; d.ncolsA = a.ncolsA; d.kvalid = a.k;
   d.tile_rows = til.tile_rows; d.tiles_per_batch = til.tiles_per_batch; d.ntiles = til.ntiles;
-  int rp = 16;
-  while (rp < til.tile_rows) rp <<= 1;
-  d.rows_pad = rp;
+  d.rows_pad = (til.tile_rows + 15) / 16 * 16;
   d.nstages = 0; d.a_batched = 0;
   d.X = a.X; d.ldx = a.ldx; d.x_bstride = a.x_bstride;
   d.Y = a.Y; d.ldy = a.ldy; d.y_bstride = a.y_bstride;

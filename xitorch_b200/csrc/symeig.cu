@@ -27,7 +27,7 @@ namespace xt {
 constexpr int SE_MAXK = 16;
 constexpr int SE_THREADS = 256;
 constexpr int SE_ROWS = 64;         // rows per CTA chunk in the tall-skinny kernels
-constexpr int EIG_THREADS = 1024;
+constexpr int EIG_THREADS = 512;
 
 struct EigCtl {
   int done;
@@ -41,162 +41,216 @@ struct EigCtl {
 };
 
 // ---------------------------------------------------------------------------- tall-skinny kernels
-// Zp = Z - V Cin  (Cin may be null);  Cout += V^T Zp (m x k);  G += Zp^T Zp (k x k).  Zp is written
-// to Zout when Zout != nullptr.  V: m basis vectors in blocks of k.  fp64 accumulation, fp64 atomics.
+// All three kernels below stream a chunk of SE_ROWS rows of the basis V (and AV) through shared memory in
+// groups of up to SE_GB blocks with cp.async (16-byte LDGSTS when aligned), so that the L2 latency of a group
+// is paid once, not once per block.  Accumulation is fp64.
+constexpr int SE_GB = 16;           // basis blocks staged per group
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// stage rows [row0, row0+rows) of blocks [blk0, blk0+nb) of a block-layout array ([block][n][k]) into
+// dst[(b * SE_ROWS + r) * k + i]
+template <typename TV>
+__device__ __forceinline__ void stage_group(TV* dst, const TV* __restrict__ src, int n, int k, int row0, int rows,
+                                            int blk0, int nb) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int cnt = rows * k;
+  const int bytes = cnt * (int)sizeof(TV);
+  for (int b = 0; b < nb; ++b) {
+    const TV* g = src + ((int64_t)(blk0 + b) * n + row0) * k;
+    TV* d = dst + (size_t)b * SE_ROWS * k;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+      const int nv = bytes >> 4;
+      for (int i = tid; i < nv; i += nt)
+        cp_async16(reinterpret_cast<char*>(d) + 16 * i, reinterpret_cast<const char*>(g) + 16 * i);
+      const int done = (nv << 4) / (int)sizeof(TV);
+      for (int i = done + tid; i < cnt; i += nt) d[i] = g[i];
+    } else {
+      for (int i = tid; i < cnt; i += nt) d[i] = g[i];
+    }
+  }
+}
+
+// tiny k x k Cholesky-QR factor on one warp: Gs (k x k Gram, smem) -> Ri = R^-1 (upper, smem); returns 0 on breakdown
+__device__ int chol_inverse_warp(double* Gs, double* Ri, int k) {
+  const int lane = threadIdx.x & 31;
+  double scale = 0.0;
+  for (int i = 0; i < k; ++i) scale = fmax(scale, Gs[i * k + i]);
+  int ok = 1;
+  for (int j = 0; j < k; ++j) {
+    const double djj = Gs[j * k + j];
+    if (!(djj > 1e-24 * scale) || !(djj == djj)) { ok = 0; break; }
+    const double ljj = sqrt(djj);
+    __syncwarp();
+    for (int i = j + lane; i < k; i += 32) Gs[i * k + j] = (i == j) ? ljj : Gs[i * k + j] / ljj;
+    __syncwarp();
+    const int t = k - j - 1;               // trailing update  G[i][c] -= L[i][j] L[c][j],  i, c > j
+    for (int e = lane; e < t * t; e += 32) {
+      const int i = j + 1 + e / t, c = j + 1 + e % t;
+      Gs[i * k + c] -= Gs[i * k + j] * Gs[c * k + j];
+    }
+    __syncwarp();
+  }
+  if (!ok) return 0;
+  // Linv column c by forward substitution (lane c), stored as Ri[c][r] = Linv[r][c] = Rinv[c][r]
+  for (int c = lane; c < k; c += 32) {
+    for (int r = 0; r < k; ++r) {
+      if (r < c) { Ri[c * k + r] = 0.0; continue; }
+      double sacc = (r == c) ? 1.0 : 0.0;
+      for (int t = c; t < r; ++t) sacc -= Gs[r * k + t] * Ri[c * k + t];
+      Ri[c * k + r] = sacc / Gs[r * k + r];
+    }
+  }
+  __syncwarp();
+  return 1;
+}
+
+// Zp = Z - V Cin  (Cin may be null);  Cout += V^T Zp (m x k);  G += Zp^T Zp (k x k); Zp -> Zout (if non-null).
+// With `finish` set, the last CTA to arrive turns (G, Cout) into Rinv = chol(G - Cout^T Cout)^-T for
+// orth_finish_kernel (or flags a breakdown).
 template <typename TV>
 __global__ void __launch_bounds__(SE_THREADS)
 subproj_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restrict__ Z, const double* __restrict__ Cin,
-               TV* __restrict__ Zout, double* __restrict__ Cout, double* __restrict__ G, const EigCtl* ctl) {
+               TV* __restrict__ Zout, double* __restrict__ Cout, double* __restrict__ G, double* __restrict__ Rinv,
+               int finish, EigCtl* ctl) {
   if (ctl->done) return;
-  __shared__ double Zs[SE_ROWS * SE_MAXK];
-  __shared__ double Vs[SE_ROWS * SE_MAXK];
-  __shared__ double Cs[SE_MAXK * SE_MAXK];
+  extern __shared__ __align__(16) unsigned char se_raw[];
+  double* Zs = reinterpret_cast<double*>(se_raw);                       // [SE_ROWS][k]
+  double* Cs = Zs + SE_ROWS * SE_MAXK;                                   // [SE_GB*k][k]  (group of Cin rows)
+  TV* Vs = reinterpret_cast<TV*>(Cs + SE_GB * SE_MAXK * SE_MAXK);        // [SE_GB][SE_ROWS][k]
+  __shared__ int is_last;
   const int row0 = blockIdx.x * SE_ROWS;
   const int rows = min(SE_ROWS, n - row0);
   const int tid = threadIdx.x;
   const int nblk = m / k;
-  // load the Z chunk
   for (int i = tid; i < rows * k; i += SE_THREADS) Zs[i] = (double)Z[(int64_t)row0 * k + i];
-  __syncthreads();
-  // subtract V Cin
   if (Cin != nullptr) {
-    for (int blk = 0; blk < nblk; ++blk) {
-      const TV* Vb = V + ((int64_t)blk * n + row0) * k;
-      for (int i = tid; i < rows * k; i += SE_THREADS) Vs[i] = (double)Vb[i];
-      for (int i = tid; i < k * k; i += SE_THREADS) Cs[i] = Cin[(int64_t)blk * k * k + i];   // rows blk*k.. of Cin (m x k)
+    for (int g0 = 0; g0 < nblk; g0 += SE_GB) {
+      const int nb = min(SE_GB, nblk - g0);
+      __syncthreads();
+      stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
+      for (int i = tid; i < nb * k * k; i += SE_THREADS) Cs[i] = Cin[(int64_t)g0 * k * k + i];
+      cp_async_wait_all();
       __syncthreads();
       for (int e = tid; e < rows * k; e += SE_THREADS) {
         const int r = e / k, j = e - r * k;
         double acc = 0.0;
-        for (int i = 0; i < k; ++i) acc += Vs[r * k + i] * Cs[i * k + j];
+        for (int b = 0; b < nb; ++b) {
+          const TV* vr = Vs + ((size_t)b * SE_ROWS + r) * k;
+          const double* cr = Cs + (size_t)b * k * k + j;
+          for (int i = 0; i < k; ++i) acc += (double)vr[i] * cr[i * k];
+        }
         Zs[e] -= acc;
       }
-      __syncthreads();
     }
-  }
-  if (Zout != nullptr)
-    for (int i = tid; i < rows * k; i += SE_THREADS) Zout[(int64_t)row0 * k + i] = (TV)Zs[i];
-  // the orthonormalisation works with the ROUNDED block (what is stored), so re-read the rounded values
-  if (Zout != nullptr && sizeof(TV) < sizeof(double)) {
-    __syncthreads();
-    for (int i = tid; i < rows * k; i += SE_THREADS) Zs[i] = (double)(TV)Zs[i];
   }
   __syncthreads();
-  // projections onto every basis block and the Gram matrix: thread <-> (i, j) pairs x row slices
-  const int npair = k * k;
-  const int nslice = SE_THREADS / npair > 0 ? SE_THREADS / npair : 1;
-  const int pr = tid % npair, sl = tid / npair;
-  const int pi = pr / k, pj = pr - pi * k;
-  const bool worker = (npair <= SE_THREADS) ? (sl < nslice) : true;
-  for (int blk = 0; blk <= nblk; ++blk) {
-    const bool gram = (blk == nblk);
-    if (!gram) {
-      const TV* Vb = V + ((int64_t)blk * n + row0) * k;
-      for (int i = tid; i < rows * k; i += SE_THREADS) Vs[i] = (double)Vb[i];
+  if (Zout != nullptr) {
+    for (int i = tid; i < rows * k; i += SE_THREADS) {
+      const TV zr = (TV)Zs[i];
+      Zout[(int64_t)row0 * k + i] = zr;
+      Zs[i] = (double)zr;                   // orthonormalise the block that is actually stored (rounded)
+    }
+  }
+  __syncthreads();
+  // Gram matrix
+  if (G != nullptr) {
+    for (int e = tid; e < k * k; e += SE_THREADS) {
+      const int i = e / k, j = e - i * k;
+      double acc = 0.0;
+      for (int r = 0; r < rows; ++r) acc += Zs[r * k + i] * Zs[r * k + j];
+      atomicAdd(&G[e], acc);
+    }
+  }
+  // projections onto the basis, group by group: thread <-> (basis vector in group, column)
+  if (Cout != nullptr) {
+    for (int g0 = 0; g0 < nblk; g0 += SE_GB) {
+      const int nb = min(SE_GB, nblk - g0);
       __syncthreads();
-    }
-    const double* L = gram ? Zs : Vs;
-    if (npair <= SE_THREADS) {
-      if (worker) {
+      stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
+      cp_async_wait_all();
+      __syncthreads();
+      for (int e = tid; e < nb * k * k; e += SE_THREADS) {
+        const int iv = e / k, j = e - iv * k;            // iv = b * k + i
+        const int b = iv / k, i = iv - b * k;
+        const TV* vcol = Vs + (size_t)b * SE_ROWS * k + i;
         double acc = 0.0;
-        for (int r = sl; r < rows; r += nslice) acc += L[r * k + pi] * Zs[r * k + pj];
-        if (gram) {
-          if (G != nullptr) atomicAdd(&G[pi * k + pj], acc);
-        } else if (Cout != nullptr) {
-          atomicAdd(&Cout[((int64_t)blk * k + pi) * k + pj], acc);
-        }
-      }
-    } else {   // k*k > threads cannot happen for k <= 16 with 256 threads; kept for safety
-      for (int e = tid; e < npair; e += SE_THREADS) {
-        const int i = e / k, j = e - i * k;
-        double acc = 0.0;
-        for (int r = 0; r < rows; ++r) acc += L[r * k + i] * Zs[r * k + j];
-        if (gram) {
-          if (G != nullptr) atomicAdd(&G[i * k + j], acc);
-        } else if (Cout != nullptr) {
-          atomicAdd(&Cout[((int64_t)blk * k + i) * k + j], acc);
-        }
+        for (int r = 0; r < rows; ++r) acc += (double)vcol[r * k] * Zs[r * k + j];
+        atomicAdd(&Cout[((int64_t)g0 * k + iv) * k + j], acc);
       }
     }
-    __syncthreads();
+  }
+  if (!finish) return;
+  // ---- last CTA: Rinv from the completed Gram / projection sums
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(&ctl->counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double* Gs = Zs;                       // reuse shared memory
+  double* Ri = Zs + SE_MAXK * SE_MAXK;
+  for (int e = tid; e < k * k; e += SE_THREADS) {
+    const int i = e / k, j = e - i * k;
+    double acc = 0.5 * (__ldcg(&G[i * k + j]) + __ldcg(&G[j * k + i]));
+    if (Cout != nullptr)
+      for (int t = 0; t < m; ++t) acc -= __ldcg(&Cout[(int64_t)t * k + i]) * __ldcg(&Cout[(int64_t)t * k + j]);
+    Gs[e] = acc;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int ok = chol_inverse_warp(Gs, Ri, k);
+    if (ok) {
+      for (int e = tid; e < k * k; e += 32) Rinv[e] = Ri[e];
+    } else if (tid == 0) {
+      ctl->breakdown = 1;
+      ctl->done = 1;
+    }
+    if (tid == 0) ctl->counter = 0;
+    __threadfence();
   }
 }
 
-// Q = (Zp - V C2) Rinv with R = chol(G - C2^T C2)^T (upper), every CTA recomputes the tiny k x k factor.
-// Writes Q to Qout (an (n,k) block).  Breakdown (non-positive pivot) -> ctl->breakdown = done = 1.
+// Q = (Zp - V C2) Rinv  -> Qout (an (n,k) block);  Rinv (upper triangular, k x k) comes from subproj_kernel.
 template <typename TV>
 __global__ void __launch_bounds__(SE_THREADS)
 orth_finish_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restrict__ Zp,
-                   const double* __restrict__ C2, const double* __restrict__ G, TV* __restrict__ Qout, EigCtl* ctl) {
+                   const double* __restrict__ C2, const double* __restrict__ Rinv, TV* __restrict__ Qout,
+                   const EigCtl* ctl) {
   if (ctl->done) return;
-  __shared__ double Zs[SE_ROWS * SE_MAXK];
-  __shared__ double Vs[SE_ROWS * SE_MAXK];
-  __shared__ double Cs[SE_MAXK * SE_MAXK];
-  __shared__ double Gs[SE_MAXK * SE_MAXK];     // Gram -> L (lower Cholesky) -> Rinv
+  extern __shared__ __align__(16) unsigned char se_raw[];
+  double* Zs = reinterpret_cast<double*>(se_raw);
+  double* Cs = Zs + SE_ROWS * SE_MAXK;
+  TV* Vs = reinterpret_cast<TV*>(Cs + SE_GB * SE_MAXK * SE_MAXK);
   __shared__ double Ri[SE_MAXK * SE_MAXK];
-  __shared__ int bad;
   const int tid = threadIdx.x;
   const int row0 = blockIdx.x * SE_ROWS;
   const int rows = min(SE_ROWS, n - row0);
   const int nblk = m / k;
-  // Gs = G - C2^T C2
-  for (int e = tid; e < k * k; e += SE_THREADS) {
-    const int i = e / k, j = e - i * k;
-    double acc = 0.5 * (G[i * k + j] + G[j * k + i]);
-    for (int t = 0; t < m; ++t) acc -= C2[(int64_t)t * k + i] * C2[(int64_t)t * k + j];
-    Gs[e] = acc;
-  }
-  if (tid == 0) bad = 0;
-  __syncthreads();
-  if (tid == 0) {
-    // Cholesky G = L L^T (lower, in place), then Rinv = (L^T)^-1 = (L^-1)^T
-    double scale = 0.0;
-    for (int i = 0; i < k; ++i) scale = fmax(scale, Gs[i * k + i]);
-    for (int j = 0; j < k && !bad; ++j) {
-      double d = Gs[j * k + j];
-      for (int t = 0; t < j; ++t) d -= Gs[j * k + t] * Gs[j * k + t];
-      if (!(d > 1e-24 * scale) || !(d == d)) { bad = 1; break; }
-      const double ljj = sqrt(d);
-      Gs[j * k + j] = ljj;
-      for (int i = j + 1; i < k; ++i) {
-        double s = Gs[i * k + j];
-        for (int t = 0; t < j; ++t) s -= Gs[i * k + t] * Gs[j * k + t];
-        Gs[i * k + j] = s / ljj;
-      }
-    }
-    if (!bad) {
-      // Linv (lower) by forward substitution, stored transposed: Ri[c][r'] ... we need Rinv = Linv^T, i.e.
-      // Q[:, j] = sum_i Z[:, i] * Rinv[i][j],  Rinv[i][j] = Linv[j][i]
-      for (int c = 0; c < k; ++c) {          // column c of Linv
-        for (int r = 0; r < k; ++r) {
-          if (r < c) { Ri[c * k + r] = 0.0; continue; }   // Linv[r][c] = 0 for r < c ; store Rinv[c][r] = Linv[r][c]
-          double s = (r == c) ? 1.0 : 0.0;
-          for (int t = c; t < r; ++t) s -= Gs[r * k + t] * Ri[c * k + t];
-          Ri[c * k + r] = s / Gs[r * k + r];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (bad) {
-    if (blockIdx.x == 0 && tid == 0) { ctl->breakdown = 1; ctl->done = 1; }
-    return;
-  }
+  for (int i = tid; i < k * k; i += SE_THREADS) Ri[i] = Rinv[i];
   for (int i = tid; i < rows * k; i += SE_THREADS) Zs[i] = (double)Zp[(int64_t)row0 * k + i];
-  __syncthreads();
-  for (int blk = 0; blk < nblk; ++blk) {
-    const TV* Vb = V + ((int64_t)blk * n + row0) * k;
-    for (int i = tid; i < rows * k; i += SE_THREADS) Vs[i] = (double)Vb[i];
-    for (int i = tid; i < k * k; i += SE_THREADS) Cs[i] = C2[(int64_t)blk * k * k + i];
+  for (int g0 = 0; g0 < nblk; g0 += SE_GB) {
+    const int nb = min(SE_GB, nblk - g0);
+    __syncthreads();
+    stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
+    for (int i = tid; i < nb * k * k; i += SE_THREADS) Cs[i] = C2[(int64_t)g0 * k * k + i];
+    cp_async_wait_all();
     __syncthreads();
     for (int e = tid; e < rows * k; e += SE_THREADS) {
       const int r = e / k, j = e - r * k;
       double acc = 0.0;
-      for (int i = 0; i < k; ++i) acc += Vs[r * k + i] * Cs[i * k + j];
+      for (int b = 0; b < nb; ++b) {
+        const TV* vr = Vs + ((size_t)b * SE_ROWS + r) * k;
+        const double* cr = Cs + (size_t)b * k * k + j;
+        for (int i = 0; i < k; ++i) acc += (double)vr[i] * cr[i * k];
+      }
       Zs[e] -= acc;
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int e = tid; e < rows * k; e += SE_THREADS) {
     const int r = e / k, j = e - r * k;
     double acc = 0.0;
@@ -210,38 +264,68 @@ orth_finish_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __re
 template <typename TV>
 __global__ void __launch_bounds__(SE_THREADS)
 ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, int m, const double* __restrict__ Sk,
-            const double* __restrict__ theta, TV* __restrict__ Xslots, double* __restrict__ evals_slots,
-            TV* __restrict__ Rout, EigCtl* ctl, int iter, float min_eps) {
+            int ldsk, int coff, const double* __restrict__ theta_all, TV* __restrict__ Xslots,
+            double* __restrict__ evals_slots, TV* __restrict__ Rout, EigCtl* ctl, int iter, float min_eps) {
   if (ctl->done) return;
-  extern __shared__ double sh[];
-  double* Ss = sh;                 // [m][k]
+  extern __shared__ __align__(16) unsigned char se_raw[];
+  TV* Vs = reinterpret_cast<TV*>(se_raw);                                  // [SE_GB][SE_ROWS][k]
+  TV* As = Vs + (size_t)SE_GB * SE_ROWS * k;                               // [SE_GB][SE_ROWS][k]
+  double* Ss = reinterpret_cast<double*>(As + (size_t)SE_GB * SE_ROWS * k);         // [SE_GB*k][k]
   __shared__ float red[32];
   const int tid = threadIdx.x;
-  for (int i = tid; i < m * k; i += SE_THREADS) Ss[i] = Sk[i];
-  __syncthreads();
+  const double* theta = theta_all + coff;
   const int slot = 1 - ctl->best_slot;
   TV* X = Xslots + (int64_t)slot * n * k;
   const int row0 = blockIdx.x * SE_ROWS;
   const int rows = min(SE_ROWS, n - row0);
   const int nblk = m / k;
-  float lmax = 0.f;
-  for (int e = tid; e < rows * k; e += SE_THREADS) {
-    const int r = e / k, j = e - r * k;
-    double x = 0.0, ax = 0.0;
-    for (int blk = 0; blk < nblk; ++blk) {
-      const TV* vr = V + ((int64_t)blk * n + row0 + r) * k;
-      const TV* ar = AV + ((int64_t)blk * n + row0 + r) * k;
-      for (int i = 0; i < k; ++i) {
-        const double s = Ss[(blk * k + i) * k + j];
-        x += (double)vr[i] * s;
-        ax += (double)ar[i] * s;
+  // each thread owns up to 2 (row, column) outputs for k <= 8 (4 for k = 16)
+  constexpr int MAXO = SE_ROWS * SE_MAXK / SE_THREADS;
+  double xacc[MAXO], aacc[MAXO];
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) { xacc[o] = 0.0; aacc[o] = 0.0; }
+  for (int g0 = 0; g0 < nblk; g0 += SE_GB) {
+    const int nb = min(SE_GB, nblk - g0);
+    __syncthreads();
+    stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
+    stage_group<TV>(As, AV, n, k, row0, rows, g0, nb);
+    for (int i = tid; i < nb * k * k; i += SE_THREADS)
+      Ss[i] = Sk[(size_t)(g0 * k + i / k) * ldsk + coff + (i % k)];
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      const int e = tid + o * SE_THREADS;
+      if (e < rows * k) {
+        const int r = e / k, j = e - r * k;
+        double x = 0.0, ax = 0.0;
+        for (int b = 0; b < nb; ++b) {
+          const TV* vr = Vs + ((size_t)b * SE_ROWS + r) * k;
+          const TV* ar = As + ((size_t)b * SE_ROWS + r) * k;
+          const double* sr = Ss + (size_t)b * k * k + j;
+          for (int i = 0; i < k; ++i) {
+            const double sv = sr[i * k];
+            x += (double)vr[i] * sv;
+            ax += (double)ar[i] * sv;
+          }
+        }
+        xacc[o] += x;
+        aacc[o] += ax;
       }
     }
-    const double res = ax - x * theta[j];
-    X[(int64_t)(row0 + r) * k + j] = (TV)x;
-    Rout[(int64_t)(row0 + r) * k + j] = (TV)res;
-    lmax = fmaxf(lmax, fabsf((float)res));
-    if (!(res == res)) lmax = INFINITY;
+  }
+  float lmax = 0.f;
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) {
+    const int e = tid + o * SE_THREADS;
+    if (e < rows * k) {
+      const int j = e % k;
+      const double res = aacc[o] - xacc[o] * theta[j];
+      X[(int64_t)row0 * k + e] = (TV)xacc[o];
+      Rout[(int64_t)row0 * k + e] = (TV)res;
+      lmax = fmaxf(lmax, fabsf((float)res));
+      if (!(res == res)) lmax = INFINITY;
+    }
   }
   lmax = block_max(lmax, red);
   if (tid == 0) {
@@ -268,145 +352,322 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
   }
 }
 
-// Out[:, 0..p) = In(:, 0..m) * S[:, order[first + c]]   (thick restart: rotate the basis onto kept Ritz vectors)
+// Out[:, 0..p) = In(:, 0..m) * Sr   (thick restart: rotate the basis onto the p kept Ritz vectors; Sr is m x p)
 template <typename TV>
 __global__ void __launch_bounds__(SE_THREADS)
-rotate_kernel(const TV* __restrict__ In, int n, int k, int m, const double* __restrict__ S, int lds,
-              const int* __restrict__ order, int first, int p, TV* __restrict__ Out, const EigCtl* ctl) {
+rotate_kernel(const TV* __restrict__ In, int n, int k, int m, const double* __restrict__ Sr, int p,
+              TV* __restrict__ Out, const EigCtl* ctl) {
   if (ctl->done) return;
-  // one thread per (row, output column); S accessed through L1/L2 (m*p doubles, shared by all threads)
   const int64_t e = (int64_t)blockIdx.x * SE_THREADS + threadIdx.x;
   if (e >= (int64_t)n * p) return;
   const int64_t row = e / p;
   const int c = (int)(e - row * p);
-  const int col = order[first + c];
   double acc = 0.0;
   const int nblk = m / k;
   for (int blk = 0; blk < nblk; ++blk) {
     const TV* vr = In + ((int64_t)blk * n + row) * k;
-    for (int i = 0; i < k; ++i) acc += (double)vr[i] * S[(int64_t)(blk * k + i) * lds + col];
+    for (int i = 0; i < k; ++i) acc += (double)vr[i] * Sr[(int64_t)(blk * k + i) * p + c];
   }
-  // output in block layout [c / k][row][c % k]
-  Out[((int64_t)(c / k) * n + row) * k + (c % k)] = (TV)acc;
+  Out[((int64_t)(c / k) * n + row) * k + (c % k)] = (TV)acc;   // block layout [c / k][row][c % k]
 }
 
-// T <- diag(w[order[first + i]]) after a restart
-__global__ void restart_T_kernel(double* T, int ldt, const double* w, const int* order, int first, int p,
-                                 const EigCtl* ctl) {
+// T <- diag(theta[0..p)) after a restart
+__global__ void restart_T_kernel(double* T, int ldt, const double* theta, int p, const EigCtl* ctl) {
   if (ctl->done) return;
   for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
     const int i = e / p, j = e - i * p;
-    T[(int64_t)i * ldt + j] = (i == j) ? w[order[first + i]] : 0.0;
+    T[(int64_t)i * ldt + j] = (i == j) ? theta[i] : 0.0;
   }
 }
 
 // ---------------------------------------------------------------------------- small dense eigh (one CTA)
-// Cyclic parallel-ordered Jacobi in fp64 on Tw (m x m, row-major, leading dimension ld), eigenvectors
-// accumulated in S (m x m, ld).  On exit w[i] = Tw[i][i] and order[] sorts them ascending.
-__device__ void jacobi_eigh_device(double* Tw, double* S, int m, int ld, double* w, int* order, double* sc,
-                                   float2* cs /* smem [m/2+1] */, int* prs /* smem [m+2] */) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int e = tid; e < m * m; e += nt) {
-    const int i = e / m, j = e - i * m;
-    S[(int64_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+// nev extreme eigenpairs of a symmetric m x m matrix, fp64, one CTA of EIG_THREADS threads:
+//   1. Householder tridiagonalisation (unblocked, LAPACK dsytd2 style; reflectors stay in the strict lower triangle)
+//   2. nev eigenvalues by parallel multi-section on Sturm counts (every thread evaluates one shift per round)
+//   3. eigenvectors of the tridiagonal matrix by inverse iteration (LU with partial pivoting, one thread per vector),
+//      modified Gram-Schmidt across the nev vectors (handles clustered / degenerate eigenvalues)
+//   4. back-transformation with the stored reflectors (one warp per eigenvector, no block barriers)
+// This replaces torch.linalg.eigh on the projected matrix (reference symeig.py:174); only the k wanted pairs
+// are computed (keep > k pairs at a thick restart).
+struct EigPlan {
+  int lds;          // leading dimension of the work matrix (odd: conflict-free column access in shared memory)
+  int as_in_smem;   // work matrix in shared memory (else in the global scratch Tw)
+  int inv_slots;    // eigenvectors processed per inverse-iteration batch
+  size_t smem_bytes;
+};
+
+static EigPlan eig_plan(int m, int nev) {
+  EigPlan pl;
+  pl.lds = m | 1;
+  const size_t budget = 220 * 1024;
+  const size_t fixed = (size_t)(6 * m + 4 * nev + 64) * 8 + (size_t)EIG_THREADS * 4 + (size_t)m * nev * 8 + 256;
+  const size_t as_bytes = (size_t)m * pl.lds * 8;
+  const size_t inv1 = (size_t)5 * m * 8;
+  pl.as_in_smem = (fixed + as_bytes + inv1 <= budget) ? 1 : 0;
+  size_t used = fixed + (pl.as_in_smem ? as_bytes : 0);
+  int slots = used + inv1 <= budget ? (int)((budget - used) / inv1) : 0;
+  if (slots > 16) slots = 16;
+  if (slots > nev) slots = nev;
+  pl.inv_slots = slots;   // 0 => does not fit at all (m * nev too large)
+  pl.smem_bytes = used + (size_t)slots * inv1;
+  return pl;
+}
+
+__device__ __forceinline__ int sturm_count(const double* d, const double* e2, int m, double x, double pivmin) {
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  int cnt = q < 0.0 ? 1 : 0;
+  for (int i = 1; i < m; ++i) {
+    q = d[i] - x - e2[i - 1] / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0 ? 1 : 0;
+  }
+  return cnt;
+}
+
+// As: work matrix (m x lds, destroyed).  Outputs: lam[nev] ascending, Y (m x nev, row-major, orthonormal columns).
+// mode 0: the nev lowest, mode 1: the nev highest.  `sh` is the carved shared memory.
+__device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode, double* sh, int inv_slots,
+                                   double* lam, double* Y) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  double* d = sh;                 // [m]
+  double* e = d + m;              // [m]
+  double* tau = e + m;            // [m]
+  double* vbuf = tau + m;         // [m]   (later: e^2)
+  double* pbuf = vbuf + m;        // [m]
+  double* red = pbuf + m;         // [64]
+  double* lo = red + 64;          // [nev]
+  double* hi = lo + nev;          // [nev]
+  int* icnt = reinterpret_cast<int*>(hi + nev);                   // [nt]
+  double* inv = reinterpret_cast<double*>(icnt + nt + (nt & 1));  // [inv_slots][5][m]
+
+  // ------------------------------------------------------------------ 1. tridiagonalisation
+  for (int j = 0; j + 2 < m; ++j) {
+    const int n = m - j - 1;
+    double part = 0.0;
+    for (int i = j + 2 + tid; i < m; i += nt) {
+      const double v = As[(size_t)i * lds + j];
+      part += v * v;
+    }
+    const double sigma = block_sum(part, red);
+    const double x0 = As[(size_t)(j + 1) * lds + j];
+    double alpha = x0, t = 0.0, scale = 0.0;
+    if (sigma > 0.0) {
+      const double nrm = sqrt(x0 * x0 + sigma);
+      alpha = x0 >= 0.0 ? -nrm : nrm;
+      t = (alpha - x0) / alpha;
+      scale = 1.0 / (x0 - alpha);
+    }
+    __syncthreads();   // everyone has read x0 before column j is overwritten
+    for (int i = tid; i < n; i += nt) {
+      const double val = (i == 0) ? 1.0 : As[(size_t)(j + 1 + i) * lds + j] * scale;
+      vbuf[i] = val;
+      As[(size_t)(j + 1 + i) * lds + j] = val;
+    }
+    if (tid == 0) { d[j] = As[(size_t)j * lds + j]; e[j] = alpha; tau[j] = t; }
+    __syncthreads();
+    if (t != 0.0) {
+      // p = t * A22 v   (TPR lanes per row, shuffle-reduced)
+      int TPR = 32;
+      while (TPR > 1 && n * TPR > nt) TPR >>= 1;
+      const int sub = tid % TPR, rowsPerPass = nt / TPR;
+      for (int i0 = 0; i0 < n; i0 += rowsPerPass) {
+        const int i = i0 + tid / TPR;
+        double acc = 0.0;
+        if (i < n) {
+          const double* row = As + (size_t)(j + 1 + i) * lds + (j + 1);
+          for (int l = sub; l < n; l += TPR) acc += row[l] * vbuf[l];
+        }
+        for (int o = TPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (i < n && sub == 0) pbuf[i] = t * acc;
+      }
+      __syncthreads();
+      double pv = 0.0;
+      for (int i = tid; i < n; i += nt) pv += pbuf[i] * vbuf[i];
+      pv = block_sum(pv, red);
+      const double hc = 0.5 * t * pv;
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) pbuf[i] -= hc * vbuf[i];
+      __syncthreads();
+      // A22 -= v w^T + w v^T
+      for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, l = idx - i * n;
+        As[(size_t)(j + 1 + i) * lds + (j + 1 + l)] -= vbuf[i] * pbuf[l] + pbuf[i] * vbuf[l];
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    if (m >= 2) {
+      d[m - 2] = As[(size_t)(m - 2) * lds + (m - 2)];
+      e[m - 2] = As[(size_t)(m - 1) * lds + (m - 2)];
+      tau[m - 2] = 0.0;
+    }
+    d[m - 1] = As[(size_t)(m - 1) * lds + (m - 1)];
+    e[m - 1] = 0.0;
+    tau[m - 1] = 0.0;
   }
   __syncthreads();
-  const int M = (m + 1) & ~1;        // even number of players (index m is a dummy when m is odd)
-  const int npairs = M / 2;
-  double* cd = reinterpret_cast<double*>(cs);   // [npairs][2] doubles (c, s)
-  for (int sweep = 0; sweep < 40; ++sweep) {
-    // convergence: off-diagonal Frobenius norm relative to the diagonal
-    double off = 0.0, dia = 0.0;
-    for (int e = tid; e < m * m; e += nt) {
-      const int i = e / m, j = e - i * m;
-      const double v = Tw[(int64_t)i * ld + j];
-      if (i == j) dia += v * v; else off += v * v;
-    }
-    off = block_sum(off, sc);
-    dia = block_sum(dia, sc);
-    if (off <= 1e-30 * dia || off == 0.0) break;
-    for (int rd = 0; rd < M - 1; ++rd) {
-      // pairing (round robin): player M-1 is fixed, the others rotate
-      if (tid < npairs) {
-        int p, q;
-        if (tid == 0) { p = M - 1; q = rd; }
-        else { p = (rd + tid) % (M - 1); q = (rd - tid + (M - 1)) % (M - 1); }
-        if (p > q) { const int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0;
-        if (q < m) {
-          const double apq = Tw[(int64_t)p * ld + q];
-          const double app = Tw[(int64_t)p * ld + p], aqq = Tw[(int64_t)q * ld + q];
-          if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * (fabs(app) + fabs(aqq))) {
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = t * c;
-          }
-        } else {
-          q = -1;   // dummy pair
-        }
-        prs[2 * tid] = p;
-        prs[2 * tid + 1] = q;
-        cd[2 * tid] = c;
-        cd[2 * tid + 1] = s;
-      }
-      __syncthreads();
-      // rows p, q of Tw
-      for (int e = tid; e < npairs * m; e += nt) {
-        const int pr = e / m, j = e - pr * m;
-        const int p = prs[2 * pr], q = prs[2 * pr + 1];
-        const double s = cd[2 * pr + 1];
-        if (q >= 0 && s != 0.0) {
-          const double c = cd[2 * pr];
-          const double tp = Tw[(int64_t)p * ld + j], tq = Tw[(int64_t)q * ld + j];
-          Tw[(int64_t)p * ld + j] = c * tp - s * tq;
-          Tw[(int64_t)q * ld + j] = s * tp + c * tq;
-        }
-      }
-      __syncthreads();
-      // columns p, q of Tw and S
-      for (int e = tid; e < npairs * m; e += nt) {
-        const int pr = e % npairs, i = e / npairs;
-        const int p = prs[2 * pr], q = prs[2 * pr + 1];
-        const double s = cd[2 * pr + 1];
-        if (q >= 0 && s != 0.0) {
-          const double c = cd[2 * pr];
-          double tp = Tw[(int64_t)i * ld + p], tq = Tw[(int64_t)i * ld + q];
-          Tw[(int64_t)i * ld + p] = c * tp - s * tq;
-          Tw[(int64_t)i * ld + q] = s * tp + c * tq;
-          tp = S[(int64_t)i * ld + p]; tq = S[(int64_t)i * ld + q];
-          S[(int64_t)i * ld + p] = c * tp - s * tq;
-          S[(int64_t)i * ld + q] = s * tp + c * tq;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = tid; i < m; i += nt) w[i] = Tw[(int64_t)i * ld + i];
-  __syncthreads();
+
+  // ------------------------------------------------------------------ 2. eigenvalues by multi-section
+  double* e2 = vbuf;
+  double gl = INFINITY, gu = -INFINITY, emax = 0.0;
   for (int i = tid; i < m; i += nt) {
-    const double wi = w[i];
-    int rank = 0;
-    for (int j = 0; j < m; ++j) {
-      const double wj = w[j];
-      rank += (wj < wi || (wj == wi && j < i)) ? 1 : 0;
+    const double el = (i > 0) ? fabs(e[i - 1]) : 0.0;
+    const double er = (i < m - 1) ? fabs(e[i]) : 0.0;
+    gl = fmin(gl, d[i] - el - er);
+    gu = fmax(gu, d[i] + el + er);
+    emax = fmax(emax, er * er);
+    e2[i] = er * er;
+  }
+  gl = -block_max(-gl, red);
+  __syncthreads();
+  gu = block_max(gu, red);
+  __syncthreads();
+  emax = block_max(emax, red);
+  __syncthreads();
+  const double tnorm = fmax(fabs(gl), fabs(gu));
+  gl -= 2.0 * tnorm * m * 2.3e-16 + 1e-300;
+  gu += 2.0 * tnorm * m * 2.3e-16 + 1e-300;
+  const double pivmin = 2.3e-308 * fmax(1.0, emax) * 1e4;
+  int P = nt / nev;
+  if (P < 1) P = 1;
+  const int slot = tid / P, pt = tid - slot * P;
+  const bool bis = slot < nev;
+  const int want = bis ? ((mode == 0) ? slot : (m - nev + slot)) : 0;
+  for (int i = tid; i < nev; i += nt) { lo[i] = gl; hi[i] = gu; }
+  __syncthreads();
+  int rounds = (int)ceil(62.0 / log2((double)P + 1.0));
+  if (rounds < 3) rounds = 3;
+  for (int r = 0; r < rounds; ++r) {
+    double l0 = 0.0, h0 = 0.0, x = 0.0;
+    int cnt = 0;
+    if (bis) {
+      l0 = lo[slot]; h0 = hi[slot];
+      x = l0 + (h0 - l0) * ((double)(pt + 1) / (double)(P + 1));
+      cnt = sturm_count(d, e2, m, x, pivmin);
+      icnt[tid] = cnt;
     }
-    order[rank] = i;
+    __syncthreads();
+    if (bis) {
+      const int cl = (pt == 0) ? -1 : icnt[tid - 1];
+      if (cl <= want && cnt > want) {          // eigenvalue `want` lies in (x_{pt-1}, x_pt]
+        hi[slot] = x;
+        if (pt > 0) lo[slot] = l0 + (h0 - l0) * ((double)pt / (double)(P + 1));
+      }
+      if (pt == P - 1 && cnt <= want) lo[slot] = x;   // it lies in (x_{P-1}, hi]
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < nev; i += nt) lam[i] = 0.5 * (lo[i] + hi[i]);
+  __syncthreads();
+
+  // ------------------------------------------------------------------ 3. inverse iteration on the tridiagonal matrix
+  const double pert = 2.3e-16 * fmax(tnorm, 1e-300);
+  for (int b0 = 0; b0 < nev; b0 += inv_slots) {
+    const int sidx = b0 + tid;
+    if (tid < inv_slots && sidx < nev) {
+      double* a = inv + (size_t)tid * 5 * m;    // diagonal of U
+      double* b = a + m;                         // first superdiagonal of U
+      double* l = b + m;                         // multipliers
+      double* u2 = l + m;                        // second superdiagonal of U
+      double* pv = u2 + m;                       // pivot flags
+      const double lamv = lam[sidx];
+      for (int i = 0; i < m; ++i) { a[i] = d[i] - lamv; b[i] = e[i]; u2[i] = 0.0; pv[i] = 0.0; }
+      for (int i = 0; i + 1 < m; ++i) {
+        const double ci = e[i];                  // subdiagonal entry (symmetric)
+        if (fabs(a[i]) >= fabs(ci)) {
+          if (a[i] == 0.0) a[i] = pert;
+          l[i] = ci / a[i];
+          a[i + 1] -= l[i] * b[i];
+        } else {
+          pv[i] = 1.0;
+          const double fact = a[i] / ci;
+          l[i] = fact;
+          const double an = a[i + 1];
+          a[i] = ci;
+          a[i + 1] = b[i] - fact * an;
+          b[i] = an;
+          if (i + 2 < m) { u2[i] = b[i + 1]; b[i + 1] = -fact * b[i + 1]; }
+        }
+      }
+      if (a[m - 1] == 0.0) a[m - 1] = pert;
+      unsigned int rng = 0x9E3779B9u * (unsigned int)(sidx + 1) + 12345u;
+      for (int i = 0; i < m; ++i) {
+        rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
+        Y[(size_t)i * nev + sidx] = (double)(rng >> 8) * (2.0 / 16777216.0) - 1.0;
+      }
+      for (int it = 0; it < 3; ++it) {
+        for (int i = 0; i + 1 < m; ++i) {
+          const double yi = Y[(size_t)i * nev + sidx], yn = Y[(size_t)(i + 1) * nev + sidx];
+          if (pv[i] != 0.0) {
+            Y[(size_t)i * nev + sidx] = yn;
+            Y[(size_t)(i + 1) * nev + sidx] = yi - l[i] * yn;
+          } else {
+            Y[(size_t)(i + 1) * nev + sidx] = yn - l[i] * yi;
+          }
+        }
+        double ymax = 0.0;
+        for (int i = m - 1; i >= 0; --i) {
+          double v = Y[(size_t)i * nev + sidx];
+          if (i + 1 < m) v -= b[i] * Y[(size_t)(i + 1) * nev + sidx];
+          if (i + 2 < m) v -= u2[i] * Y[(size_t)(i + 2) * nev + sidx];
+          v /= a[i];
+          Y[(size_t)i * nev + sidx] = v;
+          ymax = fmax(ymax, fabs(v));
+        }
+        const double sc = ymax > 0.0 ? 1.0 / ymax : 1.0;
+        for (int i = 0; i < m; ++i) Y[(size_t)i * nev + sidx] *= sc;
+      }
+    }
+    __syncthreads();
+  }
+  // modified Gram-Schmidt over the nev vectors (warp 0)
+  if (warp == 0) {
+    for (int c = 0; c < nev; ++c) {
+      for (int j = 0; j < c; ++j) {
+        double dot = 0.0;
+        for (int i = lane; i < m; i += 32) dot += Y[(size_t)i * nev + j] * Y[(size_t)i * nev + c];
+        dot = warp_sum(dot);
+        for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] -= dot * Y[(size_t)i * nev + j];
+        __syncwarp();
+      }
+      double nn = 0.0;
+      for (int i = lane; i < m; i += 32) nn += Y[(size_t)i * nev + c] * Y[(size_t)i * nev + c];
+      nn = warp_sum(nn);
+      const double sc = nn > 0.0 ? rsqrt(nn) : 0.0;
+      for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] *= sc;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ 4. back-transformation (one warp per eigenvector)
+  for (int c = warp; c < nev; c += nw) {
+    for (int j = m - 3; j >= 0; --j) {
+      const double t = tau[j];
+      if (t == 0.0) continue;
+      const int n = m - j - 1;
+      double dot = 0.0;
+      for (int i = lane; i < n; i += 32) dot += As[(size_t)(j + 1 + i) * lds + j] * Y[(size_t)(j + 1 + i) * nev + c];
+      dot = warp_sum(dot) * t;
+      for (int i = lane; i < n; i += 32) Y[(size_t)(j + 1 + i) * nev + c] -= dot * As[(size_t)(j + 1 + i) * lds + j];
+      __syncwarp();
+    }
   }
   __syncthreads();
 }
 
-// T[:, new block] = C (and its transpose), Tw = T, eigh, select k extreme pairs -> theta (k), Sk (m x k)
+// T[:, new block] = C (and its transpose); then the nev extreme eigenpairs of T:
+//   theta[nev] (ascending), Sk (m x nev row-major).  The k wanted Ritz pairs are columns [0,k) for mode 0 and
+//   [nev-k, nev) for mode 1.
 __global__ void __launch_bounds__(EIG_THREADS)
-rr_kernel(double* T, int ldt, const double* C, int m, int k, double* Tw, double* S, double* w, int* order,
-          double* Sk, double* theta, int mode, int have_new_block, const EigCtl* ctl) {
+rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw, double* Sk, double* theta, int mode,
+          int lds, int as_in_smem, int inv_slots, const EigCtl* ctl) {
   if (ctl->done) return;
-  __shared__ double sc[64];
   extern __shared__ double dyn[];
-  float2* cs = reinterpret_cast<float2*>(dyn);                       // (m/2+1) * 2 doubles
-  int* prs = reinterpret_cast<int*>(dyn + 2 * (m / 2 + 2));          // m + 2 ints
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (have_new_block) {
+  {
     const int c0 = m - k;
     for (int e = tid; e < m * k; e += nt) {
       const int i = e / k, j = e - i * k;
@@ -417,32 +678,39 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, double* Tw, double*
     }
     __syncthreads();
   }
+  double* lamv = dyn;                       // [nev]
+  double* Y = lamv + nev + (nev & 1);       // [m * nev]
+  double* rest = Y + (size_t)m * nev;
+  double* As = as_in_smem ? rest : Tw;
+  double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
   for (int e = tid; e < m * m; e += nt) {
     const int i = e / m, j = e - i * m;
-    Tw[(int64_t)i * ldt + j] = T[(int64_t)i * ldt + j];
+    As[(size_t)i * lds + j] = T[(int64_t)i * ldt + j];
   }
   __syncthreads();
-  jacobi_eigh_device(Tw, S, m, ldt, w, order, sc, cs, prs);
-  const int first = (mode == 0) ? 0 : (m - k);
-  for (int e = tid; e < m * k; e += nt) {
-    const int i = e / k, j = e - i * k;
-    Sk[e] = S[(int64_t)i * ldt + order[first + j]];
-  }
-  for (int j = tid; j < k; j += nt) theta[j] = w[order[first + j]];
+  eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y);
+  for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
+  for (int j = tid; j < nev; j += nt) theta[j] = lamv[j];
 }
 
 __global__ void __launch_bounds__(EIG_THREADS)
-small_eigh_kernel(double* T, int m, double* w_sorted, double* S_sorted, double* S, double* w, int* order) {
-  __shared__ double sc[64];
+small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double* w_out, double* S_out, int lds,
+                  int as_in_smem, int inv_slots) {
   extern __shared__ double dyn[];
-  float2* cs = reinterpret_cast<float2*>(dyn);
-  int* prs = reinterpret_cast<int*>(dyn + 2 * (m / 2 + 2));
-  jacobi_eigh_device(T, S, m, m, w, order, sc, cs, prs);
-  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* lamv = dyn;
+  double* Y = lamv + nev + (nev & 1);
+  double* rest = Y + (size_t)m * nev;
+  double* As = as_in_smem ? rest : Tw;
+  double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
+  for (int e = tid; e < m * m; e += nt) {
     const int i = e / m, j = e - i * m;
-    S_sorted[e] = S[(int64_t)i * m + order[j]];
+    As[(size_t)i * lds + j] = T[(size_t)i * m + j];
   }
-  for (int j = threadIdx.x; j < m; j += blockDim.x) w_sorted[j] = w[order[j]];
+  __syncthreads();
+  eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y);
+  for (int e = tid; e < m * nev; e += nt) S_out[e] = Y[e];
+  for (int j = tid; j < nev; j += nt) w_out[j] = lamv[j];
 }
 
 // final copy of the best pair into the caller's tensors
@@ -477,8 +745,7 @@ __global__ void init_ctl_kernel(EigCtl* ctl) {
 // ============================================================================ host driver
 struct EigWs {
   void *V, *AV, *Zbuf, *Rblk, *Xslots, *Vtmp;
-  double *T, *Tw, *S, *w, *Sk, *theta, *C, *C2, *G, *evals_slots;
-  int* order;
+  double *T, *Tw, *Sk, *theta, *C, *C2, *G, *Rinv, *evals_slots;
   EigCtl* ctl;
 };
 
@@ -492,15 +759,13 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb) {
   W.Vtmp = ar.take<char>((size_t)(mb / k) * blk);
   W.T = ar.take<double>((size_t)mb * mb);
   W.Tw = ar.take<double>((size_t)mb * mb);
-  W.S = ar.take<double>((size_t)mb * mb);
-  W.w = ar.take<double>(mb);
-  W.Sk = ar.take<double>((size_t)mb * k);
-  W.theta = ar.take<double>(SE_MAXK);
+  W.Sk = ar.take<double>((size_t)mb * mb);
+  W.theta = ar.take<double>(mb);
   W.C = ar.take<double>((size_t)mb * k);
   W.C2 = ar.take<double>((size_t)mb * k);
   W.G = ar.take<double>(2 * SE_MAXK * SE_MAXK);
+  W.Rinv = ar.take<double>(SE_MAXK * SE_MAXK);
   W.evals_slots = ar.take<double>(2 * SE_MAXK);
-  W.order = ar.take<int>(mb);
   W.ctl = ar.take<EigCtl>(1);
   return ar.ok();
 }
@@ -528,7 +793,17 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const int grid_rows = (n + SE_ROWS - 1) / SE_ROWS;
   const int ce = g->check_every > 0 ? g->check_every : 1;
   const int keep = ((mb / 2) / k) * k >= k ? ((mb / 2) / k) * k : k;   // Ritz vectors kept at a restart
-  const size_t eig_smem = (size_t)(2 * (mb / 2 + 2)) * sizeof(double) + (size_t)(mb + 2) * sizeof(int) + 64;
+  const size_t sp_smem = (size_t)(SE_ROWS * SE_MAXK + SE_GB * SE_MAXK * SE_MAXK) * sizeof(double) +
+                         (size_t)SE_GB * SE_ROWS * k * sizeof(TV) + 64;
+  const size_t rz_smem = (size_t)2 * SE_GB * SE_ROWS * k * sizeof(TV) + (size_t)SE_GB * k * k * sizeof(double) + 64;
+  static bool attrs_set = false;   // per TV instantiation
+  if (!attrs_set) {
+    XT_CUDA_OK(cudaFuncSetAttribute(rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XT_CUDA_OK(cudaFuncSetAttribute(ritz_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    XT_CUDA_OK(cudaFuncSetAttribute(subproj_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    XT_CUDA_OK(cudaFuncSetAttribute(orth_finish_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attrs_set = true;
+  }
 
   int64_t napply = 0;
   int all_conv = 1;
@@ -544,9 +819,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
                                                        g->ldv0, n, k, Rblk); XT_LAUNCHED();
     for (int pass = 0; pass < 2; ++pass) {
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
-      subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, 0, pass == 0 ? Rblk : V, nullptr, Zbuf, nullptr,
-                                                            W.G, W.ctl); XT_LAUNCHED();
-      orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, 0, Zbuf, W.C2, W.G, V, W.ctl); XT_LAUNCHED();
+      subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, pass == 0 ? Rblk : V, nullptr, Zbuf,
+                                                                  nullptr, W.G, W.Rinv, 1, W.ctl); XT_LAUNCHED();
+      orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, Zbuf, W.C2, W.Rinv, V, W.ctl); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
 
@@ -570,17 +845,22 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       ++napply;
       // 2. C = V^T W  (new block column of T)
       XT_CUDA_OK(cudaMemsetAsync(W.C, 0, sizeof(double) * (size_t)m * k, st));
-      subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, W.C, nullptr,
-                                                            W.ctl); XT_LAUNCHED();
-      // 3. Rayleigh-Ritz on T
-      rr_kernel<<<1, EIG_THREADS, eig_smem, st>>>(W.T, mb, W.C, m, k, W.Tw, W.S, W.w, W.order, W.Sk, W.theta, g->mode,
-                                                  1, W.ctl); XT_LAUNCHED();
+      subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, W.C,
+                                                                  nullptr, nullptr, 0, W.ctl); XT_LAUNCHED();
+      // 3. Rayleigh-Ritz on T: the k wanted pairs, or `keep` pairs when a thick restart follows this iteration
+      const bool can_expand = (iter < g->max_niter) && (m + k <= n);
+      const bool restart = can_expand && (m + k > mb);
+      const int nev = restart ? keep : k;
+      const int coff = (g->mode == 0) ? 0 : (nev - k);
+      const EigPlan pl = eig_plan(m, nev);
+      XT_REQUIRE(pl.inv_slots >= 1, "symeig: projected problem %d x %d (nev=%d) exceeds the on-chip eigensolver", m, m, nev);
+      rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, st>>>(W.T, mb, W.C, m, k, nev, W.Tw, W.Sk, W.theta, g->mode, pl.lds,
+                                                        pl.as_in_smem, pl.inv_slots, W.ctl); XT_LAUNCHED();
       // 4. Ritz vectors, residual, bookkeeping
-      ritz_kernel<TV><<<grid_rows, SE_THREADS, (size_t)m * k * sizeof(double), st>>>(
-          V, AV, n, k, m, W.Sk, W.theta, Xslots, W.evals_slots, Rblk, W.ctl, iter, (float)g->min_eps); XT_LAUNCHED();
+      ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(
+          V, AV, n, k, m, W.Sk, nev, coff, W.theta, Xslots, W.evals_slots, Rblk, W.ctl, iter, (float)g->min_eps); XT_LAUNCHED();
       XT_CUDA_OK(cudaGetLastError());
-      if (iter >= g->max_niter) break;
-      if (m + k > n) break;                      // the basis cannot grow any further (symeig.py:202-203)
+      if (!can_expand) break;                    // max_niter reached, or the basis cannot grow (symeig.py:202-203)
       if (iter % ce == 0) {
         int done = 0;
         XT_CUDA_OK(cudaMemcpyAsync(&done, &W.ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -591,28 +871,30 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       XT_CUDA_OK(cudaMemsetAsync(W.C2, 0, sizeof(double) * (size_t)m * k, st));
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
       if (g->expansion == 1) {
-        subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, AV + j * blk, W.C, Zbuf, W.C2, W.G, W.ctl);
+        subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, W.C, Zbuf, W.C2, W.G,
+                                                                    W.Rinv, 1, W.ctl);
       } else {
-        subproj_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Rblk, nullptr, Zbuf, W.C2, W.G, W.ctl);
+        subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Rblk, nullptr, Zbuf, W.C2, W.G,
+                                                                    W.Rinv, 1, W.ctl);
       }
       XT_LAUNCHED();
-      if (m + k > mb) {
-        // thick restart: finish the new block against the OLD basis first, then compress V / AV / T
-        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Zbuf, W.C2, W.G, Rblk, W.ctl); XT_LAUNCHED();
-        const int first = (g->mode == 0) ? 0 : (m - keep);
+      if (restart) {
+        // thick restart: finish the new block against the OLD basis first, then compress V / AV / T onto the
+        // `keep` Ritz vectors computed by this iteration's rr_kernel (Sk is m x keep)
+        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Zbuf, W.C2, W.Rinv, Rblk, W.ctl); XT_LAUNCHED();
         const int64_t tot = (int64_t)n * keep;
         const int rg = (int)((tot + SE_THREADS - 1) / SE_THREADS);
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl); XT_LAUNCHED();
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, W.Sk, keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, W.S, mb, W.order, first, keep, Vtmp, W.ctl); XT_LAUNCHED();
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, W.Sk, keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(AV, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.w, W.order, first, keep, W.ctl); XT_LAUNCHED();
+        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.theta, keep, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, Rblk, (size_t)blk * sizeof(TV),
                                    cudaMemcpyDeviceToDevice, st));
         m = keep + k;
       } else {
-        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, 0, st>>>(V, n, k, m, Zbuf, W.C2, W.G, V + (int64_t)(m / k) * blk,
-                                                                  W.ctl); XT_LAUNCHED();
+        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Zbuf, W.C2, W.Rinv,
+                                                                        V + (int64_t)(m / k) * blk, W.ctl); XT_LAUNCHED();
         m += k;
       }
       XT_CUDA_OK(cudaGetLastError());
@@ -662,16 +944,18 @@ int xt_symeig_krylov(const xt_symeig_args* g) {
   return g->dtype == XT_F64 ? xt::run_symeig<double>(g) : xt::run_symeig<float>(g);
 }
 
-int xt_small_eigh(double* T, int32_t m, double* w, double* S, void* stream) {
-  // workspace-free test hook: w/S double as outputs; scratch is taken from the tail of S's caller buffer
-  // layout expected from the caller: S has room for 2*m*m doubles, w for 2*m doubles + m ints (as doubles)
-  XT_REQUIRE(T && w && S && m >= 1 && m <= 1024, "small_eigh: bad arguments");
+int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out, double* scratch,
+                  void* stream) {
+  // nev extreme eigenpairs of the symmetric m x m matrix T (row-major, fp64, device): w_out[nev] ascending,
+  // S_out (m x nev row-major).  scratch: >= m*(m|1) doubles (used when the matrix does not fit on chip).
+  XT_REQUIRE(T && w_out && S_out && scratch && m >= 1 && m <= 1024 && nev >= 1 && nev <= m && nev <= xt::EIG_THREADS,
+             "small_eigh: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  double* Sraw = S + (size_t)m * m;
-  double* wraw = w + m;
-  int* order = reinterpret_cast<int*>(w + 2 * m);
-  const size_t smem = (size_t)(2 * (m / 2 + 2)) * sizeof(double) + (size_t)(m + 2) * sizeof(int) + 64;
-  xt::small_eigh_kernel<<<1, xt::EIG_THREADS, smem, st>>>(T, m, w, S, Sraw, wraw, order); XT_LAUNCHED();
+  const xt::EigPlan pl = xt::eig_plan(m, nev);
+  XT_REQUIRE(pl.inv_slots >= 1, "small_eigh: m=%d nev=%d exceeds the on-chip eigensolver", m, nev);
+  XT_CUDA_OK(cudaFuncSetAttribute(xt::small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  xt::small_eigh_kernel<<<1, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
+                                                                  pl.as_in_smem, pl.inv_slots); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }
