@@ -215,6 +215,32 @@ template <int K> __device__ __forceinline__ void fma_row(double a, const double 
   for (int i = 0; i < K; ++i) acc[i] = fma(a, x[i], acc[i]);
 }
 
+// One consumer thread's share of one stage: NV 16-byte vectors of its row (precomputed swizzled offsets aoff[])
+// against the matching X rows (xbase + v * EPV*K*sizeof(TV)).  Fully unrolled: all shared-memory loads of a
+// vector are independent of the previous vector's FMAs, so ptxas can software-pipeline them.
+template <typename TA, typename TV, int K, int NV>
+__device__ __forceinline__ void consume_stage(uint32_t a_s, uint32_t xbase, const uint32_t (&aoff)[8], TV (&acc)[K]) {
+  using Tr = ElemTraits<TA>;
+  constexpr int EPV = Tr::EPV;
+  TV loc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) loc[i] = TV(0);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 raw = lds128(a_s + aoff[v]);
+    TV a[EPV];
+    Tr::unpack(raw, a);
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) {
+      TV x[K];
+      load_xrow<K, TV>(xbase + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
+      fma_row<K>(a[j], x, loc);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] += loc[i];
+}
+
 constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 128 B
 
 template <typename TA, typename TV, int K, int NC>
@@ -320,6 +346,14 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     const int cw = warp - 2;
     const uint32_t a_row_off = (uint32_t)(r * 128);
     const uint32_t sw = (uint32_t)(r & 7);
+    // per-thread constants: swizzled shared-memory offsets of its nvec vectors inside a stage, X offset
+    uint32_t aoff[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const int gv = q * nvec + (v < nvec ? v : 0);
+      aoff[v] = (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off + ((((uint32_t)gv & 7u) ^ sw) << 4);
+    }
+    const uint32_t x_q_off = (uint32_t)(q * nvec * EPV * K * (int)sizeof(TV));
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -335,30 +369,37 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
         const int kc = ch * KC;
         mbar_wait(&full[s], ph);
         if (active) {
-          const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES) + a_row_off;
-          const uint32_t xs = smem_u32(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
-          TV loc[K];
+          const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+          const uint32_t xs = a_s + MV_STAGE_A_BYTES + x_q_off;
+          if (kc + KC <= p.ncolsA) {
+            // full chunk: every vector of this thread is in bounds
+            if (nvec == 4) consume_stage<TA, TV, K, 4>(a_s, xs, aoff, acc);
+            else if (nvec == 8) consume_stage<TA, TV, K, 8>(a_s, xs, aoff, acc);
+            else if (nvec == 2) consume_stage<TA, TV, K, 2>(a_s, xs, aoff, acc);
+            else consume_stage<TA, TV, K, 1>(a_s, xs, aoff, acc);
+          } else {
+            // ragged last chunk: skip vectors whose box was not loaded (columns past the end are zero-filled)
+            TV loc[K];
 #pragma unroll
-          for (int i = 0; i < K; ++i) loc[i] = TV(0);
-#pragma unroll 2
-          for (int v = 0; v < nvec; ++v) {
-            const int gv = q * nvec + v;
-            const int bx = gv >> 3;
-            if (kc + bx * BOXC < p.ncolsA) {
-              const float4 raw = lds128(a_s + bx * (MV_TILE_ROWS * 128) + (((uint32_t)(gv & 7) ^ sw) << 4));
-              TV a[EPV];
-              Tr::unpack(raw, a);
-              const uint32_t xr = xs + (uint32_t)(gv * EPV * K * (int)sizeof(TV));
+            for (int i = 0; i < K; ++i) loc[i] = TV(0);
+            for (int v = 0; v < nvec; ++v) {
+              const int gv = q * nvec + v;
+              if (kc + (gv >> 3) * BOXC < p.ncolsA) {
+                const float4 raw = lds128(a_s + (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off +
+                                          ((((uint32_t)gv & 7u) ^ sw) << 4));
+                TV a[EPV];
+                Tr::unpack(raw, a);
 #pragma unroll
-              for (int j = 0; j < EPV; ++j) {
-                TV x[K];
-                load_xrow<K, TV>(xr + (uint32_t)(j * K * (int)sizeof(TV)), x);
-                fma_row<K>(a[j], x, loc);
+                for (int j = 0; j < EPV; ++j) {
+                  TV x[K];
+                  load_xrow<K, TV>(xs + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
+                  fma_row<K>(a[j], x, loc);
+                }
               }
             }
-          }
 #pragma unroll
-          for (int i = 0; i < K; ++i) acc[i] += loc[i];
+            for (int i = 0; i < K; ++i) acc[i] += loc[i];
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

@@ -413,14 +413,22 @@ static EigPlan eig_plan(int m, int nev) {
   return pl;
 }
 
+// number of eigenvalues of the tridiagonal matrix (d, e^2) that are < x: sign changes of the Sturm sequence
+// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, evaluated without divisions and rescaled against over/underflow
 __device__ __forceinline__ int sturm_count(const double* d, const double* e2, int m, double x, double pivmin) {
-  double q = d[0] - x;
-  if (fabs(q) < pivmin) q = -pivmin;
-  int cnt = q < 0.0 ? 1 : 0;
+  double pm = 1.0;                 // p_{i-1}
+  double p = d[0] - x;             // p_i
+  if (p == 0.0) p = -pivmin;
+  int cnt = p < 0.0 ? 1 : 0;
   for (int i = 1; i < m; ++i) {
-    q = d[i] - x - e2[i - 1] / q;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += q < 0.0 ? 1 : 0;
+    double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+    if (pn == 0.0) pn = (p > 0.0) ? -pivmin * fabs(p) : pivmin * fabs(p);   // treat an exact zero as a sign change
+    cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+    pm = p;
+    p = pn;
+    const double ap = fabs(p);
+    if (ap > 1e150) { p *= 1e-150; pm *= 1e-150; }
+    else if (ap < 1e-150) { p *= 1e150; pm *= 1e150; }
   }
   return cnt;
 }
@@ -442,30 +450,35 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   double* inv = reinterpret_cast<double*>(icnt + nt + (nt & 1));  // [inv_slots][5][m]
 
   // ------------------------------------------------------------------ 1. tridiagonalisation
+  // per column j: [warp 0] Householder vector -> barrier -> [all] p = t A22 v -> barrier -> [warp 0] w = p - (t/2)(p.v) v
+  // -> barrier -> [all] A22 -= v w^T + w v^T -> barrier
   for (int j = 0; j + 2 < m; ++j) {
     const int n = m - j - 1;
-    double part = 0.0;
-    for (int i = j + 2 + tid; i < m; i += nt) {
-      const double v = As[(size_t)i * lds + j];
-      part += v * v;
+    if (warp == 0) {
+      double part = 0.0;
+      for (int i = j + 2 + lane; i < m; i += 32) {
+        const double v = As[(size_t)i * lds + j];
+        part += v * v;
+      }
+      const double sigma = warp_sum(part);
+      const double x0 = As[(size_t)(j + 1) * lds + j];
+      double alpha = x0, t = 0.0, scale = 0.0;
+      if (sigma > 0.0) {
+        const double nrm = sqrt(x0 * x0 + sigma);
+        alpha = x0 >= 0.0 ? -nrm : nrm;
+        t = (alpha - x0) / alpha;
+        scale = 1.0 / (x0 - alpha);
+      }
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) {
+        const double val = (i == 0) ? 1.0 : As[(size_t)(j + 1 + i) * lds + j] * scale;
+        vbuf[i] = val;
+        As[(size_t)(j + 1 + i) * lds + j] = val;
+      }
+      if (lane == 0) { d[j] = As[(size_t)j * lds + j]; e[j] = alpha; tau[j] = t; }
     }
-    const double sigma = block_sum(part, red);
-    const double x0 = As[(size_t)(j + 1) * lds + j];
-    double alpha = x0, t = 0.0, scale = 0.0;
-    if (sigma > 0.0) {
-      const double nrm = sqrt(x0 * x0 + sigma);
-      alpha = x0 >= 0.0 ? -nrm : nrm;
-      t = (alpha - x0) / alpha;
-      scale = 1.0 / (x0 - alpha);
-    }
-    __syncthreads();   // everyone has read x0 before column j is overwritten
-    for (int i = tid; i < n; i += nt) {
-      const double val = (i == 0) ? 1.0 : As[(size_t)(j + 1 + i) * lds + j] * scale;
-      vbuf[i] = val;
-      As[(size_t)(j + 1 + i) * lds + j] = val;
-    }
-    if (tid == 0) { d[j] = As[(size_t)j * lds + j]; e[j] = alpha; tau[j] = t; }
     __syncthreads();
+    const double t = tau[j];
     if (t != 0.0) {
       // p = t * A22 v   (TPR lanes per row, shuffle-reduced)
       int TPR = 32;
@@ -482,17 +495,19 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
         if (i < n && sub == 0) pbuf[i] = t * acc;
       }
       __syncthreads();
-      double pv = 0.0;
-      for (int i = tid; i < n; i += nt) pv += pbuf[i] * vbuf[i];
-      pv = block_sum(pv, red);
-      const double hc = 0.5 * t * pv;
+      if (warp == 0) {
+        double pv = 0.0;
+        for (int i = lane; i < n; i += 32) pv += pbuf[i] * vbuf[i];
+        pv = warp_sum(pv);
+        const double hc = 0.5 * t * pv;
+        for (int i = lane; i < n; i += 32) pbuf[i] -= hc * vbuf[i];
+      }
       __syncthreads();
-      for (int i = tid; i < n; i += nt) pbuf[i] -= hc * vbuf[i];
-      __syncthreads();
-      // A22 -= v w^T + w v^T
-      for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, l = idx - i * n;
-        As[(size_t)(j + 1 + i) * lds + (j + 1 + l)] -= vbuf[i] * pbuf[l] + pbuf[i] * vbuf[l];
+      // A22 -= v w^T + w v^T : one row per warp, lanes across the columns (no integer division)
+      for (int i = warp; i < n; i += nw) {
+        const double vi = vbuf[i], wi = pbuf[i];
+        double* row = As + (size_t)(j + 1 + i) * lds + (j + 1);
+        for (int l = lane; l < n; l += 32) row[l] -= vi * pbuf[l] + wi * vbuf[l];
       }
       __syncthreads();
     }
@@ -592,6 +607,7 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
         }
       }
       if (a[m - 1] == 0.0) a[m - 1] = pert;
+      for (int i = 0; i < m; ++i) a[i] = 1.0 / a[i];     // reciprocal pivots: the sweeps below are division-free
       unsigned int rng = 0x9E3779B9u * (unsigned int)(sidx + 1) + 12345u;
       for (int i = 0; i < m; ++i) {
         rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
@@ -607,17 +623,19 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
             Y[(size_t)(i + 1) * nev + sidx] = yn - l[i] * yi;
           }
         }
-        double ymax = 0.0;
+        double ymax = 0.0, y1 = 0.0, y2 = 0.0;
         for (int i = m - 1; i >= 0; --i) {
-          double v = Y[(size_t)i * nev + sidx];
-          if (i + 1 < m) v -= b[i] * Y[(size_t)(i + 1) * nev + sidx];
-          if (i + 2 < m) v -= u2[i] * Y[(size_t)(i + 2) * nev + sidx];
-          v /= a[i];
+          double v = Y[(size_t)i * nev + sidx] - b[i] * y1 - u2[i] * y2;     // b[m-1] = u2[m-1] = u2[m-2] = 0
+          v *= a[i];
           Y[(size_t)i * nev + sidx] = v;
+          y2 = y1;
+          y1 = v;
           ymax = fmax(ymax, fabs(v));
         }
         const double sc = ymax > 0.0 ? 1.0 / ymax : 1.0;
         for (int i = 0; i < m; ++i) Y[(size_t)i * nev + sidx] *= sc;
+        // growth of the iterate = 1 / (distance to the eigenvalue): converged once it is huge
+        if (it >= 1 && ymax * pert * 1e3 > 1.0) break;
       }
     }
     __syncthreads();
