@@ -148,9 +148,17 @@ typedef struct {
   int64_t* napply_out;                        /* host, may be NULL: block operator applications (all items) */
   void* workspace; size_t workspace_bytes;
   void* stream;
+  /* row-partitioned operator over `world` GPUs (world <= 1: A is the whole matrix).  A then holds
+   * this rank's rows [rank*n/world, (rank+1)*n/world) as an (n/world, n) row-major block, and `allgather` is
+   * called once per operator application: void allgather(user, buf, count_per_rank, elem_size, stream) must
+   * all-gather IN PLACE the `world` equal chunks of `count_per_rank` elements stored back to back in `buf`
+   * (chunk r is this rank's contribution when r == rank), ordered on `stream`.  nbatch must be 1. */
+  int32_t world, rank;
+  void* allgather;
+  void* allgather_user;
 } xt_symeig_args;
 
-size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis);
+size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);
 int xt_symeig_krylov(const xt_symeig_args* args);
 
 /* small dense symmetric eigensolver used for the projected problem (device, one CTA; replaces torch.linalg.eigh

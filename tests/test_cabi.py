@@ -49,8 +49,8 @@ def test_workspace_queries_need_no_gpu():
     assert L.xt_solve_workspace_bytes(b"bicgstab", _lib.XT_F32, 4096, 64, 1, 100, 0) > 64 * 4096 * 4 * 8
     assert L.xt_solve_workspace_bytes(b"gmres", _lib.XT_F32, 100, 1, 2, 50, 0) > 51 * 100 * 2 * 4
     assert L.xt_solve_workspace_bytes(b"nope", 0, 10, 1, 1, 1, 0) == 0
-    assert L.xt_symeig_workspace_bytes(_lib.XT_F32, 16384, 8, 128) > 2 * 16384 * 128 * 4
-    assert L.xt_symeig_workspace_bytes(_lib.XT_F32, 10, 8, 128) == 0
+    assert L.xt_symeig_workspace_bytes(_lib.XT_F32, 16384, 8, 128, 1) > 2 * 16384 * 128 * 4
+    assert L.xt_symeig_workspace_bytes(_lib.XT_F32, 10, 8, 128, 1) == 0
 
 
 def test_invalid_arguments_return_status_not_crash():

@@ -22,14 +22,14 @@ def _tol(dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
 @pytest.mark.parametrize("n,k", [(64, 1), (100, 3), (256, 8), (1000, 2), (1024, 16), (2048, 5), (4100, 8)])
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_matvec_square(dtype, n, k, impl):
     g = torch.Generator().manual_seed(n * 31 + k)
     A = torch.randn(n, n, generator=g).to(dtype)
     X = torch.randn(n, k, generator=g)
     vdt = torch.float64 if dtype == torch.float64 else torch.float32
     es = A.element_size()
-    if impl == 1 and (n * es) % 16 != 0:
+    if impl in (1, 3) and (n * es) % 16 != 0:
         pytest.skip("row stride not 16-byte aligned: TMA path not applicable")
     y = _dense.block_matvec(A.to(DEV), X.to(vdt).to(DEV), impl=impl)
     ref = _ref(A, X.to(vdt))
@@ -46,7 +46,7 @@ def test_matvec_rect_batched_shift(dtype):
     X = torch.randn(3, 200, 4, generator=g).to(dtype)
     E = torch.randn(3, 4, generator=g).to(dtype)
     Z = torch.randn(3, 200, 4, generator=g).to(dtype)
-    for impl in (1, 2):
+    for impl in (1, 2, 3):
         y = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), Z=Z.to(DEV), impl=impl)
         assert (y.double().cpu() - _ref(A, X, E, Z)).abs().max().item() <= _tol(dtype) * 200
         y = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), impl=impl)
@@ -60,6 +60,18 @@ def test_matvec_rect_batched_shift(dtype):
     X3 = torch.randn(96, 2, generator=g).to(dtype)
     y = _dense.block_matvec(A2.to(DEV), X3.to(DEV), adjoint=True)
     assert (y.double().cpu() - A2.double().t() @ X3.double()).abs().max().item() <= _tol(dtype) * 200
+
+
+def test_matvec_colslice_shapes():
+    # the column-slice kernel (fp32, k in 5..16): ragged tiles / chunks, many tiles per CTA, batched
+    g = torch.Generator().manual_seed(11)
+    for (nb, rows, cols, k) in [(1, 1000, 1000, 8), (1, 20000, 600, 16), (3, 200, 200, 7), (1, 72, 4100, 12)]:
+        A = torch.randn(nb, rows, cols, generator=g)
+        X = torch.randn(nb, cols, k, generator=g)
+        y = _dense.block_matvec(A.to(DEV), X.to(DEV), impl=1)
+        ref = A.double() @ X.double()
+        scale = (A.abs().double() @ X.abs().double()).max().item()
+        assert (y.double().cpu() - ref).abs().max().item() <= 2e-6 * scale
 
 
 def test_matvec_many_columns_and_tiles():

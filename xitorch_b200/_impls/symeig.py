@@ -96,9 +96,23 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     else:
         raise ValueError("Unknown v_init type: %s" % v_init)
 
+    A3, a_bs, lda = _mat3(Amat, batch)
+    evals, evecs = _call_engine(A3, lda, (a_bs if nb > 1 else 0), n, nb, neig, mode, expansion, V0, max_niter,
+                                max_basis, check_every, min_eps, info, name)
+    evals = evals.reshape(*batch, neig)
+    evecs = evecs.reshape(*batch, n, neig)
+    if LinvT is not None:
+        evecs = torch.matmul(LinvT, evecs)
+    return evals, evecs
+
+
+def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max_basis, check_every, min_eps,
+                 info, name, dist_ctx=None):
+    """fill `xt_symeig_args` and run `xt_symeig_krylov`.  dist_ctx = (world, rank, group) for the row-partitioned
+    operator: A3 is then this rank's (n/world, n) row block and the per-iteration all-gather hook is installed."""
+    vdt, dev = A3.dtype, A3.device
     if max_basis is None:
         max_basis = _default_max_basis(n, neig)
-    A3, a_bs, lda = _mat3(Amat, batch)
     evals = torch.empty((nb, neig), dtype=vdt, device=dev)
     evecs = torch.empty((nb, n, neig), dtype=vdt, device=dev)
     L_ = _lib.lib()
@@ -107,35 +121,71 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     g.n, g.nbatch, g.neig = n, nb, neig
     g.mode = 0 if mode == "lowest" else 1
     g.expansion = expansion
-    g.A, g.lda, g.a_bstride = A3.data_ptr(), lda, (a_bs if nb > 1 else 0)
+    g.A, g.lda, g.a_bstride = A3.data_ptr(), lda, a_bs
     g.V0, g.ldv0, g.v0_bstride = V0.data_ptr(), neig, n * neig
     g.evals, g.evals_bstride = evals.data_ptr(), neig
     g.evecs, g.ldv, g.evecs_bstride = evecs.data_ptr(), neig, n * neig
     g.max_niter, g.max_basis = int(max_niter), int(max_basis)
+    world = dist_ctx[0] if dist_ctx is not None else 1
     if check_every is None:
-        t_iter = max(n * n * Amat.element_size() / 6.0e12, 3e-5)
+        t_iter = max((n // world) * n * A3.element_size() / 6.0e12, 3e-5)
         check_every = max(1, min(16, int(3e-4 / t_iter)))
     g.check_every = int(check_every)
     g.min_eps = float(min_eps)
     niter, conv, best, napply = C.c_int32(0), C.c_int32(0), C.c_double(0.0), C.c_int64(0)
     g.niter_out, g.converged_out = C.pointer(niter), C.pointer(conv)
     g.best_resid_out, g.napply_out = C.pointer(best), C.pointer(napply)
-    wsb = L_.xt_symeig_workspace_bytes(g.dtype, n, neig, g.max_basis)
+    wsb = L_.xt_symeig_workspace_bytes(g.dtype, n, neig, g.max_basis, world)
     if wsb == 0:
         raise RuntimeError("xitorch_b200.%s: n=%d is too small for neig=%d (need n >= 2*neig)" % (name, n, neig))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
     g.stream = _lib.stream_ptr(dev)
+    keep = [ws]
+    if dist_ctx is not None and world > 1:
+        import torch.distributed as dist
+        _, rank, group = dist_ctx
+        base = ws.data_ptr()
+
+        def _gather(user, buf, count, esize, stream):
+            # in-place all-gather of `world` chunks of `count` elements inside the workspace tensor
+            off = buf - base
+            whole = ws[off: off + world * count * esize].view(vdt)
+            mine = whole[rank * count: (rank + 1) * count]
+            dist.all_gather_into_tensor(whole, mine, group=group)
+
+        cb = _lib.ALLGATHER_FN(_gather)
+        keep.append(cb)
+        g.world, g.rank = world, rank
+        g.allgather = C.cast(cb, C.c_void_p)
     with torch.cuda.device(dev):
         _lib.check(L_.xt_symeig_krylov(g), name)
     if info is not None:
         info.update(niter=niter.value, converged=bool(conv.value), best_resid=best.value, napply=napply.value,
                     max_basis=int(max_basis))
-    evals = evals.reshape(*batch, neig)
-    evecs = evecs.reshape(*batch, n, neig)
-    if LinvT is not None:
-        evecs = torch.matmul(LinvT, evecs)
+    del keep
     return evals, evecs
+
+
+def _krylov_row_partitioned(A_local, n, neig, mode, expansion, group, min_eps, max_niter, max_basis, check_every,
+                            info):
+    """row-partitioned operator: every rank holds rows [rank*n/world, (rank+1)*n/world)."""
+    import torch.distributed as dist
+    _lib.require_cuda(A_local, "symeig on a row-partitioned operator")
+    if A_local.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("row-partitioned symeig supports float32 / float64 operators")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if tuple(A_local.shape) != (n // world, n) or n % world != 0:
+        raise RuntimeError("expected a local row block of shape %s, got %s" % ((n // world, n), tuple(A_local.shape)))
+    A_local = A_local.contiguous()
+    gen = torch.Generator(device=A_local.device)
+    gen.manual_seed(12421)                      # same start block on every rank
+    V0 = torch.randn((1, n, neig), dtype=A_local.dtype, device=A_local.device, generator=gen)
+    evals, evecs = _call_engine(A_local, A_local.stride(0), 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis,
+                                check_every, min_eps, info, "lanczos" if expansion == 1 else "davidson",
+                                dist_ctx=(world, rank, group))
+    return evals[0], evecs[0]
 
 
 def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,

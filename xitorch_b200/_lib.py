@@ -70,8 +70,12 @@ class SymeigArgs(C.Structure):
         ("best_resid_out", C.POINTER(C.c_double)), ("napply_out", C.POINTER(C.c_int64)),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("stream", C.c_void_p),
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("allgather", C.c_void_p), ("allgather_user", C.c_void_p),
     ]
 
+
+ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
 
 _lock = threading.Lock()
 _lib = None
@@ -106,7 +110,7 @@ def lib():
         L.xt_solve_workspace_bytes.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_int32, C.c_int32]
         L.xt_solve_workspace_bytes.restype = C.c_size_t
-        L.xt_symeig_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.xt_symeig_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.xt_symeig_workspace_bytes.restype = C.c_size_t
         L.xt_symeig_krylov.argtypes = [C.POINTER(SymeigArgs)]
         L.xt_symeig_krylov.restype = C.c_int

@@ -21,6 +21,7 @@
 #include <cstdarg>
 #include <mutex>
 #include <vector>
+#include <type_traits>
 
 namespace xt {
 
@@ -243,6 +244,101 @@ __device__ __forceinline__ void consume_stage(uint32_t a_s, uint32_t xbase, cons
 
 constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 128 B
 
+// ---- roles shared by both consumer layouts -------------------------------------------------------------------
+// TMA producer (one elected lane): two boxes of tile_rows x 128 B per stage, L2 evict-first
+template <typename TA, int STAGE_BYTES>
+__device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
+                                            uint64_t* empty, int NS, int nchunks) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);
+  constexpr int KC = 2 * BOXC;
+  const uint64_t pol = l2_policy_evict_first();
+  int s = 0;
+  uint32_t ph = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int b = tile / p.tiles_per_batch;
+    const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+    const int bA = p.a_batched ? b : 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int kc = ch * KC;
+      const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
+      // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128));
+      for (int bx = 0; bx < nb; ++bx)
+        tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA, pol);
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  }
+}
+
+// X staging warp: all loads of a chunk are issued back to back (KC*K/32 independent loads per lane) and one
+// chunk ahead of the shared-memory slot becoming free, so their L2 latency overlaps the wait.
+template <typename TA, typename TV, int K, int STAGE_BYTES>
+__device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty, int NS,
+                                           int nchunks, int lane) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);
+  constexpr int KC = 2 * BOXC;
+  const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
+  constexpr int NPL = KC * K / 32;
+  TV vals[NPL];
+  auto load_chunk = [&](int tile, int ch) {
+    const int b = tile / p.tiles_per_batch;
+    const TV* Xb = Xg + (int64_t)b * p.x_bstride;
+    const int kc = ch * KC;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int idx = lane + 32 * i;
+      const int c = idx / K, v = idx - c * K;
+      vals[i] = (kc + c < p.ncolsA && v < p.kvalid) ? Xb[(int64_t)(kc + c) * p.ldx + v] : TV(0);
+    }
+  };
+  int s = 0;
+  uint32_t ph = 0;
+  int tile = blockIdx.x, ch = 0;
+  if (tile < p.ntiles) load_chunk(tile, 0);
+  while (tile < p.ntiles) {
+    mbar_wait(&empty[s], ph ^ 1);
+    TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[s]);
+    if (++s == NS) { s = 0; ph ^= 1; }
+    if (++ch == nchunks) { ch = 0; tile += gridDim.x; }
+    if (tile < p.ntiles) load_chunk(tile, ch);
+  }
+}
+
+// per-row epilogue shared by both consumer layouts: shift term, store Y, partial dot products
+template <typename TV, int K>
+__device__ __forceinline__ void row_epilogue(const MvDev& p, int b, int64_t row, TV (&y)[K], double (&d0)[K],
+                                             double (&d1)[K]) {
+  if (p.E != nullptr) {
+    const TV* Eb = reinterpret_cast<const TV*>(p.E) + (int64_t)b * p.e_bstride;
+    const TV* Zr = (p.Z != nullptr) ? reinterpret_cast<const TV*>(p.Z) + (int64_t)b * p.z_bstride + row * p.ldz
+                                    : reinterpret_cast<const TV*>(p.X) + (int64_t)b * p.x_bstride + row * p.ldx;
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+      if (i < p.kvalid) y[i] -= Eb[i] * Zr[i];
+  }
+  TV* Yr = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride + row * p.ldy;
+#pragma unroll
+  for (int i = 0; i < K; ++i)
+    if (i < p.kvalid) Yr[i] = y[i];
+  if (p.dot_out != nullptr) {
+    const TV* Ur = (p.U != nullptr) ? reinterpret_cast<const TV*>(p.U) + (int64_t)b * p.u_bstride + row * p.ldu
+                                    : nullptr;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      if (i < p.kvalid) {
+        d1[i] = (double)y[i] * (double)y[i];
+        if (Ur != nullptr) d0[i] = (double)Ur[i] * (double)y[i];
+      }
+    }
+  }
+}
+
 template <typename TA, typename TV, int K, int NC>
 __global__ void __launch_bounds__(NC + 64, 1)
 mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
@@ -278,61 +374,9 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   __syncthreads();
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint64_t pol = l2_policy_evict_first();
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int b = tile / p.tiles_per_batch;
-        const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
-        const int bA = p.a_batched ? b : 0;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int kc = ch * KC;
-          const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
-          // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128));
-          for (int bx = 0; bx < nb; ++bx)
-            tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), &tmA, &full[s], kc + bx * BOXC, row0, bA, pol);
-          if (++s == NS) { s = 0; ph ^= 1; }
-        }
-      }
-    }
+    if (lane == 0) mv_producer<TA, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ X staging warp
-    // All loads of a chunk are issued back to back (KC*K/32 independent loads per lane) and one chunk
-    // ahead of the shared-memory slot becoming free, so their L2 latency overlaps the wait.
-    const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
-    constexpr int NPL = KC * K / 32;
-    TV vals[NPL];
-    auto load_chunk = [&](int tile, int ch) {
-      const int b = tile / p.tiles_per_batch;
-      const TV* Xb = Xg + (int64_t)b * p.x_bstride;
-      const int kc = ch * KC;
-#pragma unroll
-      for (int i = 0; i < NPL; ++i) {
-        const int idx = lane + 32 * i;
-        const int c = idx / K, v = idx - c * K;
-        vals[i] = (kc + c < p.ncolsA && v < p.kvalid) ? Xb[(int64_t)(kc + c) * p.ldx + v] : TV(0);
-      }
-    };
-    int s = 0;
-    uint32_t ph = 0;
-    int tile = blockIdx.x, ch = 0;
-    if (tile < p.ntiles) load_chunk(tile, 0);
-    while (tile < p.ntiles) {
-      mbar_wait(&empty[s], ph ^ 1);
-      TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
-#pragma unroll
-      for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
-      if (++s == NS) { s = 0; ph ^= 1; }
-      if (++ch == nchunks) { ch = 0; tile += gridDim.x; }
-      if (tile < p.ntiles) load_chunk(tile, ch);
-    }
+    mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
   } else {
     // ------------------------------------------------------------------ consumers
     // thread <-> (row r, k-slice q): rows_pad = tile_rows rounded up to 16, ksplit = largest power of two with
@@ -420,32 +464,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 #pragma unroll
           for (int i = 0; i < K; ++i) acc[i] += red[(size_t)(qq * p.rows_pad + r) * K + i];
         }
-        const int64_t row = row0 + r;
-        if (p.E != nullptr) {
-          const TV* Eb = reinterpret_cast<const TV*>(p.E) + (int64_t)b * p.e_bstride;
-          const TV* Zr = (p.Z != nullptr)
-                             ? reinterpret_cast<const TV*>(p.Z) + (int64_t)b * p.z_bstride + row * p.ldz
-                             : reinterpret_cast<const TV*>(p.X) + (int64_t)b * p.x_bstride + row * p.ldx;
-#pragma unroll
-          for (int i = 0; i < K; ++i)
-            if (i < p.kvalid) acc[i] -= Eb[i] * Zr[i];
-        }
-        TV* Yr = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride + row * p.ldy;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-          if (i < p.kvalid) Yr[i] = acc[i];
-        if (p.dot_out != nullptr) {
-          const TV* Ur = (p.U != nullptr)
-                             ? reinterpret_cast<const TV*>(p.U) + (int64_t)b * p.u_bstride + row * p.ldu
-                             : nullptr;
-#pragma unroll
-          for (int i = 0; i < K; ++i) {
-            if (i < p.kvalid) {
-              d1[i] = (double)acc[i] * (double)acc[i];
-              if (Ur != nullptr) d0[i] = (double)Ur[i] * (double)acc[i];
-            }
-          }
-        }
+        row_epilogue<TV, K>(p, b, (int64_t)row0 + r, acc, d0, d1);
       }
       if (p.dot_out != nullptr) {
         // rows of this tile live in the q == 0 threads: tc < rows_pad  <=> consumer warps 0..rows_pad/32-1
@@ -472,6 +491,160 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       }
       // the next tile's first red[]/dscr[] writes happen after its whole K sweep and a barrier: no hazard with
       // the reads above except dscr (written after the next first barrier) -> safe as well.
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- column-slice layout (wide blocks)
+// For K >= 8 the row-slice layout above is bound by shared-memory traffic: every 16-byte vector of A needs
+// K more LDS.128 for its X rows.  Here a consumer WARP owns a column slice (2 vectors = 8 columns of every
+// stage) for ALL rows of the tile and each LANE a row (up to 4 row passes): the slice's X values live in
+// registers for the whole stage, A is read with one conflict-free LDS.128 per (row, vector), and the 8 slices
+// are summed through shared memory at tile end.  LDS per FFMA2 drops from 9:16 to 3:16.
+template <int K>
+__global__ void __launch_bounds__(256 + 64, 1)
+mv_tma_colslice_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
+  using TA = float;
+  using TV = float;
+  constexpr int NC = 256, NW = NC / 32, PASSES = 4;
+  constexpr int BOXC = 32, KC = 64, EPV = 4;
+  constexpr int XBYTES = KC * K * (int)sizeof(TV);
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;
+  uint8_t* stage_base = smem;
+  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);                       // [NW][MV_TILE_ROWS][K]
+  double* dscr = reinterpret_cast<double*>(red + (size_t)NW * MV_TILE_ROWS * K);          // [NW][2][K]
+  uint64_t* full = reinterpret_cast<uint64_t*>(dscr + NW * 2 * K);
+  uint64_t* empty = full + NS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.ncolsA + KC - 1) / KC;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], NW);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mv_producer<TA, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+  } else if (warp == 1) {
+    mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
+  } else {
+    const int tc = threadIdx.x - 64;
+    const int cw = warp - 2;
+    const int npass = (p.tile_rows + 31) / 32;
+    // vectors 2cw, 2cw+1 of the 16 per stage row: box, swizzled 16-byte slot for this lane's rows (r & 7 == lane & 7)
+    uint32_t abase[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gv = 2 * cw + h;
+      abase[h] = (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + (uint32_t)(lane * 128) +
+                 ((((uint32_t)gv & 7u) ^ ((uint32_t)lane & 7u)) << 4);
+    }
+    const uint32_t xoff = (uint32_t)(2 * cw * EPV * K * (int)sizeof(TV));
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+      const int rows = min(p.tile_rows, p.nrows - row0);
+      // two-level (blocked) summation where the register budget allows it (K = 8); single level for K = 16
+      constexpr bool TWO = (K <= 8);
+      constexpr int LP = TWO ? PASSES : 1;
+      TV acc[PASSES][K], loc2[LP][K];
+#pragma unroll
+      for (int q = 0; q < PASSES; ++q)
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc[q][i] = 0.f;
+#pragma unroll
+      for (int q = 0; q < LP; ++q)
+#pragma unroll
+        for (int i = 0; i < K; ++i) loc2[q][i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int kc = ch * KC;
+        mbar_wait(&full[s], ph);
+        const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+        const uint32_t xs = a_s + MV_STAGE_A_BYTES + xoff;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int gv = 2 * cw + h;
+          if (kc + (gv >> 3) * BOXC < p.ncolsA) {          // warp-uniform: this slice's box was loaded
+            TV x[EPV][K];
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) load_xrow<K, TV>(xs + (uint32_t)((h * EPV + j) * K * (int)sizeof(TV)), x[j]);
+#pragma unroll
+            for (int q = 0; q < PASSES; ++q) {
+              if (q < npass && q * 32 + lane < rows) {
+                const float4 raw = lds128(a_s + abase[h] + (uint32_t)(q * 32 * 128));
+                TV(&dst)[K] = TWO ? loc2[TWO ? q : 0] : acc[q];
+                fma_row<K>(raw.x, x[0], dst);
+                fma_row<K>(raw.y, x[1], dst);
+                fma_row<K>(raw.z, x[2], dst);
+                fma_row<K>(raw.w, x[3], dst);
+              }
+            }
+          }
+        }
+        if (TWO && (ch & 15) == 15) {                       // blocked summation: fold every 16 stages
+#pragma unroll
+          for (int q = 0; q < LP; ++q)
+#pragma unroll
+            for (int i = 0; i < K; ++i) { acc[q][i] += loc2[q][i]; loc2[q][i] = 0.f; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+      // ---- sum the NW column slices through shared memory, then the per-row epilogue
+#pragma unroll
+      for (int q = 0; q < PASSES; ++q) {
+        const int r = q * 32 + lane;
+        if (q < npass && r < rows) {
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            red[((size_t)cw * MV_TILE_ROWS + r) * K + i] = TWO ? acc[q][i] + loc2[TWO ? q : 0][i] : acc[q][i];
+        }
+      }
+      named_bar_sync(1, NC);
+      double d0[K], d1[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
+      if (tc < rows) {
+        TV y[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) y[i] = 0.f;
+        for (int w = 0; w < NW; ++w) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) y[i] += red[((size_t)w * MV_TILE_ROWS + tc) * K + i];
+        }
+        row_epilogue<TV, K>(p, b, (int64_t)row0 + tc, y, d0, d1);
+      }
+      if (p.dot_out != nullptr) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          d0[i] = warp_sum(d0[i]);
+          d1[i] = warp_sum(d1[i]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            dscr[(cw * 2 + 0) * K + i] = d0[i];
+            dscr[(cw * 2 + 1) * K + i] = d1[i];
+          }
+        }
+      }
+      named_bar_sync(1, NC);
+      if (p.dot_out != nullptr && tc < 2 * K) {
+        const int which = tc / K, i = tc - which * K;
+        double sum = 0.0;
+        for (int w = 0; w < NW; ++w) sum += dscr[(w * 2 + which) * K + i];
+        p.dot_out[((size_t)tile * 2 + which) * MV_MAXK + i] = sum;
+      }
     }
   }
 }
@@ -583,13 +756,54 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   return XT_OK;
 }
 
+template <int K>
+static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
+  constexpr int XBYTES = 64 * K * 4;
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
+  const size_t fixed = (size_t)8 * MV_TILE_ROWS * K * 4 + 8 * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
+  if (ns > 6) ns = 6;
+  if (ns < 2) {
+    set_last_error("matvec: not enough shared memory for 2 stages");
+    return XT_ERR_INVALID;
+  }
+  const size_t smem = (size_t)ns * STAGE_BYTES + fixed;
+  MvDev dev = dev0;
+  dev.nstages = ns;
+  CUtensorMap tm;
+  bool batched = false;
+  int rc = make_tmap(a, til.tile_rows, &tm, &batched);
+  if (rc != XT_OK) return rc;
+  dev.a_batched = batched ? 1 : 0;
+  auto kern = mv_tma_colslice_kernel<K>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  prof_mv_begin(st);
+  kern<<<til.grid, 256 + 64, smem, st>>>(tm, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
 template <typename TA, typename TV>
 static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
+  // wide fp32 blocks: column-slice layout (impl == 3 forces the row-slice layout for comparison)
+  if constexpr (std::is_same<TA, float>::value) {
+    if (a.impl != 3 && a.k > 4) {
+      if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
+      return launch_colslice<16>(a, dev, til, st);
+    }
+  }
+  constexpr int NCW = std::is_same<TV, double>::value ? 256 : 512;   // fp64 accumulators need the larger register cap
   // 512 consumer threads (16 warps) where the register budget allows it, 256 for the widest blocks
   if (a.k <= 1) return launch_tma_k<TA, TV, 1, 512>(a, dev, til, st);
   if (a.k <= 2) return launch_tma_k<TA, TV, 2, 512>(a, dev, til, st);
   if (a.k <= 4) return launch_tma_k<TA, TV, 4, 512>(a, dev, til, st);
-  if (a.k <= 8) return launch_tma_k<TA, TV, 8, 512>(a, dev, til, st);
+  if (a.k <= 8) return launch_tma_k<TA, TV, 8, NCW>(a, dev, til, st);
   return launch_tma_k<TA, TV, 16, 256>(a, dev, til, st);
 }
 
@@ -624,8 +838,8 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
 
-  bool use_tma = (a.impl == 1) || (a.impl == 0 && mv_tma_ok(a));
-  if (a.impl == 1 && !mv_tma_ok(a)) {
+  bool use_tma = (a.impl == 1 || a.impl == 3) || (a.impl == 0 && mv_tma_ok(a));
+  if ((a.impl == 1 || a.impl == 3) && !mv_tma_ok(a)) {
     set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
     return XT_ERR_INVALID;
   }

@@ -30,7 +30,9 @@ constexpr int SE_ROWS = 64;         // rows per CTA chunk in the tall-skinny ker
 constexpr int EIG_THREADS = 512;
 
 struct EigCtl {
-  int done;
+  int done;             // global stop flag (every kernel returns at once when set)
+  int local_done;       // this rank's stop decision; equals `done` unless the operator is row-partitioned
+  int collective;       // 1: `done` is derived from the all-gathered local_done flags (multi-GPU)
   int converged;
   int breakdown;
   int niter;
@@ -205,9 +207,14 @@ subproj_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restri
     const int ok = chol_inverse_warp(Gs, Ri, k);
     if (ok) {
       for (int e = tid; e < k * k; e += 32) Rinv[e] = Ri[e];
-    } else if (tid == 0) {
-      ctl->breakdown = 1;
-      ctl->done = 1;
+    } else {
+      // breakdown: stop (collectively when row-partitioned); a zero factor keeps later kernels well defined
+      for (int e = tid; e < k * k; e += 32) Rinv[e] = 0.0;
+      if (tid == 0) {
+        ctl->breakdown = 1;
+        ctl->local_done = 1;
+        if (!ctl->collective) ctl->done = 1;
+      }
     }
     if (tid == 0) ctl->counter = 0;
     __threadfence();
@@ -343,7 +350,8 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
       }
       if (rmax < min_eps) {
         ctl->converged = 1;
-        ctl->done = 1;
+        ctl->local_done = 1;
+        if (!ctl->collective) ctl->done = 1;
       }
       ctl->counter = 0;
       ctl->resmax_bits = 0;
@@ -755,19 +763,41 @@ __global__ void gather_block_kernel(const TV* src, int64_t ld, int n, int k, TV*
   }
 }
 
-__global__ void init_ctl_kernel(EigCtl* ctl) {
+// row-partitioned operator: staging layout Wg[rank][(n_local + 1) * k]; the extra row carries the rank's stop flag
+template <typename TV> __global__ void pack_flag_kernel(TV* slot_flag_row, int k, const EigCtl* ctl) {
+  if (threadIdx.x < k) slot_flag_row[threadIdx.x] = (TV)(ctl->local_done ? 1 : 0);
+}
+template <typename TV>
+__global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int n_local, int k, TV* __restrict__ W,
+                                       EigCtl* ctl) {
+  const int64_t per = (int64_t)(n_local + 1) * k;
+  const int64_t tot = (int64_t)world * n_local * k;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pr = e / ((int64_t)n_local * k);
+    const int64_t off = e - pr * (int64_t)n_local * k;
+    W[e] = Wg[pr * per + off];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int any = 0;
+    for (int pr = 0; pr < world; ++pr) any |= (Wg[pr * per + (int64_t)n_local * k] != TV(0)) ? 1 : 0;
+    if (any) ctl->done = 1;          // every rank sees the same flags at the same iteration
+  }
+}
+
+__global__ void init_ctl_kernel(EigCtl* ctl, int collective) {
+  ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
 }
 
 // ============================================================================ host driver
 struct EigWs {
-  void *V, *AV, *Zbuf, *Rblk, *Xslots, *Vtmp;
+  void *V, *AV, *Zbuf, *Rblk, *Xslots, *Vtmp, *Wg;
   double *T, *Tw, *Sk, *theta, *C, *C2, *G, *Rinv, *evals_slots;
   EigCtl* ctl;
 };
 
-static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb) {
+static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int world) {
   const size_t blk = (size_t)n * k * vs;
   W.V = ar.take<char>((size_t)(mb / k) * blk);
   W.AV = ar.take<char>((size_t)(mb / k) * blk);
@@ -775,6 +805,7 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb) {
   W.Rblk = ar.take<char>(blk);
   W.Xslots = ar.take<char>(2 * blk);
   W.Vtmp = ar.take<char>((size_t)(mb / k) * blk);
+  W.Wg = world > 1 ? ar.take<char>((size_t)world * ((size_t)(n / world) + 1) * k * vs) : nullptr;
   W.T = ar.take<double>((size_t)mb * mb);
   W.Tw = ar.take<double>((size_t)mb * mb);
   W.Sk = ar.take<double>((size_t)mb * mb);
@@ -797,7 +828,15 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   XT_REQUIRE(mb >= 2 * k, "symeig: max_basis=%d too small for neig=%d (n=%d)", mb, k, n);
   Arena ar(g->workspace, g->workspace_bytes);
   EigWs W;
-  if (!carve(ar, W, sizeof(TV), n, k, mb)) {
+  const int world = g->world > 1 ? g->world : 1;
+  const bool collective = world > 1;
+  if (collective) {
+    XT_REQUIRE(n % world == 0, "symeig: n=%d is not divisible by the world size %d", n, world);
+    XT_REQUIRE(g->allgather != nullptr && g->rank >= 0 && g->rank < world && g->nbatch == 1,
+               "symeig: row-partitioned mode needs an all-gather hook, a valid rank and nbatch = 1");
+  }
+  const int n_local = n / world;
+  if (!carve(ar, W, sizeof(TV), n, k, mb, world)) {
     set_last_error("symeig: workspace too small (%zu needed, %zu given)", ar.off, ar.cap);
     return XT_ERR_WORKSPACE;
   }
@@ -831,7 +870,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
-    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl); XT_LAUNCHED();
+    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl, collective ? 1 : 0); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
     gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
                                                        g->ldv0, n, k, Rblk); XT_LAUNCHED();
@@ -853,14 +892,24 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       MvArgs a;
       memset(&a, 0, sizeof(a));
       a.dtype = g->dtype;
-      a.nbatch = 1; a.nrows = n; a.ncolsA = n; a.k = k;
+      a.nbatch = 1; a.nrows = n_local; a.ncolsA = n; a.k = k;
       a.A = Ab; a.lda = g->lda; a.a_bstride = 0;
       a.X = V + j * blk; a.ldx = k; a.x_bstride = 0;
-      a.Y = AV + j * blk; a.ldy = k; a.y_bstride = 0;
+      TV* Wg = static_cast<TV*>(W.Wg);
+      const int64_t per = (int64_t)(n_local + 1) * k;
+      a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
+      a.ldy = k; a.y_bstride = 0;
       a.done_flag = &W.ctl->done;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
+      if (collective) {
+        // one all-gather per operator application; the stop flag rides along
+        pack_flag_kernel<TV><<<1, 32, 0, st>>>(Wg + (int64_t)g->rank * per + (int64_t)n_local * k, k, W.ctl); XT_LAUNCHED();
+        typedef void (*gather_fn)(void*, void*, int64_t, int32_t, void*);
+        reinterpret_cast<gather_fn>(g->allgather)(g->allgather_user, Wg, per, (int32_t)sizeof(TV), g->stream);
+        unpack_gathered_kernel<TV><<<num_sms(), 256, 0, st>>>(Wg, world, n_local, k, AV + j * blk, W.ctl); XT_LAUNCHED();
+      }
       // 2. C = V^T W  (new block column of T)
       XT_CUDA_OK(cudaMemsetAsync(W.C, 0, sizeof(double) * (size_t)m * k, st));
       subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, W.C,
@@ -939,7 +988,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
 
 extern "C" {
 
-size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis) {
+size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world) {
   if (neig < 1 || n < 1) return 0;
   int mb = max_basis;
   if (mb > n) mb = (n / neig) * neig;
@@ -947,7 +996,7 @@ size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t
   if (mb < 2 * neig) return 0;
   xt::Arena ar(nullptr, 0);
   xt::EigWs W;
-  xt::carve(ar, W, dtype == XT_F64 ? 8 : 4, n, neig, mb);
+  xt::carve(ar, W, dtype == XT_F64 ? 8 : 4, n, neig, mb, world > 1 ? world : 1);
   return ar.off + 1024;
 }
 
