@@ -65,8 +65,9 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
  * or Z = NULL for Z = X).
  *   A: (nbatch, nrows, ncolsA) row-major, row stride lda;   X: (nbatch, ncolsA, k), row stride ldx
  *   Y: (nbatch, nrows, k), row stride ldy;                  E: (nbatch, k) or NULL
- *   k >= 1 (handled in column groups of <= 16).  `impl`: 0 = auto, 1 = force the TMA kernel,
- *   2 = force the plain-load kernel (used by the tests to cross-check the two).
+ *   k >= 1 (handled in column groups of <= 16).  `impl`: 0 = auto, 1 = force a TMA kernel (auto layout),
+ *   2 = force the plain-load kernel, 3 = TMA row-slice layout, 4 = TMA column-slice layout (fp32, k > 4);
+ *   2-4 are used by the tests to cross-check the kernels.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t dtype;

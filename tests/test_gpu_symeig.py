@@ -109,7 +109,7 @@ def _small_eigh(T, nev, mode):
     return w.cpu(), S.cpu()
 
 
-@pytest.mark.parametrize("m", [2, 3, 8, 33, 104, 128, 160, 200])
+@pytest.mark.parametrize("m", [2, 3, 8, 33, 104, 128, 160, 200, 256])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_small_eigh_kernel_random(m, mode):
     g = torch.Generator().manual_seed(m)
@@ -139,7 +139,7 @@ def test_small_eigh_kernel_special_cases():
     mats.append(bt)
     for T in mats:
         T = (T + T.t()) / 2
-        for nev, mode in ((8, 0), (8, 1), (48, 0), (48, 1)):
+        for nev, mode in ((8, 0), (8, 1), (48, 0), (48, 1), (96, 0)):
             w, S = _small_eigh(T, nev, mode)
             wr = torch.linalg.eigvalsh(T)
             wr = wr[:nev] if mode == 0 else wr[-nev:]

@@ -47,7 +47,9 @@ def custom_exacteig(A, neig, mode, M=None, **options):
 
 
 def _default_max_basis(n: int, neig: int) -> int:
-    mb = max(16 * neig, 64)
+    # up to 128 the projected matrix stays in the shared memory of the one-CTA eigensolver
+    mb = min(max(16 * neig, 64), 128)
+    mb = max(mb, 4 * neig)
     mb = min(mb, 512, n)
     return max((mb // neig) * neig, 2 * neig)
 

@@ -67,10 +67,11 @@ int num_sms() {
   return cached[dev];
 }
 
-MvTiling mv_tiling(int nbatch, int nrows) {
+MvTiling mv_tiling(int nbatch, int nrows, int reserve_sms) {
   MvTiling t;
   const int64_t total = (int64_t)nbatch * nrows;
-  const int G = num_sms();
+  int G = num_sms() - reserve_sms;
+  if (G < 1) G = 1;
   // rows per tile so that one wave of G CTAs covers everything, rounded up to the TMA box height
   int64_t th = (total + (int64_t)G * MV_BOX_ROWS - 1) / ((int64_t)G * MV_BOX_ROWS) * MV_BOX_ROWS;
   if (th > MV_TILE_ROWS) th = MV_TILE_ROWS;
@@ -143,6 +144,7 @@ struct MvDev {
   int rows_pad;     // tile_rows rounded up to a multiple of 16
   int nstages;
   int a_batched;
+  int x_bulk;       // X chunks are contiguous and aligned: the TMA lane stages them with cp.async.bulk (no X warp)
   const void* X; int64_t ldx, x_bstride;
   void* Y; int64_t ldy, y_bstride;
   const void* E; int64_t e_bstride;
@@ -178,22 +180,30 @@ template <> struct ElemTraits<double> {
   }
 };
 
-// K values of one X row from shared memory (explicit ld.shared, widest loads)
-template <int K, typename TV> __device__ __forceinline__ void load_xrow(uint32_t addr, TV (&x)[K]) {
-  constexpr int BYTES = K * (int)sizeof(TV);
-  if constexpr (BYTES % 16 == 0) {
-    float4* x4 = reinterpret_cast<float4*>(x);
+// K values of one X row from shared memory (explicit ld.shared, widest loads; no type punning through pointers
+// so that the row stays in registers)
+template <int K> __device__ __forceinline__ void load_xrow(uint32_t addr, float (&x)[K]) {
+  if constexpr (K % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < BYTES / 16; ++i) x4[i] = lds128(addr + 16 * i);
-  } else if constexpr (BYTES == 8) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    *reinterpret_cast<float2*>(x) = v;
+    for (int i = 0; i < K / 4; ++i) {
+      const float4 v = lds128(addr + 16 * i);
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+  } else if constexpr (K == 2) {
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x[0]), "=f"(x[1]) : "r"(addr));
   } else {
-    static_assert(BYTES == 4, "unexpected X row size");
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    *reinterpret_cast<float*>(x) = v;
+    static_assert(K == 1, "unexpected X row size");
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[0]) : "r"(addr));
+  }
+}
+template <int K> __device__ __forceinline__ void load_xrow(uint32_t addr, double (&x)[K]) {
+  if constexpr (K % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < K / 2; ++i)
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x[2 * i]), "=d"(x[2 * i + 1]) : "r"(addr + 16 * i));
+  } else {
+    static_assert(K == 1, "unexpected X row size");
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x[0]) : "r"(addr));
   }
 }
 
@@ -234,7 +244,7 @@ __device__ __forceinline__ void consume_stage(uint32_t a_s, uint32_t xbase, cons
 #pragma unroll
     for (int j = 0; j < EPV; ++j) {
       TV x[K];
-      load_xrow<K, TV>(xbase + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
+      load_xrow<K>(xbase + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
       fma_row<K>(a[j], x, loc);
     }
   }
@@ -246,11 +256,12 @@ constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 1
 
 // ---- roles shared by both consumer layouts -------------------------------------------------------------------
 // TMA producer (one elected lane): two boxes of tile_rows x 128 B per stage, L2 evict-first
-template <typename TA, int STAGE_BYTES>
+template <typename TA, typename TV, int K, int STAGE_BYTES>
 __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
                                             uint64_t* empty, int NS, int nchunks) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
+  const char* Xg = reinterpret_cast<const char*>(p.X);
   const uint64_t pol = l2_policy_evict_first();
   int s = 0;
   uint32_t ph = 0;
@@ -264,9 +275,17 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
       // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
-      mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128));
+      uint32_t xbytes = 0;
+      if (p.x_bulk) {
+        const int cols = min(KC, p.ncolsA - kc);
+        xbytes = (uint32_t)(cols * K * (int)sizeof(TV));
+      }
+      mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128) + xbytes);
       for (int bx = 0; bx < nb; ++bx)
         tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA, pol);
+      if (p.x_bulk)
+        bulk_load_1d(dst + MV_STAGE_A_BYTES,
+                     Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV), xbytes, &full[s]);
       if (++s == NS) { s = 0; ph ^= 1; }
     }
   }
@@ -365,18 +384,25 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 2);                    // TMA lane (expect_tx) + X-staging warp
+      mbar_init(&full[s], p.x_bulk ? 1 : 2);     // TMA lane (expect_tx) [+ X-staging warp]
       mbar_init(&empty[s], NC / 32);   // one arrival per consumer warp
     }
     fence_mbar_init();
     prefetch_tmap(&tmA);
   }
+  if (p.x_bulk) {   // X slots start as zeros: a ragged last chunk copies fewer bytes and must never expose NaN garbage
+    for (int s = 0; s < NS; ++s) {
+      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+      for (int i = threadIdx.x; i < XBYTES / 4; i += blockDim.x) xz[i] = 0u;
+    }
+    fence_proxy_async();
+  }
   __syncthreads();
 
   if (warp == 0) {
-    if (lane == 0) mv_producer<TA, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+    if (lane == 0) mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
   } else if (warp == 1) {
-    mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
+    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
   } else {
     // ------------------------------------------------------------------ consumers
     // thread <-> (row r, k-slice q): rows_pad = tile_rows rounded up to 16, ksplit = largest power of two with
@@ -436,7 +462,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 #pragma unroll
                 for (int j = 0; j < EPV; ++j) {
                   TV x[K];
-                  load_xrow<K, TV>(xs + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
+                  load_xrow<K>(xs + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
                   fma_row<K>(a[j], x, loc);
                 }
               }
@@ -523,17 +549,24 @@ mv_tma_colslice_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   const int nchunks = (p.ncolsA + KC - 1) / KC;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 2);
+      mbar_init(&full[s], p.x_bulk ? 1 : 2);
       mbar_init(&empty[s], NW);
     }
     fence_mbar_init();
     prefetch_tmap(&tmA);
   }
+  if (p.x_bulk) {
+    for (int s = 0; s < NS; ++s) {
+      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+      for (int i = threadIdx.x; i < XBYTES / 4; i += blockDim.x) xz[i] = 0u;
+    }
+    fence_proxy_async();
+  }
   __syncthreads();
   if (warp == 0) {
-    if (lane == 0) mv_producer<TA, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+    if (lane == 0) mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
   } else if (warp == 1) {
-    mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
+    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
   } else {
     const int tc = threadIdx.x - 64;
     const int cw = warp - 2;
@@ -576,7 +609,7 @@ mv_tma_colslice_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
           if (kc + (gv >> 3) * BOXC < p.ncolsA) {          // warp-uniform: this slice's box was loaded
             TV x[EPV][K];
 #pragma unroll
-            for (int j = 0; j < EPV; ++j) load_xrow<K, TV>(xs + (uint32_t)((h * EPV + j) * K * (int)sizeof(TV)), x[j]);
+            for (int j = 0; j < EPV; ++j) load_xrow<K>(xs + (uint32_t)((h * EPV + j) * K * (int)sizeof(TV)), x[j]);
 #pragma unroll
             for (int q = 0; q < PASSES; ++q) {
               if (q < npass && q * 32 + lane < rows) {
@@ -721,6 +754,15 @@ mv_plain_kernel(const TA* __restrict__ A, int64_t lda, int64_t a_bstride, const 
 }
 
 // ============================================================================ launch
+// X can be staged by the TMA lane (cp.async.bulk) when every chunk is one contiguous, 16-byte aligned run
+template <typename TV, int K> static bool x_bulk_ok(const MvArgs& a) {
+  if (a.k != K || a.ldx != K) return false;
+  if (reinterpret_cast<uintptr_t>(a.X) % 16) return false;
+  if (((size_t)a.ncolsA * K * sizeof(TV)) % 16) return false;
+  if (a.nbatch > 1 && ((size_t)a.x_bstride * sizeof(TV)) % 16) return false;
+  return true;
+}
+
 template <typename TA, typename TV, int K, int NC>
 static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
@@ -742,6 +784,7 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
+  dev.x_bulk = x_bulk_ok<TV, K>(a) ? 1 : 0;
   auto kern = mv_tma_kernel<TA, TV, K, NC>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
@@ -775,6 +818,7 @@ static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& t
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
+  dev.x_bulk = x_bulk_ok<float, K>(a) ? 1 : 0;
   auto kern = mv_tma_colslice_kernel<K>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -793,7 +837,8 @@ template <typename TA, typename TV>
 static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
   // wide fp32 blocks: column-slice layout (impl == 3 forces the row-slice layout for comparison)
   if constexpr (std::is_same<TA, float>::value) {
-    if (a.impl != 3 && a.k > 4) {
+    // measured on B200 (N = 16384): k = 8 row-slice 6074 GB/s vs column-slice 5834; k = 16 column-slice 3888 vs 3680
+    if ((a.impl != 3 && a.k > 8) || (a.impl == 4 && a.k > 4)) {
       if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
       return launch_colslice<16>(a, dev, til, st);
     }
@@ -824,12 +869,12 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
              a.ncolsA);
   XT_REQUIRE(a.A && a.X && a.Y, "matvec: null pointer");
   XT_REQUIRE(a.E == nullptr || a.Z != nullptr || a.nrows == a.ncolsA, "matvec: shift with Z = X needs a square A");
-  const MvTiling til = mv_tiling(a.nbatch, a.nrows);
+  const MvTiling til = mv_tiling(a.nbatch, a.nrows, a.reserve_sms);
   MvDev d;
   d.nbatch = a.nbatch; d.nrows = a.nrows; d.ncolsA = a.ncolsA; d.kvalid = a.k;
   d.tile_rows = til.tile_rows; d.tiles_per_batch = til.tiles_per_batch; d.ntiles = til.ntiles;
   d.rows_pad = (til.tile_rows + 15) / 16 * 16;
-  d.nstages = 0; d.a_batched = 0;
+  d.nstages = 0; d.a_batched = 0; d.x_bulk = 0;
   d.X = a.X; d.ldx = a.ldx; d.x_bstride = a.x_bstride;
   d.Y = a.Y; d.ldy = a.ldy; d.y_bstride = a.y_bstride;
   d.E = a.E; d.e_bstride = a.e_bstride;
@@ -838,8 +883,8 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
 
-  bool use_tma = (a.impl == 1 || a.impl == 3) || (a.impl == 0 && mv_tma_ok(a));
-  if ((a.impl == 1 || a.impl == 3) && !mv_tma_ok(a)) {
+  bool use_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4) || (a.impl == 0 && mv_tma_ok(a));
+  if ((a.impl == 1 || a.impl == 3 || a.impl == 4) && !mv_tma_ok(a)) {
     set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
     return XT_ERR_INVALID;
   }
@@ -908,6 +953,7 @@ int xt_block_matvec(const xt_matvec_args* g) {
     a.U = nullptr; a.ldu = 0; a.u_bstride = 0; a.dot_out = nullptr;
     a.impl = g->impl;
     a.done_flag = nullptr;
+    a.reserve_sms = 0;
     int rc = xt::mv_launch(a, st);
     if (rc != XT_OK) return rc;
   }

@@ -18,7 +18,7 @@ struct MvTiling {
   int ntiles;
   int grid;
 };
-MvTiling mv_tiling(int nbatch, int nrows);
+MvTiling mv_tiling(int nbatch, int nrows, int reserve_sms = 0);
 
 // Y_b = A_b X_b [- Z_b diag(E_b)], plus optional fused per-tile partial dot products
 //   dot_out[tile][0][c] = sum_rows U[row][c] * Y[row][c]      (if U != nullptr)
@@ -36,6 +36,7 @@ struct MvArgs {
   double* dot_out;                             // optional (needs U or self-dot), see above
   int impl;                                    // 0 auto, 1 TMA, 2 plain
   const int* done_flag;                        // optional device flag: kernel exits immediately when *done_flag != 0
+  int reserve_sms;                             // leave this many SMs free (for kernels overlapped on another stream)
 };
 
 // enqueue on `stream`; returns xt_status

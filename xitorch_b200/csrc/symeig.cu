@@ -400,6 +400,7 @@ __global__ void restart_T_kernel(double* T, int ldt, const double* theta, int p,
 struct EigPlan {
   int lds;          // leading dimension of the work matrix (odd: conflict-free column access in shared memory)
   int as_in_smem;   // work matrix in shared memory (else in the global scratch Tw)
+  int y_in_smem;    // eigenvector block Y (m x nev) in shared memory (else directly in the global output Sk)
   int inv_slots;    // eigenvectors processed per inverse-iteration batch
   size_t smem_bytes;
 };
@@ -408,9 +409,12 @@ static EigPlan eig_plan(int m, int nev) {
   EigPlan pl;
   pl.lds = m | 1;
   const size_t budget = 220 * 1024;
-  const size_t fixed = (size_t)(6 * m + 4 * nev + 64) * 8 + (size_t)EIG_THREADS * 4 + (size_t)m * nev * 8 + 256;
+  size_t fixed = (size_t)(6 * m + 4 * nev + 64) * 8 + (size_t)EIG_THREADS * 4 + 256;
+  const size_t y_bytes = (size_t)m * nev * 8;
   const size_t as_bytes = (size_t)m * pl.lds * 8;
   const size_t inv1 = (size_t)5 * m * 8;
+  pl.y_in_smem = (fixed + y_bytes + inv1 <= budget / 2) ? 1 : 0;     // keep at least half for the work matrix
+  if (pl.y_in_smem) fixed += y_bytes;
   pl.as_in_smem = (fixed + as_bytes + inv1 <= budget) ? 1 : 0;
   size_t used = fixed + (pl.as_in_smem ? as_bytes : 0);
   int slots = used + inv1 <= budget ? (int)((budget - used) / inv1) : 0;
@@ -689,7 +693,7 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
 //   [nev-k, nev) for mode 1.
 __global__ void __launch_bounds__(EIG_THREADS)
 rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw, double* Sk, double* theta, int mode,
-          int lds, int as_in_smem, int inv_slots, const EigCtl* ctl) {
+          int lds, int as_in_smem, int y_in_smem, int inv_slots, const EigCtl* ctl) {
   if (ctl->done) return;
   extern __shared__ double dyn[];
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -705,8 +709,9 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
     __syncthreads();
   }
   double* lamv = dyn;                       // [nev]
-  double* Y = lamv + nev + (nev & 1);       // [m * nev]
-  double* rest = Y + (size_t)m * nev;
+  double* ysm = lamv + nev + (nev & 1);     // [m * nev] when it fits
+  double* Y = y_in_smem ? ysm : Sk;
+  double* rest = y_in_smem ? ysm + (size_t)m * nev : ysm;
   double* As = as_in_smem ? rest : Tw;
   double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
   for (int e = tid; e < m * m; e += nt) {
@@ -715,18 +720,20 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
   }
   __syncthreads();
   eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y);
-  for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
+  if (y_in_smem)
+    for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
   for (int j = tid; j < nev; j += nt) theta[j] = lamv[j];
 }
 
 __global__ void __launch_bounds__(EIG_THREADS)
 small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double* w_out, double* S_out, int lds,
-                  int as_in_smem, int inv_slots) {
+                  int as_in_smem, int y_in_smem, int inv_slots) {
   extern __shared__ double dyn[];
   const int tid = threadIdx.x, nt = blockDim.x;
   double* lamv = dyn;
-  double* Y = lamv + nev + (nev & 1);
-  double* rest = Y + (size_t)m * nev;
+  double* ysm = lamv + nev + (nev & 1);
+  double* Y = y_in_smem ? ysm : S_out;
+  double* rest = y_in_smem ? ysm + (size_t)m * nev : ysm;
   double* As = as_in_smem ? rest : Tw;
   double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
   for (int e = tid; e < m * m; e += nt) {
@@ -735,7 +742,8 @@ small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double*
   }
   __syncthreads();
   eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y);
-  for (int e = tid; e < m * nev; e += nt) S_out[e] = Y[e];
+  if (y_in_smem)
+    for (int e = tid; e < m * nev; e += nt) S_out[e] = Y[e];
   for (int j = tid; j < nev; j += nt) w_out[j] = lamv[j];
 }
 
@@ -794,6 +802,7 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective) {
 struct EigWs {
   void *V, *AV, *Zbuf, *Rblk, *Xslots, *Vtmp, *Wg;
   double *T, *Tw, *Sk, *theta, *C, *C2, *G, *Rinv, *evals_slots;
+  double *SkB, *thetaB, *CB;      // second parity set for the overlapped Rayleigh-Ritz
   EigCtl* ctl;
 };
 
@@ -811,6 +820,9 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
   W.Sk = ar.take<double>((size_t)mb * mb);
   W.theta = ar.take<double>(mb);
   W.C = ar.take<double>((size_t)mb * k);
+  W.CB = ar.take<double>((size_t)mb * k);
+  W.SkB = ar.take<double>((size_t)mb * mb);
+  W.thetaB = ar.take<double>(mb);
   W.C2 = ar.take<double>((size_t)mb * k);
   W.G = ar.take<double>(2 * SE_MAXK * SE_MAXK);
   W.Rinv = ar.take<double>(SE_MAXK * SE_MAXK);
@@ -867,6 +879,24 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   double worst_resid = 0.0;
   int last_niter = 0;
 
+  const bool overlap = (g->expansion == 1) && (num_sms() > 8);
+  cudaStream_t side = nullptr;
+  cudaEvent_t evC[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr};
+  struct SideGuard {           // streams/events are host-side handles, released on every exit path
+    cudaStream_t* s; cudaEvent_t* a; cudaEvent_t* b;
+    ~SideGuard() {
+      for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); }
+      if (*s) cudaStreamDestroy(*s);
+    }
+  } guard{&side, evC, evR};
+  if (overlap) {
+    XT_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      XT_CUDA_OK(cudaEventCreateWithFlags(&evC[i], cudaEventDisableTiming));
+      XT_CUDA_OK(cudaEventCreateWithFlags(&evR[i], cudaEventDisableTiming));
+    }
+  }
+
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
@@ -884,10 +914,26 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
 
     int m = k;          // current basis size
     int iter = 0;
-    bool stop = false;
-    while (!stop) {
+    // Overlap mode (Lanczos expansion): the expansion block does not depend on the Rayleigh-Ritz result, so
+    // rr_kernel runs on a side stream (on the SM the matvec grid leaves free) while the main stream goes on with
+    // orthogonalisation and the next matvec; the Ritz-vector / residual kernel of iteration j is issued one
+    // iteration later on the main stream.  Convergence is therefore detected one matvec late, never missed.
+    double* Cpar[2] = {W.C, overlap ? W.CB : W.C};
+    double* Skpar[2] = {W.Sk, overlap ? W.SkB : W.Sk};
+    double* thpar[2] = {W.theta, overlap ? W.thetaB : W.theta};
+    struct Pending { bool valid; int par, m, iter, nev, coff; } pend = {false, 0, 0, 0, 0, 0};
+    bool ev_used[2] = {false, false};
+    auto launch_ritz = [&](int par_, int m_, int iter_, int nev_, int coff_) -> int {
+      if (overlap) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par_], 0));
+      ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(V, AV, n, k, m_, Skpar[par_], nev_, coff_, thpar[par_],
+                                                              Xslots, W.evals_slots, Rblk, W.ctl, iter_,
+                                                              (float)g->min_eps); XT_LAUNCHED();
+      return XT_OK;
+    };
+    while (true) {
       ++iter;
       const int j = m / k - 1;     // newest block
+      const int par = overlap ? (iter & 1) : 0;
       // 1. W = A Q_j
       MvArgs a;
       memset(&a, 0, sizeof(a));
@@ -900,6 +946,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
       a.done_flag = &W.ctl->done;
+      a.reserve_sms = overlap ? 1 : 0;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
@@ -911,8 +958,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         unpack_gathered_kernel<TV><<<num_sms(), 256, 0, st>>>(Wg, world, n_local, k, AV + j * blk, W.ctl); XT_LAUNCHED();
       }
       // 2. C = V^T W  (new block column of T)
-      XT_CUDA_OK(cudaMemsetAsync(W.C, 0, sizeof(double) * (size_t)m * k, st));
-      subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, W.C,
+      if (overlap && ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));   // rr of iteration iter-2 is done with C[par]
+      XT_CUDA_OK(cudaMemsetAsync(Cpar[par], 0, sizeof(double) * (size_t)m * k, st));
+      subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, Cpar[par],
                                                                   nullptr, nullptr, 0, W.ctl); XT_LAUNCHED();
       // 3. Rayleigh-Ritz on T: the k wanted pairs, or `keep` pairs when a thick restart follows this iteration
       const bool can_expand = (iter < g->max_niter) && (m + k <= n);
@@ -921,13 +969,33 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       const int coff = (g->mode == 0) ? 0 : (nev - k);
       const EigPlan pl = eig_plan(m, nev);
       XT_REQUIRE(pl.inv_slots >= 1, "symeig: projected problem %d x %d (nev=%d) exceeds the on-chip eigensolver", m, m, nev);
-      rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, st>>>(W.T, mb, W.C, m, k, nev, W.Tw, W.Sk, W.theta, g->mode, pl.lds,
-                                                        pl.as_in_smem, pl.inv_slots, W.ctl); XT_LAUNCHED();
-      // 4. Ritz vectors, residual, bookkeeping
-      ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(
-          V, AV, n, k, m, W.Sk, nev, coff, W.theta, Xslots, W.evals_slots, Rblk, W.ctl, iter, (float)g->min_eps); XT_LAUNCHED();
+      cudaStream_t rs = st;
+      if (overlap) {
+        XT_CUDA_OK(cudaEventRecord(evC[par], st));
+        XT_CUDA_OK(cudaStreamWaitEvent(side, evC[par], 0));
+        rs = side;
+      }
+      rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, Cpar[par], m, k, nev, W.Tw, Skpar[par], thpar[par],
+                                                        g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots,
+                                                        W.ctl); XT_LAUNCHED();
+      if (overlap) {
+        XT_CUDA_OK(cudaEventRecord(evR[par], side));
+        ev_used[par] = true;
+      } else {
+        // 4. Ritz vectors, residual, bookkeeping (in overlap mode this is issued one iteration later)
+        rc = launch_ritz(par, m, iter, nev, coff);
+        if (rc != XT_OK) return rc;
+      }
       XT_CUDA_OK(cudaGetLastError());
-      if (!can_expand) break;                    // max_niter reached, or the basis cannot grow (symeig.py:202-203)
+      if (!can_expand) {                         // max_niter reached, or the basis cannot grow (symeig.py:202-203)
+        if (overlap) {
+          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
+          pend.valid = false;
+          rc = launch_ritz(par, m, iter, nev, coff);
+          if (rc != XT_OK) return rc;
+        }
+        break;
+      }
       if (iter % ce == 0) {
         int done = 0;
         XT_CUDA_OK(cudaMemcpyAsync(&done, &W.ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -938,7 +1006,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       XT_CUDA_OK(cudaMemsetAsync(W.C2, 0, sizeof(double) * (size_t)m * k, st));
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
       if (g->expansion == 1) {
-        subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, W.C, Zbuf, W.C2, W.G,
+        subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, Cpar[par], Zbuf, W.C2, W.G,
                                                                     W.Rinv, 1, W.ctl);
       } else {
         subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Rblk, nullptr, Zbuf, W.C2, W.G,
@@ -948,23 +1016,39 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       if (restart) {
         // thick restart: finish the new block against the OLD basis first, then compress V / AV / T onto the
         // `keep` Ritz vectors computed by this iteration's rr_kernel (Sk is m x keep)
+        if (overlap) {   // the restart needs this iteration's Ritz coefficients now: catch up with the side stream
+          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
+          pend.valid = false;
+          rc = launch_ritz(par, m, iter, nev, coff);
+          if (rc != XT_OK) return rc;
+        }
         orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Zbuf, W.C2, W.Rinv, Rblk, W.ctl); XT_LAUNCHED();
         const int64_t tot = (int64_t)n * keep;
         const int rg = (int)((tot + SE_THREADS - 1) / SE_THREADS);
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, W.Sk, keep, Vtmp, W.ctl); XT_LAUNCHED();
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(V, n, k, m, Skpar[par], keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, W.Sk, keep, Vtmp, W.ctl); XT_LAUNCHED();
+        rotate_kernel<TV><<<rg, SE_THREADS, 0, st>>>(AV, n, k, m, Skpar[par], keep, Vtmp, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(AV, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.theta, keep, W.ctl); XT_LAUNCHED();
+        restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, thpar[par], keep, W.ctl); XT_LAUNCHED();
         XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, Rblk, (size_t)blk * sizeof(TV),
                                    cudaMemcpyDeviceToDevice, st));
         m = keep + k;
       } else {
         orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Zbuf, W.C2, W.Rinv,
                                                                         V + (int64_t)(m / k) * blk, W.ctl); XT_LAUNCHED();
+        if (overlap) {
+          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
+          pend.valid = true; pend.par = par; pend.m = m; pend.iter = iter; pend.nev = nev; pend.coff = coff;
+        }
         m += k;
       }
       XT_CUDA_OK(cudaGetLastError());
+    }
+    if (overlap) {
+      // drain: the last pending Ritz check (a no-op once `done` is set), then join the side stream
+      if (pend.valid) { int rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
+      for (int q = 0; q < 2; ++q)
+        if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
     }
     // ---- output
     output_kernel<TV><<<grid_rows, 256, 0, st>>>(Xslots, W.evals_slots, n, k,
@@ -1022,7 +1106,7 @@ int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double*
   XT_REQUIRE(pl.inv_slots >= 1, "small_eigh: m=%d nev=%d exceeds the on-chip eigensolver", m, nev);
   XT_CUDA_OK(cudaFuncSetAttribute(xt::small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   xt::small_eigh_kernel<<<1, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
-                                                                  pl.as_in_smem, pl.inv_slots); XT_LAUNCHED();
+                                                                  pl.as_in_smem, pl.y_in_smem, pl.inv_slots); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   return XT_OK;
 }
