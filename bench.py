@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--neig", type=int, default=8)
     ap.add_argument("--min-eps", dest="min_eps", type=float, default=1e-4)
     ap.add_argument("--method", default="davidson")
+    ap.add_argument("--expansion", default="krylov", choices=["krylov", "residual"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--seed", type=int, default=7, help="make_herm seed (7: the reference's own fp32 davidson survives on it)")
@@ -196,8 +197,9 @@ def main():
 
     def solve(o):
         info = {}
+        extra = {"expansion": args.expansion} if args.method == "davidson" else {}
         ev, vec = xt.linalg.symeig(o, neig=args.neig, mode="lowest", method=args.method, min_eps=args.min_eps,
-                                   info=info)
+                                   info=info, **extra)
         return ev, vec, info
 
     for _ in range(warmup):
@@ -282,8 +284,10 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "C2: symeig %s neig=%d N=%d fp32 make_herm min_eps=%g, one independent problem per GPU"
-                            % (args.method, args.neig, args.n, args.min_eps),
+                "workload": "C2: symeig %s (expansion=%s) neig=%d N=%d fp32 make_herm(seed=%d) min_eps=%g, one "
+                            "independent problem per GPU" % (args.method, args.expansion, args.neig, args.n,
+                                                             args.seed, args.min_eps),
+                "matvecs_per_step": n_mv / args.steps,
                 "iters_per_step": iters / args.steps, "converged": bool(all_conv),
                 "l2": "inputs larger than L2 (A = %.2f GiB per pass)" % (bytes_per_launch / 2 ** 30),
                 "eig_rel_err_vs_fp64_rayleigh": eig_rel, "max_abs_residual": resid,

@@ -26,8 +26,11 @@ def _check_pairs(A, evals, evecs, ref_evals, min_eps):
     assert (gram - torch.eye(gram.shape[-1], dtype=torch.float64)).abs().max().item() <= 1e-4
 
 
-@pytest.mark.parametrize("method", ["davidson", "lanczos"])
+@pytest.mark.parametrize("method", ["davidson", "davidson-residual", "lanczos"])
 def test_golden_davidson_cases(golden, method):
+    extra = {}
+    if method == "davidson-residual":
+        method, extra = "davidson", {"expansion": "residual"}
     for case in golden["davidson"]:
         n, neig, mode, dtype = case["n"], case["neig"], case["mode"], case["dtype"]
         if case["A"] is not None:
@@ -36,7 +39,7 @@ def test_golden_davidson_cases(golden, method):
             A = oracle.make_herm(n, neig, torch.float64, seed=case["seed"]).to(dtype)
         info = {}
         evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, mode=mode,
-                                        method=method, min_eps=case["min_eps"], info=info)
+                                        method=method, min_eps=case["min_eps"], info=info, **extra)
         assert evals.dtype == dtype and tuple(evals.shape) == (*case["batch"], neig)
         assert info["converged"], (case["n"], mode, info)
         _check_pairs(A, evals, evecs, case["evals"], case["min_eps"])                # vs the reference's davidson
@@ -79,11 +82,13 @@ def test_thick_restart_slow_spectrum():
     A = oracle.make_slow_herm(n, torch.float64)
     ref = torch.linalg.eigvalsh(A)[:neig]
     info = {}
-    evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, method="davidson",
-                                    min_eps=1e-7, max_basis=32, max_niter=2000, info=info)
-    assert info["converged"], info
-    _check_pairs(A, evals, evecs, ref, 1e-7)
-    assert info["niter"] > 32 // neig          # i.e. at least one restart happened
+    for expansion in ("krylov", "residual"):
+        info = {}
+        evals, evecs = xt.linalg.symeig(xt.LinearOperator.m(A.to(DEV), True), neig=neig, method="davidson",
+                                        min_eps=1e-7, max_basis=32, max_niter=2000, info=info, expansion=expansion)
+        assert info["converged"], info
+        _check_pairs(A, evals, evecs, ref, 1e-7)
+        assert info["niter"] > 32 // neig          # i.e. at least one restart happened
 
 
 def test_uppest_and_batch():

@@ -1,0 +1,43 @@
+"""Plug-in mode: our method callables handed to the UNMODIFIED upstream xitorch through its
+`method=` hook.  Needs the reference checkout (present only in the build container) -- skipped elsewhere.
+On CPU the callables must be reached (signature accepted by upstream) and then refuse loudly (no CPU path);
+on a GPU box with the reference installed the same test runs the kernels under upstream's autograd Functions."""
+import os
+import sys
+
+import pytest
+import torch
+
+REF = os.environ.get("XITORCH_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "xitorch")), reason="reference checkout not present")
+
+
+def _upstream():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import xitorch
+    import xitorch.linalg
+    return xitorch
+
+
+def test_upstream_accepts_our_callables():
+    up = _upstream()
+    import xitorch_b200._impls.solve as bs
+    import xitorch_b200._impls.symeig as be
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    torch.manual_seed(0)
+    n = 64
+    A = torch.randn(n, n, dtype=torch.float64)
+    A = (A @ A.t() / n + torch.eye(n, dtype=torch.float64)).to(dev)
+    B = torch.randn(n, 2, dtype=torch.float64, device=dev)
+    op = up.LinearOperator.m(A, is_hermitian=True)              # upstream MatrixLinearOperator
+    if dev == "cpu":
+        with pytest.raises(RuntimeError, match="CUDA"):
+            up.linalg.solve(op, B, method=bs.cg)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            up.linalg.symeig(op, neig=2, method=be.davidson)
+        return
+    x = up.linalg.solve(op, B, method=bs.cg, rtol=1e-10, bck_options={"method": bs.cg, "rtol": 1e-10})
+    assert torch.allclose(A @ x, B, atol=1e-7)
+    ev, vec = up.linalg.symeig(op, neig=2, method=be.davidson, min_eps=1e-8)
+    assert torch.allclose(A @ vec, vec * ev, atol=1e-6)

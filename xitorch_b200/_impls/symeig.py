@@ -194,7 +194,7 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
              max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
              max_addition: Optional[int] = None, min_eps: float = 1e-6, verbose: bool = False,
              max_basis: Optional[int] = None, check_every: Optional[int] = None,
-             info: Optional[dict] = None, **unused):
+             info: Optional[dict] = None, expansion: str = "krylov", **unused):
     """
     Block Davidson (Rayleigh-Ritz on span{V0, r0, r1, ...}) on the B200.
 
@@ -218,9 +218,18 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
         Host polls the device convergence flag every this many iterations
     info: dict or None
         If given, receives ``niter``, ``converged``, ``best_resid``, ``napply``, ``max_basis``
+    expansion: str
+        ``"krylov"`` (default): the subspace is expanded with the orthonormalised ``A @ (last block)``.  Without a
+        preconditioner the reference's expansion block ``-R`` (the Ritz residuals) spans exactly the same space
+        (``R = Q_next @ (k x k)``), so the Ritz pairs and iteration counts are the same, but the expansion no
+        longer waits for the Rayleigh-Ritz step, which then overlaps with the next matvec on the GPU.
+        ``"residual"``: append the orthonormalised Ritz residuals literally as the reference does
+        (symeig.py:207-220); Rayleigh-Ritz is then on the critical path of every iteration.
     """
-    return _krylov(A, neig, mode, M, 0, max_niter, nguess, v_init, min_eps, max_basis, check_every, info,
-                   "davidson")
+    if expansion not in ("krylov", "residual"):
+        raise RuntimeError("Unknown expansion: %s" % expansion)
+    return _krylov(A, neig, mode, M, 1 if expansion == "krylov" else 0, max_niter, nguess, v_init, min_eps,
+                   max_basis, check_every, info, "davidson")
 
 
 def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
