@@ -409,7 +409,7 @@ static EigPlan eig_plan(int m, int nev) {
   EigPlan pl;
   pl.lds = m | 1;
   const size_t budget = 220 * 1024;
-  size_t fixed = (size_t)(6 * m + 4 * nev + 64) * 8 + (size_t)EIG_THREADS * 4 + 256;
+  size_t fixed = (size_t)(6 * m + 4 * nev + 64 + 96) * 8 + (size_t)EIG_THREADS * 4 + 256;
   const size_t y_bytes = (size_t)m * nev * 8;
   const size_t as_bytes = (size_t)m * pl.lds * 8;
   const size_t inv1 = (size_t)5 * m * 8;
@@ -457,25 +457,40 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   double* vbuf = tau + m;         // [m]   (later: e^2)
   double* pbuf = vbuf + m;        // [m]
   double* red = pbuf + m;         // [64]
-  double* lo = red + 64;          // [nev]
+  double* wpart = red + 64;       // [96]  per-warp partial sums of the tridiagonalisation
+  double* lo = wpart + 96;        // [nev]
   double* hi = lo + nev;          // [nev]
   int* icnt = reinterpret_cast<int*>(hi + nev);                   // [nt]
   double* inv = reinterpret_cast<double*>(icnt + nt + (nt & 1));  // [inv_slots][5][m]
 
   // ------------------------------------------------------------------ 1. tridiagonalisation
-  // Two block barriers per column: every warp recomputes the (cheap) Householder scalars and the scalar p.v
-  // redundantly instead of waiting for one warp to broadcast them.
-  //   phase 1: sigma, alpha, tau, scale (all warps, from the raw column j);  p = tau * A22 v   -> pbuf   | barrier
-  //   phase 2: hc = tau/2 * p.v (all warps);  A22 -= v w^T + w v^T with w = p - hc v on the fly;
-  //            warp 0 stores the scaled reflector into column j (for the back-transformation)            | barrier
-  for (int j = 0; j + 2 < m; ++j) {
-    const int n = m - j - 1;
+  // Two block barriers per column and no block-wide reduction trees: the two scalars a column needs
+  // (sigma = squared norm of its sub-column, pv = p.v) are left as one partial per warp by the phase that
+  // produces their terms; every thread then adds the <= 32 partials and recomputes the Householder scalars.
+  //   phase 1: scalars from (sigma_j, x0);  p = tau * A22 v  with v read on the fly from the raw column j;
+  //            pvpart[warp] = sum of this warp's p_i v_i;  vbuf <- v                                   | barrier
+  //   phase 2: A22 -= v w^T + w v^T, w = p - (tau/2) pv v;  sgpart[warp] = this warp's share of
+  //            sigma_{j+1};  warp 0 stores the scaled reflector into column j                           | barrier
+  double* sgpart = wpart;          // [2][32]
+  double* pvpart = wpart + 64;     // [32]
+  for (int i = tid; i < 96; i += nt) wpart[i] = 0.0;
+  __syncthreads();
+  if (m > 2) {
     double part = 0.0;
-    for (int i = j + 2 + lane; i < m; i += 32) {
-      const double v = As[(size_t)i * lds + j];
+    for (int i = 2 + tid; i < m; i += nt) {
+      const double v = As[(size_t)i * lds];
       part += v * v;
     }
-    const double sigma = warp_sum(part);
+    part = warp_sum(part);
+    if (lane == 0) sgpart[warp] = part;
+  }
+  __syncthreads();
+  for (int j = 0; j + 2 < m; ++j) {
+    const int n = m - j - 1;
+    const int pj = j & 1;
+    double sigma = 0.0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) sigma += sgpart[pj * 32 + w];
     const double x0 = As[(size_t)(j + 1) * lds + j];
     double alpha = x0, t = 0.0, scale = 0.0;
     if (sigma > 0.0) {
@@ -484,40 +499,66 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
       t = (alpha - x0) / alpha;
       scale = 1.0 / (x0 - alpha);
     }
-    // v (scaled reflector) into vbuf: every warp writes the same values to the slots it owns
     for (int i = tid; i < n; i += nt) vbuf[i] = (i == 0) ? 1.0 : As[(size_t)(j + 1 + i) * lds + j] * scale;
-    __syncthreads();
+    double pvw = 0.0;
     if (t != 0.0) {
       int TPR = 32;
       while (TPR > 1 && n * TPR > nt) TPR >>= 1;
       const int sub = tid % TPR, rowsPerPass = nt / TPR;
+      const double* colj = As + (size_t)(j + 1) * lds + j;      // raw (unscaled) reflector column
       for (int i0 = 0; i0 < n; i0 += rowsPerPass) {
         const int i = i0 + tid / TPR;
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0;
         if (i < n) {
           const double* row = As + (size_t)(j + 1 + i) * lds + (j + 1);
-          for (int l = sub; l < n; l += TPR) acc += row[l] * vbuf[l];
+          int l = sub;
+          for (; l + TPR < n; l += 2 * TPR) {
+            const double v0 = (l == 0) ? 1.0 : colj[(size_t)l * lds] * scale;
+            const double v1 = colj[(size_t)(l + TPR) * lds] * scale;
+            a0 += row[l] * v0;
+            a1 += row[l + TPR] * v1;
+          }
+          if (l < n) a0 += row[l] * ((l == 0) ? 1.0 : colj[(size_t)l * lds] * scale);
         }
+        double acc = a0 + a1;
         for (int o = TPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (i < n && sub == 0) pbuf[i] = t * acc;
+        if (i < n && sub == 0) {
+          const double pi = t * acc;
+          pbuf[i] = pi;
+          pvw += pi * ((i == 0) ? 1.0 : colj[(size_t)i * lds] * scale);
+        }
       }
+      pvw = warp_sum(pvw);
     }
+    if (lane == 0) pvpart[warp] = pvw;
     __syncthreads();
     if (warp == 0) {
       for (int i = lane; i < n; i += 32) As[(size_t)(j + 1 + i) * lds + j] = vbuf[i];
       if (lane == 0) { d[j] = As[(size_t)j * lds + j]; e[j] = alpha; tau[j] = t; }
     }
+    double sgw = 0.0;
     if (t != 0.0) {
       double pv = 0.0;
-      for (int i = lane; i < n; i += 32) pv += pbuf[i] * vbuf[i];
-      pv = warp_sum(pv);
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) pv += pvpart[w];
       const double hc = 0.5 * t * pv;
       for (int i = warp; i < n; i += nw) {
         const double vi = vbuf[i], wi = pbuf[i] - hc * vi;
         double* row = As + (size_t)(j + 1 + i) * lds + (j + 1);
-        for (int l = lane; l < n; l += 32) row[l] -= vi * (pbuf[l] - hc * vbuf[l]) + wi * vbuf[l];
+        for (int l = lane; l < n; l += 32) {
+          const double nv = row[l] - (vi * (pbuf[l] - hc * vbuf[l]) + wi * vbuf[l]);
+          row[l] = nv;
+          if (l == 0 && i >= 2) sgw += nv * nv;        // sub-column (rows >= j+3) of the next reflector (lane 0 only)
+        }
       }
+    } else {
+      for (int i = 2 + tid; i < n; i += nt) {
+        const double v = As[(size_t)(j + 1 + i) * lds + (j + 1)];
+        sgw += v * v;
+      }
+      sgw = warp_sum(sgw);
     }
+    if (lane == 0) sgpart[(pj ^ 1) * 32 + warp] = sgw;
     __syncthreads();
   }
   if (tid == 0) {
@@ -561,7 +602,9 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   const int want = bis ? ((mode == 0) ? slot : (m - nev + slot)) : 0;
   for (int i = tid; i < nev; i += nt) { lo[i] = gl; hi[i] = gu; }
   __syncthreads();
-  int rounds = (int)ceil(62.0 / log2((double)P + 1.0));
+  // isolate every wanted eigenvalue to ~2^-38 of the spectral range; the two inverse-iteration sweeps below then
+  // converge to working precision and the Rayleigh quotient of the tridiagonal matrix restores the last digits
+  int rounds = (int)ceil(38.0 / log2((double)P + 1.0));
   if (rounds < 3) rounds = 3;
   for (int r = 0; r < rounds; ++r) {
     double l0 = 0.0, h0 = 0.0, x = 0.0;
@@ -651,23 +694,41 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     __syncthreads();
   }
   if (dbg && tid == 0) dbg[3] = clock64();
-  // modified Gram-Schmidt over the nev vectors (warp 0)
+  // Gram-Schmidt only inside clusters of close eigenvalues (LAPACK's dstein criterion: gap < 1e-3 ||T||), then
+  // normalisation and the Rayleigh quotient of the tridiagonal matrix (warp 0)
   if (warp == 0) {
+    const double ortol = 1e-3 * tnorm;
     for (int c = 0; c < nev; ++c) {
-      for (int j = 0; j < c; ++j) {
-        double dot = 0.0;
-        for (int i = lane; i < m; i += 32) dot += Y[(size_t)i * nev + j] * Y[(size_t)i * nev + c];
+      for (int j = c - 1; j >= 0; --j) {
+        if (fabs(lam[c] - lam[j]) >= ortol) break;          // eigenvalues are ascending: the cluster is contiguous
+        double dot = 0.0, nj = 0.0;
+        for (int i = lane; i < m; i += 32) {
+          const double yj = Y[(size_t)i * nev + j];
+          dot += yj * Y[(size_t)i * nev + c];
+          nj += yj * yj;
+        }
         dot = warp_sum(dot);
-        for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] -= dot * Y[(size_t)i * nev + j];
+        nj = warp_sum(nj);
+        const double f = nj > 0.0 ? dot / nj : 0.0;       // the vectors are normalised only afterwards
+        for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] -= f * Y[(size_t)i * nev + j];
         __syncwarp();
       }
-      double nn = 0.0;
-      for (int i = lane; i < m; i += 32) nn += Y[(size_t)i * nev + c] * Y[(size_t)i * nev + c];
-      nn = warp_sum(nn);
-      const double sc = nn > 0.0 ? rsqrt(nn) : 0.0;
-      for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] *= sc;
-      __syncwarp();
     }
+  }
+  __syncthreads();
+  // one thread per vector: norm and Rayleigh quotient  theta = y^T T y / y^T y   (O(m), tridiagonal T)
+  if (tid < nev) {
+    const int c = tid;
+    double nn = 0.0, rq = 0.0, yprev = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double yi = Y[(size_t)i * nev + c];
+      nn += yi * yi;
+      rq += d[i] * yi * yi + ((i > 0) ? 2.0 * e[i - 1] * yprev * yi : 0.0);
+      yprev = yi;
+    }
+    const double sc = nn > 0.0 ? rsqrt(nn) : 0.0;
+    if (nn > 0.0) lam[c] = rq / nn;
+    for (int i = 0; i < m; ++i) Y[(size_t)i * nev + c] *= sc;
   }
   __syncthreads();
 
