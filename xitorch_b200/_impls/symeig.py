@@ -131,7 +131,7 @@ def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max
     world = dist_ctx[0] if dist_ctx is not None else 1
     if check_every is None:
         t_iter = max((n // world) * n * A3.element_size() / 6.0e12, 3e-5)
-        check_every = max(1, min(16, int(3e-4 / t_iter)))
+        check_every = max(4, min(16, int(1e-3 / t_iter)))
     g.check_every = int(check_every)
     g.min_eps = float(min_eps)
     niter, conv, best, napply = C.c_int32(0), C.c_int32(0), C.c_double(0.0), C.c_int64(0)

@@ -305,13 +305,15 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
+  int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
   for (int k = 0; k < maxk; ++k) {
     int rc = apply_op<TV>(op, S.Q + (int64_t)k * len, S.w, mx, nullptr, nullptr, 0, done_flag, st, &napply);
     if (rc != XT_OK) return rc;
     gm_step_kernel<TV><<<g->nbatch, SV_THREADS, smem_step, st>>>(S, k); XT_LAUNCHED();
     XT_CUDA_OK(cudaGetLastError());
-    if ((k + 1) % ce == 0 || k + 1 == maxk) {
+    if (k + 1 == next_check || k + 1 == maxk) {
+      next_check += (next_check < ce) ? next_check : ce;
       int done = 0;
       rc = poll_done(S.ctl, st, &done);
       if (rc != XT_OK) return rc;

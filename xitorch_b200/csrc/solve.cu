@@ -417,6 +417,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
+  int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
   for (int k = 1; k <= g->max_niter; ++k) {
     rc = apply_op<TV>(op, S.p, S.q, mx, S.p, S.dots, S.dots_gstride, done_flag, st, &napply);
@@ -431,7 +432,8 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
       cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
-    if (k % ce == 0 || k == g->max_niter) {
+    if (k == next_check || k == g->max_niter) {
+      next_check += (next_check < ce) ? next_check : ce;
       int done = 0;
       rc = poll_done(S.ctl, st, &done);
       if (rc != XT_OK) return rc;
@@ -456,6 +458,7 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
   const int ce = g->check_every > 0 ? g->check_every : 1;
+  int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
   for (int k = 1; k <= g->max_niter; ++k) {
     bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1); XT_LAUNCHED();
@@ -474,7 +477,8 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
       bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 5); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
-    if (k % ce == 0 || k == g->max_niter) {
+    if (k == next_check || k == g->max_niter) {
+      next_check += (next_check < ce) ? next_check : ce;
       int done = 0;
       rc = poll_done(S.ctl, st, &done);
       if (rc != XT_OK) return rc;

@@ -753,13 +753,27 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
 // T[:, new block] = C (and its transpose); then the nev extreme eigenpairs of T:
 //   theta[nev] (ascending), Sk (m x nev row-major).  The k wanted Ritz pairs are columns [0,k) for mode 0 and
 //   [nev-k, nev) for mode 1.
+// T[:, new block] = C and its transpose (the new block column / row of the projected matrix)
+__global__ void __launch_bounds__(256)
+t_update_kernel(double* T, int ldt, const double* C, int m, int k, const EigCtl* ctl) {
+  if (ctl->done) return;
+  const int c0 = m - k;
+  for (int e = threadIdx.x; e < m * k; e += blockDim.x) {
+    const int i = e / k, j = e - i * k;
+    double v = C[e];
+    if (i >= c0) v = 0.5 * (C[e] + C[(int64_t)(c0 + j) * k + (i - c0)]);   // symmetrise the diagonal block
+    T[(int64_t)i * ldt + c0 + j] = v;
+    T[(int64_t)(c0 + j) * ldt + i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(EIG_THREADS)
 rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw, double* Sk, double* theta, int mode,
           int lds, int as_in_smem, int y_in_smem, int inv_slots, const EigCtl* ctl) {
   if (ctl->done) return;
   extern __shared__ double dyn[];
   const int tid = threadIdx.x, nt = blockDim.x;
-  {
+  if (C != nullptr) {
     const int c0 = m - k;
     for (int e = tid; e < m * k; e += nt) {
       const int i = e / k, j = e - i * k;
@@ -866,7 +880,8 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective) {
 struct EigWs {
   void *V, *AV, *Zbuf, *Rblk, *Xslots, *Vtmp, *Wg;
   double *T, *Tw, *Sk, *theta, *C, *C2, *G, *Rinv, *evals_slots;
-  double *SkB, *thetaB, *CB;      // second parity set for the overlapped Rayleigh-Ritz
+  double *SkB, *thetaB, *CB;      // second and third slot for the overlapped Rayleigh-Ritz
+  double *SkC, *thetaC, *CC, *TwB;
   EigCtl* ctl;
 };
 
@@ -880,13 +895,17 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
   W.Vtmp = ar.take<char>((size_t)(mb / k) * blk);
   W.Wg = world > 1 ? ar.take<char>((size_t)world * ((size_t)(n / world) + 1) * k * vs) : nullptr;
   W.T = ar.take<double>((size_t)mb * mb);
-  W.Tw = ar.take<double>((size_t)mb * mb);
+  W.Tw = ar.take<double>((size_t)mb * (mb | 1));
   W.Sk = ar.take<double>((size_t)mb * mb);
   W.theta = ar.take<double>(mb);
   W.C = ar.take<double>((size_t)mb * k);
   W.CB = ar.take<double>((size_t)mb * k);
   W.SkB = ar.take<double>((size_t)mb * mb);
   W.thetaB = ar.take<double>(mb);
+  W.CC = ar.take<double>((size_t)mb * k);
+  W.SkC = ar.take<double>((size_t)mb * mb);
+  W.thetaC = ar.take<double>(mb);
+  W.TwB = ar.take<double>((size_t)mb * (mb | 1));
   W.C2 = ar.take<double>((size_t)mb * k);
   W.G = ar.take<double>(2 * SE_MAXK * SE_MAXK);
   W.Rinv = ar.take<double>(SE_MAXK * SE_MAXK);
@@ -944,18 +963,19 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   int last_niter = 0;
 
   const bool overlap = (g->expansion == 1) && (num_sms() > 8);
-  cudaStream_t side = nullptr;
-  cudaEvent_t evC[2] = {nullptr, nullptr}, evR[2] = {nullptr, nullptr};
+  constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t evC[NSLOT] = {nullptr, nullptr, nullptr}, evR[NSLOT] = {nullptr, nullptr, nullptr};
   struct SideGuard {           // streams/events are host-side handles, released on every exit path
     cudaStream_t* s; cudaEvent_t* a; cudaEvent_t* b;
     ~SideGuard() {
-      for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); }
-      if (*s) cudaStreamDestroy(*s);
+      for (int i = 0; i < NSLOT; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); }
+      for (int i = 0; i < 2; ++i) if (s[i]) cudaStreamDestroy(s[i]);
     }
-  } guard{&side, evC, evR};
+  } guard{side, evC, evR};
   if (overlap) {
-    XT_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < NSLOT; ++i) {
       XT_CUDA_OK(cudaEventCreateWithFlags(&evC[i], cudaEventDisableTiming));
       XT_CUDA_OK(cudaEventCreateWithFlags(&evR[i], cudaEventDisableTiming));
     }
@@ -978,15 +998,18 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
 
     int m = k;          // current basis size
     int iter = 0;
-    // Overlap mode (Lanczos expansion): the expansion block does not depend on the Rayleigh-Ritz result, so
-    // rr_kernel runs on a side stream (on the SM the matvec grid leaves free) while the main stream goes on with
-    // orthogonalisation and the next matvec; the Ritz-vector / residual kernel of iteration j is issued one
-    // iteration later on the main stream.  Convergence is therefore detected one matvec late, never missed.
-    double* Cpar[2] = {W.C, overlap ? W.CB : W.C};
-    double* Skpar[2] = {W.Sk, overlap ? W.SkB : W.Sk};
-    double* thpar[2] = {W.theta, overlap ? W.thetaB : W.theta};
-    struct Pending { bool valid; int par, m, iter, nev, coff; } pend = {false, 0, 0, 0, 0, 0};
-    bool ev_used[2] = {false, false};
+    int next_check = ce < 2 ? ce : 2;
+    // Overlap mode (Lanczos expansion): the expansion block does not depend on the Rayleigh-Ritz result, so the
+    // rr_kernels run on two alternating side streams (on the two SMs the matvec grid leaves free) while the main
+    // stream goes on with orthogonalisation and the next matvecs; the Ritz-vector / residual kernel of iteration j
+    // is issued two iterations later on the main stream.  Convergence is detected two matvecs late, never missed.
+    double* Cpar[NSLOT] = {W.C, overlap ? W.CB : W.C, overlap ? W.CC : W.C};
+    double* Skpar[NSLOT] = {W.Sk, overlap ? W.SkB : W.Sk, overlap ? W.SkC : W.Sk};
+    double* thpar[NSLOT] = {W.theta, overlap ? W.thetaB : W.theta, overlap ? W.thetaC : W.theta};
+    double* Twpar[2] = {W.Tw, overlap ? W.TwB : W.Tw};
+    struct Pending { bool valid; int par, m, iter, nev, coff; };
+    Pending pendq[2] = {{false, 0, 0, 0, 0, 0}, {false, 0, 0, 0, 0, 0}};     // [0] = older
+    bool ev_used[NSLOT] = {false, false, false};
     auto launch_ritz = [&](int par_, int m_, int iter_, int nev_, int coff_) -> int {
       if (overlap) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par_], 0));
       ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(V, AV, n, k, m_, Skpar[par_], nev_, coff_, thpar[par_],
@@ -994,10 +1017,21 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
                                                               (float)g->min_eps); XT_LAUNCHED();
       return XT_OK;
     };
+    auto flush_pending = [&](int keep_newest) -> int {       // issue pending Ritz checks, oldest first
+      for (int q = 0; q < 2 - keep_newest; ++q) {
+        if (pendq[0].valid) {
+          int rc_ = launch_ritz(pendq[0].par, pendq[0].m, pendq[0].iter, pendq[0].nev, pendq[0].coff);
+          if (rc_ != XT_OK) return rc_;
+        }
+        pendq[0] = pendq[1];
+        pendq[1].valid = false;
+      }
+      return XT_OK;
+    };
     while (true) {
       ++iter;
       const int j = m / k - 1;     // newest block
-      const int par = overlap ? (iter & 1) : 0;
+      const int par = overlap ? (iter % NSLOT) : 0;
       // 1. W = A Q_j
       MvArgs a;
       memset(&a, 0, sizeof(a));
@@ -1010,7 +1044,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
       a.done_flag = &W.ctl->done;
-      a.reserve_sms = overlap ? 1 : 0;
+      a.reserve_sms = overlap ? 2 : 0;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
@@ -1022,7 +1056,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         unpack_gathered_kernel<TV><<<num_sms(), 256, 0, st>>>(Wg, world, n_local, k, AV + j * blk, W.ctl); XT_LAUNCHED();
       }
       // 2. C = V^T W  (new block column of T)
-      if (overlap && ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));   // rr of iteration iter-2 is done with C[par]
+      if (overlap && ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));   // rr of iteration iter-3 is done with C[par]
       XT_CUDA_OK(cudaMemsetAsync(Cpar[par], 0, sizeof(double) * (size_t)m * k, st));
       subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, Cpar[par],
                                                                   nullptr, nullptr, 0, W.ctl); XT_LAUNCHED();
@@ -1034,33 +1068,41 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       const EigPlan pl = eig_plan(m, nev);
       XT_REQUIRE(pl.inv_slots >= 1, "symeig: projected problem %d x %d (nev=%d) exceeds the on-chip eigensolver", m, m, nev);
       cudaStream_t rs = st;
+      const double* Crr = Cpar[par];
       if (overlap) {
+        // the T update stays on the main stream so that two Rayleigh-Ritz kernels (alternating side streams, one
+        // spare SM each) can run concurrently: rr of iteration i only reads the leading m_i x m_i part of T
+        t_update_kernel<<<1, 256, 0, st>>>(W.T, mb, Cpar[par], m, k, W.ctl); XT_LAUNCHED();
+        Crr = nullptr;
+        rs = side[iter & 1];
         XT_CUDA_OK(cudaEventRecord(evC[par], st));
-        XT_CUDA_OK(cudaStreamWaitEvent(side, evC[par], 0));
-        rs = side;
+        XT_CUDA_OK(cudaStreamWaitEvent(rs, evC[par], 0));
       }
-      rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, Cpar[par], m, k, nev, W.Tw, Skpar[par], thpar[par],
+      rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, Crr, m, k, nev, Twpar[iter & 1], Skpar[par], thpar[par],
                                                         g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots,
                                                         W.ctl); XT_LAUNCHED();
       if (overlap) {
-        XT_CUDA_OK(cudaEventRecord(evR[par], side));
+        XT_CUDA_OK(cudaEventRecord(evR[par], rs));
         ev_used[par] = true;
       } else {
-        // 4. Ritz vectors, residual, bookkeeping (in overlap mode this is issued one iteration later)
+        // 4. Ritz vectors, residual, bookkeeping (in overlap mode this is issued two iterations later)
         rc = launch_ritz(par, m, iter, nev, coff);
         if (rc != XT_OK) return rc;
       }
       XT_CUDA_OK(cudaGetLastError());
       if (!can_expand) {                         // max_niter reached, or the basis cannot grow (symeig.py:202-203)
         if (overlap) {
-          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
-          pend.valid = false;
+          rc = flush_pending(0);
+          if (rc != XT_OK) return rc;
           rc = launch_ritz(par, m, iter, nev, coff);
           if (rc != XT_OK) return rc;
         }
         break;
       }
-      if (iter % ce == 0) {
+      if (iter == next_check) {
+        // the flag is polled at iterations 2, 4, 8, ... and then every `ce`: a poll drains the launch pipeline,
+        // while kernels launched after convergence are no-ops that cost ~2 us each
+        next_check += (next_check < ce) ? next_check : ce;
         int done = 0;
         XT_CUDA_OK(cudaMemcpyAsync(&done, &W.ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
         XT_CUDA_OK(cudaStreamSynchronize(st));
@@ -1080,9 +1122,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       if (restart) {
         // thick restart: finish the new block against the OLD basis first, then compress V / AV / T onto the
         // `keep` Ritz vectors computed by this iteration's rr_kernel (Sk is m x keep)
-        if (overlap) {   // the restart needs this iteration's Ritz coefficients now: catch up with the side stream
-          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
-          pend.valid = false;
+        if (overlap) {   // the restart needs this iteration's Ritz coefficients now: catch up with the side streams
+          rc = flush_pending(0);
+          if (rc != XT_OK) return rc;
           rc = launch_ritz(par, m, iter, nev, coff);
           if (rc != XT_OK) return rc;
         }
@@ -1101,8 +1143,10 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, Zbuf, W.C2, W.Rinv,
                                                                         V + (int64_t)(m / k) * blk, W.ctl); XT_LAUNCHED();
         if (overlap) {
-          if (pend.valid) { rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
-          pend.valid = true; pend.par = par; pend.m = m; pend.iter = iter; pend.nev = nev; pend.coff = coff;
+          // keep at most two Ritz checks outstanding: the one from two iterations ago is issued now
+          if (pendq[1].valid) { rc = flush_pending(1); if (rc != XT_OK) return rc; }
+          Pending pn = {true, par, m, iter, nev, coff};
+          if (!pendq[0].valid) pendq[0] = pn; else pendq[1] = pn;
         }
         m += k;
       }
@@ -1110,8 +1154,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     }
     if (overlap) {
       // drain: the last pending Ritz check (a no-op once `done` is set), then join the side stream
-      if (pend.valid) { int rc = launch_ritz(pend.par, pend.m, pend.iter, pend.nev, pend.coff); if (rc != XT_OK) return rc; }
-      for (int q = 0; q < 2; ++q)
+      int rc = flush_pending(0);
+      if (rc != XT_OK) return rc;
+      for (int q = 0; q < NSLOT; ++q)
         if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
     }
     // ---- output
