@@ -54,6 +54,25 @@ def _default_max_basis(n: int, neig: int) -> int:
     return max((mb // neig) * neig, 2 * neig)
 
 
+_V0_CACHE = {}
+
+
+def _start_block(kind, nb, n, neig, dtype, dev):
+    """seeded start block; it only depends on (kind, shape, dtype, device), so it is generated once and kept
+    (the engine never writes to it)."""
+    key = (kind, nb, n, neig, dtype, str(dev))
+    v = _V0_CACHE.get(key)
+    if v is None:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(12421)
+        fn = torch.randn if kind == "randn" else torch.rand
+        v = fn((nb, n, neig), dtype=dtype, device=dev, generator=gen)
+        if len(_V0_CACHE) > 8:
+            _V0_CACHE.clear()
+        _V0_CACHE[key] = v
+    return v
+
+
 def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator], expansion: int,
             max_niter: int, nguess: Optional[int], v_init: str, min_eps: float, max_basis: Optional[int],
             check_every: Optional[int], info: Optional[dict], name: str):
@@ -91,10 +110,7 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     if kind == "eye":
         V0 = torch.eye(n, neig, dtype=vdt, device=dev).expand(nb, n, neig).contiguous()
     elif kind in ("randn", "rand", "random"):
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(12421)
-        fn = torch.randn if kind == "randn" else torch.rand
-        V0 = fn((nb, n, neig), dtype=vdt, device=dev, generator=gen)
+        V0 = _start_block(kind, nb, n, neig, vdt, dev)
     else:
         raise ValueError("Unknown v_init type: %s" % v_init)
 
@@ -181,9 +197,7 @@ def _krylov_row_partitioned(A_local, n, neig, mode, expansion, group, min_eps, m
     if tuple(A_local.shape) != (n // world, n) or n % world != 0:
         raise RuntimeError("expected a local row block of shape %s, got %s" % ((n // world, n), tuple(A_local.shape)))
     A_local = A_local.contiguous()
-    gen = torch.Generator(device=A_local.device)
-    gen.manual_seed(12421)                      # same start block on every rank
-    V0 = torch.randn((1, n, neig), dtype=A_local.dtype, device=A_local.device, generator=gen)
+    V0 = _start_block("randn", 1, n, neig, A_local.dtype, A_local.device)      # same start block on every rank
     evals, evecs = _call_engine(A_local, A_local.stride(0), 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis,
                                 check_every, min_eps, info, "lanczos" if expansion == 1 else "davidson",
                                 dist_ctx=(world, rank, group))

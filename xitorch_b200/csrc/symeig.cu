@@ -21,6 +21,7 @@
 
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 namespace xt {
 
@@ -40,7 +41,14 @@ struct EigCtl {
   unsigned int counter;
   unsigned int resmax_bits;   // max |R| of the current iteration (float bits, atomicMax)
   float best_resid;
+  unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------------------- tall-skinny kernels
 // All three kernels below stream a chunk of SE_ROWS rows of the basis V (and AV) through shared memory in
@@ -280,6 +288,7 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
   double* Ss = reinterpret_cast<double*>(As + (size_t)SE_GB * SE_ROWS * k);         // [SE_GB*k][k]
   __shared__ float red[32];
   const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0 && iter < 64) ctl->trace[iter][2] = gtimer();
   const double* theta = theta_all + coff;
   const int slot = 1 - ctl->best_slot;
   TV* X = Xslots + (int64_t)slot * n * k;
@@ -355,6 +364,7 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
       }
       ctl->counter = 0;
       ctl->resmax_bits = 0;
+      if (iter < 64) ctl->trace[iter][3] = gtimer();
       __threadfence();
     }
   }
@@ -448,7 +458,8 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
 // As: work matrix (m x lds, destroyed).  Outputs: lam[nev] ascending, Y (m x nev, row-major, orthonormal columns).
 // mode 0: the nev lowest, mode 1: the nev highest.  `sh` is the carved shared memory.
 __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode, double* sh, int inv_slots,
-                                   double* lam, double* Y, long long* dbg = nullptr) {
+                                   double* lam, double* Y, long long* dbg = nullptr,
+                                   const int* abort_flag = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   if (dbg && tid == 0) dbg[0] = clock64();
   double* d = sh;                 // [m]
@@ -485,7 +496,13 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     if (lane == 0) sgpart[warp] = part;
   }
   __syncthreads();
+  __shared__ int abort_s;
   for (int j = 0; j + 2 < m; ++j) {
+    if (abort_flag != nullptr && (j & 7) == 0) {        // a stale Rayleigh-Ritz (the solve already converged) stops early
+      if (tid == 0) abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
+      __syncthreads();
+      if (abort_s) return;
+    }
     const int n = m - j - 1;
     const int pj = j & 1;
     double sigma = 0.0;
@@ -574,6 +591,11 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   __syncthreads();
 
   if (dbg && tid == 0) dbg[1] = clock64();
+  if (abort_flag != nullptr) {
+    if (tid == 0) abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
+    __syncthreads();
+    if (abort_s) return;
+  }
   // ------------------------------------------------------------------ 2. eigenvalues by multi-section
   double* e2 = vbuf;
   double gl = INFINITY, gu = -INFINITY, emax = 0.0;
@@ -630,6 +652,11 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   __syncthreads();
 
   if (dbg && tid == 0) dbg[2] = clock64();
+  if (abort_flag != nullptr) {
+    if (tid == 0) abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
+    __syncthreads();
+    if (abort_s) return;
+  }
   // ------------------------------------------------------------------ 3. inverse iteration on the tridiagonal matrix
   const double pert = 2.3e-16 * fmax(tnorm, 1e-300);
   for (int b0 = 0; b0 < nev; b0 += inv_slots) {
@@ -769,10 +796,11 @@ t_update_kernel(double* T, int ldt, const double* C, int m, int k, const EigCtl*
 
 __global__ void __launch_bounds__(EIG_THREADS)
 rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw, double* Sk, double* theta, int mode,
-          int lds, int as_in_smem, int y_in_smem, int inv_slots, const EigCtl* ctl) {
+          int lds, int as_in_smem, int y_in_smem, int inv_slots, EigCtl* ctl, int iter) {
   if (ctl->done) return;
   extern __shared__ double dyn[];
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0 && iter < 64) ctl->trace[iter][0] = gtimer();
   if (C != nullptr) {
     const int c0 = m - k;
     for (int e = tid; e < m * k; e += nt) {
@@ -795,10 +823,12 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
     As[(size_t)i * lds + j] = T[(int64_t)i * ldt + j];
   }
   __syncthreads();
-  eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y);
+  eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y, nullptr, &ctl->done);
+  if (ctl->done) return;               // aborted: results are not needed any more
   if (y_in_smem)
     for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
   for (int j = tid; j < nev; j += nt) theta[j] = lamv[j];
+  if (tid == 0 && iter < 64) ctl->trace[iter][1] = gtimer();
 }
 
 __global__ void __launch_bounds__(EIG_THREADS)
@@ -871,6 +901,7 @@ __global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int
 }
 
 __global__ void init_ctl_kernel(EigCtl* ctl, int collective) {
+  for (int i = 0; i < 64; ++i) for (int q = 0; q < 4; ++q) ctl->trace[i][q] = 0ull;
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
@@ -950,7 +981,12 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const size_t rz_smem = (size_t)2 * SE_GB * SE_ROWS * k * sizeof(TV) + (size_t)SE_GB * k * k * sizeof(double) + 64;
   static bool attrs_set = false;   // per TV instantiation
   if (!attrs_set) {
-    XT_CUDA_OK(cudaFuncSetAttribute(rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    {
+      cudaFuncAttributes fa;
+      XT_CUDA_OK(cudaFuncGetAttributes(&fa, rr_kernel));
+      XT_CUDA_OK(cudaFuncSetAttribute(rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)fa.sharedSizeBytes));
+    }
     XT_CUDA_OK(cudaFuncSetAttribute(ritz_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(subproj_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(orth_finish_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -964,20 +1000,32 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
 
   const bool overlap = (g->expansion == 1) && (num_sms() > 8);
   constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
-  cudaStream_t side[2] = {nullptr, nullptr};
-  cudaEvent_t evC[NSLOT] = {nullptr, nullptr, nullptr}, evR[NSLOT] = {nullptr, nullptr, nullptr};
-  struct SideGuard {           // streams/events are host-side handles, released on every exit path
-    cudaStream_t* s; cudaEvent_t* a; cudaEvent_t* b;
-    ~SideGuard() {
-      for (int i = 0; i < NSLOT; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); }
-      for (int i = 0; i < 2; ++i) if (s[i]) cudaStreamDestroy(s[i]);
-    }
-  } guard{side, evC, evR};
+  // side streams / events are host-side handles: created once per device and thread, reused by every call
+  struct SidePool {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
+    int dev = -1;
+  };
+  static thread_local SidePool pool;
+  cudaStream_t* side = pool.s;
+  cudaEvent_t* evC = pool.c;
+  cudaEvent_t* evR = pool.r;
   if (overlap) {
-    for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
-    for (int i = 0; i < NSLOT; ++i) {
-      XT_CUDA_OK(cudaEventCreateWithFlags(&evC[i], cudaEventDisableTiming));
-      XT_CUDA_OK(cudaEventCreateWithFlags(&evR[i], cudaEventDisableTiming));
+    int dev = 0;
+    XT_CUDA_OK(cudaGetDevice(&dev));
+    if (pool.dev != dev) {
+      for (int i = 0; i < 2; ++i) { if (pool.s[i]) cudaStreamDestroy(pool.s[i]); pool.s[i] = nullptr; }
+      for (int i = 0; i < NSLOT; ++i) {
+        if (pool.c[i]) cudaEventDestroy(pool.c[i]);
+        if (pool.r[i]) cudaEventDestroy(pool.r[i]);
+        pool.c[i] = pool.r[i] = nullptr;
+      }
+      for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
+      for (int i = 0; i < NSLOT; ++i) {
+        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.c[i], cudaEventDisableTiming));
+        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.r[i], cudaEventDisableTiming));
+      }
+      pool.dev = dev;
     }
   }
 
@@ -1044,7 +1092,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
       a.done_flag = &W.ctl->done;
-      a.reserve_sms = overlap ? 2 : 0;
+      // one free SM is enough: two Rayleigh-Ritz CTAs (512 threads, 64 registers, <= ~110 KB each up to m ~ 104)
+      // co-reside on it; reserving two SMs would shrink the matvec grid from 147 to 137 tiles (-13 % throughput)
+      a.reserve_sms = overlap ? 1 : 0;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
@@ -1080,7 +1130,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       }
       rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, Crr, m, k, nev, Twpar[iter & 1], Skpar[par], thpar[par],
                                                         g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots,
-                                                        W.ctl); XT_LAUNCHED();
+                                                        W.ctl, iter); XT_LAUNCHED();
       if (overlap) {
         XT_CUDA_OK(cudaEventRecord(evR[par], rs));
         ev_used[par] = true;
@@ -1166,6 +1216,14 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     EigCtl h;
     XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
     XT_CUDA_OK(cudaStreamSynchronize(st));
+    if (getenv("XT_TRACE") != nullptr) {
+      unsigned long long t0 = ~0ull;
+      for (int i = 1; i < 64; ++i) if (h.trace[i][0] && h.trace[i][0] < t0) t0 = h.trace[i][0];
+      for (int i = 1; i < 64 && i <= iter; ++i)
+        fprintf(stderr, "xt-trace iter %2d: rr %8.1f .. %8.1f us   ritz %8.1f .. %8.1f us\n", i,
+                h.trace[i][0] ? (h.trace[i][0] - t0) * 1e-3 : -1.0, h.trace[i][1] ? (h.trace[i][1] - t0) * 1e-3 : -1.0,
+                h.trace[i][2] ? (h.trace[i][2] - t0) * 1e-3 : -1.0, h.trace[i][3] ? (h.trace[i][3] - t0) * 1e-3 : -1.0);
+    }
     if (!h.converged) all_conv = 0;
     if (h.best_resid > worst_resid || !(h.best_resid == h.best_resid)) worst_resid = h.best_resid;
     last_niter = h.niter;
@@ -1213,7 +1271,12 @@ int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const xt::EigPlan pl = xt::eig_plan(m, nev);
   XT_REQUIRE(pl.inv_slots >= 1, "small_eigh: m=%d nev=%d exceeds the on-chip eigensolver", m, nev);
-  XT_CUDA_OK(cudaFuncSetAttribute(xt::small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  {
+    cudaFuncAttributes fa;
+    XT_CUDA_OK(cudaFuncGetAttributes(&fa, xt::small_eigh_kernel));
+    XT_CUDA_OK(cudaFuncSetAttribute(xt::small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024 - (int)fa.sharedSizeBytes));
+  }
   xt::small_eigh_kernel<<<1, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
                                                                   pl.as_in_smem, pl.y_in_smem, pl.inv_slots); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
