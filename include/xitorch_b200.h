@@ -66,8 +66,9 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
  *   A: (nbatch, nrows, ncolsA) row-major, row stride lda;   X: (nbatch, ncolsA, k), row stride ldx
  *   Y: (nbatch, nrows, k), row stride ldy;                  E: (nbatch, k) or NULL
  *   k >= 1 (handled in column groups of <= 16).  `impl`: 0 = auto, 1 = force a TMA kernel (auto layout),
- *   2 = force the plain-load kernel, 3 = TMA row-slice layout, 4 = TMA column-slice layout (fp32, k > 4);
- *   2-4 are used by the tests to cross-check the kernels.
+ *   2 = force the plain-load kernel, 3 = TMA row-slice layout, 4 = TMA column-slice layout (fp32, k > 4),
+ *   5 = TMA row-slice layout with one row per thread (k = 8 defaults to two);
+ *   2-5 are used by the tests to cross-check the kernels.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t dtype;
@@ -141,7 +142,8 @@ typedef struct {
   const void* V0; int64_t ldv0, v0_bstride;
   void* evals;   int64_t evals_bstride;
   void* evecs;   int64_t ldv, evecs_bstride;
-  int32_t max_niter, max_basis, check_every;
+  int32_t max_niter, max_basis, check_every;  /* check_every: accepted and ignored -- the eigen-engine watches a host-mapped
+                                                 copy of the stop flag through a 3-iteration run-ahead window */
   double min_eps;
   int32_t* niter_out;                         /* host, may be NULL: iterations of the last batch item */
   int32_t* converged_out;                     /* host, may be NULL: 1 iff every batch item met min_eps */

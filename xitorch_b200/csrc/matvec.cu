@@ -19,6 +19,7 @@
 #include "matvec.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include <type_traits>
@@ -38,21 +39,28 @@ const char* last_error() { return g_err; }
 // ---------------------------------------------------------------------------- launch accounting / profiling
 struct ProfState {
   bool on = false;
-  std::vector<cudaEvent_t> ev;     // pairs (begin, end)
+  std::vector<cudaEvent_t> ev;     // pairs (begin, end); created once and reused across resets
+  size_t used = 0;
   int64_t launches = 0, mv_launches = 0;
 };
 static ProfState g_prof;
 void note_launch(int n) { g_prof.launches += n; }
+static void prof_record(cudaStream_t st) {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof.ev.push_back(e);
+  }
+  cudaEventRecord(g_prof.ev[g_prof.used++], st);
+}
 void prof_mv_begin(cudaStream_t st) {
   ++g_prof.mv_launches;
   if (!g_prof.on) return;
-  cudaEvent_t e;
-  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof.ev.push_back(e); }
+  prof_record(st);
 }
 void prof_mv_end(cudaStream_t st) {
-  if (!g_prof.on || (g_prof.ev.size() & 1) == 0) return;
-  cudaEvent_t e;
-  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); g_prof.ev.push_back(e); }
+  if (!g_prof.on || (g_prof.used & 1) == 0) return;
+  prof_record(st);
 }
 
 int num_sms() {
@@ -72,12 +80,20 @@ MvTiling mv_tiling(int nbatch, int nrows, int reserve_sms) {
   const int64_t total = (int64_t)nbatch * nrows;
   int G = num_sms() - reserve_sms;
   if (G < 1) G = 1;
-  // rows per tile so that one wave of G CTAs covers everything, rounded up to the TMA box height
-  int64_t th = (total + (int64_t)G * MV_BOX_ROWS - 1) / ((int64_t)G * MV_BOX_ROWS) * MV_BOX_ROWS;
+  // rows per tile so that one wave of G CTAs covers everything.  Any row count works: a stage holds two TMA boxes
+  // of tile_rows x 128 B at fixed 16 KB offsets, so the swizzle atoms stay 1024-B aligned (N = 16384 on 148 SMs:
+  // 111 rows -> 148 tiles; leaving 3 SMs free costs 113 rows -> 145 tiles, < 2 %).
+  int64_t th = (total + G - 1) / G;
   if (th > MV_TILE_ROWS) th = MV_TILE_ROWS;
-  if (th > ((nrows + MV_BOX_ROWS - 1) / MV_BOX_ROWS) * MV_BOX_ROWS)
-    th = ((nrows + MV_BOX_ROWS - 1) / MV_BOX_ROWS) * MV_BOX_ROWS;
+  if (th > nrows) th = nrows;
   if (th < MV_BOX_ROWS) th = MV_BOX_ROWS;
+  // several batches: the per-batch round-up can push the tile count just past one wave
+  while (th < MV_TILE_ROWS && nbatch > 1 && (int64_t)nbatch * ((nrows + th - 1) / th) > G &&
+         (int64_t)nbatch * ((nrows + th - 1) / th) < 2 * (int64_t)G) ++th;
+  if (const char* ov = getenv("XT_MV_TILE_ROWS")) {      // tuning knob for experiments (tests/gpu_tile_sweep.py)
+    const int v = atoi(ov);
+    if (v >= MV_BOX_ROWS && v <= MV_TILE_ROWS) th = v;
+  }
   t.tile_rows = (int)th;
   t.tiles_per_batch = (nrows + t.tile_rows - 1) / t.tile_rows;
   t.ntiles = t.tiles_per_batch * nbatch;
@@ -226,30 +242,41 @@ template <int K> __device__ __forceinline__ void fma_row(double a, const double 
   for (int i = 0; i < K; ++i) acc[i] = fma(a, x[i], acc[i]);
 }
 
-// One consumer thread's share of one stage: NV 16-byte vectors of its row (precomputed swizzled offsets aoff[])
-// against the matching X rows (xbase + v * EPV*K*sizeof(TV)).  Fully unrolled: all shared-memory loads of a
-// vector are independent of the previous vector's FMAs, so ptxas can software-pipeline them.
-template <typename TA, typename TV, int K, int NV>
-__device__ __forceinline__ void consume_stage(uint32_t a_s, uint32_t xbase, const uint32_t (&aoff)[8], TV (&acc)[K]) {
+// One consumer thread's share of one stage: NV 16-byte vectors of each of its RP rows (precomputed swizzled offsets
+// aoff[], rows `hoff` bytes apart) against the matching X rows (xbase + v * EPV*K*sizeof(TV)).  With RP = 2 every X
+// row fetched from shared memory feeds two rows of A, which halves the X share of the LDS traffic (for K = 8 the
+// one-row form is bound by the shared-memory pipe: 0.85 wavefronts per clock in profiles/r1i_full_*).
+// Fully unrolled: all shared-memory loads of a vector are independent of the previous vector's FMAs.
+template <typename TA, typename TV, int K, int NV, int RP>
+__device__ __forceinline__ void consume_stage(uint32_t a_s, uint32_t xbase, const uint32_t (&aoff)[8], uint32_t hoff,
+                                              TV (&acc)[RP][K]) {
   using Tr = ElemTraits<TA>;
   constexpr int EPV = Tr::EPV;
-  TV loc[K];
+  TV loc[RP][K];
 #pragma unroll
-  for (int i = 0; i < K; ++i) loc[i] = TV(0);
+  for (int h = 0; h < RP; ++h)
+#pragma unroll
+    for (int i = 0; i < K; ++i) loc[h][i] = TV(0);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float4 raw = lds128(a_s + aoff[v]);
-    TV a[EPV];
-    Tr::unpack(raw, a);
+    TV a[RP][EPV];
+#pragma unroll
+    for (int h = 0; h < RP; ++h) {
+      const float4 raw = lds128(a_s + aoff[v] + (uint32_t)h * hoff);
+      Tr::unpack(raw, a[h]);
+    }
 #pragma unroll
     for (int j = 0; j < EPV; ++j) {
       TV x[K];
       load_xrow<K>(xbase + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
-      fma_row<K>(a[j], x, loc);
+#pragma unroll
+      for (int h = 0; h < RP; ++h) fma_row<K>(a[h][j], x, loc[h]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < K; ++i) acc[i] += loc[i];
+  for (int h = 0; h < RP; ++h)
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[h][i] += loc[h][i];
 }
 
 constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 128 B
@@ -358,7 +385,7 @@ __device__ __forceinline__ void row_epilogue(const MvDev& p, int b, int64_t row,
   }
 }
 
-template <typename TA, typename TV, int K, int NC>
+template <typename TA, typename TV, int K, int NC, int RP>
 __global__ void __launch_bounds__(NC + 64, 1)
 mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   using Tr = ElemTraits<TA>;
@@ -405,8 +432,10 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
   } else {
     // ------------------------------------------------------------------ consumers
-    // thread <-> (row r, k-slice q): rows_pad = tile_rows rounded up to 16, ksplit = largest power of two with
-    // ksplit * rows_pad <= NC; threads with q >= ksplit idle (whole warps, never partial quarter-warps)
+    // thread <-> (row group r, k-slice q).  A thread owns RP rows: r, r + rows_pad, ... (rows_pad = ceil(tile_rows /
+    // RP) rounded up to a multiple of 16 for RP = 1, of 8 for RP = 2, so that the rows of a thread share one
+    // swizzle phase and quarter-warps never straddle a k-slice); ksplit = largest power of two with
+    // ksplit * rows_pad <= NC; threads with q >= ksplit idle.
     const int tc = threadIdx.x - 64;
     const int r = tc % p.rows_pad;
     const int q = tc / p.rows_pad;
@@ -415,6 +444,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     const int nvec = 16 / ksplit;
     const int cw = warp - 2;
     const uint32_t a_row_off = (uint32_t)(r * 128);
+    const uint32_t hoff = (uint32_t)(p.rows_pad * 128);
     const uint32_t sw = (uint32_t)(r & 7);
     // per-thread constants: swizzled shared-memory offsets of its nvec vectors inside a stage, X offset
     uint32_t aoff[8];
@@ -430,10 +460,12 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       const int b = tile / p.tiles_per_batch;
       const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
       const int rows = min(p.tile_rows, p.nrows - row0);
-      const bool active = (r < rows) && (q < ksplit);
-      TV acc[K];
+      const bool active = (r < rows) && (q < ksplit);      // row r of a thread is its lowest: none active if r is not
+      TV acc[RP][K];
 #pragma unroll
-      for (int i = 0; i < K; ++i) acc[i] = TV(0);
+      for (int h = 0; h < RP; ++h)
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc[h][i] = TV(0);
 
       for (int ch = 0; ch < nchunks; ++ch) {
         const int kc = ch * KC;
@@ -442,33 +474,34 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
           const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
           const uint32_t xs = a_s + MV_STAGE_A_BYTES + x_q_off;
           if (kc + KC <= p.ncolsA) {
-            // full chunk: every vector of this thread is in bounds
-            if (nvec == 4) consume_stage<TA, TV, K, 4>(a_s, xs, aoff, acc);
-            else if (nvec == 8) consume_stage<TA, TV, K, 8>(a_s, xs, aoff, acc);
-            else if (nvec == 2) consume_stage<TA, TV, K, 2>(a_s, xs, aoff, acc);
-            else consume_stage<TA, TV, K, 1>(a_s, xs, aoff, acc);
+            // full chunk: every vector of this thread is in bounds (rows past the tile read stale, finite-or-not
+            // shared memory into accumulators that are never stored)
+            if (nvec == 4) consume_stage<TA, TV, K, 4, RP>(a_s, xs, aoff, hoff, acc);
+            else if (nvec == 8) consume_stage<TA, TV, K, 8, RP>(a_s, xs, aoff, hoff, acc);
+            else if (nvec == 2) consume_stage<TA, TV, K, 2, RP>(a_s, xs, aoff, hoff, acc);
+            else consume_stage<TA, TV, K, 1, RP>(a_s, xs, aoff, hoff, acc);
           } else {
             // ragged last chunk: skip vectors whose box was not loaded (columns past the end are zero-filled)
-            TV loc[K];
-#pragma unroll
-            for (int i = 0; i < K; ++i) loc[i] = TV(0);
             for (int v = 0; v < nvec; ++v) {
               const int gv = q * nvec + v;
               if (kc + (gv >> 3) * BOXC < p.ncolsA) {
-                const float4 raw = lds128(a_s + (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off +
-                                          ((((uint32_t)gv & 7u) ^ sw) << 4));
-                TV a[EPV];
-                Tr::unpack(raw, a);
+                const uint32_t off = (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off +
+                                     ((((uint32_t)gv & 7u) ^ sw) << 4);
+                TV a[RP][EPV];
+#pragma unroll
+                for (int h = 0; h < RP; ++h) {
+                  const float4 raw = lds128(a_s + off + (uint32_t)h * hoff);
+                  Tr::unpack(raw, a[h]);
+                }
 #pragma unroll
                 for (int j = 0; j < EPV; ++j) {
                   TV x[K];
                   load_xrow<K>(xs + (uint32_t)((v * EPV + j) * K * (int)sizeof(TV)), x);
-                  fma_row<K>(a[j], x, loc);
+#pragma unroll
+                  for (int h = 0; h < RP; ++h) fma_row<K>(a[h][j], x, acc[h]);
                 }
               }
             }
-#pragma unroll
-            for (int i = 0; i < K; ++i) acc[i] += loc[i];
           }
         }
         __syncwarp();
@@ -476,25 +509,35 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
         if (++s == NS) { s = 0; ph ^= 1; }
       }
 
-      // ---- reduce the k-slices, then the per-row epilogue (threads with q == 0)
-      if (q > 0 && q < ksplit) {
-#pragma unroll
-        for (int i = 0; i < K; ++i) red[(size_t)tc * K + i] = acc[i];
-      }
-      named_bar_sync(1, NC);
+      // ---- reduce the k-slices (one round per owned row through red[NC][K]), then the per-row epilogue (q == 0)
       double d0[K], d1[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
-      if (q == 0 && active) {
-        for (int qq = 1; qq < ksplit; ++qq) {
 #pragma unroll
-          for (int i = 0; i < K; ++i) acc[i] += red[(size_t)(qq * p.rows_pad + r) * K + i];
+      for (int h = 0; h < RP; ++h) {
+        if (h > 0) named_bar_sync(1, NC);        // red[] is reused
+        if (q > 0 && q < ksplit) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) red[(size_t)tc * K + i] = acc[h][i];
         }
-        row_epilogue<TV, K>(p, b, (int64_t)row0 + r, acc, d0, d1);
+        named_bar_sync(1, NC);
+        const int rr = r + h * p.rows_pad;
+        if (q == 0 && rr < rows) {
+          for (int qq = 1; qq < ksplit; ++qq) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) acc[h][i] += red[(size_t)(qq * p.rows_pad + r) * K + i];
+          }
+          double e0[K], e1[K];
+#pragma unroll
+          for (int i = 0; i < K; ++i) { e0[i] = 0.0; e1[i] = 0.0; }
+          row_epilogue<TV, K>(p, b, (int64_t)row0 + rr, acc[h], e0, e1);
+#pragma unroll
+          for (int i = 0; i < K; ++i) { d0[i] += e0[i]; d1[i] += e1[i]; }
+        }
       }
       if (p.dot_out != nullptr) {
-        // rows of this tile live in the q == 0 threads: tc < rows_pad  <=> consumer warps 0..rows_pad/32-1
-        // (rows_pad = 16 shares warp 0 with q = 1 whose d's are zero)
+        // rows of this tile live in the q == 0 threads: tc < rows_pad  <=> the first consumer warps (a warp shared
+        // with q = 1 threads only adds their zeros)
 #pragma unroll
         for (int i = 0; i < K; ++i) {
           d0[i] = warp_sum(d0[i]);
@@ -763,7 +806,7 @@ template <typename TV, int K> static bool x_bulk_ok(const MvArgs& a) {
   return true;
 }
 
-template <typename TA, typename TV, int K, int NC>
+template <typename TA, typename TV, int K, int NC, int RP>
 static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
@@ -785,7 +828,8 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
   dev.x_bulk = x_bulk_ok<TV, K>(a) ? 1 : 0;
-  auto kern = mv_tma_kernel<TA, TV, K, NC>;
+  dev.rows_pad = RP == 1 ? (til.tile_rows + 15) / 16 * 16 : ((til.tile_rows + RP - 1) / RP + 7) / 8 * 8;
+  auto kern = mv_tma_kernel<TA, TV, K, NC, RP>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -838,18 +882,23 @@ static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cu
   // wide fp32 blocks: column-slice layout (impl == 3 forces the row-slice layout for comparison)
   if constexpr (std::is_same<TA, float>::value) {
     // measured on B200 (N = 16384): k = 8 row-slice 6074 GB/s vs column-slice 5834; k = 16 column-slice 3888 vs 3680
-    if ((a.impl != 3 && a.k > 8) || (a.impl == 4 && a.k > 4)) {
+    if ((a.impl != 3 && a.impl != 5 && a.k > 8) || (a.impl == 4 && a.k > 4)) {
       if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
       return launch_colslice<16>(a, dev, til, st);
     }
   }
   constexpr int NCW = std::is_same<TV, double>::value ? 256 : 512;   // fp64 accumulators need the larger register cap
   // 512 consumer threads (16 warps) where the register budget allows it, 256 for the widest blocks
-  if (a.k <= 1) return launch_tma_k<TA, TV, 1, 512>(a, dev, til, st);
-  if (a.k <= 2) return launch_tma_k<TA, TV, 2, 512>(a, dev, til, st);
-  if (a.k <= 4) return launch_tma_k<TA, TV, 4, 512>(a, dev, til, st);
-  if (a.k <= 8) return launch_tma_k<TA, TV, 8, NCW>(a, dev, til, st);
-  return launch_tma_k<TA, TV, 16, 256>(a, dev, til, st);
+  if (a.k <= 1) return launch_tma_k<TA, TV, 1, 512, 1>(a, dev, til, st);
+  if (a.k <= 2) return launch_tma_k<TA, TV, 2, 512, 1>(a, dev, til, st);
+  if (a.k <= 4) return launch_tma_k<TA, TV, 4, 512, 1>(a, dev, til, st);
+  // k = 8: two rows per thread (impl == 5 keeps the one-row form for comparison)
+  if (a.k <= 8) {
+    if (a.impl == 5) return launch_tma_k<TA, TV, 8, NCW, 1>(a, dev, til, st);
+    return launch_tma_k<TA, TV, 8, NCW, 2>(a, dev, til, st);
+  }
+  if (a.impl == 5) return launch_tma_k<TA, TV, 16, 256, 1>(a, dev, til, st);
+  return launch_tma_k<TA, TV, 16, 256, 2>(a, dev, til, st);
 }
 
 template <typename TA, typename TV>
@@ -883,8 +932,9 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
 
-  bool use_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4) || (a.impl == 0 && mv_tma_ok(a));
-  if ((a.impl == 1 || a.impl == 3 || a.impl == 4) && !mv_tma_ok(a)) {
+  const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5);
+  bool use_tma = forced_tma || (a.impl == 0 && mv_tma_ok(a));
+  if (forced_tma && !mv_tma_ok(a)) {
     set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
     return XT_ERR_INVALID;
   }
@@ -910,8 +960,7 @@ extern "C" {
 int xt_version(void) { return 100; }
 
 void xt_profile_reset(int enable) {
-  for (cudaEvent_t e : xt::g_prof.ev) cudaEventDestroy(e);
-  xt::g_prof.ev.clear();
+  xt::g_prof.used = 0;
   xt::g_prof.on = enable != 0;
   xt::g_prof.launches = 0;
   xt::g_prof.mv_launches = 0;
@@ -922,7 +971,7 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
   // as matvecs (duration below 20 % of the longest one)
   double ms = 0.0;
   int64_t eff = xt::g_prof.mv_launches;
-  const size_t np = xt::g_prof.ev.size() / 2;
+  const size_t np = xt::g_prof.used / 2;
   if (np > 0) {
     XT_CUDA_OK(cudaEventSynchronize(xt::g_prof.ev[2 * np - 1]));
     std::vector<float> t(np, 0.f);

@@ -13,7 +13,7 @@ constexpr int MV_THREADS = MV_CONSUMERS + 64;   // + TMA warp + X-staging warp
 // Work decomposition of one block matvec launch (identical for both kernels, so that the
 // per-tile partial dot products have one layout).
 struct MvTiling {
-  int tile_rows;        // TH: multiple of 8, <= 128
+  int tile_rows;        // TH: 8 .. 128 rows (any integer)
   int tiles_per_batch;
   int ntiles;
   int grid;

@@ -18,6 +18,7 @@
 // Layout in HBM: basis V and AV as blocks [block][n][k] (each block is an (n,k) row-major array, so
 // block j is directly the X / Y operand of the matvec kernel); T, S row-major fp64.
 #include "matvec.cuh"
+#include <chrono>
 
 #include <cstring>
 #include <cmath>
@@ -41,8 +42,17 @@ struct EigCtl {
   unsigned int counter;
   unsigned int resmax_bits;   // max |R| of the current iteration (float bits, atomicMax)
   float best_resid;
+  int* host_done;       // host-mapped mirror of `done` (lets the host stop launching without draining the stream)
   unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
 };
+
+__device__ __forceinline__ void signal_done(EigCtl* ctl) {
+  ctl->done = 1;
+  if (ctl->host_done) {
+    *reinterpret_cast<volatile int*>(ctl->host_done) = 1;
+    __threadfence_system();
+  }
+}
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -177,12 +187,16 @@ subproj_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restri
   }
   // projections onto the basis, group by group: thread <-> (basis vector in group, column)
   if (Cout != nullptr) {
+    // when the whole basis was one group, the copy staged for the subtraction pass is still in shared memory
+    const bool staged = (Cin != nullptr) && (nblk <= SE_GB);
     for (int g0 = 0; g0 < nblk; g0 += SE_GB) {
       const int nb = min(SE_GB, nblk - g0);
-      __syncthreads();
-      stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
-      cp_async_wait_all();
-      __syncthreads();
+      if (!staged) {
+        __syncthreads();
+        stage_group<TV>(Vs, V, n, k, row0, rows, g0, nb);
+        cp_async_wait_all();
+        __syncthreads();
+      }
       for (int e = tid; e < nb * k * k; e += SE_THREADS) {
         const int iv = e / k, j = e - iv * k;            // iv = b * k + i
         const int b = iv / k, i = iv - b * k;
@@ -206,7 +220,9 @@ subproj_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restri
   for (int e = tid; e < k * k; e += SE_THREADS) {
     const int i = e / k, j = e - i * k;
     double acc = 0.5 * (__ldcg(&G[i * k + j]) + __ldcg(&G[j * k + i]));
-    if (Cout != nullptr)
+    // |Zp - V C2|^2 = G - C2^T C2.  After a first projection pass (Cin given) C2 is at rounding level
+    // (~1e-7 |Z|), so the correction is ~1e-14 |Z|^2 and is skipped; a single-pass caller needs it.
+    if (Cout != nullptr && Cin == nullptr)
       for (int t = 0; t < m; ++t) acc -= __ldcg(&Cout[(int64_t)t * k + i]) * __ldcg(&Cout[(int64_t)t * k + j]);
     Gs[e] = acc;
   }
@@ -221,7 +237,7 @@ subproj_kernel(const TV* __restrict__ V, int n, int k, int m, const TV* __restri
       if (tid == 0) {
         ctl->breakdown = 1;
         ctl->local_done = 1;
-        if (!ctl->collective) ctl->done = 1;
+        if (!ctl->collective) signal_done(ctl);
       }
     }
     if (tid == 0) ctl->counter = 0;
@@ -360,7 +376,7 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
       if (rmax < min_eps) {
         ctl->converged = 1;
         ctl->local_done = 1;
-        if (!ctl->collective) ctl->done = 1;
+        if (!ctl->collective) signal_done(ctl);
       }
       ctl->counter = 0;
       ctl->resmax_bits = 0;
@@ -858,8 +874,9 @@ small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double*
 // final copy of the best pair into the caller's tensors
 template <typename TV>
 __global__ void output_kernel(const TV* Xslots, const double* evals_slots, int n, int k, TV* evecs, int64_t ldv,
-                              TV* evals, const EigCtl* ctl) {
+                              TV* evals, EigCtl* ctl) {
   const int slot = ctl->best_slot;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trace[0][1] = gtimer();
   const TV* X = Xslots + (int64_t)slot * n * k;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n * k;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -896,15 +913,17 @@ __global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int any = 0;
     for (int pr = 0; pr < world; ++pr) any |= (Wg[pr * per + (int64_t)n_local * k] != TV(0)) ? 1 : 0;
-    if (any) ctl->done = 1;          // every rank sees the same flags at the same iteration
+    if (any) signal_done(ctl);          // every rank sees the same flags at the same iteration
   }
 }
 
-__global__ void init_ctl_kernel(EigCtl* ctl, int collective) {
+__global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
+  ctl->host_done = host_done;
   for (int i = 0; i < 64; ++i) for (int q = 0; q < 4; ++q) ctl->trace[i][q] = 0ull;
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
+  ctl->trace[0][0] = gtimer();
 }
 
 // ============================================================================ host driver
@@ -974,7 +993,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   TV* Vtmp = static_cast<TV*>(W.Vtmp);
   const int64_t blk = (int64_t)n * k;
   const int grid_rows = (n + SE_ROWS - 1) / SE_ROWS;
-  const int ce = g->check_every > 0 ? g->check_every : 1;
+  (void)g->check_every;   // accepted for API compatibility: the stop flag is watched through a run-ahead window
   const int keep = ((mb / 2) / k) * k >= k ? ((mb / 2) / k) * k : k;   // Ritz vectors kept at a restart
   const size_t sp_smem = (size_t)(SE_ROWS * SE_MAXK + SE_GB * SE_MAXK * SE_MAXK) * sizeof(double) +
                          (size_t)SE_GB * SE_ROWS * k * sizeof(TV) + 64;
@@ -999,18 +1018,22 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   int last_niter = 0;
 
   const bool overlap = (g->expansion == 1) && (num_sms() > 8);
+  constexpr int LOOKAHEAD = 3; // the host enqueues at most this many iterations beyond the last one known complete
   constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
   // side streams / events are host-side handles: created once per device and thread, reused by every call
   struct SidePool {
     cudaStream_t s[2] = {nullptr, nullptr};
     cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
+    cudaEvent_t it[LOOKAHEAD + 1] = {nullptr, nullptr, nullptr, nullptr};   // end-of-iteration marks (run-ahead window)
+    volatile int* hflag = nullptr;      // pinned, mapped: the kernels mirror ctl->done here
+    int* hflag_dev = nullptr;
     int dev = -1;
   };
   static thread_local SidePool pool;
   cudaStream_t* side = pool.s;
   cudaEvent_t* evC = pool.c;
   cudaEvent_t* evR = pool.r;
-  if (overlap) {
+  {
     int dev = 0;
     XT_CUDA_OK(cudaGetDevice(&dev));
     if (pool.dev != dev) {
@@ -1020,6 +1043,15 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         if (pool.r[i]) cudaEventDestroy(pool.r[i]);
         pool.c[i] = pool.r[i] = nullptr;
       }
+      for (int i = 0; i <= LOOKAHEAD; ++i) {
+        if (pool.it[i]) cudaEventDestroy(pool.it[i]);
+        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.it[i], cudaEventDisableTiming));
+      }
+      if (pool.hflag) cudaFreeHost(const_cast<int*>(pool.hflag));
+      void* hp = nullptr;
+      XT_CUDA_OK(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+      pool.hflag = static_cast<volatile int*>(hp);
+      XT_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pool.hflag_dev), hp, 0));
       for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
       for (int i = 0; i < NSLOT; ++i) {
         XT_CUDA_OK(cudaEventCreateWithFlags(&pool.c[i], cudaEventDisableTiming));
@@ -1032,7 +1064,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
-    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl, collective ? 1 : 0); XT_LAUNCHED();
+    *pool.hflag = 0;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
     gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
                                                        g->ldv0, n, k, Rblk); XT_LAUNCHED();
@@ -1046,7 +1080,6 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
 
     int m = k;          // current basis size
     int iter = 0;
-    int next_check = ce < 2 ? ce : 2;
     // Overlap mode (Lanczos expansion): the expansion block does not depend on the Rayleigh-Ritz result, so the
     // rr_kernels run on two alternating side streams (on the two SMs the matvec grid leaves free) while the main
     // stream goes on with orthogonalisation and the next matvecs; the Ritz-vector / residual kernel of iteration j
@@ -1078,6 +1111,13 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     };
     while (true) {
       ++iter;
+      if (iter > LOOKAHEAD) {
+        // run-ahead window instead of polling: wait (normally not at all) until iteration iter-LOOKAHEAD has
+        // finished on the device, then look at the host mirror of the stop flag.  The stream is never drained and
+        // at most LOOKAHEAD iterations of no-op kernels are enqueued after convergence.
+        XT_CUDA_OK(cudaEventSynchronize(pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)]));
+        if (*pool.hflag) { --iter; break; }
+      }
       const int j = m / k - 1;     // newest block
       const int par = overlap ? (iter % NSLOT) : 0;
       // 1. W = A Q_j
@@ -1092,9 +1132,10 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
       a.done_flag = &W.ctl->done;
-      // one free SM is enough: two Rayleigh-Ritz CTAs (512 threads, 64 registers, <= ~110 KB each up to m ~ 104)
-      // co-reside on it; reserving two SMs would shrink the matvec grid from 147 to 137 tiles (-13 % throughput)
-      a.reserve_sms = overlap ? 1 : 0;
+      // two free SMs, one per Rayleigh-Ritz kernel in flight (alternating side streams), so that no matvec CTA ever
+      // waits for an SM.  Free: with two rows per consumer thread the k = 8 matvec runs at the same 6.26 TB/s for
+      // any tile height 112..128 (tests/gpu_tile_sweep.py), i.e. on 145 SMs as well as on 147.
+      a.reserve_sms = overlap ? 2 : 0;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
@@ -1149,15 +1190,6 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         }
         break;
       }
-      if (iter == next_check) {
-        // the flag is polled at iterations 2, 4, 8, ... and then every `ce`: a poll drains the launch pipeline,
-        // while kernels launched after convergence are no-ops that cost ~2 us each
-        next_check += (next_check < ce) ? next_check : ce;
-        int done = 0;
-        XT_CUDA_OK(cudaMemcpyAsync(&done, &W.ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
-        XT_CUDA_OK(cudaStreamSynchronize(st));
-        if (done) break;
-      }
       // 5. expansion block, orthogonalised against V
       XT_CUDA_OK(cudaMemsetAsync(W.C2, 0, sizeof(double) * (size_t)m * k, st));
       XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
@@ -1200,6 +1232,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         }
         m += k;
       }
+      XT_CUDA_OK(cudaEventRecord(pool.it[iter % (LOOKAHEAD + 1)], st));
       XT_CUDA_OK(cudaGetLastError());
     }
     if (overlap) {
@@ -1217,8 +1250,10 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
     XT_CUDA_OK(cudaStreamSynchronize(st));
     if (getenv("XT_TRACE") != nullptr) {
-      unsigned long long t0 = ~0ull;
-      for (int i = 1; i < 64; ++i) if (h.trace[i][0] && h.trace[i][0] < t0) t0 = h.trace[i][0];
+      const unsigned long long t0 = h.trace[0][0];
+      fprintf(stderr, "xt-trace device span %.1f us, host span %.1f us, %d iterations enqueued\n",
+              (h.trace[0][1] - t0) * 1e-3,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count(), iter);
       for (int i = 1; i < 64 && i <= iter; ++i)
         fprintf(stderr, "xt-trace iter %2d: rr %8.1f .. %8.1f us   ritz %8.1f .. %8.1f us\n", i,
                 h.trace[i][0] ? (h.trace[i][0] - t0) * 1e-3 : -1.0, h.trace[i][1] ? (h.trace[i][1] - t0) * 1e-3 : -1.0,
