@@ -69,6 +69,9 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
  *   2 = force the plain-load kernel, 3 = TMA row-slice layout, 4 = TMA column-slice layout (fp32, k > 4),
  *   5 = TMA row-slice layout with one row per thread (k = 8 defaults to two);
  *   2-5 are used by the tests to cross-check the kernels.
+ *   Bit 8 of `impl` (+256) makes the pass read A's columns last-to-first and bits 16..23 give the MB of the end of
+ *   the pass to leave in L2 (evict-last): callers that apply the same A repeatedly alternate the direction so that
+ *   each pass starts on the part of A the previous one left in the 126 MB L2.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t dtype;

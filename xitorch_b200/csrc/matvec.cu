@@ -168,6 +168,9 @@ struct MvDev {
   const void* U; int64_t ldu, u_bstride;
   double* dot_out;
   const int* done_flag;
+  int reverse;      // traverse the column chunks of A from the last to the first
+  int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
+                    // oppositely ordered pass finds the tail of this one in L2
 };
 
 template <typename TA> struct ElemTraits;
@@ -289,7 +292,8 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   const char* Xg = reinterpret_cast<const char*>(p.X);
-  const uint64_t pol = l2_policy_evict_first();
+  const uint64_t pol_first = l2_policy_evict_first();
+  const uint64_t pol_keep = l2_policy_evict_last();
   int s = 0;
   uint32_t ph = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -297,7 +301,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
     const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
     const int bA = p.a_batched ? b : 0;
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int kc = ch * KC;
+      const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
       const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
@@ -309,7 +313,8 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
       }
       mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128) + xbytes);
       for (int bx = 0; bx < nb; ++bx)
-        tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA, pol);
+        tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA,
+                    ch >= p.keep_from ? pol_keep : pol_first);
       if (p.x_bulk)
         bulk_load_1d(dst + MV_STAGE_A_BYTES,
                      Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV), xbytes, &full[s]);
@@ -331,7 +336,7 @@ __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, 
   auto load_chunk = [&](int tile, int ch) {
     const int b = tile / p.tiles_per_batch;
     const TV* Xb = Xg + (int64_t)b * p.x_bstride;
-    const int kc = ch * KC;
+    const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int idx = lane + 32 * i;
@@ -468,7 +473,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
         for (int i = 0; i < K; ++i) acc[h][i] = TV(0);
 
       for (int ch = 0; ch < nchunks; ++ch) {
-        const int kc = ch * KC;
+        const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
         mbar_wait(&full[s], ph);
         if (active) {
           const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
@@ -642,7 +647,7 @@ mv_tma_colslice_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 #pragma unroll
         for (int i = 0; i < K; ++i) loc2[q][i] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch) {
-        const int kc = ch * KC;
+        const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
         mbar_wait(&full[s], ph);
         const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
         const uint32_t xs = a_s + MV_STAGE_A_BYTES + xoff;
@@ -879,10 +884,11 @@ static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& t
 
 template <typename TA, typename TV>
 static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cudaStream_t st) {
-  // wide fp32 blocks: column-slice layout (impl == 3 forces the row-slice layout for comparison)
+  // The column-slice layout (fp32, impl == 4) is kept as a cross-check only.  Measured on B200 (N = 16384):
+  // k = 8: row-slice with two rows per thread 6260 GB/s, one row 6230 (5690 for tiles > 112 rows), column-slice 5850;
+  // k = 16: row-slice with two rows per thread 4220 GB/s, column-slice 3890, one row 3680.
   if constexpr (std::is_same<TA, float>::value) {
-    // measured on B200 (N = 16384): k = 8 row-slice 6074 GB/s vs column-slice 5834; k = 16 column-slice 3888 vs 3680
-    if ((a.impl != 3 && a.impl != 5 && a.k > 8) || (a.impl == 4 && a.k > 4)) {
+    if (a.impl == 4 && a.k > 4) {
       if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
       return launch_colslice<16>(a, dev, til, st);
     }
@@ -931,6 +937,21 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.U = a.U; d.ldu = a.ldu; d.u_bstride = a.u_bstride;
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
+  d.reverse = a.reverse ? 1 : 0;
+  {
+    // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB
+    const int64_t es = a.dtype == XT_F64 ? 8 : (a.dtype == XT_BF16 ? 2 : 4);
+    const int64_t kc_cols = 2 * (128 / es);
+    const int nchunks = (int)((a.ncolsA + kc_cols - 1) / kc_cols);
+    int64_t keep_mb = a.l2_keep_mb;
+    if (const char* ov = getenv("XT_MV_L2_KEEP_MB")) keep_mb = atoi(ov);
+    d.keep_from = nchunks;
+    if (keep_mb > 0 && til.ntiles <= til.grid) {
+      const int64_t chunk_bytes = (int64_t)a.nbatch * a.nrows * kc_cols * es;
+      const int64_t kch = (keep_mb << 20) / (chunk_bytes > 0 ? chunk_bytes : 1);
+      d.keep_from = kch >= nchunks ? 0 : nchunks - (int)kch;
+    }
+  }
 
   const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5);
   bool use_tma = forced_tma || (a.impl == 0 && mv_tma_ok(a));
@@ -1007,9 +1028,11 @@ int xt_block_matvec(const xt_matvec_args* g) {
     a.E = g->E ? static_cast<const char*>(g->E) + c0 * vs : nullptr; a.e_bstride = g->e_bstride;
     a.Z = g->Z ? static_cast<const char*>(g->Z) + c0 * vs : nullptr; a.ldz = g->ldz; a.z_bstride = g->z_bstride;
     a.U = nullptr; a.ldu = 0; a.u_bstride = 0; a.dot_out = nullptr;
-    a.impl = g->impl;
+    a.impl = g->impl & 0xff;
     a.done_flag = nullptr;
     a.reserve_sms = 0;
+    a.reverse = (g->impl >> 8) & 1;          // bit 8: last-to-first column traversal
+    a.l2_keep_mb = (g->impl >> 16) & 0xff;   // bits 16..23: MB of the pass's tail to keep in L2 (see matvec.cuh)
     int rc = xt::mv_launch(a, st);
     if (rc != XT_OK) return rc;
   }

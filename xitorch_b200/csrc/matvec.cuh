@@ -9,6 +9,10 @@ constexpr int MV_TILE_ROWS = 128;    // max rows of a CTA tile
 constexpr int MV_BOX_ROWS = 8;       // rows of one TMA box (= one 128B-swizzle atom: 8 x 128 B)
 constexpr int MV_CONSUMERS = 256;    // consumer threads (8 warps)
 constexpr int MV_THREADS = MV_CONSUMERS + 64;   // + TMA warp + X-staging warp
+// L2 carry-over between alternating passes (tests/gpu_l2_sweep.py, N = 16384, k = 8): alternating the direction gives
+// 167.9 us instead of 173.2 us per pass; the evict-last tail adds nothing measurable beyond that (167.0 us at 32 MB)
+// because hits and misses share the same ~6.4 TB/s L2-slice throughput cap.
+constexpr int MV_L2_KEEP_MB = 32;
 
 // Work decomposition of one block matvec launch (identical for both kernels, so that the
 // per-tile partial dot products have one layout).
@@ -37,6 +41,8 @@ struct MvArgs {
   int impl;                                    // 0 auto, 1 TMA, 2 plain
   const int* done_flag;                        // optional device flag: kernel exits immediately when *done_flag != 0
   int reserve_sms;                             // leave this many SMs free (for kernels overlapped on another stream)
+  int reverse;                                 // traverse A's column chunks last-to-first (alternate per call, see l2_keep_mb)
+  int l2_keep_mb;                              // MB of the end of this pass to keep in L2 for the next, reversed pass
 };
 
 // enqueue on `stream`; returns xt_status

@@ -1136,6 +1136,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       // waits for an SM.  Free: with two rows per consumer thread the k = 8 matvec runs at the same 6.26 TB/s for
       // any tile height 112..128 (tests/gpu_tile_sweep.py), i.e. on 145 SMs as well as on 147.
       a.reserve_sms = overlap ? 2 : 0;
+      // consecutive passes run in opposite column order: the tail of the previous pass is still in L2
+      a.reverse = iter & 1;
+      a.l2_keep_mb = MV_L2_KEEP_MB;
       int rc = mv_launch(a, st);
       if (rc != XT_OK) return rc;
       ++napply;
