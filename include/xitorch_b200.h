@@ -170,7 +170,7 @@ int xt_symeig_krylov(const xt_symeig_args* args);
 /* small dense symmetric eigensolver used for the projected problem (device, one CTA; replaces torch.linalg.eigh
  * at xitorch/_impls/linalg/symeig.py:174): the nev lowest (mode 0) or highest (mode 1) eigenpairs of the m x m
  * row-major fp64 matrix T -> w_out[nev] ascending, S_out (m x nev row-major, orthonormal columns).
- * scratch: >= m*(m|1) + 8 doubles (the last 8 receive phase clock stamps).  Exposed for the parity tests. */
+ * scratch: >= m*(m|1) + 16 doubles (the last 16 receive phase clock stamps).  Exposed for the parity tests. */
 int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out,
                   double* scratch, void* stream);
 

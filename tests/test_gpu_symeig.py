@@ -105,7 +105,7 @@ def _small_eigh(T, nev, mode):
     Td = T.contiguous().to(DEV)
     w = torch.zeros(nev, dtype=torch.float64, device=DEV)
     S = torch.zeros(m, nev, dtype=torch.float64, device=DEV)
-    scratch = torch.zeros(m * (m | 1) + 8, dtype=torch.float64, device=DEV)
+    scratch = torch.zeros(m * (m | 1) + 16, dtype=torch.float64, device=DEV)
     vp = ctypes.c_void_p
     rc = L.xt_small_eigh(vp(Td.data_ptr()), m, nev, mode, vp(w.data_ptr()), vp(S.data_ptr()), vp(scratch.data_ptr()),
                          vp(torch.cuda.current_stream().cuda_stream))

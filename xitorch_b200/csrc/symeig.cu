@@ -436,6 +436,7 @@ static EigPlan eig_plan(int m, int nev) {
   pl.lds = m | 1;
   const size_t budget = 220 * 1024;
   size_t fixed = (size_t)(6 * m + 4 * nev + 64 + 96) * 8 + (size_t)EIG_THREADS * 4 + 256;
+  if (m <= 128) fixed += (size_t)18 * 128 * 8 + 16;     // ppart and vp (16-byte aligned) of tridiag_regs
   const size_t y_bytes = (size_t)m * nev * 8;
   const size_t as_bytes = (size_t)m * pl.lds * 8;
   const size_t inv1 = (size_t)5 * m * 8;
@@ -452,23 +453,291 @@ static EigPlan eig_plan(int m, int nev) {
 }
 
 // number of eigenvalues of the tridiagonal matrix (d, e^2) that are < x: sign changes of the Sturm sequence
-// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, evaluated without divisions and rescaled against over/underflow
-__device__ __forceinline__ int sturm_count(const double* d, const double* e2, int m, double x, double pivmin) {
+// p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}, evaluated without divisions.  The matrix is pre-scaled to norm <= 1
+// (growth <= 2.5 per step), so the over/underflow guard runs once per 8 steps and stays off the dependent chain
+// p_{i-1} -> p_i, which is one DFMA plus the exact-zero fix-up.
+__device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int m, double x,
+                                           double pivmin) {
   double pm = 1.0;                 // p_{i-1}
   double p = d[0] - x;             // p_i
   if (p == 0.0) p = -pivmin;
   int cnt = p < 0.0 ? 1 : 0;
-  for (int i = 1; i < m; ++i) {
+  int i = 1;
+  for (; i + 8 <= m; i += 8) {
+    // fast path: 8 steps whose only dependent chain is the DFMA; exact zeros (which need the sign fix-up) are only
+    // detected, and the block is redone carefully in that (rare) case
+    const double p0 = p, pm0 = pm;
+    int c8 = 0;
+    bool zero = false;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double pn = fma(d[i + u] - x, p, -e2[i + u - 1] * pm);
+      zero |= (pn == 0.0);
+      c8 += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+      pm = p;
+      p = pn;
+    }
+    if (zero) {
+      p = p0; pm = pm0; c8 = 0;
+      for (int u = 0; u < 8; ++u) {
+        double pn = fma(d[i + u] - x, p, -e2[i + u - 1] * pm);
+        if (pn == 0.0) pn = (p > 0.0) ? -pivmin * fabs(p) : pivmin * fabs(p);   // treat an exact zero as a sign change
+        c8 += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+        pm = p;
+        p = pn;
+      }
+    }
+    cnt += c8;
+    const double ap = fabs(p);
+    if (ap > 1e100) { p *= 1e-100; pm *= 1e-100; }
+    else if (ap < 1e-100) { p *= 1e100; pm *= 1e100; }
+  }
+  for (; i < m; ++i) {
     double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
-    if (pn == 0.0) pn = (p > 0.0) ? -pivmin * fabs(p) : pivmin * fabs(p);   // treat an exact zero as a sign change
+    if (pn == 0.0) pn = (p > 0.0) ? -pivmin * fabs(p) : pivmin * fabs(p);
     cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
     pm = p;
     p = pn;
-    const double ap = fabs(p);
-    if (ap > 1e150) { p *= 1e-150; pm *= 1e-150; }
-    else if (ap < 1e-150) { p *= 1e150; pm *= 1e150; }
   }
   return cnt;
+}
+
+__device__ int g_eig_debug = 0;     // tuning/debug switches (XT_EIG_DEBUG): 1 = shared-memory tridiagonalisation, 2 = unpaired back-transformation, 4 = IEEE sqrt/div in tridiag_regs
+
+// ---------------------------------------------------------------------------- register-resident tridiagonalisation
+// Householder tridiagonalisation (dsytd2, lower variant) of a symmetric m x m matrix, m <= 128, with the MATRIX IN
+// REGISTERS: 16 warps; warp w owns rows w, w+16, ... (MR of them), lane l owns columns l, l+32, ... (MC of them).
+// The shared-memory version below spends its time re-reading and re-writing the trailing matrix through the LDS/STS
+// pipe (3 loads + 1 store of 8 bytes per element and column: ~6600 clk per column at m = 104, measured); here a
+// column costs 12 broadcast loads, MR*MC*3 DFMAs per thread and three block barriers:
+//   A. every thread recomputes the Householder scalars from the column extracted by the previous step (xcol) and the
+//      per-warp partial sums of its squared norm (sgpart)
+//   B. p = A22 v by COLUMN sums (A22 is symmetric): a thread sums its rows for each of its columns -- no shuffles --
+//      and the 16 warps leave their partials in ppart[warp][column]                                        | barrier
+//   C1. threads c < m add the 16 partials -> pbuf[c] = tau * p_c, per-warp partials of p.v, store the reflector | barrier
+//   C2. rank-2 update in registers, extraction of the next column / diagonal entry / norm partials          | barrier
+// Reflectors are stored in the strict lower triangle of As (column j, rows j+1.., v_{j+1} = 1) exactly as the
+// shared-memory version does, so the back-transformation is common.
+// 1/x to ~1 ulp for normal x: MUFU seed (2^-20) + two Newton steps; about half the latency of an IEEE division
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double err = fma(-x, r, 1.0);
+  r = fma(r, err, r);
+  err = fma(-x, r, 1.0);
+  return fma(r, err, r);
+}
+
+// (no __restrict__ here: these arrays carry data BETWEEN threads across the barriers, and with the qualifier nvcc
+// moves loads over __syncthreads -- observed as wrong results for every instantiation but <2,1>)
+template <int MR, int MC>
+__device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
+                                          double* e, double* tau, double* xcol,
+                                          double2* vp, double* ppart,
+                                          double* sgpart, double* pvpart,
+                                          const int* abort_flag, int* abort_s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a[MR][MC];
+#pragma unroll
+  for (int rr = 0; rr < MR; ++rr) {
+    const int r = warp + 16 * rr;
+#pragma unroll
+    for (int cc = 0; cc < MC; ++cc) {
+      const int c = lane + 32 * cc;
+      a[rr][cc] = (r < m && c < m) ? As[(size_t)r * lds + c] : 0.0;
+    }
+  }
+  __syncthreads();            // As is reused for the reflectors from here on
+  // column 0 / diagonal entry 0 / norm partial of rows >= 2
+  if (lane == 0) {
+    double sg = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < MR; ++rr) {
+      const int r = warp + 16 * rr;
+      if (r >= 1 && r < m) xcol[r] = a[rr][0];
+      if (r >= 2 && r < m) sg += a[rr][0] * a[rr][0];
+      if (r == 0) d[0] = a[rr][0];
+    }
+    sgpart[warp] = sg;
+  }
+  if (tid == 0) *abort_s = 0;
+  __syncthreads();
+  constexpr int H0 = (MR + 1) / 2;       // rows are processed in two halves (register budget)
+  for (int j = 0; j + 2 < m; ++j) {
+    const int pj = j & 1;
+    // ---- A. Householder scalars (every thread, redundantly).  The operands of phase B are fetched first so that
+    // their latency hides behind the scalar chain.
+    double xr[MR];
+#pragma unroll
+    for (int rr = 0; rr < MR; ++rr) {
+      const int r = warp + 16 * rr;
+      xr[rr] = xcol[r < m ? r : m - 1];
+    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      s0 += sgpart[pj * 16 + w];
+      s1 += sgpart[pj * 16 + 4 + w];
+      s2 += sgpart[pj * 16 + 8 + w];
+      s3 += sgpart[pj * 16 + 12 + w];
+    }
+    const double sigma = (s0 + s1) + (s2 + s3);
+    const double x0 = xcol[j + 1];
+    double alpha = x0, t = 0.0, scale = 0.0;
+    if (sigma > 0.0) {
+      const double ss = fma(x0, x0, sigma);
+      const double inv = rsqrt(ss);
+      const double nrm = ss * inv;
+      const double ax0 = fabs(x0);
+      alpha = x0 >= 0.0 ? -nrm : nrm;
+      t = fma(ax0, inv, 1.0);                         // (alpha - x0) / alpha = 1 + |x0| / nrm
+      const double sc = fast_rcp(ax0 + nrm);          // 1 / (x0 - alpha) = sign(x0) / (|x0| + nrm)
+      scale = x0 >= 0.0 ? sc : -sc;
+      if (g_eig_debug & 4) {
+        const double nrm2 = sqrt(ss);
+        alpha = x0 >= 0.0 ? -nrm2 : nrm2;
+        t = (alpha - x0) / alpha;
+        scale = 1.0 / (x0 - alpha);
+      }
+    }
+    // ---- B. column sums of A22 v over this thread's rows
+    if (t != 0.0) {
+      double acc[MC], acc2[MC];
+#pragma unroll
+      for (int cc = 0; cc < MC; ++cc) { acc[cc] = 0.0; acc2[cc] = 0.0; }
+#pragma unroll
+      for (int rr = 0; rr < MR; ++rr) {
+        const int r = warp + 16 * rr;
+        if (r > j && r < m) {                                            // warp-uniform row predicate
+          const double vrr = (r == j + 1) ? 1.0 : xr[rr] * scale;
+#pragma unroll
+          for (int cc = 0; cc < MC; ++cc) {
+            if (rr & 1) acc2[cc] = fma(a[rr][cc], vrr, acc2[cc]);
+            else acc[cc] = fma(a[rr][cc], vrr, acc[cc]);
+          }
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < MC; ++cc) {
+        const int c = lane + 32 * cc;
+        if (c < m) ppart[warp * 128 + c] = acc[cc] + acc2[cc];
+      }
+    }
+    if (abort_flag != nullptr && (j & 7) == 0 && tid == 0) *abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
+    __syncthreads();
+    if (*abort_s) return;
+    // ---- C1. p = tau * (sum of the partials), partials of p.v, (v, p) pairs -> vp[], reflector -> column j of As
+    if (tid < 128) {
+      const int c = tid;
+      double pvw = 0.0;
+      if (c > j && c < m) {
+        const double vcc = (c == j + 1) ? 1.0 : xcol[c] * scale;
+        double pc = 0.0;
+        if (t != 0.0) {
+          double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            q0 += ppart[w * 128 + c];
+            q1 += ppart[(4 + w) * 128 + c];
+            q2 += ppart[(8 + w) * 128 + c];
+            q3 += ppart[(12 + w) * 128 + c];
+          }
+          pc = t * ((q0 + q1) + (q2 + q3));
+          pvw = pc * vcc;
+        }
+        vp[c] = make_double2(vcc, pc);
+        As[(size_t)c * lds + j] = vcc;
+      }
+      pvw = warp_sum(pvw);
+      if (lane == 0) pvpart[warp] = pvw;
+      if (tid == 0) { e[j] = alpha; tau[j] = t; }
+    }
+    __syncthreads();
+    // ---- C2. rank-2 update A22 -= v w^T + w v^T, w = p - (tau/2)(p.v) v;  next column, diagonal entry, norm partials
+    if (t != 0.0) {
+      double vc[MC], wc[MC];
+#pragma unroll
+      for (int cc = 0; cc < MC; ++cc) {
+        const int c = lane + 32 * cc;
+        const double2 q = vp[c < m ? c : m - 1];
+        vc[cc] = q.x; wc[cc] = q.y;
+      }
+      double2 qa[H0];
+#pragma unroll
+      for (int h = 0; h < H0; ++h) {
+        const int r = warp + 16 * h;
+        qa[h] = vp[r < m ? r : m - 1];
+      }
+      const double hc = 0.5 * t * ((pvpart[0] + pvpart[1]) + (pvpart[2] + pvpart[3]));
+#pragma unroll
+      for (int cc = 0; cc < MC; ++cc) {
+        const int c = lane + 32 * cc;
+        const bool in = (c > j && c < m);
+        wc[cc] = in ? fma(-hc, vc[cc], wc[cc]) : 0.0;
+        vc[cc] = in ? vc[cc] : 0.0;
+      }
+      double2 qb[MR - H0 > 0 ? MR - H0 : 1];
+#pragma unroll
+      for (int h = 0; h < MR - H0; ++h) {
+        const int r = warp + 16 * (H0 + h);
+        qb[h] = vp[r < m ? r : m - 1];
+      }
+#pragma unroll
+      for (int rr = 0; rr < H0; ++rr) {
+        const int r = warp + 16 * rr;
+        if (r > j && r < m) {                                            // warp-uniform
+          const double vrr = qa[rr].x;
+          const double wr = fma(-hc, vrr, qa[rr].y);
+#pragma unroll
+          for (int cc = 0; cc < MC; ++cc) a[rr][cc] = fma(-wr, vc[cc], fma(-vrr, wc[cc], a[rr][cc]));
+        }
+      }
+#pragma unroll
+      for (int rr = H0; rr < MR; ++rr) {
+        const int r = warp + 16 * rr;
+        if (r > j && r < m) {
+          const double vrr = qb[rr - H0].x;
+          const double wr = fma(-hc, vrr, qb[rr - H0].y);
+#pragma unroll
+          for (int cc = 0; cc < MC; ++cc) a[rr][cc] = fma(-wr, vc[cc], fma(-vrr, wc[cc], a[rr][cc]));
+        }
+      }
+    }
+    {
+      const int jn = j + 1;
+      if (lane == (jn & 31)) {
+        double sg = 0.0, sg2 = 0.0;
+        const int occ = jn >> 5;
+#pragma unroll
+        for (int rr = 0; rr < MR; ++rr) {
+          double v = a[rr][0];                      // select chain (a dynamic index would push a[][] to local memory)
+#pragma unroll
+          for (int cc = 1; cc < MC; ++cc) v = (occ == cc) ? a[rr][cc] : v;
+          const int r = warp + 16 * rr;
+          if (r > jn && r < m) xcol[r] = v;
+          if (r > jn + 1 && r < m) { if (rr & 1) sg2 = fma(v, v, sg2); else sg = fma(v, v, sg); }
+          if (r == jn) d[jn] = v;
+        }
+        sgpart[(pj ^ 1) * 16 + warp] = sg + sg2;
+      }
+    }
+    __syncthreads();
+  }
+  // trailing 2 x 2 (or smaller) block
+  if (m >= 2) {
+    const int r = m - 1;
+    if (warp == (r & 15) && lane == (r & 31)) {
+      double v = a[0][0];
+#pragma unroll
+      for (int rr = 0; rr < MR; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < MC; ++cc) v = ((r >> 4) == rr && (r >> 5) == cc) ? a[rr][cc] : v;
+      d[r] = v;
+    }
+    if (tid == 0) { e[m - 2] = xcol[m - 1]; tau[m - 2] = 0.0; }
+  }
+  if (tid == 0) { e[m - 1] = 0.0; tau[m - 1] = 0.0; }
+  __syncthreads();
 }
 
 // As: work matrix (m x lds, destroyed).  Outputs: lam[nev] ascending, Y (m x nev, row-major, orthonormal columns).
@@ -488,7 +757,8 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   double* lo = wpart + 96;        // [nev]
   double* hi = lo + nev;          // [nev]
   int* icnt = reinterpret_cast<int*>(hi + nev);                   // [nt]
-  double* inv = reinterpret_cast<double*>(icnt + nt + (nt & 1));  // [inv_slots][5][m]
+  double* ppart = reinterpret_cast<double*>(icnt + nt + (nt & 1));   // [16][128] when m <= 128
+  double* inv = ppart + (m <= 128 ? 18 * 128 + 2 : 0);               // [inv_slots][5][m]
 
   // ------------------------------------------------------------------ 1. tridiagonalisation
   // Two block barriers per column and no block-wide reduction trees: the two scalars a column needs
@@ -500,6 +770,17 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   //            sigma_{j+1};  warp 0 stores the scaled reflector into column j                           | barrier
   double* sgpart = wpart;          // [2][32]
   double* pvpart = wpart + 64;     // [32]
+  __shared__ int abort_s;
+  const bool in_regs = (m <= 128) && (nt == EIG_THREADS) && (g_eig_debug & 1) == 0;
+  if (in_regs) {
+    double2* vp = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(ppart + 16 * 128) + 15) & ~uintptr_t(15));
+    if (m <= 32) tridiag_regs<2, 1>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    else if (m <= 64) tridiag_regs<4, 2>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    else if (m <= 96) tridiag_regs<6, 3>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    else if (m <= 112) tridiag_regs<7, 4>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    else tridiag_regs<8, 4>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    if (abort_s) return;
+  } else {
   for (int i = tid; i < 96; i += nt) wpart[i] = 0.0;
   __syncthreads();
   if (m > 2) {
@@ -512,7 +793,6 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     if (lane == 0) sgpart[warp] = part;
   }
   __syncthreads();
-  __shared__ int abort_s;
   for (int j = 0; j + 2 < m; ++j) {
     if (abort_flag != nullptr && (j & 7) == 0) {        // a stale Rayleigh-Ritz (the solve already converged) stops early
       if (tid == 0) abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
@@ -605,6 +885,7 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     tau[m - 1] = 0.0;
   }
   __syncthreads();
+  }   // !in_regs
 
   if (dbg && tid == 0) dbg[1] = clock64();
   if (abort_flag != nullptr) {
@@ -613,27 +894,34 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     if (abort_s) return;
   }
   // ------------------------------------------------------------------ 2. eigenvalues by multi-section
+  // on a copy of the tridiagonal matrix scaled to unit norm (ds = d / tnorm, e2 = (e / tnorm)^2)
   double* e2 = vbuf;
-  double gl = INFINITY, gu = -INFINITY, emax = 0.0;
+  double* ds = pbuf;
+  double gl = INFINITY, gu = -INFINITY;
   for (int i = tid; i < m; i += nt) {
     const double el = (i > 0) ? fabs(e[i - 1]) : 0.0;
     const double er = (i < m - 1) ? fabs(e[i]) : 0.0;
     gl = fmin(gl, d[i] - el - er);
     gu = fmax(gu, d[i] + el + er);
-    emax = fmax(emax, er * er);
-    e2[i] = er * er;
   }
   gl = -block_max(-gl, red);
   __syncthreads();
   gu = block_max(gu, red);
   __syncthreads();
-  emax = block_max(emax, red);
-  __syncthreads();
-  const double tnorm = fmax(fabs(gl), fabs(gu));
-  gl -= 2.0 * tnorm * m * 2.3e-16 + 1e-300;
-  gu += 2.0 * tnorm * m * 2.3e-16 + 1e-300;
-  const double pivmin = 2.3e-308 * fmax(1.0, emax) * 1e4;
+  const double tnorm = fmax(fmax(fabs(gl), fabs(gu)), 1e-300);
+  const double rnorm = 1.0 / tnorm;
+  for (int i = tid; i < m; i += nt) {
+    const double es = (i < m - 1) ? e[i] * rnorm : 0.0;
+    ds[i] = d[i] * rnorm;
+    e2[i] = es * es;
+  }
+  gl = gl * rnorm - (2.0 * m * 2.3e-16 + 1e-300);
+  gu = gu * rnorm + (2.0 * m * 2.3e-16 + 1e-300);
+  const double pivmin = 1e-290;
+  // P shifts per eigenvalue and round (every thread evaluates one shift).  The Sturm recurrence is bound by the FP64
+  // pipe when all 16 warps run it, so at most 32 shifts per eigenvalue are used (nev = 8: 8 warps, 5 bits per round).
   int P = nt / nev;
+  if (P > 32) P = 32;
   if (P < 1) P = 1;
   const int slot = tid / P, pt = tid - slot * P;
   const bool bis = slot < nev;
@@ -644,13 +932,14 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   // converge to working precision and the Rayleigh quotient of the tridiagonal matrix restores the last digits
   int rounds = (int)ceil(38.0 / log2((double)P + 1.0));
   if (rounds < 3) rounds = 3;
+  const double frac_hi = (double)(pt + 1) / (double)(P + 1), frac_lo = (double)pt / (double)(P + 1);
   for (int r = 0; r < rounds; ++r) {
     double l0 = 0.0, h0 = 0.0, x = 0.0;
     int cnt = 0;
     if (bis) {
       l0 = lo[slot]; h0 = hi[slot];
-      x = l0 + (h0 - l0) * ((double)(pt + 1) / (double)(P + 1));
-      cnt = sturm_count(d, e2, m, x, pivmin);
+      x = fma(h0 - l0, frac_hi, l0);
+      cnt = sturm_count(ds, e2, m, x, pivmin);
       icnt[tid] = cnt;
     }
     __syncthreads();
@@ -658,13 +947,13 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
       const int cl = (pt == 0) ? -1 : icnt[tid - 1];
       if (cl <= want && cnt > want) {          // eigenvalue `want` lies in (x_{pt-1}, x_pt]
         hi[slot] = x;
-        if (pt > 0) lo[slot] = l0 + (h0 - l0) * ((double)pt / (double)(P + 1));
+        if (pt > 0) lo[slot] = fma(h0 - l0, frac_lo, l0);
       }
       if (pt == P - 1 && cnt <= want) lo[slot] = x;   // it lies in (x_{P-1}, hi]
     }
     __syncthreads();
   }
-  for (int i = tid; i < nev; i += nt) lam[i] = 0.5 * (lo[i] + hi[i]);
+  for (int i = tid; i < nev; i += nt) lam[i] = 0.5 * (lo[i] + hi[i]) * tnorm;
   __syncthreads();
 
   if (dbg && tid == 0) dbg[2] = clock64();
@@ -674,62 +963,80 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     if (abort_s) return;
   }
   // ------------------------------------------------------------------ 3. inverse iteration on the tridiagonal matrix
+  // One vector per WARP (lane 0 works: the pivoting branches of different vectors never diverge inside a warp).  The
+  // values on the dependent chain (current pivot row, current iterate entry) are carried in registers; shared memory
+  // only sees independent, prefetchable loads and fire-and-forget stores.
   const double pert = 2.3e-16 * fmax(tnorm, 1e-300);
-  for (int b0 = 0; b0 < nev; b0 += inv_slots) {
-    const int sidx = b0 + tid;
-    if (tid < inv_slots && sidx < nev) {
-      double* a = inv + (size_t)tid * 5 * m;    // diagonal of U
-      double* b = a + m;                         // first superdiagonal of U
-      double* l = b + m;                         // multipliers
-      double* u2 = l + m;                        // second superdiagonal of U
-      double* pv = u2 + m;                       // pivot flags
+  const int vslots = inv_slots < nw ? inv_slots : nw;
+  for (int b0 = 0; b0 < nev; b0 += vslots) {
+    const int sidx = b0 + warp;
+    if (lane == 0 && warp < vslots && sidx < nev) {
+      double* __restrict__ a = inv + (size_t)warp * 5 * m;    // reciprocal diagonal of U
+      double* __restrict__ b = a + m;                          // first superdiagonal of U
+      double* __restrict__ l = b + m;                          // multipliers
+      double* __restrict__ u2 = l + m;                         // second superdiagonal of U
+      double* __restrict__ pv = u2 + m;                        // pivot flags
+      double* __restrict__ y = Y + sidx;                       // stride nev
       const double lamv = lam[sidx];
-      for (int i = 0; i < m; ++i) { a[i] = d[i] - lamv; b[i] = e[i]; u2[i] = 0.0; pv[i] = 0.0; }
+      double ai = d[0] - lamv, bi = (m > 1) ? e[0] : 0.0;      // row i of the partially eliminated matrix: (ai, bi, 0)
       for (int i = 0; i + 1 < m; ++i) {
-        const double ci = e[i];                  // subdiagonal entry (symmetric)
-        if (fabs(a[i]) >= fabs(ci)) {
-          if (a[i] == 0.0) a[i] = pert;
-          l[i] = ci / a[i];
-          a[i + 1] -= l[i] * b[i];
-        } else {
-          pv[i] = 1.0;
-          const double fact = a[i] / ci;
-          l[i] = fact;
-          const double an = a[i + 1];
-          a[i] = ci;
-          a[i + 1] = b[i] - fact * an;
-          b[i] = an;
-          if (i + 2 < m) { u2[i] = b[i + 1]; b[i + 1] = -fact * b[i + 1]; }
+        const double ci = e[i];                                // subdiagonal entry (symmetric)
+        const double an = d[i + 1] - lamv;                     // row i+1 before elimination: (ci, an, bn)
+        const double bn = (i + 2 < m) ? e[i + 1] : 0.0;
+        if (fabs(ai) >= fabs(ci)) {
+          if (ai == 0.0) ai = pert;
+          const double ri = fast_rcp(ai);
+          const double li = ci * ri;
+          a[i] = ri; b[i] = bi; u2[i] = 0.0; l[i] = li; pv[i] = 0.0;
+          ai = fma(-li, bi, an);
+          bi = bn;
+        } else {                                               // swap rows i and i+1
+          const double ri = fast_rcp(ci);
+          const double fact = ai * ri;
+          a[i] = ri; b[i] = an; u2[i] = bn; l[i] = fact; pv[i] = 1.0;
+          ai = fma(-fact, an, bi);
+          bi = -fact * bn;
         }
       }
-      if (a[m - 1] == 0.0) a[m - 1] = pert;
-      for (int i = 0; i < m; ++i) a[i] = 1.0 / a[i];     // reciprocal pivots: the sweeps below are division-free
+      if (ai == 0.0) ai = pert;
+      a[m - 1] = 1.0 / ai; b[m - 1] = 0.0; u2[m - 1] = 0.0;
       unsigned int rng = 0x9E3779B9u * (unsigned int)(sidx + 1) + 12345u;
       for (int i = 0; i < m; ++i) {
         rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
-        Y[(size_t)i * nev + sidx] = (double)(rng >> 8) * (2.0 / 16777216.0) - 1.0;
+        y[(size_t)i * nev] = (double)(rng >> 8) * (2.0 / 16777216.0) - 1.0;
       }
       for (int it = 0; it < 3; ++it) {
-        for (int i = 0; i + 1 < m; ++i) {
-          const double yi = Y[(size_t)i * nev + sidx], yn = Y[(size_t)(i + 1) * nev + sidx];
-          if (pv[i] != 0.0) {
-            Y[(size_t)i * nev + sidx] = yn;
-            Y[(size_t)(i + 1) * nev + sidx] = yi - l[i] * yn;
-          } else {
-            Y[(size_t)(i + 1) * nev + sidx] = yn - l[i] * yi;
+        double cur = y[0];
+        {
+          // forward substitution with the recorded row swaps; operands of step i+1 are fetched before step i's result
+          double yn = (m > 1) ? y[(size_t)nev] : 0.0, li = l[0], pf = pv[0];
+          for (int i = 0; i + 1 < m; ++i) {
+            const int nx = (i + 2 < m) ? i + 1 : i;
+            const double yn2 = y[(size_t)(nx + 1) * nev], li2 = l[nx], pf2 = pv[nx];
+            const bool sw = pf != 0.0;
+            y[(size_t)i * nev] = sw ? yn : cur;
+            cur = sw ? fma(-li, yn, cur) : fma(-li, cur, yn);
+            yn = yn2; li = li2; pf = pf2;
           }
         }
+        y[(size_t)(m - 1) * nev] = cur;
         double ymax = 0.0, y1 = 0.0, y2 = 0.0;
-        for (int i = m - 1; i >= 0; --i) {
-          double v = Y[(size_t)i * nev + sidx] - b[i] * y1 - u2[i] * y2;     // b[m-1] = u2[m-1] = u2[m-2] = 0
-          v *= a[i];
-          Y[(size_t)i * nev + sidx] = v;
-          y2 = y1;
-          y1 = v;
-          ymax = fmax(ymax, fabs(v));
+        {
+          // back substitution (b[m-1] = u2[m-1] = u2[m-2] = 0), same prefetching
+          double yi = y[(size_t)(m - 1) * nev], bb = b[m - 1], uu = u2[m - 1], aa = a[m - 1];
+          for (int i = m - 1; i >= 0; --i) {
+            const int nx = i > 0 ? i - 1 : 0;
+            const double yi2 = y[(size_t)nx * nev], bb2 = b[nx], uu2 = u2[nx], aa2 = a[nx];
+            const double v = fma(-bb, y1, fma(-uu, y2, yi)) * aa;
+            y[(size_t)i * nev] = v;
+            y2 = y1;
+            y1 = v;
+            ymax = fmax(ymax, fabs(v));
+            yi = yi2; bb = bb2; uu = uu2; aa = aa2;
+          }
         }
         const double sc = ymax > 0.0 ? 1.0 / ymax : 1.0;
-        for (int i = 0; i < m; ++i) Y[(size_t)i * nev + sidx] *= sc;
+        for (int i = 0; i < m; ++i) y[(size_t)i * nev] *= sc;
         // growth of the iterate = 1 / (distance to the eigenvalue): converged once it is huge
         if (it >= 1 && ymax * pert * 1e3 > 1.0) break;
       }
@@ -759,34 +1066,92 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
     }
   }
   __syncthreads();
-  // one thread per vector: norm and Rayleigh quotient  theta = y^T T y / y^T y   (O(m), tridiagonal T)
-  if (tid < nev) {
-    const int c = tid;
-    double nn = 0.0, rq = 0.0, yprev = 0.0;
-    for (int i = 0; i < m; ++i) {
+  // one warp per vector: norm and Rayleigh quotient  theta = y^T T y / y^T y   (O(m), tridiagonal T)
+  for (int c = warp; c < nev; c += nw) {
+    double nn = 0.0, rq = 0.0;
+    for (int i = lane; i < m; i += 32) {
       const double yi = Y[(size_t)i * nev + c];
-      nn += yi * yi;
-      rq += d[i] * yi * yi + ((i > 0) ? 2.0 * e[i - 1] * yprev * yi : 0.0);
-      yprev = yi;
+      const double yp = (i > 0) ? Y[(size_t)(i - 1) * nev + c] : 0.0;
+      nn = fma(yi, yi, nn);
+      rq += yi * fma(d[i], yi, (i > 0) ? 2.0 * e[i - 1] * yp : 0.0);
     }
+    nn = warp_sum(nn);
+    rq = warp_sum(rq);
     const double sc = nn > 0.0 ? rsqrt(nn) : 0.0;
-    if (nn > 0.0) lam[c] = rq / nn;
-    for (int i = 0; i < m; ++i) Y[(size_t)i * nev + c] *= sc;
+    if (lane == 0 && nn > 0.0) lam[c] = rq / nn;
+    for (int i = lane; i < m; i += 32) Y[(size_t)i * nev + c] *= sc;
   }
   __syncthreads();
 
   if (dbg && tid == 0) dbg[4] = clock64();
   // ------------------------------------------------------------------ 4. back-transformation (one warp per eigenvector)
-  for (int c = warp; c < nev; c += nw) {
-    for (int j = m - 3; j >= 0; --j) {
-      const double t = tau[j];
-      if (t == 0.0) continue;
-      const int n = m - j - 1;
-      double dot = 0.0;
-      for (int i = lane; i < n; i += 32) dot += As[(size_t)(j + 1 + i) * lds + j] * Y[(size_t)(j + 1 + i) * nev + c];
-      dot = warp_sum(dot) * t;
-      for (int i = lane; i < n; i += 32) Y[(size_t)(j + 1 + i) * nev + c] -= dot * As[(size_t)(j + 1 + i) * lds + j];
-      __syncwarp();
+  if (m <= 128) {
+    // the vector lives in registers (4 rows per lane); per reflector: one conflict-free column load, a warp sum, an axpy
+    for (int c = warp; c < nev; c += nw) {
+      double y[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = lane + 32 * q;
+        y[q] = (row < m) ? Y[(size_t)row * nev + c] : 0.0;
+      }
+      // reflectors j and j-1 together:  H_{j-1} H_j y = y - tj dj vj - tk (dk - tj dj g) vk  with dj = vj.y, dk = vk.y,
+      // g = vk.vj -- one round of (pipelined) warp sums per pair instead of one per reflector
+      int j = m - 3;
+      for (; j >= 1 && (g_eig_debug & 2) == 0; j -= 2) {
+        const double tj = tau[j], tk = tau[j - 1];
+        double vj[4], vk[4], dj = 0.0, dk = 0.0, g = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = lane + 32 * q;
+          vj[q] = (row > j && row < m) ? As[(size_t)row * lds + j] : 0.0;
+          vk[q] = (row > j - 1 && row < m) ? As[(size_t)row * lds + j - 1] : 0.0;
+          dj = fma(vj[q], y[q], dj);
+          dk = fma(vk[q], y[q], dk);
+          g = fma(vk[q], vj[q], g);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dj += __shfl_xor_sync(0xffffffffu, dj, o);
+          dk += __shfl_xor_sync(0xffffffffu, dk, o);
+          g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        const double cj = tj * dj;
+        const double ck = tk * fma(-cj, g, dk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = fma(-ck, vk[q], fma(-cj, vj[q], y[q]));
+      }
+      for (; j >= 0; --j) {
+        const double t = tau[j];
+        if (t == 0.0) continue;
+        double v[4], dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = lane + 32 * q;
+          v[q] = (row > j && row < m) ? As[(size_t)row * lds + j] : 0.0;
+          dot = fma(v[q], y[q], dot);
+        }
+        dot = warp_sum(dot) * t;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = fma(-dot, v[q], y[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = lane + 32 * q;
+        if (row < m) Y[(size_t)row * nev + c] = y[q];
+      }
+    }
+  } else {
+    for (int c = warp; c < nev; c += nw) {
+      for (int j = m - 3; j >= 0; --j) {
+        const double t = tau[j];
+        if (t == 0.0) continue;
+        const int n = m - j - 1;
+        double dot = 0.0;
+        for (int i = lane; i < n; i += 32) dot += As[(size_t)(j + 1 + i) * lds + j] * Y[(size_t)(j + 1 + i) * nev + c];
+        dot = warp_sum(dot) * t;
+        for (int i = lane; i < n; i += 32) Y[(size_t)(j + 1 + i) * nev + c] -= dot * As[(size_t)(j + 1 + i) * lds + j];
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
@@ -1303,10 +1668,14 @@ int xt_symeig_krylov(const xt_symeig_args* g) {
 int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out, double* scratch,
                   void* stream) {
   // nev extreme eigenpairs of the symmetric m x m matrix T (row-major, fp64, device): w_out[nev] ascending,
-  // S_out (m x nev row-major).  scratch: >= m*(m|1) doubles (used when the matrix does not fit on chip).
+  // S_out (m x nev row-major).  scratch: >= m*(m|1) + 16 doubles (work matrix when it does not fit on chip + phase clocks).
   XT_REQUIRE(T && w_out && S_out && scratch && m >= 1 && m <= 1024 && nev >= 1 && nev <= m && nev <= xt::EIG_THREADS,
              "small_eigh: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (const char* dv = getenv("XT_EIG_DEBUG")) {
+    const int v = atoi(dv);
+    XT_CUDA_OK(cudaMemcpyToSymbol(xt::g_eig_debug, &v, sizeof(int)));
+  }
   const xt::EigPlan pl = xt::eig_plan(m, nev);
   XT_REQUIRE(pl.inv_slots >= 1, "small_eigh: m=%d nev=%d exceeds the on-chip eigensolver", m, nev);
   {
