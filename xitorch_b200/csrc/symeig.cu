@@ -42,8 +42,11 @@ struct EigCtl {
   unsigned int counter;
   unsigned int resmax_bits;   // max |R| of the current iteration (float bits, atomicMax)
   float best_resid;
+  unsigned int bar_count, bar_gen;   // grid barrier of the fused expansion kernel
   int* host_done;       // host-mapped mirror of `done` (lets the host stop launching without draining the stream)
   unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
+  unsigned long long ptrace[64][12]; // fused expansion kernel of iteration i (CTA 0): start and 10 phase stamps
+  unsigned long long barr[4][160];   // iteration 8: per-CTA arrival / release stamps of the two grid barriers
 };
 
 __device__ __forceinline__ void signal_done(EigCtl* ctl) {
@@ -125,6 +128,59 @@ __device__ int chol_inverse_warp(double* Gs, double* Ri, int k) {
     }
   }
   __syncwarp();
+  return 1;
+}
+
+// k x k Cholesky-QR factor entirely in registers (fully unrolled, every lane of the calling warp redundantly):
+// G (row-major, k x k, shared) -> Ri[c*k + r] = (chol(G)^-T)[c][r] as chol_inverse_warp produces it.  rsqrt and
+// multiplications only.  Returns 0 on breakdown.
+template <int KP>
+__device__ __forceinline__ int chol_inverse_regs(const double* Gs, double* Ri, int k) {
+  double L[KP][KP];
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < KP; ++i)
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      L[i][j] = (i < k && j < k) ? Gs[i * k + j] : ((i == j) ? 1.0 : 0.0);       // identity padding
+      if (i == j && i < k) scale = fmax(scale, L[i][j]);
+    }
+  double rd[KP];
+  int ok = 1;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    const double djj = L[j][j];
+    if (j < k && (!(djj > 1e-24 * scale) || !(djj == djj))) ok = 0;
+    const double rs = rsqrt(djj);
+    rd[j] = rs;                                   // 1 / L_jj
+#pragma unroll
+    for (int i = j + 1; i < KP; ++i) L[i][j] *= rs;
+#pragma unroll
+    for (int i = j + 1; i < KP; ++i)
+#pragma unroll
+      for (int c = j + 1; c <= i; ++c) L[i][c] = fma(-L[i][j], L[c][j], L[i][c]);
+  }
+  if (!ok) return 0;
+  // X = L^-1 by forward substitution, column c: X[r][c] (r >= c)
+  double X[KP][KP];
+#pragma unroll
+  for (int c = 0; c < KP; ++c) {
+#pragma unroll
+    for (int r = 0; r < KP; ++r) {
+      if (r < c) { X[r][c] = 0.0; continue; }
+      double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = c; t < r; ++t) sacc = fma(-L[r][t], X[t][c], sacc);
+      X[r][c] = sacc * rd[r];
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < KP; ++c)
+#pragma unroll
+      for (int r = 0; r < KP; ++r)
+        if (c < k && r < k) Ri[c * k + r] = X[r][c];
+  }
   return 1;
 }
 
@@ -384,6 +440,414 @@ ritz_kernel(const TV* __restrict__ V, const TV* __restrict__ AV, int n, int k, i
       __threadfence();
     }
   }
+}
+
+// ---------------------------------------------------------------------------- fused expansion step
+// Everything between two block matvecs in ONE cooperative launch (Krylov expansion):
+//   P0  (optional) the Ritz check that is due: X = V S, R = AV S - X theta, max|R|      [was ritz_kernel]
+//   P1  C  = V^T W                          new block column of T                        [was memset + subproj_kernel]
+//   --- grid barrier ---   stop test / best-pair bookkeeping, T[:, new] = C               [was ritz last-CTA, t_update_kernel]
+//   P2  W' = W - V C;  C2 = V^T W';  G = W'^T W'                                          [was 2 memsets + subproj_kernel]
+//   --- grid barrier ---
+//   P3  Q = (W' - V C2) chol(G)^-T  -> next basis block                                   [was orth_finish_kernel]
+// CTA c owns rows [c R, (c+1) R) in every phase, so its slice of the basis is staged into shared memory once and W',
+// W'' never leave the chip.  Cross-CTA sums are fp64 atomics + a grid barrier (all CTAs co-resident: cooperative launch,
+// one CTA per SM on the SMs the matvec uses).
+constexpr int PO_THREADS = 512;
+constexpr int PO_NCOPY = 8;        // accumulator copies (CTA c adds into copy c % 8): spreads the atomics over 8x more L2 addresses
+
+struct PostArgs {
+  const void* V; const void* AV; const void* W; void* Qout;
+  int n, k, m, R;
+  double* acc;                                // [2][PO_NCOPY][acc_stride]: set 0 = C, set 1 = C2 with the Gram matrix as rows m..m+k-1
+  int acc_stride;
+  double* T; int ldt;
+  EigCtl* ctl;
+  int iter;
+  int rz_m, rz_iter, rz_ld, rz_coff;          // pending Ritz check (rz_m == 0: none)
+  const double* rz_S; const double* rz_theta;
+  void* Xslots; double* evals_slots; float min_eps;
+};
+
+// sense-reversing grid barrier; returns false (after raising `done`) if the other CTAs never arrive
+__device__ __forceinline__ bool grid_barrier(EigCtl* ctl, unsigned int nblocks, unsigned long long* tin = nullptr,
+                                             unsigned long long* tout = nullptr) {
+  __shared__ int ok_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ok = 1;
+    if (tin) tin[blockIdx.x] = gtimer();
+    const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&ctl->bar_gen);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if (atomicAdd(&ctl->bar_count, 1u) == nblocks - 1) {
+      ctl->bar_count = 0;
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      atomicAdd(&ctl->bar_gen, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned int*>(&ctl->bar_gen) == gen) {
+        if (clock64() - t0 > 1500000000LL) { ok = 0; break; }      // ~0.8 s: never hang the device
+      }
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if (tout) tout[blockIdx.x] = gtimer();
+    if (!ok) { ctl->breakdown = 2; ctl->local_done = 1; signal_done(ctl); }
+    ok_s = ok;
+  }
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// k values of one staged basis row -> double registers (vector loads when the row is full width)
+template <typename TV, int KP>
+__device__ __forceinline__ void po_load_row(const TV* p, int k, double (&v)[KP]) {
+  if (k == KP) {
+    if constexpr (sizeof(TV) == 4 && KP % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < KP / 4; ++q) {
+        const float4 f = reinterpret_cast<const float4*>(p)[q];
+        v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+      }
+      return;
+    } else if constexpr (sizeof(TV) == 8 && KP % 2 == 0) {
+#pragma unroll
+      for (int q = 0; q < KP / 2; ++q) {
+        const double2 f = reinterpret_cast<const double2*>(p)[q];
+        v[2 * q] = f.x; v[2 * q + 1] = f.y;
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KP; ++i) v[i] = (i < k) ? (double)p[i] : 0.0;
+}
+
+// rows [row0, row0+rows) of blocks [0, nb) of a block-layout array ([block][n][k]) -> dst[(b * R + r) * k + i]
+template <typename TV>
+__device__ __forceinline__ void po_stage(TV* dst, const TV* __restrict__ src, int n, int k, int row0, int rows, int R,
+                                         int nb) {
+  const int tid = threadIdx.x;
+  const int cnt = rows * k;
+  const int bytes = cnt * (int)sizeof(TV);
+  for (int b = 0; b < nb; ++b) {
+    const TV* g = src + ((int64_t)b * n + row0) * k;
+    TV* d = dst + (size_t)b * R * k;
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+      const int nv = bytes >> 4;
+      for (int i = tid; i < nv; i += PO_THREADS)
+        cp_async16(reinterpret_cast<char*>(d) + 16 * i, reinterpret_cast<const char*>(g) + 16 * i);
+      const int done = (nv << 4) / (int)sizeof(TV);
+      for (int i = done + tid; i < cnt; i += PO_THREADS) d[i] = g[i];
+    } else {
+      for (int i = tid; i < cnt; i += PO_THREADS) d[i] = g[i];
+    }
+  }
+}
+
+// Cout[iv][j] += sum_r V[r][iv] Z[r][j] for the m basis vectors and, when `gram` is set, for the k columns of Z itself
+// (rows m .. m+k-1 of Cout then hold the Gram matrix Z^T Z).  This CTA's rows; fp64 atomics.
+template <typename TV, int KP>
+__device__ __forceinline__ void po_project(const TV* Vs, const double* Zs, int rows, int R, int k, int m, bool gram,
+                                           double* part, double* Cout) {
+  const int tid = threadIdx.x;
+  const int mt = gram ? m + k : m;
+  const int nsplit = (4 * mt <= PO_THREADS) ? 4 : ((2 * mt <= PO_THREADS) ? 2 : 1);   // row groups (thread count permitting)
+  const int half = (rows + nsplit - 1) / nsplit;
+  for (int e0 = 0; e0 < mt * nsplit; e0 += PO_THREADS) {
+    const int e = e0 + tid;
+    const bool act = e < mt * nsplit;
+    const int h = act ? e / mt : 0;
+    const int iv = act ? e - h * mt : 0;
+    const int r0 = h * half, r1 = min(rows, r0 + half);
+    double acc[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acc[j] = 0.0;
+    if (act) {
+      if (iv < m) {
+        const int b = iv / k, i = iv - b * k;
+        const TV* vcol = Vs + (size_t)b * R * k + i;
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          const double v = (double)vcol[(size_t)r * k];
+          const double* z = Zs + (size_t)r * KP;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) acc[j] = fma(v, z[j], acc[j]);
+        }
+      } else {
+        const int i = iv - m;
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          const double* z = Zs + (size_t)r * KP;
+          const double v = z[i];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) acc[j] = fma(v, z[j], acc[j]);
+        }
+      }
+    }
+    if (nsplit > 1) {
+      if (act && h > 0) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) part[((size_t)(h - 1) * mt + iv) * KP + j] = acc[j];
+      }
+      __syncthreads();
+      if (act && h == 0) {
+        for (int g = 0; g < nsplit - 1; ++g) {
+#pragma unroll
+          for (int j = 0; j < KP; ++j) acc[j] += part[((size_t)g * mt + iv) * KP + j];
+        }
+      }
+      __syncthreads();
+    }
+    if (act && h == 0) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (j < k) atomicAdd(&Cout[(size_t)iv * k + j], acc[j]);
+    }
+  }
+}
+
+// Z[r][:] -= sum_iv V[r][iv] Cs[iv][:]    (Cs: [m][KP] in shared memory)
+template <typename TV, int KP>
+__device__ __forceinline__ void po_subtract(const TV* Vs, const double* Cs, double* Zs, int rows, int R, int k,
+                                            int nblk, int skip = 0) {
+  // `skip` leading threads do not take part (they are busy elsewhere)
+  constexpr int NS = KP >= 8 ? 4 : 2;
+  constexpr int JW = KP / NS;
+  if ((int)threadIdx.x < skip) return;
+  for (int e = threadIdx.x - skip; e < rows * NS; e += PO_THREADS - skip) {
+    const int r = e / NS, sl = e - r * NS;
+    double acc[JW];
+#pragma unroll
+    for (int j = 0; j < JW; ++j) acc[j] = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      double v[KP];
+      po_load_row<TV, KP>(Vs + ((size_t)b * R + r) * k, k, v);
+      const double* cb = Cs + (size_t)b * k * KP + sl * JW;
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        if (i < k) {
+#pragma unroll
+          for (int j = 0; j < JW; ++j) acc[j] = fma(v[i], cb[i * KP + j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < JW; ++j) Zs[(size_t)r * KP + sl * JW + j] -= acc[j];
+  }
+}
+
+template <typename TV, int KP>
+__global__ void __launch_bounds__(PO_THREADS)
+expand_fused_kernel(const PostArgs p) {
+  EigCtl* ctl = p.ctl;
+  if (ctl->done) return;                 // written only by earlier launches of this stream: uniform over the grid
+  extern __shared__ __align__(16) unsigned char po_raw[];
+  const int tid = threadIdx.x;
+  const int n = p.n, k = p.k, m = p.m, R = p.R;
+  const int nblk = m / k, rz_nblk = p.rz_m / k;
+  const int row0 = blockIdx.x * R;
+  const int rows = max(0, min(R, n - row0));
+  const bool last_cta = (blockIdx.x == gridDim.x - 1);
+  double* Zs = reinterpret_cast<double*>(po_raw);              // [R][KP]   W, W', W'' rows of this CTA
+  double* Cs = Zs + (size_t)R * KP;                            // [m][KP]   S / C / C2
+  double* part = Cs + (size_t)m * KP;                          // [3][m + k][KP]
+  double* Gs = part + (size_t)3 * (m + KP) * KP;               // [k][k]
+  double* Ri = Gs + KP * KP;                                   // [k][k]
+  TV* Vs = reinterpret_cast<TV*>(Ri + KP * KP);                // [nblk][R][k]
+  TV* AVs = Vs + (size_t)nblk * R * k;                         // [rz_nblk][R][k]
+  __shared__ float redmax[32];
+  __shared__ int chol_ok;
+  const TV* V = static_cast<const TV*>(p.V);
+  const TV* W = static_cast<const TV*>(p.W);
+
+  const bool tr = (blockIdx.x == 0 && tid == 0 && p.iter < 64);
+  if (tr) ctl->ptrace[p.iter][0] = gtimer();
+  po_stage<TV>(Vs, V, n, k, row0, rows, R, nblk);
+  if (rz_nblk > 0) po_stage<TV>(AVs, static_cast<const TV*>(p.AV), n, k, row0, rows, R, rz_nblk);
+  for (int e = tid; e < R * KP; e += PO_THREADS) {
+    const int r = e / KP, j = e - r * KP;
+    Zs[e] = (r < rows && j < k) ? (double)W[((int64_t)row0 + r) * k + j] : 0.0;
+  }
+  const int slot = 1 - ctl->best_slot;
+  if (rz_nblk > 0) {
+    for (int e = tid; e < p.rz_m * KP; e += PO_THREADS) {
+      const int i = e / KP, j = e - i * KP;
+      Cs[e] = (j < k) ? p.rz_S[(size_t)i * p.rz_ld + p.rz_coff + j] : 0.0;
+    }
+  }
+  double* accC = p.acc + (size_t)(blockIdx.x % PO_NCOPY) * p.acc_stride;                  // this CTA's copy of set 0
+  double* accC2 = p.acc + (size_t)(PO_NCOPY + blockIdx.x % PO_NCOPY) * p.acc_stride;      // ... of set 1
+  {                                      // clear set 1 (the previous launch is done with it), all CTAs share the work
+    double* set1 = p.acc + (size_t)PO_NCOPY * p.acc_stride;
+    const int tot = PO_NCOPY * p.acc_stride;
+    for (int e = blockIdx.x * PO_THREADS + tid; e < tot; e += gridDim.x * PO_THREADS) set1[e] = 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (tr) ctl->ptrace[p.iter][1] = gtimer();
+
+  // ---- P0: the Ritz check that is due (lagged: its Rayleigh-Ritz ran on a side stream meanwhile)
+  if (rz_nblk > 0) {
+    constexpr int NS = KP >= 8 ? 4 : 2;
+    constexpr int JW = KP / NS;
+    const double* theta = p.rz_theta + p.rz_coff;
+    TV* X = static_cast<TV*>(p.Xslots) + (int64_t)slot * n * k;
+    float lmax = 0.f;
+    for (int e = tid; e < rows * NS; e += PO_THREADS) {
+      const int r = e / NS, sl = e - r * NS;
+      double x[JW], ax[JW];
+#pragma unroll
+      for (int j = 0; j < JW; ++j) { x[j] = 0.0; ax[j] = 0.0; }
+      for (int b = 0; b < rz_nblk; ++b) {
+        double v[KP], av[KP];
+        po_load_row<TV, KP>(Vs + ((size_t)b * R + r) * k, k, v);
+        po_load_row<TV, KP>(AVs + ((size_t)b * R + r) * k, k, av);
+        const double* cb = Cs + (size_t)b * k * KP + sl * JW;
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          if (i < k) {
+#pragma unroll
+            for (int j = 0; j < JW; ++j) {
+              const double sv = cb[i * KP + j];
+              x[j] = fma(v[i], sv, x[j]);
+              ax[j] = fma(av[i], sv, ax[j]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < JW; ++j) {
+        const int col = sl * JW + j;
+        if (col < k) {
+          const double res = ax[j] - x[j] * theta[col];
+          X[((int64_t)row0 + r) * k + col] = (TV)x[j];
+          lmax = fmaxf(lmax, fabsf((float)res));
+          if (!(res == res)) lmax = INFINITY;
+        }
+      }
+    }
+    lmax = block_max(lmax, redmax);
+    if (tid == 0) atomicMax(&ctl->resmax_bits, __float_as_uint(lmax));
+    __syncthreads();                     // Cs is reused below
+  }
+
+  if (tr) ctl->ptrace[p.iter][2] = gtimer();
+  // ---- P1: C = V^T W
+  po_project<TV, KP>(Vs, Zs, rows, R, k, m, false, part, accC);
+  if (tr) ctl->ptrace[p.iter][3] = gtimer();
+  const bool btr = (p.iter == 8 && gridDim.x <= 160);
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr)) return;
+  if (tr) ctl->ptrace[p.iter][4] = gtimer();
+
+  if (rz_nblk > 0 && last_cta && tid == 0) {
+    // the reference's bookkeeping (symeig.py:196-201): best pair (slot flip) and the stop test
+    const float rmax = __uint_as_float(atomicAdd(&ctl->resmax_bits, 0u));
+    ctl->niter = p.rz_iter;
+    for (int j = 0; j < k; ++j) p.evals_slots[slot * SE_MAXK + j] = p.rz_theta[p.rz_coff + j];
+    if (rmax < ctl->best_resid) {
+      ctl->best_resid = rmax;
+      ctl->best_slot = slot;
+    }
+    if (rmax < p.min_eps) {
+      ctl->converged = 1;
+      ctl->local_done = 1;
+      if (!ctl->collective) signal_done(ctl);
+    }
+    ctl->resmax_bits = 0;
+    if (p.rz_iter < 64) ctl->trace[p.rz_iter][3] = gtimer();
+    __threadfence();
+  }
+
+  // ---- P2: W' = W - V C;  C2 = V^T W';  G = W'^T W';  T[:, new block] = C
+  for (int e = tid; e < m * KP; e += PO_THREADS) {
+    const int i = e / KP, j = e - i * KP;
+    double v = 0.0;
+    if (j < k) {
+#pragma unroll
+      for (int c = 0; c < PO_NCOPY; ++c) v += __ldcg(&p.acc[(size_t)c * p.acc_stride + (size_t)i * k + j]);
+    }
+    Cs[e] = v;
+  }
+  __syncthreads();
+  po_subtract<TV, KP>(Vs, Cs, Zs, rows, R, k, nblk);
+  if (last_cta) {
+    const int c0 = m - k;
+    for (int e = tid; e < m * k; e += PO_THREADS) {
+      const int i = e / k, j = e - i * k;
+      double v = Cs[(size_t)i * KP + j];
+      if (i >= c0) v = 0.5 * (v + Cs[(size_t)(c0 + j) * KP + (i - c0)]);     // symmetrise the diagonal block
+      p.T[(int64_t)i * p.ldt + c0 + j] = v;
+      p.T[(int64_t)(c0 + j) * p.ldt + i] = v;
+    }
+  }
+  __syncthreads();
+  if (tr) ctl->ptrace[p.iter][5] = gtimer();
+  po_project<TV, KP>(Vs, Zs, rows, R, k, m, true, part, accC2);
+  if (tr) ctl->ptrace[p.iter][6] = gtimer();
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr)) return;
+  if (tr) ctl->ptrace[p.iter][7] = gtimer();
+
+  // ---- P3: Q = (W' - V C2) Rinv
+  {
+    const double* set1 = p.acc + (size_t)PO_NCOPY * p.acc_stride;
+    for (int e = tid; e < m * KP; e += PO_THREADS) {
+      const int i = e / KP, j = e - i * KP;
+      double v = 0.0;
+      if (j < k) {
+#pragma unroll
+        for (int c = 0; c < PO_NCOPY; ++c) v += __ldcg(&set1[(size_t)c * p.acc_stride + (size_t)i * k + j]);
+      }
+      Cs[e] = v;
+    }
+    for (int e = tid; e < k * k; e += PO_THREADS) {
+      const int i = e / k, j = e - i * k;
+      // |W' - V C2|^2 = G - C2^T C2 with C2 at rounding level after the first projection: the correction is skipped
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < PO_NCOPY; ++c)
+        v += __ldcg(&set1[(size_t)c * p.acc_stride + (size_t)(m + i) * k + j]) +
+             __ldcg(&set1[(size_t)c * p.acc_stride + (size_t)(m + j) * k + i]);
+      Gs[e] = 0.5 * v;
+    }
+    // every CTA has read set 0 (before the second barrier): clear it for the next launch
+    const int tot = PO_NCOPY * p.acc_stride;
+    for (int e = blockIdx.x * PO_THREADS + tid; e < tot; e += gridDim.x * PO_THREADS) p.acc[e] = 0.0;
+  }
+  __syncthreads();
+  if (tr) ctl->ptrace[p.iter][8] = gtimer();
+  if (tid < 32) {
+    int ok;
+    if constexpr (KP <= 8) ok = chol_inverse_regs<KP>(Gs, Ri, k);      // 16 x 16 does not fit the register file
+    else ok = chol_inverse_warp(Gs, Ri, k);
+    if (tid == 0) chol_ok = ok;
+  }
+  po_subtract<TV, KP>(Vs, Cs, Zs, rows, R, k, nblk, 32);       // warps 1.. while warp 0 factorises
+  __syncthreads();
+  if (tr) ctl->ptrace[p.iter][9] = gtimer();
+  TV* Q = static_cast<TV*>(p.Qout);
+  if (chol_ok) {
+    for (int e = tid; e < rows * k; e += PO_THREADS) {
+      const int r = e / k, j = e - r * k;
+      double acc = 0.0;
+      for (int i = 0; i <= j; ++i) acc = fma(Zs[(size_t)r * KP + i], Ri[i * k + j], acc);
+      Q[(int64_t)row0 * k + e] = (TV)acc;
+    }
+  } else {
+    // breakdown: stop (a zero block keeps later kernels well defined)
+    for (int e = tid; e < rows * k; e += PO_THREADS) Q[(int64_t)row0 * k + e] = TV(0);
+    if (last_cta && tid == 0) {
+      ctl->breakdown = 1;
+      ctl->local_done = 1;
+      if (!ctl->collective) signal_done(ctl);
+    }
+  }
+  if (tr) ctl->ptrace[p.iter][10] = gtimer();
+}
+
+constexpr int PO_SMEM_MAX = 200 * 1024;
+static size_t po_smem_bytes(size_t vs, int KP, int R, int k, int m, int rz_m) {
+  return ((size_t)R * KP + (size_t)(4 * m + 3 * KP) * KP + (size_t)2 * KP * KP) * sizeof(double) +
+         ((size_t)m + rz_m) * R * vs + 32;
 }
 
 // Out[:, 0..p) = In(:, 0..m) * Sr   (thick restart: rotate the basis onto the p kept Ritz vectors; Sr is m x p)
@@ -1284,10 +1748,12 @@ __global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int
 
 __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
   ctl->host_done = host_done;
-  for (int i = 0; i < 64; ++i) for (int q = 0; q < 4; ++q) ctl->trace[i][q] = 0ull;
+  for (int i = 0; i < 64; ++i) { for (int q = 0; q < 4; ++q) ctl->trace[i][q] = 0ull; for (int q = 0; q < 12; ++q) ctl->ptrace[i][q] = 0ull; }
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
+  ctl->bar_count = 0; ctl->bar_gen = 0;
+  for (int q = 0; q < 4; ++q) for (int c = 0; c < 160; ++c) ctl->barr[q][c] = 0ull;
   ctl->trace[0][0] = gtimer();
 }
 
@@ -1297,6 +1763,7 @@ struct EigWs {
   double *T, *Tw, *Sk, *theta, *C, *C2, *G, *Rinv, *evals_slots;
   double *SkB, *thetaB, *CB;      // second and third slot for the overlapped Rayleigh-Ritz
   double *SkC, *thetaC, *CC, *TwB;
+  double* Pacc;                   // accumulators of the fused expansion kernel
   EigCtl* ctl;
 };
 
@@ -1325,6 +1792,7 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
   W.G = ar.take<double>(2 * SE_MAXK * SE_MAXK);
   W.Rinv = ar.take<double>(SE_MAXK * SE_MAXK);
   W.evals_slots = ar.take<double>(2 * SE_MAXK);
+  W.Pacc = ar.take<double>((size_t)2 * PO_NCOPY * (size_t)(mb + SE_MAXK) * k);
   W.ctl = ar.take<EigCtl>(1);
   return ar.ok();
 }
@@ -1374,8 +1842,26 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     XT_CUDA_OK(cudaFuncSetAttribute(ritz_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(subproj_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(orth_finish_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
     attrs_set = true;
   }
+  // fused expansion step (one cooperative launch per iteration instead of ~8 stream operations): Krylov expansion on
+  // one GPU, whenever this CTA's slice of the basis fits in shared memory
+  int coop = 0;
+  {
+    int dev = 0;
+    XT_CUDA_OK(cudaGetDevice(&dev));
+    XT_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  }
+  const int KP = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
+  const int po_gmax = num_sms() > 8 ? num_sms() - 2 : num_sms();      // the SMs the matvec uses
+  const int po_R = (n + po_gmax - 1) / po_gmax;
+  const int po_grid = (n + po_R - 1) / po_R;
+  const void* po_fn = KP == 4 ? (const void*)expand_fused_kernel<TV, 4>
+                              : (KP == 8 ? (const void*)expand_fused_kernel<TV, 8> : (const void*)expand_fused_kernel<TV, 16>);
+  const bool fuse_enabled = coop != 0 && !collective && g->expansion == 1 && num_sms() > 8 && getenv("XT_NO_FUSE") == nullptr;
 
   int64_t napply = 0;
   int all_conv = 1;
@@ -1456,6 +1942,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     struct Pending { bool valid; int par, m, iter, nev, coff; };
     Pending pendq[2] = {{false, 0, 0, 0, 0, 0}, {false, 0, 0, 0, 0, 0}};     // [0] = older
     bool ev_used[NSLOT] = {false, false, false};
+    bool c_zero = false;        // W.C is known to be all zeros (left so by the fused expansion kernel)
     auto launch_ritz = [&](int par_, int m_, int iter_, int nev_, int coff_) -> int {
       if (overlap) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par_], 0));
       ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(V, AV, n, k, m_, Skpar[par_], nev_, coff_, thpar[par_],
@@ -1513,6 +2000,59 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         typedef void (*gather_fn)(void*, void*, int64_t, int32_t, void*);
         reinterpret_cast<gather_fn>(g->allgather)(g->allgather_user, Wg, per, (int32_t)sizeof(TV), g->stream);
         unpack_gathered_kernel<TV><<<num_sms(), 256, 0, st>>>(Wg, world, n_local, k, AV + j * blk, W.ctl); XT_LAUNCHED();
+      }
+      {
+        const bool can_expand_f = (iter < g->max_niter) && (m + k <= n);
+        const bool restart_f = can_expand_f && (m + k > mb);
+        if (fuse_enabled && overlap && can_expand_f && !restart_f) {
+          // the Ritz check that is due now (two iterations old) rides along when its AV slice fits as well
+          bool have_rz = pendq[1].valid;
+          size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0);
+          if (have_rz && po_smem > (size_t)PO_SMEM_MAX) {
+            rc = flush_pending(1);
+            if (rc != XT_OK) return rc;
+            have_rz = false;
+            po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, 0);
+          }
+          if (po_smem <= (size_t)PO_SMEM_MAX) {
+            PostArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.V = V; pa.AV = AV; pa.W = AV + j * blk; pa.Qout = V + (int64_t)(m / k) * blk;
+            pa.n = n; pa.k = k; pa.m = m; pa.R = po_R;
+            pa.acc = W.Pacc; pa.acc_stride = (mb + SE_MAXK) * k; pa.T = W.T; pa.ldt = mb;
+            pa.ctl = W.ctl; pa.iter = iter;
+            pa.Xslots = Xslots; pa.evals_slots = W.evals_slots; pa.min_eps = (float)g->min_eps;
+            if (have_rz) {
+              const Pending& q = pendq[0];
+              XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q.par], 0));
+              pa.rz_m = q.m; pa.rz_iter = q.iter; pa.rz_ld = q.nev; pa.rz_coff = q.coff;
+              pa.rz_S = Skpar[q.par]; pa.rz_theta = thpar[q.par];
+            }
+            if (!c_zero) XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)PO_NCOPY * (mb + SE_MAXK) * k, st));
+            void* kargs[1] = {&pa};
+            XT_CUDA_OK(cudaLaunchCooperativeKernel(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, po_smem, st));
+            XT_LAUNCHED();
+            c_zero = true;                           // the kernel leaves C cleared for the next launch
+            if (have_rz) { pendq[0] = pendq[1]; pendq[1].valid = false; }
+            // Rayleigh-Ritz of this iteration on a side stream (T was updated inside the kernel)
+            const EigPlan plf = eig_plan(m, k);
+            XT_REQUIRE(plf.inv_slots >= 1, "symeig: projected problem %d x %d exceeds the on-chip eigensolver", m, m);
+            cudaStream_t rsf = side[iter & 1];
+            XT_CUDA_OK(cudaEventRecord(evC[par], st));
+            XT_CUDA_OK(cudaStreamWaitEvent(rsf, evC[par], 0));
+            rr_kernel<<<1, EIG_THREADS, plf.smem_bytes, rsf>>>(W.T, mb, nullptr, m, k, k, Twpar[iter & 1], Skpar[par],
+                                                               thpar[par], g->mode, plf.lds, plf.as_in_smem,
+                                                               plf.y_in_smem, plf.inv_slots, W.ctl, iter); XT_LAUNCHED();
+            XT_CUDA_OK(cudaEventRecord(evR[par], rsf));
+            ev_used[par] = true;
+            Pending pn = {true, par, m, iter, k, 0};
+            if (!pendq[0].valid) pendq[0] = pn; else pendq[1] = pn;
+            m += k;
+            XT_CUDA_OK(cudaEventRecord(pool.it[iter % (LOOKAHEAD + 1)], st));
+            XT_CUDA_OK(cudaGetLastError());
+            continue;
+          }
+        }
       }
       // 2. C = V^T W  (new block column of T)
       if (overlap && ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));   // rr of iteration iter-3 is done with C[par]
@@ -1622,10 +2162,26 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       fprintf(stderr, "xt-trace device span %.1f us, host span %.1f us, %d iterations enqueued\n",
               (h.trace[0][1] - t0) * 1e-3,
               std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count(), iter);
+      for (int q = 0; q < 4; ++q) {
+        unsigned long long lo = ~0ull, hi = 0; int ilo = -1, ihi = -1;
+        for (int c = 0; c < 160; ++c) if (h.barr[q][c]) {
+          if (h.barr[q][c] < lo) { lo = h.barr[q][c]; ilo = c; }
+          if (h.barr[q][c] > hi) { hi = h.barr[q][c]; ihi = c; }
+        }
+        if (ilo >= 0) fprintf(stderr, "xt-trace barrier %d %s: first %.1f us (cta %d), last %.1f us (cta %d) after the kernel start\n", q / 2,
+                              (q & 1) ? "release" : "arrival", (lo - h.ptrace[8][0]) * 1e-3, ilo, (hi - h.ptrace[8][0]) * 1e-3, ihi);
+      }
       for (int i = 1; i < 64 && i <= iter; ++i)
-        fprintf(stderr, "xt-trace iter %2d: rr %8.1f .. %8.1f us   ritz %8.1f .. %8.1f us\n", i,
+      {
+        fprintf(stderr, "xt-trace iter %2d: rr %8.1f .. %8.1f us   ritz %8.1f .. %8.1f us   expand %8.1f |", i,
                 h.trace[i][0] ? (h.trace[i][0] - t0) * 1e-3 : -1.0, h.trace[i][1] ? (h.trace[i][1] - t0) * 1e-3 : -1.0,
-                h.trace[i][2] ? (h.trace[i][2] - t0) * 1e-3 : -1.0, h.trace[i][3] ? (h.trace[i][3] - t0) * 1e-3 : -1.0);
+                h.trace[i][2] ? (h.trace[i][2] - t0) * 1e-3 : -1.0, h.trace[i][3] ? (h.trace[i][3] - t0) * 1e-3 : -1.0,
+                h.ptrace[i][0] ? (h.ptrace[i][0] - t0) * 1e-3 : -1.0);
+        // stage | P0 | project | barrier | load C + subtract | project + gram | barrier | load C2 | chol + subtract | store
+        for (int q = 1; q <= 10; ++q)
+          fprintf(stderr, " %5.1f", h.ptrace[i][q] ? (h.ptrace[i][q] - h.ptrace[i][q - 1]) * 1e-3 : -1.0);
+        fprintf(stderr, " us\n");
+      }
     }
     if (!h.converged) all_conv = 0;
     if (h.best_resid > worst_resid || !(h.best_resid == h.best_resid)) worst_resid = h.best_resid;
