@@ -115,6 +115,14 @@ typedef struct {
   int64_t* napply_out;                        /* host, may be NULL: number of block operator applications */
   void* workspace; size_t workspace_bytes;
   void* stream;
+  /* matrix-free operator (reference: any LinearOperator whose _mv is user code, e.g. the autograd Jacobian of
+   * xitorch/grad/jachess.py:98-208 that the rootfinder backward solves with, xitorch/optimize/rootfinder.py:346-348).
+   * When `apply` is non-NULL, A / M / E are ignored and every operator application calls
+   *     apply(apply_user, X, Y, stream):   Y = Op(X)   for X, Y contiguous (nbatch, n, ncols) device blocks inside
+   * the workspace, ordered on `stream`.  The solver loop (all vector updates, dot products, the stop test) still
+   * runs in the library's kernels; only the operator is the caller's. */
+  void* apply;
+  void* apply_user;
 } xt_solve_args;
 
 size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, int32_t nbatch,

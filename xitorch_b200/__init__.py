@@ -15,5 +15,6 @@ from xitorch_b200.linop import LinearOperator, MatrixLinearOperator   # noqa: F4
 from xitorch_b200._utils import ConvergenceWarning, MathWarning        # noqa: F401
 from xitorch_b200.debug import is_debug_enabled, set_debug_mode, enable_debug, disable_debug  # noqa: F401
 from xitorch_b200 import linalg                                        # noqa: F401
+from xitorch_b200 import optimize, grad                                # noqa: F401
 
 __version__ = "0.1.0"

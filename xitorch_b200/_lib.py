@@ -53,7 +53,12 @@ class SolveArgs(C.Structure):
         ("best_resid_out", C.POINTER(C.c_double)), ("napply_out", C.POINTER(C.c_int64)),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("stream", C.c_void_p),
+        ("apply", C.c_void_p), ("apply_user", C.c_void_p),
     ]
+
+
+# matrix-free operator callback of xt_solve_args: apply(user, X, Y, stream)
+APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class SymeigArgs(C.Structure):

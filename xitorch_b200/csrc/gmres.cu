@@ -288,6 +288,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
     return XT_ERR_WORKSPACE;
   }
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, nullptr, 0, 0, nullptr, 0};
+  op.apply = g->apply; op.apply_user = g->apply_user;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem_init = (size_t)(2 * g->ncols + 2 * SV_THREADS + 64) * sizeof(double);
   const size_t smem_step =
@@ -348,7 +349,7 @@ extern "C" int xt_gmres(const xt_solve_args* g) {
   XT_REQUIRE(g != nullptr, "gmres: null args");
   XT_REQUIRE(g->n >= 1 && g->nbatch >= 1 && g->ncols >= 1, "gmres: empty problem");
   XT_REQUIRE(g->ncols <= 32 * xt::SV_MAXCS, "gmres: ncols=%d exceeds %d", g->ncols, 32 * xt::SV_MAXCS);
-  XT_REQUIRE(g->A && g->B && g->X && g->workspace, "gmres: null pointer");
+  XT_REQUIRE((g->A || g->apply) && g->B && g->X && g->workspace, "gmres: null pointer");
   XT_REQUIRE(g->E == nullptr && g->M == nullptr, "gmres: E / M are not supported (as in the reference method)");
   return g->dtype == XT_F64 ? xt::run_gmres<double>(g) : xt::run_gmres<float>(g);
 }

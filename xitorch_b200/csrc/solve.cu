@@ -377,7 +377,7 @@ static int check_solve_args(const xt_solve_args* g) {
   XT_REQUIRE(g != nullptr, "solve: null args");
   XT_REQUIRE(g->n >= 1 && g->nbatch >= 1 && g->ncols >= 1, "solve: empty problem");
   XT_REQUIRE(g->ncols <= 32 * SV_MAXCS, "solve: ncols=%d exceeds %d", g->ncols, 32 * SV_MAXCS);
-  XT_REQUIRE(g->A && g->B && g->X && g->workspace, "solve: null pointer");
+  XT_REQUIRE((g->A || g->apply) && g->B && g->X && g->workspace, "solve: null pointer");
   XT_REQUIRE(g->max_niter >= 0, "solve: negative max_niter");
   XT_REQUIRE(g->M == nullptr || g->E != nullptr, "solve: M without E");
   return XT_OK;
@@ -411,6 +411,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
+  op.apply = g->apply; op.apply_user = g->apply_user;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0); XT_LAUNCHED();
@@ -452,6 +453,7 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
+  op.apply = g->apply; op.apply_user = g->apply_user;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1); XT_LAUNCHED();

@@ -88,13 +88,64 @@ struct OpDesc {
   const void* A; int64_t lda, a_bstride;
   const void* M; int64_t ldm, m_bstride;
   const void* E; int64_t e_bstride;
+  void* apply = nullptr;        // matrix-free operator callback (xt_solve_args.apply)
+  void* apply_user = nullptr;
 };
+
+typedef void (*xt_apply_fn)(void* user, const void* X, void* Y, void* stream);
+
+// per-tile partial dot products of a matrix-free operator application, in the layout the block matvec produces:
+//   dots[group][tile][0][c] = sum_rows U Y,  dots[group][tile][1][c] = sum_rows Y^2      (one CTA per tile)
+template <typename TV>
+__global__ void __launch_bounds__(256)
+tile_dots_kernel(const TV* __restrict__ U, const TV* __restrict__ Y, int n, int ncols, int tile_rows,
+                 int tiles_per_batch, double* __restrict__ dots, int64_t dots_gstride, const int* done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  __shared__ double red[2][8];
+  const int tile = blockIdx.x;
+  const int b = tile / tiles_per_batch;
+  const int row0 = (tile - b * tiles_per_batch) * tile_rows;
+  const int rows = min(tile_rows, n - row0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)b * n + row0) * ncols;
+  for (int c = 0; c < ncols; ++c) {
+    double d0 = 0.0, d1 = 0.0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+      const double y = (double)Y[base + (int64_t)r * ncols + c];
+      d1 += y * y;
+      if (U != nullptr) d0 += (double)U[base + (int64_t)r * ncols + c] * y;
+    }
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = d0; red[1][warp] = d1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+      dots[(int64_t)(c / MV_MAXK) * dots_gstride + ((size_t)tile * 2 + threadIdx.x) * MV_MAXK + (c % MV_MAXK)] = s;
+    }
+  }
+}
 
 // Y = A X - (M X) E  (+ fused dots with U on the A pass); `mx` is scratch for M X
 template <typename TV>
 static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const TV* U, double* dots, int64_t dots_gstride,
                     const int* done_flag, cudaStream_t st, int64_t* napply) {
   const int64_t len = (int64_t)op.n * op.ncols;
+  if (op.apply != nullptr) {
+    // matrix-free operator: the caller applies it, the dot products the dense path fuses into the matvec epilogue
+    // come from one small kernel with the same per-tile layout
+    reinterpret_cast<xt_apply_fn>(op.apply)(op.apply_user, X, Y, st);
+    if (dots != nullptr) {
+      const MvTiling til = mv_tiling(op.nbatch, op.n);
+      tile_dots_kernel<TV><<<til.ntiles, 256, 0, st>>>(U, Y, op.n, op.ncols, til.tile_rows, til.tiles_per_batch, dots,
+                                                       dots_gstride, done_flag); XT_LAUNCHED();
+      XT_CUDA_OK(cudaGetLastError());
+    }
+    if (napply) ++(*napply);
+    return XT_OK;
+  }
   for (int c0 = 0, gi = 0; c0 < op.ncols; c0 += MV_MAXK, ++gi) {
     const int kg = (op.ncols - c0 < MV_MAXK) ? (op.ncols - c0) : MV_MAXK;
     MvArgs a;

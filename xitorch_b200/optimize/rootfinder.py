@@ -1,0 +1,92 @@
+"""
+`rootfinder` / `equilibrium` -- public functionals + autograd boundary (BASELINE config 4; reference:
+/root/reference/xitorch/optimize/rootfinder.py:35-366).
+
+Same signatures, default method ("broyden1") and analytic backward as the reference: the backward builds the
+matrix-free Jacobian ``df/dy`` at the root (`xitorch_b200.grad.jac`), solves the adjoint system
+``(df/dy)^H g = -grad_y`` by re-entering `linalg.solve` with `bck_options` (rootfinder.py:346-348) and pulls the
+parameter gradients through one more evaluation of ``fcn`` (:352-362).  With CUDA tensors that adjoint solve runs in
+the fused Krylov kernels (default for n > 5: "bicgstab") with the Jacobian applied through the operator callback of
+the C ABI.
+
+`fcn` must be pure with respect to `(y, *params)` (see `xitorch_b200.grad`); `minimize` is not part of the Krylov
+hot path and is not provided.
+"""
+from typing import Any, Callable, Mapping, Sequence, Union
+
+import torch
+
+from xitorch_b200._utils import get_method
+from xitorch_b200._impls.rootsolver import broyden1, broyden2, linearmixing
+from xitorch_b200.grad import jac
+from xitorch_b200.linalg.solve import solve
+
+__all__ = ["rootfinder", "equilibrium"]
+
+_RF_METHODS = {"broyden1": broyden1, "broyden2": broyden2, "linearmixing": linearmixing}
+
+
+def rootfinder(fcn: Callable[..., torch.Tensor], y0: torch.Tensor, params: Sequence[Any] = [],
+               bck_options: Mapping[str, Any] = {}, method: Union[str, Callable, None] = None,
+               **fwd_options) -> torch.Tensor:
+    r"""Solve :math:`\mathbf{0} = \mathbf{f}(\mathbf{y}, \theta)` for ``y`` (shape of ``y0``).
+
+    ``fcn(y, *params)`` returns a tensor of the shape of ``y``; ``method``: "broyden1" (default) | "broyden2" |
+    "linearmixing" | callable ``fcn_method(fcn, y0, params, **opts)``; ``bck_options``: options of the adjoint
+    `linalg.solve` in backward (``method`` among them); ``**fwd_options``: options of the method.
+    """
+    fwd_options["method"] = "broyden1" if method is None else method
+    return _RootFinder.apply(fcn, y0, fcn, fwd_options, bck_options, len(params), *params)
+
+
+def equilibrium(fcn: Callable[..., torch.Tensor], y0: torch.Tensor, params: Sequence[Any] = [],
+                bck_options: Mapping[str, Any] = {}, method: Union[str, Callable, None] = None,
+                **fwd_options) -> torch.Tensor:
+    r"""Solve :math:`\mathbf{y} = \mathbf{f}(\mathbf{y}, \theta)` for ``y`` (rootfinder on ``f(y) - y``)."""
+    def resid(y, *prm):
+        return y - fcn(y, *prm)
+
+    fwd_options["method"] = "broyden1" if method is None else method
+    return _RootFinder.apply(resid, y0, resid, fwd_options, bck_options, len(params), *params)
+
+
+class _RootFinder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fcn, y0, fwd_fcn, options, bck_options, nparams, *params):
+        config = dict(options)
+        ctx.bck_options = dict(bck_options)
+        method = config.pop("method")
+        method_fcn = get_method("rootfinder", _RF_METHODS, method)
+        y = method_fcn(fwd_fcn, y0, params, **config)
+        ctx.fcn = fcn
+        ctx.is_tensor = [isinstance(p, torch.Tensor) for p in params]
+        ctx.nontensors = [p for p in params if not isinstance(p, torch.Tensor)]
+        ctx.save_for_backward(y, *[p for p in params if isinstance(p, torch.Tensor)])
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_yout):
+        yout = ctx.saved_tensors[0]
+        tensors = list(ctx.saved_tensors[1:])
+        fcn = ctx.fcn
+
+        def rebuild(tens):
+            it, jt = iter(tens), iter(ctx.nontensors)
+            return [next(it) if flag else next(jt) for flag in ctx.is_tensor]
+
+        params = rebuild(tensors)
+        # dL/df: adjoint solve with the matrix-free Jacobian at the root
+        with torch.enable_grad():
+            y_lin = yout.detach().requires_grad_()
+        jac_dfdy = jac(fcn, params=(y_lin, *params), idxs=[0])[0]
+        gyfcn = solve(A=jac_dfdy.H, B=-grad_yout.reshape(-1, 1), bck_options=ctx.bck_options, **ctx.bck_options)
+        gyfcn = gyfcn.reshape(grad_yout.shape)
+        # gradients of the parameters through one more evaluation of fcn
+        with torch.enable_grad():
+            copies = [p.clone().requires_grad_() for p in tensors]
+            yfcn = fcn(yout, *rebuild(copies))
+        grads = torch.autograd.grad(yfcn, copies, grad_outputs=gyfcn, create_graph=torch.is_grad_enabled(),
+                                    allow_unused=True) if copies else ()
+        it = iter(grads)
+        grad_params = [next(it) if flag else None for flag in ctx.is_tensor]
+        return (None, None, None, None, None, None, *grad_params)
