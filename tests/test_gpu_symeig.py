@@ -188,3 +188,36 @@ def test_full_size_residual_property():
     rq = (evecs.double() * (A.double() @ evecs.double())).sum(0)
     assert ((rq - evals.double()).abs() / rq.abs()).max().item() <= EIG_RTOL
     assert ((evals.cpu() - (1 + torch.arange(neig))).abs() < 0.05).all()
+
+
+@pytest.mark.parametrize("env", ["XT_PO_NOSTAGE", "XT_NO_FUSE"])
+def test_expansion_step_variants(env, monkeypatch):
+    """the fused expansion kernel with the basis read from L2 (what large n uses) and the multi-kernel path give the
+    same eigenpairs as the default (basis slice staged in shared memory)"""
+    n, neig = 2048, 8
+    A = oracle.make_herm(n, neig, torch.float32, seed=5).to(DEV)
+    op = xt.LinearOperator.m(A, True)
+    ev0, _ = xt.linalg.symeig(op, neig=neig, method="davidson", min_eps=1e-4)
+    monkeypatch.setenv(env, "1")
+    info = {}
+    ev1, vec1 = xt.linalg.symeig(op, neig=neig, method="davidson", min_eps=1e-4, info=info)
+    monkeypatch.delenv(env)
+    assert info["converged"]
+    assert ((ev1 - ev0).abs() / ev0.abs()).max().item() <= 1e-6
+    R = A.double() @ vec1.double() - vec1.double() * ev1.double()
+    assert R.abs().max().item() <= 2e-3
+
+
+def test_lanczos_k16_large_n_fused_path():
+    """k = 16 block at a size whose basis slice does not fit in shared memory (the C5 shape on one GPU, scaled down)"""
+    n, neig = 24576, 16
+    A = oracle.make_herm(n, neig, torch.float32, seed=9).to(DEV)
+    info = {}
+    ev, vec = xt.linalg.symeig(xt.LinearOperator.m(A, True), neig=neig, method="lanczos", min_eps=1e-4, info=info)
+    assert info["converged"]
+    ref = torch.arange(1, neig + 1, dtype=torch.float64)
+    assert ((ev.double().cpu() - ref).abs() / ref).max().item() <= 2e-3          # make_herm: eigenvalues near 1..16
+    R = A.double() @ vec.double() - vec.double() * ev.double()
+    assert R.abs().max().item() <= 2e-3
+    G = vec.double().t() @ vec.double()
+    assert (G - torch.eye(neig, dtype=torch.float64, device=DEV)).abs().max().item() <= 1e-4

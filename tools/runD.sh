@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-for v in v1 v2 v3; do echo "== variant $v"; MS=32,33,48,104 XT_LIB_OVERRIDE=$PWD/tools/variants/lib_$v.so timeout 120 python tools/check_eigh.py 2>&1 | grep -E "mode=0|rror"; done > gpurun_out/D_check.log 2>&1
-cat gpurun_out/D_check.log
+MS=104 XT_EIG_DEBUG=8 timeout 100 python tools/check_eigh.py > gpurun_out/D_check.log 2>&1
+grep -E "xt-eig|mode=0" gpurun_out/D_check.log
+timeout 100 python tests/gpu_eigh_phases.py 2>&1 | grep -v phases

@@ -24,7 +24,7 @@ from xitorch_b200 import _lib
 from xitorch_b200._utils import ConvergenceWarning, bcast_dims, normalize_bcast_dims
 from xitorch_b200.linop import LinearOperator, MatrixLinearOperator
 
-__all__ = ["exactsolve", "custom_exactsolve", "cg", "bicgstab", "gmres", "get_batchdims"]
+__all__ = ["exactsolve", "custom_exactsolve", "cg", "bicgstab", "gmres", "broyden1_solve", "get_batchdims"]
 
 
 def get_batchdims(A, B, E, M):
@@ -418,3 +418,24 @@ def gmres(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, 
     if max_niter is None:
         max_niter = min(int(A.shape[-1]), 256)
     return _run_krylov("gmres", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, 0, check_every, info)
+
+
+def broyden1_solve(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None,
+                   M: Optional[LinearOperator] = None, **options) -> torch.Tensor:
+    """Solve the linear system as the root of ``A X - M X E - B`` with the first Broyden method
+    (reference: _rootfinder_solve, /root/reference/xitorch/_impls/linalg/solve.py:448-478); options of
+    :func:`xitorch_b200._impls.rootsolver.broyden1`."""
+    from xitorch_b200._impls.rootsolver import broyden1
+    nr, ncols = A.shape[-1], B.shape[-1]
+
+    def resid(xi):
+        x = xi.reshape(*xi.shape[:-1], nr, ncols)
+        y = A.mm(x) - B
+        if E is not None:
+            y = y - (M.mm(x) if M is not None else x) * E.unsqueeze(-2)
+        return y.reshape(*xi.shape[:-1], -1)
+
+    batch = get_batchdims(A, B, E, M)
+    x0 = torch.zeros((*batch, nr * ncols), dtype=A.dtype, device=A.device)
+    x = broyden1(resid, x0, **options)
+    return x.reshape(*x.shape[:-1], nr, ncols)

@@ -464,6 +464,7 @@ struct PostArgs {
   double* T; int ldt;
   EigCtl* ctl;
   int iter;
+  int stage_v;                                // 1: this CTA's slice of V (and AV) is staged in shared memory; 0: read from L2
   int rz_m, rz_iter, rz_ld, rz_coff;          // pending Ritz check (rz_m == 0: none)
   const double* rz_S; const double* rz_theta;
   void* Xslots; double* evals_slots; float min_eps;
@@ -547,7 +548,7 @@ __device__ __forceinline__ void po_stage(TV* dst, const TV* __restrict__ src, in
 // Cout[iv][j] += sum_r V[r][iv] Z[r][j] for the m basis vectors and, when `gram` is set, for the k columns of Z itself
 // (rows m .. m+k-1 of Cout then hold the Gram matrix Z^T Z).  This CTA's rows; fp64 atomics.
 template <typename TV, int KP>
-__device__ __forceinline__ void po_project(const TV* Vs, const double* Zs, int rows, int R, int k, int m, bool gram,
+__device__ __forceinline__ void po_project(const TV* Vs, const double* Zs, int rows, int64_t R, int k, int m, bool gram,
                                            double* part, double* Cout) {
   const int tid = threadIdx.x;
   const int mt = gram ? m + k : m;
@@ -566,7 +567,7 @@ __device__ __forceinline__ void po_project(const TV* Vs, const double* Zs, int r
       if (iv < m) {
         const int b = iv / k, i = iv - b * k;
         const TV* vcol = Vs + (size_t)b * R * k + i;
-#pragma unroll 4
+#pragma unroll 8
         for (int r = r0; r < r1; ++r) {
           const double v = (double)vcol[(size_t)r * k];
           const double* z = Zs + (size_t)r * KP;
@@ -608,7 +609,7 @@ __device__ __forceinline__ void po_project(const TV* Vs, const double* Zs, int r
 
 // Z[r][:] -= sum_iv V[r][iv] Cs[iv][:]    (Cs: [m][KP] in shared memory)
 template <typename TV, int KP>
-__device__ __forceinline__ void po_subtract(const TV* Vs, const double* Cs, double* Zs, int rows, int R, int k,
+__device__ __forceinline__ void po_subtract(const TV* Vs, const double* Cs, double* Zs, int rows, int64_t R, int k,
                                             int nblk, int skip = 0) {
   // `skip` leading threads do not take part (they are busy elsewhere)
   constexpr int NS = KP >= 8 ? 4 : 2;
@@ -662,8 +663,15 @@ expand_fused_kernel(const PostArgs p) {
 
   const bool tr = (blockIdx.x == 0 && tid == 0 && p.iter < 64);
   if (tr) ctl->ptrace[p.iter][0] = gtimer();
-  po_stage<TV>(Vs, V, n, k, row0, rows, R, nblk);
-  if (rz_nblk > 0) po_stage<TV>(AVs, static_cast<const TV*>(p.AV), n, k, row0, rows, R, rz_nblk);
+  if (p.stage_v) {
+    po_stage<TV>(Vs, V, n, k, row0, rows, R, nblk);
+    if (rz_nblk > 0) po_stage<TV>(AVs, static_cast<const TV*>(p.AV), n, k, row0, rows, R, rz_nblk);
+  }
+  // the basis slice as the phases below see it: staged copy (block stride R rows) or global memory (block stride n rows,
+  // large n: the basis stays in the 126 MB L2 between the passes)
+  const TV* Vb = p.stage_v ? Vs : V + (int64_t)row0 * k;
+  const TV* AVb = p.stage_v ? AVs : static_cast<const TV*>(p.AV) + (int64_t)row0 * k;
+  const int64_t vbs = p.stage_v ? (int64_t)R : (int64_t)n;
   for (int e = tid; e < R * KP; e += PO_THREADS) {
     const int r = e / KP, j = e - r * KP;
     Zs[e] = (r < rows && j < k) ? (double)W[((int64_t)row0 + r) * k + j] : 0.0;
@@ -700,8 +708,8 @@ expand_fused_kernel(const PostArgs p) {
       for (int j = 0; j < JW; ++j) { x[j] = 0.0; ax[j] = 0.0; }
       for (int b = 0; b < rz_nblk; ++b) {
         double v[KP], av[KP];
-        po_load_row<TV, KP>(Vs + ((size_t)b * R + r) * k, k, v);
-        po_load_row<TV, KP>(AVs + ((size_t)b * R + r) * k, k, av);
+        po_load_row<TV, KP>(Vb + ((size_t)b * vbs + r) * k, k, v);
+        po_load_row<TV, KP>(AVb + ((size_t)b * vbs + r) * k, k, av);
         const double* cb = Cs + (size_t)b * k * KP + sl * JW;
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
@@ -733,7 +741,7 @@ expand_fused_kernel(const PostArgs p) {
 
   if (tr) ctl->ptrace[p.iter][2] = gtimer();
   // ---- P1: C = V^T W
-  po_project<TV, KP>(Vs, Zs, rows, R, k, m, false, part, accC);
+  po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, false, part, accC);
   if (tr) ctl->ptrace[p.iter][3] = gtimer();
   const bool btr = (p.iter == 8 && gridDim.x <= 160);
   if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr)) return;
@@ -769,7 +777,7 @@ expand_fused_kernel(const PostArgs p) {
     Cs[e] = v;
   }
   __syncthreads();
-  po_subtract<TV, KP>(Vs, Cs, Zs, rows, R, k, nblk);
+  po_subtract<TV, KP>(Vb, Cs, Zs, rows, vbs, k, nblk);
   if (last_cta) {
     const int c0 = m - k;
     for (int e = tid; e < m * k; e += PO_THREADS) {
@@ -782,7 +790,7 @@ expand_fused_kernel(const PostArgs p) {
   }
   __syncthreads();
   if (tr) ctl->ptrace[p.iter][5] = gtimer();
-  po_project<TV, KP>(Vs, Zs, rows, R, k, m, true, part, accC2);
+  po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, true, part, accC2);
   if (tr) ctl->ptrace[p.iter][6] = gtimer();
   if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr)) return;
   if (tr) ctl->ptrace[p.iter][7] = gtimer();
@@ -821,7 +829,7 @@ expand_fused_kernel(const PostArgs p) {
     else ok = chol_inverse_warp(Gs, Ri, k);
     if (tid == 0) chol_ok = ok;
   }
-  po_subtract<TV, KP>(Vs, Cs, Zs, rows, R, k, nblk, 32);       // warps 1.. while warp 0 factorises
+  po_subtract<TV, KP>(Vb, Cs, Zs, rows, vbs, k, nblk, 32);       // warps 1.. while warp 0 factorises
   __syncthreads();
   if (tr) ctl->ptrace[p.iter][9] = gtimer();
   TV* Q = static_cast<TV*>(p.Qout);
@@ -845,9 +853,9 @@ expand_fused_kernel(const PostArgs p) {
 }
 
 constexpr int PO_SMEM_MAX = 200 * 1024;
-static size_t po_smem_bytes(size_t vs, int KP, int R, int k, int m, int rz_m) {
+static size_t po_smem_bytes(size_t vs, int KP, int R, int k, int m, int rz_m, bool stage_v) {
   return ((size_t)R * KP + (size_t)(4 * m + 3 * KP) * KP + (size_t)2 * KP * KP) * sizeof(double) +
-         ((size_t)m + rz_m) * R * vs + 32;
+         (stage_v ? ((size_t)m + rz_m) * R * vs : 0) + 32;
 }
 
 // Out[:, 0..p) = In(:, 0..m) * Sr   (thick restart: rotate the basis onto the p kept Ritz vectors; Sr is m x p)
@@ -966,6 +974,7 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   return cnt;
 }
 
+__device__ long long g_eig_stamp[16];
 __device__ int g_eig_debug = 0;     // tuning/debug switches (XT_EIG_DEBUG): 1 = shared-memory tridiagonalisation, 2 = unpaired back-transformation, 4 = IEEE sqrt/div in tridiag_regs
 
 // ---------------------------------------------------------------------------- register-resident tridiagonalisation
@@ -1027,8 +1036,11 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
   if (tid == 0) *abort_s = 0;
   __syncthreads();
   constexpr int H0 = (MR + 1) / 2;       // rows are processed in two halves (register budget)
+  const int dbgw = g_eig_debug;           // read once: a global load per column would sit on the dependent chain
   for (int j = 0; j + 2 < m; ++j) {
     const int pj = j & 1;
+    const bool st = (dbgw & 8) && j == m / 2 && tid == 0;
+    if (st) g_eig_stamp[0] = clock64();
     // ---- A. Householder scalars (every thread, redundantly).  The operands of phase B are fetched first so that
     // their latency hides behind the scalar chain.
     double xr[MR];
@@ -1057,13 +1069,14 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
       t = fma(ax0, inv, 1.0);                         // (alpha - x0) / alpha = 1 + |x0| / nrm
       const double sc = fast_rcp(ax0 + nrm);          // 1 / (x0 - alpha) = sign(x0) / (|x0| + nrm)
       scale = x0 >= 0.0 ? sc : -sc;
-      if (g_eig_debug & 4) {
+      if (dbgw & 4) {
         const double nrm2 = sqrt(ss);
         alpha = x0 >= 0.0 ? -nrm2 : nrm2;
         t = (alpha - x0) / alpha;
         scale = 1.0 / (x0 - alpha);
       }
     }
+    if (st) g_eig_stamp[1] = clock64();
     // ---- B. column sums of A22 v over this thread's rows
     if (t != 0.0) {
       double acc[MC], acc2[MC];
@@ -1087,9 +1100,11 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
         if (c < m) ppart[warp * 128 + c] = acc[cc] + acc2[cc];
       }
     }
+    if (st) g_eig_stamp[2] = clock64();
     if (abort_flag != nullptr && (j & 7) == 0 && tid == 0) *abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
     __syncthreads();
     if (*abort_s) return;
+    if (st) g_eig_stamp[3] = clock64();
     // ---- C1. p = tau * (sum of the partials), partials of p.v, (v, p) pairs -> vp[], reflector -> column j of As
     if (tid < 128) {
       const int c = tid;
@@ -1116,7 +1131,9 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
       if (lane == 0) pvpart[warp] = pvw;
       if (tid == 0) { e[j] = alpha; tau[j] = t; }
     }
+    if (st) g_eig_stamp[4] = clock64();
     __syncthreads();
+    if (st) g_eig_stamp[5] = clock64();
     // ---- C2. rank-2 update A22 -= v w^T + w v^T, w = p - (tau/2)(p.v) v;  next column, diagonal entry, norm partials
     if (t != 0.0) {
       double vc[MC], wc[MC];
@@ -1167,6 +1184,7 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
         }
       }
     }
+    if (st) g_eig_stamp[6] = clock64();
     {
       const int jn = j + 1;
       if (lane == (jn & 31)) {
@@ -1185,7 +1203,9 @@ __device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
         sgpart[(pj ^ 1) * 16 + warp] = sg + sg2;
       }
     }
+    if (st) g_eig_stamp[7] = clock64();
     __syncthreads();
+    if (st) g_eig_stamp[8] = clock64();
   }
   // trailing 2 x 2 (or smaller) block
   if (m >= 2) {
@@ -1861,7 +1881,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const int po_grid = (n + po_R - 1) / po_R;
   const void* po_fn = KP == 4 ? (const void*)expand_fused_kernel<TV, 4>
                               : (KP == 8 ? (const void*)expand_fused_kernel<TV, 8> : (const void*)expand_fused_kernel<TV, 16>);
-  const bool fuse_enabled = coop != 0 && !collective && g->expansion == 1 && num_sms() > 8 && getenv("XT_NO_FUSE") == nullptr;
+  const bool fuse_enabled = coop != 0 && g->expansion == 1 && num_sms() > 8 && getenv("XT_NO_FUSE") == nullptr;
 
   int64_t napply = 0;
   int all_conv = 1;
@@ -2006,13 +2026,12 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         const bool restart_f = can_expand_f && (m + k > mb);
         if (fuse_enabled && overlap && can_expand_f && !restart_f) {
           // the Ritz check that is due now (two iterations old) rides along when its AV slice fits as well
-          bool have_rz = pendq[1].valid;
-          size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0);
-          if (have_rz && po_smem > (size_t)PO_SMEM_MAX) {
-            rc = flush_pending(1);
-            if (rc != XT_OK) return rc;
-            have_rz = false;
-            po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, 0);
+          const bool have_rz = pendq[1].valid;
+          bool stage_v = true;
+          size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0, true);
+          if (po_smem > (size_t)PO_SMEM_MAX || getenv("XT_PO_NOSTAGE") != nullptr) {       // large n: leave the basis in L2
+            stage_v = false;
+            po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0, false);
           }
           if (po_smem <= (size_t)PO_SMEM_MAX) {
             PostArgs pa;
@@ -2020,7 +2039,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
             pa.V = V; pa.AV = AV; pa.W = AV + j * blk; pa.Qout = V + (int64_t)(m / k) * blk;
             pa.n = n; pa.k = k; pa.m = m; pa.R = po_R;
             pa.acc = W.Pacc; pa.acc_stride = (mb + SE_MAXK) * k; pa.T = W.T; pa.ldt = mb;
-            pa.ctl = W.ctl; pa.iter = iter;
+            pa.ctl = W.ctl; pa.iter = iter; pa.stage_v = stage_v ? 1 : 0;
             pa.Xslots = Xslots; pa.evals_slots = W.evals_slots; pa.min_eps = (float)g->min_eps;
             if (have_rz) {
               const Pending& q = pendq[0];
@@ -2243,6 +2262,15 @@ int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double*
   xt::small_eigh_kernel<<<1, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
                                                                   pl.as_in_smem, pl.y_in_smem, pl.inv_slots); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
+  if (const char* dv = getenv("XT_EIG_DEBUG")) {
+    if (atoi(dv) & 8) {
+      long long hs[16];
+      XT_CUDA_OK(cudaStreamSynchronize(st));
+      XT_CUDA_OK(cudaMemcpyFromSymbol(hs, xt::g_eig_stamp, sizeof(hs)));
+      fprintf(stderr, "xt-eig column %d of %d (clk): A %lld  B %lld  bar1 %lld  C1 %lld  bar2 %lld  C2 %lld  extract %lld  bar3 %lld\n", m / 2, m,
+              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5], hs[7] - hs[6], hs[8] - hs[7]);
+    }
+  }
   return XT_OK;
 }
 

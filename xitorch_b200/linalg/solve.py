@@ -35,6 +35,7 @@ def _solve_methods():
         "cg": _impl.cg,
         "bicgstab": _impl.bicgstab,
         "gmres": _impl.gmres,
+        "broyden1": _impl.broyden1_solve,
     }
 
 
