@@ -23,13 +23,14 @@
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
+#include <cstddef>
 
 namespace xt {
 
 constexpr int SE_MAXK = 16;
 constexpr int SE_THREADS = 256;
 constexpr int SE_ROWS = 64;         // rows per CTA chunk in the tall-skinny kernels
-constexpr int EIG_THREADS = 512;
+constexpr int EIG_THREADS = 256;     // 8 warps of fat threads (255 registers): see tridiag_regs
 
 struct EigCtl {
   int done;             // global stop flag (every kernel returns at once when set)
@@ -974,8 +975,7 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const d
   return cnt;
 }
 
-__device__ long long g_eig_stamp[16];
-__device__ int g_eig_debug = 0;     // tuning/debug switches (XT_EIG_DEBUG): 1 = shared-memory tridiagonalisation, 2 = unpaired back-transformation, 4 = IEEE sqrt/div in tridiag_regs
+__device__ int g_eig_debug = 0;     // tuning/debug switches (XT_EIG_DEBUG): 1 = shared-memory tridiagonalisation, 2 = unpaired back-transformation
 
 // ---------------------------------------------------------------------------- register-resident tridiagonalisation
 // Householder tridiagonalisation (dsytd2, lower variant) of a symmetric m x m matrix, m <= 128, with the MATRIX IN
@@ -1002,225 +1002,172 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // (no __restrict__ here: these arrays carry data BETWEEN threads across the barriers, and with the qualifier nvcc
-// moves loads over __syncthreads -- observed as wrong results for every instantiation but <2,1>)
+// moves loads over __syncthreads -- observed as wrong results)
+//
+// 8 warps of fat threads (up to 16 x 4 matrix entries each): a PC-sampling profile of the 16-warp version showed the
+// column loop bound by instruction ISSUE (about 900 instructions per warp and column, 10 % of them DFMAs), so the
+// per-thread bookkeeping is amortised over twice the entries, inactive rows are skipped by one warp-uniform branch
+// per row, padding / retired entries are kept at zero instead of being masked, the Householder scalars are computed
+// by warp 0 only -- concurrently with the column sums of the other warps, which are formed with the RAW column
+// u (v = scale u + (1 - scale u_0) e_0, so A v = scale (A u) + (1 - scale u_0) A e_0, and A e_0 is the next column,
+// extracted together with the current one) -- and the column extraction switches on the (uniform) register column.
 template <int MR, int MC>
-__device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d,
-                                          double* e, double* tau, double* xcol,
-                                          double2* vp, double* ppart,
-                                          double* sgpart, double* pvpart,
-                                          const int* abort_flag, int* abort_s) {
+__device__ __noinline__ void tridiag_regs(double* As, int lds, int m, double* d, double* e, double* tau, double* xcol,
+                                          double* xnext, double2* vp, double* ppart, double* sgpart, double* pvpart,
+                                          double* scal, const int* abort_flag, int* abort_s) {
+  constexpr int NW = EIG_THREADS / 32;        // 8 warps
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double a[MR][MC];
 #pragma unroll
   for (int rr = 0; rr < MR; ++rr) {
-    const int r = warp + 16 * rr;
+    const int r = warp + NW * rr;
 #pragma unroll
     for (int cc = 0; cc < MC; ++cc) {
       const int c = lane + 32 * cc;
-      a[rr][cc] = (r < m && c < m) ? As[(size_t)r * lds + c] : 0.0;
+      a[rr][cc] = (r < m && c < m) ? As[(size_t)r * lds + c] : 0.0;       // zero padding: never masked again
     }
   }
-  __syncthreads();            // As is reused for the reflectors from here on
-  // column 0 / diagonal entry 0 / norm partial of rows >= 2
-  if (lane == 0) {
-    double sg = 0.0;
-#pragma unroll
-    for (int rr = 0; rr < MR; ++rr) {
-      const int r = warp + 16 * rr;
-      if (r >= 1 && r < m) xcol[r] = a[rr][0];
-      if (r >= 2 && r < m) sg += a[rr][0] * a[rr][0];
-      if (r == 0) d[0] = a[rr][0];
-    }
-    sgpart[warp] = sg;
-  }
+  for (int i = tid; i < 128; i += EIG_THREADS) { vp[i] = make_double2(0.0, 0.0); xcol[i] = 0.0; xnext[i] = 0.0; }
   if (tid == 0) *abort_s = 0;
-  __syncthreads();
-  constexpr int H0 = (MR + 1) / 2;       // rows are processed in two halves (register budget)
-  const int dbgw = g_eig_debug;           // read once: a global load per column would sit on the dependent chain
-  for (int j = 0; j + 2 < m; ++j) {
-    const int pj = j & 1;
-    const bool st = (dbgw & 8) && j == m / 2 && tid == 0;
-    if (st) g_eig_stamp[0] = clock64();
-    // ---- A. Householder scalars (every thread, redundantly).  The operands of phase B are fetched first so that
-    // their latency hides behind the scalar chain.
-    double xr[MR];
+  __syncthreads();            // As is reused for the reflectors from here on
+
+  // columns jn (-> xcol, rows >= jn incl. the diagonal entry) and jn + 1 (-> xnext, rows >= jn) of the current matrix,
+  // norm partial of rows >= jn + 2 of column jn
+  auto extract = [&](int jn) {
+    const int occ = jn >> 5, occ2 = (jn + 1) >> 5;
+    if (lane == (jn & 31)) {
+      double sg = 0.0, sg2 = 0.0;
 #pragma unroll
-    for (int rr = 0; rr < MR; ++rr) {
-      const int r = warp + 16 * rr;
-      xr[rr] = xcol[r < m ? r : m - 1];
-    }
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int cc = 0; cc < MC; ++cc) {
+        if (cc == occ) {                      // warp-uniform: picks the register column without a select chain
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      s0 += sgpart[pj * 16 + w];
-      s1 += sgpart[pj * 16 + 4 + w];
-      s2 += sgpart[pj * 16 + 8 + w];
-      s3 += sgpart[pj * 16 + 12 + w];
+          for (int rr = 0; rr < MR; ++rr) {
+            const int r = warp + NW * rr;
+            const double v = a[rr][cc];
+            if (r > jn && r < m) xcol[r] = v;
+            if (r > jn + 1) { if (rr & 1) sg2 = fma(v, v, sg2); else sg = fma(v, v, sg); }   // padding rows are zero
+            if (r == jn) d[jn] = v;
+          }
+        }
+      }
+      sgpart[warp] = sg + sg2;
     }
-    const double sigma = (s0 + s1) + (s2 + s3);
-    const double x0 = xcol[j + 1];
-    double alpha = x0, t = 0.0, scale = 0.0;
-    if (sigma > 0.0) {
-      const double ss = fma(x0, x0, sigma);
-      const double inv = rsqrt(ss);
-      const double nrm = ss * inv;
-      const double ax0 = fabs(x0);
-      alpha = x0 >= 0.0 ? -nrm : nrm;
-      t = fma(ax0, inv, 1.0);                         // (alpha - x0) / alpha = 1 + |x0| / nrm
-      const double sc = fast_rcp(ax0 + nrm);          // 1 / (x0 - alpha) = sign(x0) / (|x0| + nrm)
-      scale = x0 >= 0.0 ? sc : -sc;
-      if (dbgw & 4) {
-        const double nrm2 = sqrt(ss);
-        alpha = x0 >= 0.0 ? -nrm2 : nrm2;
-        t = (alpha - x0) / alpha;
-        scale = 1.0 / (x0 - alpha);
+    if (lane == ((jn + 1) & 31) && jn + 1 < m) {
+#pragma unroll
+      for (int cc = 0; cc < MC; ++cc) {
+        if (cc == occ2) {
+#pragma unroll
+          for (int rr = 0; rr < MR; ++rr) {
+            const int r = warp + NW * rr;
+            if (r >= jn && r < m) xnext[r] = a[rr][cc];
+          }
+        }
       }
     }
-    if (st) g_eig_stamp[1] = clock64();
-    // ---- B. column sums of A22 v over this thread's rows
-    if (t != 0.0) {
+  };
+  extract(0);
+  __syncthreads();
+
+  for (int j = 0; j + 2 < m; ++j) {
+    const int rrmin = (j >= warp) ? (j - warp) / NW + 1 : 0;      // rows w + 8 rr > j  <=>  rr >= rrmin (warp-uniform)
+    // ---- A (warp 0 only): Householder scalars from the norm partials -> scal[] = (tau, scale, 1 - scale x0, alpha)
+    if (warp == 0) {
+      const double sigma = ((sgpart[0] + sgpart[1]) + (sgpart[2] + sgpart[3])) + ((sgpart[4] + sgpart[5]) + (sgpart[6] + sgpart[7]));
+      const double x0 = xcol[j + 1];
+      double alpha = x0, t = 0.0, scale = 0.0;
+      if (sigma > 0.0) {
+        const double ss = fma(x0, x0, sigma);
+        const double inv = rsqrt(ss);
+        const double nrm = ss * inv;
+        const double ax0 = fabs(x0);
+        alpha = x0 >= 0.0 ? -nrm : nrm;
+        t = fma(ax0, inv, 1.0);                         // (alpha - x0) / alpha = 1 + |x0| / nrm
+        const double sc = fast_rcp(ax0 + nrm);          // 1 / (x0 - alpha) = sign(x0) / (|x0| + nrm)
+        scale = x0 >= 0.0 ? sc : -sc;
+      }
+      if (lane == 0) {
+        scal[0] = t; scal[1] = scale; scal[2] = fma(-scale, x0, 1.0); scal[3] = alpha;
+        e[j] = alpha; tau[j] = t;
+      }
+    }
+    // ---- B (all warps): column sums of A22 u over this thread's rows, u = raw column j (rows > j)
+    {
       double acc[MC], acc2[MC];
 #pragma unroll
       for (int cc = 0; cc < MC; ++cc) { acc[cc] = 0.0; acc2[cc] = 0.0; }
 #pragma unroll
       for (int rr = 0; rr < MR; ++rr) {
-        const int r = warp + 16 * rr;
-        if (r > j && r < m) {                                            // warp-uniform row predicate
-          const double vrr = (r == j + 1) ? 1.0 : xr[rr] * scale;
+        if (rr >= rrmin) {
+          const double ur = xcol[warp + NW * rr];      // index < 128; entries >= m are zero
 #pragma unroll
           for (int cc = 0; cc < MC; ++cc) {
-            if (rr & 1) acc2[cc] = fma(a[rr][cc], vrr, acc2[cc]);
-            else acc[cc] = fma(a[rr][cc], vrr, acc[cc]);
+            if (rr & 1) acc2[cc] = fma(a[rr][cc], ur, acc2[cc]);
+            else acc[cc] = fma(a[rr][cc], ur, acc[cc]);
           }
         }
       }
 #pragma unroll
-      for (int cc = 0; cc < MC; ++cc) {
-        const int c = lane + 32 * cc;
-        if (c < m) ppart[warp * 128 + c] = acc[cc] + acc2[cc];
-      }
+      for (int cc = 0; cc < MC; ++cc) ppart[warp * 128 + lane + 32 * cc] = acc[cc] + acc2[cc];
     }
-    if (st) g_eig_stamp[2] = clock64();
     if (abort_flag != nullptr && (j & 7) == 0 && tid == 0) *abort_s = *reinterpret_cast<const volatile int*>(abort_flag);
     __syncthreads();
     if (*abort_s) return;
-    if (st) g_eig_stamp[3] = clock64();
-    // ---- C1. p = tau * (sum of the partials), partials of p.v, (v, p) pairs -> vp[], reflector -> column j of As
+    // ---- C1 (threads 0..127): p = tau (scale A u + (1 - scale x0) A e_0), partials of p.v, (v, p) -> vp[], reflector
     if (tid < 128) {
       const int c = tid;
+      const double t = scal[0], scale = scal[1], w0 = scal[2];
       double pvw = 0.0;
       if (c > j && c < m) {
         const double vcc = (c == j + 1) ? 1.0 : xcol[c] * scale;
         double pc = 0.0;
         if (t != 0.0) {
-          double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            q0 += ppart[w * 128 + c];
-            q1 += ppart[(4 + w) * 128 + c];
-            q2 += ppart[(8 + w) * 128 + c];
-            q3 += ppart[(12 + w) * 128 + c];
-          }
-          pc = t * ((q0 + q1) + (q2 + q3));
+          const double q = ((ppart[c] + ppart[128 + c]) + (ppart[256 + c] + ppart[384 + c])) +
+                           ((ppart[512 + c] + ppart[640 + c]) + (ppart[768 + c] + ppart[896 + c]));
+          pc = t * fma(scale, q, w0 * xnext[c]);
           pvw = pc * vcc;
         }
         vp[c] = make_double2(vcc, pc);
         As[(size_t)c * lds + j] = vcc;
+      } else if (c == j) {
+        vp[c] = make_double2(0.0, 0.0);              // retired column: stays zero from now on (no masks in C2)
       }
       pvw = warp_sum(pvw);
       if (lane == 0) pvpart[warp] = pvw;
-      if (tid == 0) { e[j] = alpha; tau[j] = t; }
     }
-    if (st) g_eig_stamp[4] = clock64();
     __syncthreads();
-    if (st) g_eig_stamp[5] = clock64();
-    // ---- C2. rank-2 update A22 -= v w^T + w v^T, w = p - (tau/2)(p.v) v;  next column, diagonal entry, norm partials
-    if (t != 0.0) {
-      double vc[MC], wc[MC];
-#pragma unroll
-      for (int cc = 0; cc < MC; ++cc) {
-        const int c = lane + 32 * cc;
-        const double2 q = vp[c < m ? c : m - 1];
-        vc[cc] = q.x; wc[cc] = q.y;
-      }
-      double2 qa[H0];
-#pragma unroll
-      for (int h = 0; h < H0; ++h) {
-        const int r = warp + 16 * h;
-        qa[h] = vp[r < m ? r : m - 1];
-      }
-      const double hc = 0.5 * t * ((pvpart[0] + pvpart[1]) + (pvpart[2] + pvpart[3]));
-#pragma unroll
-      for (int cc = 0; cc < MC; ++cc) {
-        const int c = lane + 32 * cc;
-        const bool in = (c > j && c < m);
-        wc[cc] = in ? fma(-hc, vc[cc], wc[cc]) : 0.0;
-        vc[cc] = in ? vc[cc] : 0.0;
-      }
-      double2 qb[MR - H0 > 0 ? MR - H0 : 1];
-#pragma unroll
-      for (int h = 0; h < MR - H0; ++h) {
-        const int r = warp + 16 * (H0 + h);
-        qb[h] = vp[r < m ? r : m - 1];
-      }
-#pragma unroll
-      for (int rr = 0; rr < H0; ++rr) {
-        const int r = warp + 16 * rr;
-        if (r > j && r < m) {                                            // warp-uniform
-          const double vrr = qa[rr].x;
-          const double wr = fma(-hc, vrr, qa[rr].y);
-#pragma unroll
-          for (int cc = 0; cc < MC; ++cc) a[rr][cc] = fma(-wr, vc[cc], fma(-vrr, wc[cc], a[rr][cc]));
-        }
-      }
-#pragma unroll
-      for (int rr = H0; rr < MR; ++rr) {
-        const int r = warp + 16 * rr;
-        if (r > j && r < m) {
-          const double vrr = qb[rr - H0].x;
-          const double wr = fma(-hc, vrr, qb[rr - H0].y);
-#pragma unroll
-          for (int cc = 0; cc < MC; ++cc) a[rr][cc] = fma(-wr, vc[cc], fma(-vrr, wc[cc], a[rr][cc]));
-        }
-      }
-    }
-    if (st) g_eig_stamp[6] = clock64();
+    // ---- C2: rank-2 update A22 -= v w^T + w v^T, w = p - (tau/2)(p.v) v;  next two columns, diagonal, norm partials
     {
-      const int jn = j + 1;
-      if (lane == (jn & 31)) {
-        double sg = 0.0, sg2 = 0.0;
-        const int occ = jn >> 5;
+      const double t = scal[0];
+      if (t != 0.0) {
+        const double hc = 0.5 * t * ((pvpart[0] + pvpart[1]) + (pvpart[2] + pvpart[3]));
+        double vc[MC], wc[MC];
+#pragma unroll
+        for (int cc = 0; cc < MC; ++cc) {
+          const double2 q = vp[lane + 32 * cc];        // zero for retired / padding columns
+          vc[cc] = q.x;
+          wc[cc] = fma(-hc, q.x, q.y);
+        }
 #pragma unroll
         for (int rr = 0; rr < MR; ++rr) {
-          double v = a[rr][0];                      // select chain (a dynamic index would push a[][] to local memory)
+          if (rr >= rrmin) {
+            const double2 q = vp[warp + NW * rr];
+            const double vrr = q.x;
+            const double wr = fma(-hc, vrr, q.y);
 #pragma unroll
-          for (int cc = 1; cc < MC; ++cc) v = (occ == cc) ? a[rr][cc] : v;
-          const int r = warp + 16 * rr;
-          if (r > jn && r < m) xcol[r] = v;
-          if (r > jn + 1 && r < m) { if (rr & 1) sg2 = fma(v, v, sg2); else sg = fma(v, v, sg); }
-          if (r == jn) d[jn] = v;
+            for (int cc = 0; cc < MC; ++cc) a[rr][cc] = fma(-wr, vc[cc], fma(-vrr, wc[cc], a[rr][cc]));
+          }
         }
-        sgpart[(pj ^ 1) * 16 + warp] = sg + sg2;
       }
+      extract(j + 1);
     }
-    if (st) g_eig_stamp[7] = clock64();
     __syncthreads();
-    if (st) g_eig_stamp[8] = clock64();
   }
-  // trailing 2 x 2 (or smaller) block
-  if (m >= 2) {
-    const int r = m - 1;
-    if (warp == (r & 15) && lane == (r & 31)) {
-      double v = a[0][0];
-#pragma unroll
-      for (int rr = 0; rr < MR; ++rr)
-#pragma unroll
-        for (int cc = 0; cc < MC; ++cc) v = ((r >> 4) == rr && (r >> 5) == cc) ? a[rr][cc] : v;
-      d[r] = v;
-    }
-    if (tid == 0) { e[m - 2] = xcol[m - 1]; tau[m - 2] = 0.0; }
+  // trailing 2 x 2 (or smaller) block: the last extract() stored d[m-2] and column m-2 (-> xcol[m-1] = e[m-2]);
+  // xnext[m-1] is the last diagonal entry
+  if (tid == 0) {
+    if (m >= 2) { e[m - 2] = xcol[m - 1]; tau[m - 2] = 0.0; d[m - 1] = xnext[m - 1]; }
+    e[m - 1] = 0.0; tau[m - 1] = 0.0;
   }
-  if (tid == 0) { e[m - 1] = 0.0; tau[m - 1] = 0.0; }
   __syncthreads();
 }
 
@@ -1257,12 +1204,16 @@ __device__ void eig_extreme_device(double* As, int lds, int m, int nev, int mode
   __shared__ int abort_s;
   const bool in_regs = (m <= 128) && (nt == EIG_THREADS) && (g_eig_debug & 1) == 0;
   if (in_regs) {
-    double2* vp = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(ppart + 16 * 128) + 15) & ~uintptr_t(15));
-    if (m <= 32) tridiag_regs<2, 1>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
-    else if (m <= 64) tridiag_regs<4, 2>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
-    else if (m <= 96) tridiag_regs<6, 3>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
-    else if (m <= 112) tridiag_regs<7, 4>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
-    else tridiag_regs<8, 4>(As, lds, m, d, e, tau, vbuf, vp, ppart, sgpart, pvpart, abort_flag, &abort_s);
+    // carve of the reserved block: ppart [8][128] | xcol [128] | xnext [128] | vp [128] (16-byte aligned) | scal [4]
+    double* xcol = ppart + 8 * 128;
+    double* xnext = xcol + 128;
+    double2* vp = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(xnext + 128) + 15) & ~uintptr_t(15));
+    double* scal = reinterpret_cast<double*>(vp + 128);
+    if (m <= 32) tridiag_regs<4, 1>(As, lds, m, d, e, tau, xcol, xnext, vp, ppart, sgpart, pvpart, scal, abort_flag, &abort_s);
+    else if (m <= 64) tridiag_regs<8, 2>(As, lds, m, d, e, tau, xcol, xnext, vp, ppart, sgpart, pvpart, scal, abort_flag, &abort_s);
+    else if (m <= 96) tridiag_regs<12, 3>(As, lds, m, d, e, tau, xcol, xnext, vp, ppart, sgpart, pvpart, scal, abort_flag, &abort_s);
+    else if (m <= 104) tridiag_regs<13, 4>(As, lds, m, d, e, tau, xcol, xnext, vp, ppart, sgpart, pvpart, scal, abort_flag, &abort_s);
+    else tridiag_regs<16, 4>(As, lds, m, d, e, tau, xcol, xnext, vp, ppart, sgpart, pvpart, scal, abort_flag, &abort_s);
     if (abort_s) return;
   } else {
   for (int i = tid; i < 96; i += nt) wpart[i] = 0.0;
@@ -1767,13 +1718,19 @@ __global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int
 }
 
 __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
+  unsigned long long* tr = &ctl->trace[0][0];
+  unsigned long long* pt = &ctl->ptrace[0][0];
+  unsigned long long* br = &ctl->barr[0][0];
+  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) tr[i] = 0ull;
+  for (int i = threadIdx.x; i < 64 * 12; i += blockDim.x) pt[i] = 0ull;
+  for (int i = threadIdx.x; i < 4 * 160; i += blockDim.x) br[i] = 0ull;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   ctl->host_done = host_done;
-  for (int i = 0; i < 64; ++i) { for (int q = 0; q < 4; ++q) ctl->trace[i][q] = 0ull; for (int q = 0; q < 12; ++q) ctl->ptrace[i][q] = 0ull; }
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
   ctl->bar_count = 0; ctl->bar_gen = 0;
-  for (int q = 0; q < 4; ++q) for (int c = 0; c < 160; ++c) ctl->barr[q][c] = 0ull;
   ctl->trace[0][0] = gtimer();
 }
 
@@ -1881,6 +1838,15 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const int po_grid = (n + po_R - 1) / po_R;
   const void* po_fn = KP == 4 ? (const void*)expand_fused_kernel<TV, 4>
                               : (KP == 8 ? (const void*)expand_fused_kernel<TV, 8> : (const void*)expand_fused_kernel<TV, 16>);
+  int lag1_m = 0;     // projected-problem size up to which the Ritz check lags ONE iteration (tuned on B200)
+  {
+    const double t_mv = (double)n_local * n * sizeof(TV) / 6.0e12;                 // one pass over A at ~6 TB/s
+    // rr_kernel(m) takes ~2.7 us * m next to a running matvec (measured at C2: 41 us at m = 8 ... 240 us at m = 88).
+    // Lag one iteration while it finishes within 1.4 matvecs: a late result stalls the stream by the difference, which
+    // is still cheaper than the whole extra iteration a lag of two costs at the end of the solve.
+    while (lag1_m + k <= 128 && 2.7e-6 * (lag1_m + k) <= 1.4 * t_mv) lag1_m += k;
+    if (const char* lv = getenv("XT_LAG1_M")) lag1_m = atoi(lv);
+  }
   const bool fuse_enabled = coop != 0 && g->expansion == 1 && num_sms() > 8 && getenv("XT_NO_FUSE") == nullptr;
 
   int64_t napply = 0;
@@ -1937,7 +1903,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
     *pool.hflag = 0;
     const auto host_t0 = std::chrono::steady_clock::now();
-    init_ctl_kernel<<<1, 1, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev); XT_LAUNCHED();
+    init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
     gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
                                                        g->ldv0, n, k, Rblk); XT_LAUNCHED();
@@ -2026,7 +1992,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         const bool restart_f = can_expand_f && (m + k > mb);
         if (fuse_enabled && overlap && can_expand_f && !restart_f) {
           // the Ritz check that is due now (two iterations old) rides along when its AV slice fits as well
-          const bool have_rz = pendq[1].valid;
+          // a Ritz check is due `lag` iterations after its Rayleigh-Ritz was launched: one while the projected problem
+          // is small enough for rr_kernel to finish within a matvec, two beyond (a late result only stalls the stream)
+          const bool have_rz = pendq[0].valid && (iter - pendq[0].iter >= (pendq[0].m <= lag1_m ? 1 : 2));
           bool stage_v = true;
           size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0, true);
           if (po_smem > (size_t)PO_SMEM_MAX || getenv("XT_PO_NOSTAGE") != nullptr) {       // large n: leave the basis in L2
@@ -2064,6 +2032,10 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
                                                                plf.y_in_smem, plf.inv_slots, W.ctl, iter); XT_LAUNCHED();
             XT_CUDA_OK(cudaEventRecord(evR[par], rsf));
             ev_used[par] = true;
+            if (pendq[0].valid && pendq[1].valid) {   // queue full (the lag just changed): the oldest check gets its own kernel
+              rc = flush_pending(1);
+              if (rc != XT_OK) return rc;
+            }
             Pending pn = {true, par, m, iter, k, 0};
             if (!pendq[0].valid) pendq[0] = pn; else pendq[1] = pn;
             m += k;
@@ -2174,7 +2146,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
                                                  static_cast<TV*>(g->evecs) + (int64_t)b * g->evecs_bstride, g->ldv,
                                                  static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, W.ctl); XT_LAUNCHED();
     EigCtl h;
-    XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    const bool tracing = getenv("XT_TRACE") != nullptr;
+    XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, tracing ? sizeof(h) : offsetof(EigCtl, trace), cudaMemcpyDeviceToHost, st));
     XT_CUDA_OK(cudaStreamSynchronize(st));
     if (getenv("XT_TRACE") != nullptr) {
       const unsigned long long t0 = h.trace[0][0];
@@ -2259,18 +2232,13 @@ int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double*
     XT_CUDA_OK(cudaFuncSetAttribute(xt::small_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024 - (int)fa.sharedSizeBytes));
   }
-  xt::small_eigh_kernel<<<1, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
+  // XT_EIG_GRID=n runs n identical copies of the one-CTA solver side by side (profiling aid: ncu's PC sampling needs
+  // more than one busy SM to collect a usable number of samples); every copy writes the same results
+  int egrid = 1;
+  if (const char* gv = getenv("XT_EIG_GRID")) egrid = atoi(gv) > 0 && pl.as_in_smem ? atoi(gv) : 1;
+  xt::small_eigh_kernel<<<egrid, xt::EIG_THREADS, pl.smem_bytes, st>>>(T, m, nev, mode, scratch, w_out, S_out, pl.lds,
                                                                   pl.as_in_smem, pl.y_in_smem, pl.inv_slots); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
-  if (const char* dv = getenv("XT_EIG_DEBUG")) {
-    if (atoi(dv) & 8) {
-      long long hs[16];
-      XT_CUDA_OK(cudaStreamSynchronize(st));
-      XT_CUDA_OK(cudaMemcpyFromSymbol(hs, xt::g_eig_stamp, sizeof(hs)));
-      fprintf(stderr, "xt-eig column %d of %d (clk): A %lld  B %lld  bar1 %lld  C1 %lld  bar2 %lld  C2 %lld  extract %lld  bar3 %lld\n", m / 2, m,
-              hs[1] - hs[0], hs[2] - hs[1], hs[3] - hs[2], hs[4] - hs[3], hs[5] - hs[4], hs[6] - hs[5], hs[7] - hs[6], hs[8] - hs[7]);
-    }
-  }
   return XT_OK;
 }
 
