@@ -67,8 +67,9 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
  *   Y: (nbatch, nrows, k), row stride ldy;                  E: (nbatch, k) or NULL
  *   k >= 1 (handled in column groups of <= 16).  `impl`: 0 = auto, 1 = force a TMA kernel (auto layout),
  *   2 = force the plain-load kernel, 3 = TMA row-slice layout, 4 = TMA column-slice layout (fp32, k > 4),
- *   5 = TMA row-slice layout with one row per thread (k = 8 defaults to two);
- *   2-5 are used by the tests to cross-check the kernels.
+ *   5 = TMA row-slice layout with one row per thread (k = 8 defaults to two), 6 = tensor-core layout (fp32, k <= 16,
+ *   error-compensated TF32 through mma.sync; exact to fp32 rounding but slower than the SIMT layouts on B200, see
+ *   csrc/matvec.cu); 2-6 are used by the tests to cross-check the kernels.
  *   Bit 8 of `impl` (+256) makes the pass read A's columns last-to-first and bits 16..23 give the MB of the end of
  *   the pass to leave in L2 (evict-last): callers that apply the same A repeatedly alternate the direction so that
  *   each pass starts on the part of A the previous one left in the 126 MB L2.

@@ -120,3 +120,27 @@ def test_full_size_linearity_property():
     # and the two kernels agree on a row sample
     yp = _dense.block_matvec(A[:256].contiguous(), X, impl=2)
     assert (yp - y1[:256]).abs().max().item() <= 2e-4 * y1.abs().max().item()
+
+
+@pytest.mark.parametrize("n,rows,k", [(1024, 1024, 16), (1000, 700, 12), (4096, 300, 9), (2080, 2080, 16), (72, 200, 16)])
+def test_matvec_tensor_core_layout(n, rows, k):
+    """fp32 wide blocks on the tensor cores (error-compensated TF32, impl = 6): same tolerance as the SIMT kernels,
+    ragged tiles / chunks, strided and batched X"""
+    g = torch.Generator().manual_seed(n + rows + k)
+    A = torch.randn(2, rows, n, generator=g)
+    X = torch.randn(2, n, k, generator=g)
+    y = _dense.block_matvec(A.to(DEV), X.to(DEV), impl=6)
+    ref = A.double() @ X.double()
+    scale = (A.double().abs() @ X.double().abs()).max().item()
+    err = (y.double().cpu() - ref).abs().max().item()
+    assert tuple(y.shape) == (2, rows, k)
+    assert err <= 2e-6 * scale, (err, scale, err / scale)
+    # agrees with the SIMT kernel to rounding level
+    y3 = _dense.block_matvec(A.to(DEV), X.to(DEV), impl=3)
+    assert (y - y3).abs().max().item() <= 4e-6 * scale
+    # values spanning many orders of magnitude (hi/lo split under scaling)
+    Xs = X * torch.logspace(-12, 12, k).reshape(1, 1, k)
+    ys = _dense.block_matvec(A.to(DEV), Xs.to(DEV), impl=6)
+    refs = A.double() @ Xs.double()
+    rel = ((ys.double().cpu() - refs).abs() / (A.double().abs() @ Xs.double().abs())).max().item()
+    assert rel <= 2e-6, rel

@@ -730,6 +730,229 @@ mv_tma_colslice_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   }
 }
 
+// ---------------------------------------------------------------------------- tensor-core layout (fp32, 8 < k <= 16)
+// For k = 16 the SIMT kernels above are bound by the FP32 pipe (16 FMAs per element of A: 4.3 TB/s measured).  Here the
+// block product is what it genuinely is -- a tall-skinny GEMM -- and runs on the tensor cores (legacy mma.sync path;
+// selectable with impl = 6, see launch_tma() for why it is not the default) with error-compensated
+// TF32 (A = A_hi + A_lo, X = X_hi + X_lo, each part a TF32 number; A_hi X_hi in one accumulator, A_lo X_hi + A_hi X_lo
+// in a second one; the dropped A_lo X_lo term is ~2^-22 relative).  Tensor-core accumulation rounds toward zero, so the
+// accumulators are flushed into round-to-nearest fp32 sums once per stage (8 k-steps): the result has the accuracy of
+// the blocked fp32 summation of the SIMT kernels.
+//   * same TMA producer / stage ring as above (two SWIZZLE_128B boxes of tile_rows x 32 floats per stage)
+//   * warp 1 stages X: it splits the 64 x 16 chunk into hi / lo parts and stores them in mma.m16n8k8 B-fragment order,
+//     one conflict-free LDS.128 {hi0, hi1, lo0, lo1} per (k-step, column tile, lane) for the consumers
+//   * 8 consumer warps, warp w owns rows 16w .. 16w+15 of the tile; per k-step 4 conflict-free LDS.32 of the swizzled A
+//     tile (fragment rows g, g+8 x columns t, t+4), the hi/lo split in registers, 6 mma.sync.m16n8k8 (2 column tiles)
+// Used for plain products (no shift, no fused dots).
+constexpr int TC_XBYTES = 8 * 2 * 32 * 16;            // 8 KB of fragment-ordered X per stage
+constexpr int TC_STAGE_BYTES = MV_STAGE_A_BYTES + TC_XBYTES;   // 40 KB, 1024-byte aligned
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256 + 64, 1)
+mv_tma_tc_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
+  constexpr int BOXC = 32, KC = 64;
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;
+  uint8_t* stage_base = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * TC_STAGE_BYTES);
+  uint64_t* empty = full + NS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.ncolsA + KC - 1) / KC;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 2);          // TMA lane (expect_tx) + X-staging warp
+      mbar_init(&empty[s], 8);         // one arrival per consumer warp
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      // TMA producer (A only; X goes through warp 1)
+      const uint64_t pol_first = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_batch;
+        const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+        const int bA = p.a_batched ? b : 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+          const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* dst = stage_base + (size_t)s * TC_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128));
+          for (int bx = 0; bx < nb; ++bx)
+            tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), &tmA, &full[s], kc + bx * BOXC, row0, bA,
+                        ch >= p.keep_from ? pol_keep : pol_first);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // X stager: 16 fragment slots per lane and stage: slot (ks, nt, lane) = {hi(b0), hi(b1), lo(b0), lo(b1)} with
+    // b0 = X[kc + 8 ks + t][8 nt + g], b1 = X[kc + 8 ks + t + 4][8 nt + g], t = lane & 3, g = lane >> 2
+    const float* __restrict__ Xg = reinterpret_cast<const float*>(p.X);
+    const int t = lane & 3, g = lane >> 2;
+    float v0[16], v1[16];
+    auto load_chunk = [&](int tile, int ch) {
+      const int b = tile / p.tiles_per_batch;
+      const float* Xb = Xg + (int64_t)b * p.x_bstride;
+      const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ks = i >> 1, nt = i & 1;
+        const int r0 = kc + 8 * ks + t, col = 8 * nt + g;
+        v0[i] = (r0 < p.ncolsA && col < p.kvalid) ? Xb[(int64_t)r0 * p.ldx + col] : 0.f;
+        v1[i] = (r0 + 4 < p.ncolsA && col < p.kvalid) ? Xb[(int64_t)(r0 + 4) * p.ldx + col] : 0.f;
+      }
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    int tile = blockIdx.x, ch = 0;
+    if (tile < p.ntiles) load_chunk(tile, 0);
+    while (tile < p.ntiles) {
+      mbar_wait(&empty[s], ph ^ 1);
+      uint4* xs = reinterpret_cast<uint4*>(stage_base + (size_t)s * TC_STAGE_BYTES + MV_STAGE_A_BYTES);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t h0 = f2tf32(v0[i]), h1 = f2tf32(v1[i]);
+        const uint32_t l0 = f2tf32(v0[i] - __uint_as_float(h0)), l1 = f2tf32(v1[i] - __uint_as_float(h1));
+        xs[i * 32 + lane] = make_uint4(h0, h1, l0, l1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      if (++s == NS) { s = 0; ph ^= 1; }
+      if (++ch == nchunks) { ch = 0; tile += gridDim.x; }
+      if (tile < p.ntiles) load_chunk(tile, ch);
+    }
+  } else {
+    const int cw = warp - 2;                     // rows 16 cw .. 16 cw + 15 of the tile
+    const int t = lane & 3, g = lane >> 2;
+    const int ra = 16 * cw + g, rb = ra + 8;
+    // byte offsets of the fragment rows inside a box; 16-byte chunk index is XORed with (row & 7) (SWIZZLE_128B)
+    const uint32_t offa = (uint32_t)(ra * 128 + t * 4), offb = (uint32_t)(rb * 128 + t * 4);
+    const uint32_t swa = (uint32_t)(ra & 7), swb = (uint32_t)(rb & 7);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+      const int rows = min(p.tile_rows, p.nrows - row0);
+      float y[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[n][i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+        mbar_wait(&full[s], ph);
+        const uint32_t a_s = smem_u32(stage_base + (size_t)s * TC_STAGE_BYTES);
+        const uint32_t x_s = a_s + MV_STAGE_A_BYTES + (uint32_t)lane * 16;
+        float mainacc[2][4], corr[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { mainacc[n][i] = 0.f; corr[n][i] = 0.f; }
+        const int nks = (kc + KC <= p.ncolsA) ? 8 : (p.ncolsA - kc + 7) / 8;    // ragged last chunk: loaded boxes only
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (ks < nks) {
+            const uint32_t box = (uint32_t)(ks >> 2) * (MV_TILE_ROWS * 128);
+            const uint32_t c0 = (uint32_t)(ks & 3) * 2;                          // 16-byte chunk of columns t, chunk + 1 of t + 4
+            float af[4];
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(af[0]) : "r"(a_s + box + offa + (((c0) ^ swa) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(af[1]) : "r"(a_s + box + offb + (((c0) ^ swb) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(af[2]) : "r"(a_s + box + offa + (((c0 + 1) ^ swa) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(af[3]) : "r"(a_s + box + offb + (((c0 + 1) ^ swb) << 4)));
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ahi[i] = f2tf32(af[i]);
+              alo[i] = f2tf32(af[i] - __uint_as_float(ahi[i]));
+            }
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              uint32_t xh0, xh1, xl0, xl1;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(xh0), "=r"(xh1), "=r"(xl0), "=r"(xl1)
+                           : "r"(x_s + (uint32_t)((ks * 2 + n) * 32 * 16)));
+              mma_tf32(mainacc[n], ahi, xh0, xh1);
+              mma_tf32(corr[n], alo, xh0, xh1);
+              mma_tf32(corr[n], ahi, xl0, xl1);
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[n][i] += mainacc[n][i] + corr[n][i];      // round-to-nearest, once per stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+      // accumulator layout: y[n][0], y[n][1] -> row ra, columns 8n + 2t, +1;  y[n][2], y[n][3] -> row rb
+      float* Yb = reinterpret_cast<float*>(p.Y) + (int64_t)b * p.y_bstride;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int col = 8 * n + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int rr = h == 0 ? ra : rb;
+          if (rr < rows) {
+            float* yr = Yb + ((int64_t)row0 + rr) * p.ldy + col;
+            if (col < p.kvalid) yr[0] = y[n][2 * h];
+            if (col + 1 < p.kvalid) yr[1] = y[n][2 * h + 1];
+          }
+        }
+      }
+    }
+  }
+}
+
+static int launch_tc(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
+  const size_t fixed = 2 * 8 * sizeof(uint64_t) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / TC_STAGE_BYTES);
+  if (ns > 6) ns = 6;
+  if (ns < 2) {
+    set_last_error("matvec: not enough shared memory for 2 stages");
+    return XT_ERR_INVALID;
+  }
+  const size_t smem = (size_t)ns * TC_STAGE_BYTES + fixed;
+  MvDev dev = dev0;
+  dev.nstages = ns;
+  CUtensorMap tm;
+  bool batched = false;
+  int rc = make_tmap(a, til.tile_rows, &tm, &batched);
+  if (rc != XT_OK) return rc;
+  dev.a_batched = batched ? 1 : 0;
+  dev.x_bulk = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XT_CUDA_OK(cudaFuncSetAttribute(mv_tma_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  prof_mv_begin(st);
+  mv_tma_tc_kernel<<<til.grid, 256 + 64, smem, st>>>(tm, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
 // ---------------------------------------------------------------------------- plain-load kernel
 // one CTA per tile (same tiling => same dot layout), one warp per row, lanes stride the columns.
 template <typename TA, typename TV>
@@ -888,6 +1111,16 @@ static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cu
   // k = 8: row-slice with two rows per thread 6260 GB/s, one row 6230 (5690 for tiles > 112 rows), column-slice 5850;
   // k = 16: row-slice with two rows per thread 4220 GB/s, column-slice 3890, one row 3680.
   if constexpr (std::is_same<TA, float>::value) {
+    // impl == 6: tensor-core layout (3xTF32 through mma.sync).  Exact to fp32 rounding level but NOT the default:
+    // measured on B200 (N = 16384, k = 16) it reaches 1.95 TB/s against 4.3 TB/s of the SIMT row-slice layout -- the
+    // legacy mma.sync TF32 path sustains only ~43 clk per m16n8k8 per SM sub-partition (~53 TFLOP/s per GPU); the
+    // tcgen05 / TMEM form of the same scheme is the round-2 item.
+    const bool tc_ok = a.E == nullptr && a.dot_out == nullptr;
+    if (a.impl == 6 && !tc_ok) {
+      set_last_error("matvec: the tensor-core layout takes plain products only (no shift, no fused dots)");
+      return XT_ERR_INVALID;
+    }
+    if (a.impl == 6) return launch_tc(a, dev, til, st);
     if (a.impl == 4 && a.k > 4) {
       if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
       return launch_colslice<16>(a, dev, til, st);
@@ -953,7 +1186,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
     }
   }
 
-  const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5);
+  const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5 || a.impl == 6);
   bool use_tma = forced_tma || (a.impl == 0 && mv_tma_ok(a));
   if (forced_tma && !mv_tma_ok(a)) {
     set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
