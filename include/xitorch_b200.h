@@ -124,6 +124,14 @@ typedef struct {
    * runs in the library's kernels; only the operator is the caller's. */
   void* apply;
   void* apply_user;
+  /* preconditioners (reference: `precond` of cg, solve.py:122,136,171; `precond_l` / `precond_r` of bicgstab,
+   * solve.py:247-248,276-287), applied through callbacks of the same signature as `apply` (a dense preconditioner's
+   * callback is one xt_block_matvec).  cg: z = precond_l(r).  bicgstab: y = precond_r(p), z = precond_r(s) (carried
+   * out as the composed operator A o precond_r on the un-preconditioned iterate), and
+   * omega = <K t, K s> / <K t, K t> with K = precond_l.  NULL = identity.  Ignored by gmres. */
+  void* precond_l;
+  void* precond_r;
+  void* precond_user;
 } xt_solve_args;
 
 size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, int32_t nbatch,

@@ -150,6 +150,36 @@ run_solve("AEM", "bicgstab", A3, B3, E=E3, M=M3, herm=True, rtol=1e-9, posdef=Tr
 run_solve("AE probe", "bicgstab", A3, B3, E=E3, herm=True, rtol=1e-9)
 cases["solve"] = sol
 
+# preconditioned cg / bicgstab (solve.py:122,136,171 and :247-248,276-287): Jacobi-like and approximate-inverse
+# preconditioners on an ill-scaled system
+print("preconditioned solve")
+pre = []
+n = 80
+dg = torch.logspace(0, 3, n, dtype=torch.float64)
+R4 = torch.rand(n, n, generator=gen(51), dtype=torch.float64) * 0.2
+A4s = torch.diag(dg) + (R4 + R4.t()) * 0.5
+A4n = torch.diag(dg) + R4
+B4 = torch.rand(n, 3, generator=gen(52), dtype=torch.float64)
+Pj = torch.diag(1.0 / dg)                                        # Jacobi
+Pa = torch.linalg.inv(A4n + 0.05 * torch.diag(dg))               # approximate inverse
+for tag, method, A, herm, kw in [
+        ("jacobi", "cg", A4s, True, {"precond": Pj}),
+        ("jacobi right", "bicgstab", A4n, False, {"precond_r": Pj}),
+        ("approx-inverse left+right", "bicgstab", A4n, False, {"precond_l": Pa, "precond_r": Pj}),
+        ("jacobi left", "bicgstab", A4n, False, {"precond_l": Pj})]:
+    ref_kw = {k: RefLinOp.m(v, is_hermitian=bool(torch.allclose(v, v.t()))) for k, v in kw.items()}
+    or_kw = {k: oracle.DenseOp(v, bool(torch.allclose(v, v.t()))) for k, v in kw.items()}
+    opts = {"rtol": 1e-10, "atol": 1e-14, "posdef": True}
+    x_ref = ref_solve(RefLinOp.m(A, is_hermitian=herm), B4, method=method, **opts, **ref_kw)
+    x_o, info = getattr(oracle, method)(oracle.DenseOp(A, herm), B4, return_info=True, **opts, **or_kw)
+    x_plain, info0 = getattr(oracle, method)(oracle.DenseOp(A, herm), B4, return_info=True, **opts)
+    check("%s %s" % (method, tag), x_o, x_ref, 1e-11, atol=1e-13)
+    print("     iterations with / without the preconditioner: %d / %d" % (info["niter"], info0["niter"]))
+    pre.append({"tag": tag, "method": method, "A": A, "B": B4, "herm": herm, "precond": kw, "opts": opts,
+                "x": x_ref, "x_exact": torch.linalg.solve(A, B4), "oracle_niter": info["niter"],
+                "plain_niter": info0["niter"]})
+cases["solve_precond"] = pre
+
 torch.save(cases, os.path.join(OUT, "krylov_golden.pt"))
 print("wrote", os.path.join(OUT, "krylov_golden.pt"),
       "%.1f KiB" % (os.path.getsize(os.path.join(OUT, "krylov_golden.pt")) / 1024),

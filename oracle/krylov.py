@@ -294,11 +294,14 @@ def _unswap(x, swapped):
 # --------------------------------------------------------------------------
 # solve: cg / bicgstab / gmres
 # --------------------------------------------------------------------------
-def cg(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=1e-8, eps=1e-12,
+def cg(A, B, E=None, M=None, posdef=None, precond=None, max_niter=None, rtol=1e-6, atol=1e-8, eps=1e-12,
        resid_calc_every=10, return_info=False, **unused):
-    """(Unpreconditioned) conjugate gradient, all columns/batches in lock-step with a GLOBAL
-    stop test and best-iterate bookkeeping (/root/reference/xitorch/_impls/linalg/solve.py:69-190)."""
+    """(Preconditioned) conjugate gradient, all columns/batches in lock-step with a GLOBAL
+    stop test and best-iterate bookkeeping (/root/reference/xitorch/_impls/linalg/solve.py:69-190;
+    `precond`: z = precond.mm(r), :122,136,171)."""
     A, M = _as_op(A), _as_op(M)
+    precond = _as_op(precond)
+    pfcn = (lambda x: x) if precond is None else precond.mm
     nr, ncols = A.shape[-1], B.shape[-1]
     if max_niter is None:
         max_niter = int(1.5 * nr)
@@ -312,7 +315,8 @@ def cg(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=1e-8, 
     shape = (ncols, *batchdims, nr, 1) if swapped else (*batchdims, nr, ncols)
     xk = torch.zeros(shape, dtype=A.dtype, device=A.device)
     rk = B2 - A_fcn(xk)                                                      # :135 (spends a matvec)
-    pk = zk = rk
+    zk = pfcn(rk)
+    pk = zk
     rkzk = _dot(rk, zk)
     converged = False
     best_resid = rk.norm(dim=-2).max().item()
@@ -333,7 +337,7 @@ def cg(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=1e-8, 
         if torch.all(rnorm < stop):
             converged = True
             break
-        zk1 = rk1
+        zk1 = pfcn(rk1)
         rkzk1 = _dot(rk1, zk1)
         beta = rkzk1 / _safedenom(rkzk, eps)
         pk = zk1 + beta * pk
@@ -348,12 +352,16 @@ def cg(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=1e-8, 
     return x
 
 
-def bicgstab(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=1e-8, eps=1e-12,
-             resid_calc_every=10, return_info=False, **unused):
-    """(Unpreconditioned) BiCGSTAB with r0hat = r0
+def bicgstab(A, B, E=None, M=None, posdef=None, precond_l=None, precond_r=None, max_niter=None, rtol=1e-6,
+             atol=1e-8, eps=1e-12, resid_calc_every=10, return_info=False, **unused):
+    """(Preconditioned) BiCGSTAB with r0hat = r0
     (/root/reference/xitorch/_impls/linalg/solve.py:192-324); first step uses the scalar
-    initial values alpha=1, omega=1, v=p=0 (:265-268)."""
+    initial values alpha=1, omega=1, v=p=0 (:265-268); y = precond_r(p), z = precond_r(s),
+    omega = <K t, K s> / <K t, K t> with K = precond_l (:276-287)."""
     A, M = _as_op(A), _as_op(M)
+    precond_l, precond_r = _as_op(precond_l), _as_op(precond_r)
+    pl = (lambda x: x) if precond_l is None else precond_l.mm
+    pr = (lambda x: x) if precond_r is None else precond_r.mm
     nr, ncols = B.shape[-2:]
     if max_niter is None:
         max_niter = int(1.5 * nr)
@@ -382,13 +390,16 @@ def bicgstab(A, B, E=None, M=None, posdef=None, max_niter=None, rtol=1e-6, atol=
         omega_den = _safedenom(omega_k, eps)
         beta = rho_new / _safedenom(rho_k, eps) * (alpha / omega_den)
         pk = rk + beta * (pk - omega_k * vk)
-        vk = A_fcn(pk)
+        y = pr(pk)
+        vk = A_fcn(y)
         alpha = rho_new / _safedenom(_dot(r0hat, vk), eps)
-        h = xk + alpha * pk
+        h = xk + alpha * y
         s = rk - alpha * vk
-        t = A_fcn(s)
-        omega_k = _dot(t, s) / _safedenom(_dot(t, t), eps)
-        xk = h + omega_k * s
+        z = pr(s)
+        t = A_fcn(z)
+        Kt = pl(t)
+        omega_k = _dot(Kt, pl(s)) / _safedenom(_dot(Kt, Kt), eps)
+        xk = h + omega_k * z
         if resid_calc_every != 0 and k % resid_calc_every == 0:
             rk = B2 - A_fcn(xk)
         else:

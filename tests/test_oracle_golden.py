@@ -56,6 +56,17 @@ def test_solvers_match_reference(golden):
         assert err <= 1e-4
 
 
+def test_preconditioned_solvers_match_reference(golden):
+    for case in golden["solve_precond"]:
+        kw = {k: oracle.DenseOp(v, bool(torch.allclose(v, v.t()))) for k, v in case["precond"].items()}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = getattr(oracle, case["method"])(oracle.DenseOp(case["A"], case["herm"]), case["B"],
+                                                      return_info=True, **case["opts"], **kw)
+        assert torch.allclose(x, case["x"], rtol=1e-10, atol=1e-12), case["tag"]
+        assert info["niter"] == case["oracle_niter"], case["tag"]
+
+
 def test_exact_helpers():
     A = oracle.make_spd_c1(32)
     B = torch.ones(32, 2, dtype=torch.float64)

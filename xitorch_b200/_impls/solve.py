@@ -106,13 +106,37 @@ def _mat3(mat: torch.Tensor, batch: Sequence[int]):
     return m3, bstride, ld
 
 
+def _block_callback(fn, ws, nbytes, vdt, shape, opdt, failure):
+    """ctypes callback `(user, X, Y, stream)` computing ``Y = fn(X)`` on (nbatch, n, ncols) blocks that live inside the
+    workspace tensor `ws`; exceptions cannot cross the C frame and are collected in `failure`."""
+    base = ws.data_ptr()
+
+    def _cb(user, xptr, yptr, stream):
+        try:
+            xv = ws[xptr - base: xptr - base + nbytes].view(vdt).view(*shape)
+            yv = ws[yptr - base: yptr - base + nbytes].view(vdt).view(*shape)
+            with torch.no_grad():
+                yv.copy_(fn(xv.to(opdt)))
+        except BaseException as exc:
+            if not failure:
+                failure.append(exc)
+
+    return _lib.APPLY_FN(_cb)
+
+
+def _check_precond(**kw):
+    for k, v in kw.items():
+        if v is not None and not isinstance(v, LinearOperator):
+            raise TypeError("%s can only be LinearOperator or None" % k)
+
+
 def _is_dense(op: Optional[LinearOperator]) -> bool:
     return op is None or isinstance(op, MatrixLinearOperator)
 
 
 def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, need_hermit: bool,
                      max_niter: int, rtol: float, atol: float, eps: float, resid_calc_every: int,
-                     info: Optional[dict]):
+                     info: Optional[dict], precond_l=None, precond_r=None):
     """Krylov solve with a matrix-free operator (user `_mv`, autograd Jacobians, composite operators).
 
     The solver loop -- every vector update, dot product, norm, the stop test and the best-iterate bookkeeping --
@@ -178,23 +202,17 @@ def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef
     ws = torch.empty(wsb, dtype=torch.uint8, device=Bf.device)
     g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
     g.stream = _lib.stream_ptr(Bf.device)
-    base = ws.data_ptr()
     nbytes = nb * n * ncols * ws.new_empty(0, dtype=vdt).element_size()
     failure = []
-
-    def _apply(user, xptr, yptr, stream):
-        # X, Y are (nbatch, n, ncols) blocks inside the workspace tensor
-        try:
-            xv = ws[xptr - base: xptr - base + nbytes].view(vdt).view(*batch, n, ncols)
-            yv = ws[yptr - base: yptr - base + nbytes].view(vdt).view(*batch, n, ncols)
-            with torch.no_grad():
-                yv.copy_(op(xv.to(opdt)))
-        except BaseException as exc:      # exceptions cannot cross the C frame: re-raised below
-            if not failure:
-                failure.append(exc)
-
-    cb = _lib.APPLY_FN(_apply)
+    shape = (*batch, n, ncols)
+    cb = _block_callback(op, ws, nbytes, vdt, shape, opdt, failure)
     g.apply = C.cast(cb, C.c_void_p)
+    keep = [cb]
+    for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
+        if pc is not None:
+            pcb = _block_callback(pc.mm, ws, nbytes, vdt, shape, opdt, failure)
+            setattr(g, field, C.cast(pcb, C.c_void_p))
+            keep.append(pcb)
     with torch.cuda.device(Bf.device):
         rc = getattr(L, "xt_" + name)(g)
     if failure:
@@ -207,17 +225,18 @@ def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef
         warnings.warn(ConvergenceWarning(
             "Convergence is not achieved after %d iterations. Max norm of best resid: %.3e"
             % (max_niter, best.value)))
-    del cb
+    del keep, cb
     return X.reshape(*batch, n, ncols).to(out_dtype)
 
 
 def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, need_hermit: bool,
                 max_niter: int, rtol: float, atol: float, eps: float, resid_calc_every: int,
-                check_every: Optional[int], info: Optional[dict]):
+                check_every: Optional[int], info: Optional[dict], precond_l=None, precond_r=None):
     _lib.require_cuda(B, "linalg.solve(method=%r)" % name)
+    _check_precond(precond_l=precond_l, precond_r=precond_r)
     if not _is_dense(A) or (E is not None and not _is_dense(M)):
         return _run_matrix_free(name, A, B, E, M, posdef, need_hermit, max_niter, rtol, atol, eps,
-                                resid_calc_every, info)
+                                resid_calc_every, info, precond_l, precond_r)
     n, ncols = A.shape[-1], B.shape[-1]
     batch = get_batchdims(A, B, E, M)
     Amat = _dense_of(A, "A")
@@ -254,6 +273,8 @@ def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, nee
             Amat = torch.matmul(AT, Afull)
             Bcol = B.expand(*batch, n, ncols).transpose(-2, -1).unsqueeze(-1).to(Amat.dtype)   # (*batch, ncols, n, 1)
             Bv = torch.matmul(AT, Bcol)
+            if precond_l is not None or precond_r is not None:
+                raise RuntimeError("xitorch_b200: preconditioners together with E and the normal equations are not supported")
             x = _call(name, Amat, None, None, Bv, (*batch, ncols), n, 1, vdt, max_niter, rtol, atol, eps,
                       resid_calc_every, check_every, info)
             return x.squeeze(-1).transpose(-2, -1).to(out_dtype)
@@ -261,12 +282,12 @@ def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, nee
         Bv = torch.matmul(AT.to(vdt), B.to(vdt))
         Amat = torch.matmul(AT, Amat)
     x = _call(name, Amat, Mmat, E, Bv, batch, n, ncols, vdt, max_niter, rtol, atol, eps, resid_calc_every,
-              check_every, info)
+              check_every, info, precond_l, precond_r)
     return x.to(out_dtype)
 
 
 def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, eps, resid_calc_every,
-          check_every, info):
+          check_every, info, precond_l=None, precond_r=None):
     L = _lib.lib()
     nb = 1
     for s in batch:
@@ -300,8 +321,21 @@ def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, e
     ws = torch.empty(wsb, dtype=torch.uint8, device=Bf.device)
     g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
     g.stream = _lib.stream_ptr(Bf.device)
+    failure = []
+    if precond_l is not None or precond_r is not None:
+        # preconditioners reach the library as block callbacks (a dense one is a single xt_block_matvec per call)
+        nbytes = nb * n * ncols * X.element_size()
+        for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
+            if pc is not None:
+                pcb = _block_callback(pc.mm, ws, nbytes, vdt, (*batch, n, ncols), pc.dtype, failure)
+                setattr(g, field, C.cast(pcb, C.c_void_p))
+                keep.append(pcb)
+        g.check_every = 1
     with torch.cuda.device(Bf.device):
-        _lib.check(getattr(L, "xt_" + name)(g), name)
+        rc = getattr(L, "xt_" + name)(g)
+    if failure:
+        raise failure[0]
+    _lib.check(rc, name)
     if info is not None:
         info.update(niter=niter.value, converged=bool(conv.value), best_resid=best.value, napply=napply.value)
     if not conv.value:
@@ -309,13 +343,6 @@ def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, e
             "Convergence is not achieved after %d iterations. Max norm of best resid: %.3e"
             % (max_niter, best.value)))
     return X.reshape(*batch, n, ncols)
-
-
-def _no_precond(**kw):
-    for k, v in kw.items():
-        if v is not None:
-            raise RuntimeError("xitorch_b200: option %s is not supported by the fused kernels yet "
-                               "(SURVEY.md 8f row f4)" % k)
 
 
 def cg(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: Optional[LinearOperator] = None,
@@ -332,7 +359,7 @@ def cg(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: 
         Whether :math:`\mathbf{AX-MXE}` is positive definite for all columns and batches.
         ``False`` (or a non-Hermitian operator) switches to the normal equations. ``None`` means True.
     precond: LinearOperator or None
-        Not supported by the fused kernel yet (must be None).
+        Preconditioner ``z = precond.mm(r)`` (one more operator application per iteration).
     max_niter: int or None
         Maximum number of iterations. If None, ``int(1.5 * A.shape[-1])``.
     rtol, atol: float
@@ -348,11 +375,10 @@ def cg(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: 
     info: dict or None
         If given, receives ``niter``, ``converged``, ``best_resid``, ``napply``.
     """
-    _no_precond(precond=precond)
     if max_niter is None:
         max_niter = int(1.5 * A.shape[-1])
     return _run_krylov("cg", A, B, E, M, posdef, True, max_niter, rtol, atol, eps, resid_calc_every,
-                       check_every, info)
+                       check_every, info, precond_l=precond)
 
 
 def bicgstab(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None,
@@ -370,7 +396,8 @@ def bicgstab(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = Non
     posdef: bool or None
         ``False`` switches to the normal equations; ``None`` means True.
     precond_l, precond_r: LinearOperator or None
-        Not supported by the fused kernel yet (must be None).
+        Left / right preconditioners, used exactly as the reference does: ``y = precond_r.mm(p)``,
+        ``z = precond_r.mm(s)`` and ``omega = <K t, K s> / <K t, K t>`` with ``K = precond_l``.
     max_niter: int or None
         Maximum number of iterations. If None, ``int(1.5 * A.shape[-1])``.
     rtol, atol: float
@@ -384,11 +411,10 @@ def bicgstab(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = Non
     check_every, info:
         As in :func:`cg`.
     """
-    _no_precond(precond_l=precond_l, precond_r=precond_r)
     if max_niter is None:
         max_niter = int(1.5 * A.shape[-1])
     return _run_krylov("bicgstab", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, resid_calc_every,
-                       check_every, info)
+                       check_every, info, precond_l=precond_l, precond_r=precond_r)
 
 
 def gmres(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, M: Optional[LinearOperator] = None,

@@ -54,6 +54,7 @@ class SolveArgs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("stream", C.c_void_p),
         ("apply", C.c_void_p), ("apply_user", C.c_void_p),
+        ("precond_l", C.c_void_p), ("precond_r", C.c_void_p), ("precond_user", C.c_void_p),
     ]
 
 

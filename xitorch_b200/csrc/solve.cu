@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, i
   if (phase == 1) return;
   col_reduce<1>(part, S.ncols, g.tx, g.ty, g.TX, g.TY, scr, res);
   norm_bookkeeping(S, b, res, iter, scr);
+  if (S.precond) return;          // z = P r, beta and p follow in cg_precond_kernel
   // beta = rz_new / safedenom(rz);  p = r + beta p
   for (int cs = 0; cs * g.TX < S.ncols; ++cs) {
     const int c = cs * g.TX + g.tx;
@@ -187,6 +188,35 @@ __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, i
   }
   __syncthreads();
   for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) S.rz[b * S.ncols + c] = res[c];
+}
+
+// preconditioned CG tail (solve.py:170-180): rz_new = r.z (fused into the application of the preconditioner),
+// beta = rz_new / safedenom(rz), p = z + beta p  (first call: p = z)
+template <typename TV>
+__global__ void __launch_bounds__(SV_THREADS) cg_precond_kernel(SolveState<TV> S, const TV* __restrict__ z, int first) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  const Geo g = geo(S.ncols);
+  double* bet = sm;                       // [ncols]
+  if (S.ctl->done) return;
+  const int64_t len = (int64_t)S.n * S.ncols;
+  const int64_t base = (int64_t)b * len;
+  for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) {
+    const double rzn = tile_dot(S, b, c, 0);
+    bet[c] = first ? 0.0 : rzn / safedenom(S.rz[b * S.ncols + c], S.eps);
+    S.rz[b * S.ncols + c] = rzn;
+  }
+  __syncthreads();
+  for (int cs = 0; cs * g.TX < S.ncols; ++cs) {
+    const int c = cs * g.TX + g.tx;
+    if (c < S.ncols) {
+      const TV beta = (TV)bet[c];
+      for (int row = g.ty; row < S.n; row += g.TY) {
+        const int64_t o = base + (int64_t)row * S.ncols + c;
+        S.p[o] = first ? z[o] : z[o] + beta * S.p[o];
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------- BiCGSTAB
@@ -349,11 +379,13 @@ static int setup_state(const xt_solve_args* g, int nvecs, Arena& ar, SolveState<
   memset(&S, 0, sizeof(S));
   S.n = g->n; S.nbatch = g->nbatch; S.ncols = g->ncols;
   S.tiles_per_batch = til.tiles_per_batch;
-  TV* vecs[10];
+  TV* vecs[16];
   for (int i = 0; i < nvecs; ++i) vecs[i] = ar.take<TV>(len);
   S.x = vecs[0]; S.r = vecs[1]; S.p = vecs[2]; S.q = vecs[3]; S.bestx = vecs[4];
   *extra = vecs[5];                       // M x scratch (or unused)
-  if (nvecs > 6) { S.s = vecs[6]; S.t = vecs[7]; S.rhat = vecs[8]; }
+  if (nvecs > 6) S.s = vecs[6];
+  if (nvecs > 8) { S.t = vecs[7]; S.rhat = vecs[8]; }
+  if (nvecs > 11) { S.ex[0] = vecs[9]; S.ex[1] = vecs[10]; S.ex[2] = vecs[11]; }
   S.dots_gstride = (int64_t)til.ntiles * 2 * MV_MAXK;
   S.dots = ar.take<double>((size_t)ngroups * S.dots_gstride);
   S.rz = ar.take<double>((size_t)g->nbatch * g->ncols);
@@ -389,8 +421,29 @@ template <typename TV> static size_t step_smem(int ncols) {
   return (size_t)(3 * ncols + 2 * SV_THREADS + 64) * sizeof(double);
 }
 
-template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>& S, int64_t napply, cudaStream_t st) {
-  solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
+template <typename TV>
+__global__ void __launch_bounds__(SV_THREADS) copy_out_kernel(const TV* __restrict__ src, int n, int ncols, TV* X,
+                                                             int64_t ldx, int64_t x_bstride) {
+  const int64_t len = (int64_t)n * ncols;
+  const TV* s = src + (int64_t)blockIdx.x * len;
+  TV* Xb = X + (int64_t)blockIdx.x * x_bstride;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+    const int64_t row = i / ncols, c = i - row * ncols;
+    Xb[row * ldx + c] = s[i];
+  }
+}
+
+template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>& S, int64_t napply, cudaStream_t st,
+                                         void* pre = nullptr) {
+  if (pre != nullptr) {
+    // x = P_r xt for the best iterate
+    solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, S.ex[1], g->ncols, (int64_t)g->n * g->ncols); XT_LAUNCHED();
+    reinterpret_cast<xt_apply_fn>(pre)(g->precond_user, S.ex[1], S.ex[2], st);
+    copy_out_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S.ex[2], g->n, g->ncols, static_cast<TV*>(g->X), g->ldx,
+                                                          g->x_bstride); XT_LAUNCHED();
+  } else {
+    solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
+  }
   XT_CUDA_OK(cudaGetLastError());
   SolveCtl h;
   XT_CUDA_OK(cudaMemcpyAsync(&h, S.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -407,7 +460,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   Arena ar(g->workspace, g->workspace_bytes);
   SolveState<TV> S;
   TV* mx;
-  int rc = setup_state<TV>(g, 6, ar, S, &mx);
+  int rc = setup_state<TV>(g, 7, ar, S, &mx);
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
@@ -420,6 +473,21 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   const int ce = g->check_every > 0 ? g->check_every : 1;
   int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
+  // preconditioner z = P r (solve.py:136,171): one more operator application per iteration, r.z fused into it
+  OpDesc pc{g->dtype, g->n, g->nbatch, g->ncols, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0};
+  pc.apply = g->precond_l; pc.apply_user = g->precond_user;
+  S.precond = g->precond_l != nullptr ? 1 : 0;
+  TV* zbuf = S.s;                         // unused by plain cg
+  auto precond_step = [&](int first) -> int {
+    int rc_ = apply_op<TV>(pc, S.r, zbuf, mx, S.r, S.dots, S.dots_gstride, done_flag, st, nullptr);
+    if (rc_ != XT_OK) return rc_;
+    cg_precond_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, zbuf, first); XT_LAUNCHED();
+    return XT_OK;
+  };
+  if (S.precond) {
+    rc = precond_step(1);
+    if (rc != XT_OK) return rc;
+  }
   for (int k = 1; k <= g->max_niter; ++k) {
     rc = apply_op<TV>(op, S.p, S.q, mx, S.p, S.dots, S.dots_gstride, done_flag, st, &napply);
     if (rc != XT_OK) return rc;
@@ -431,6 +499,10 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
       rc = apply_op<TV>(op, S.x, S.q, mx, nullptr, nullptr, 0, done_flag, st, &napply);
       if (rc != XT_OK) return rc;
       cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
+    }
+    if (S.precond) {
+      rc = precond_step(0);
+      if (rc != XT_OK) return rc;
     }
     XT_CUDA_OK(cudaGetLastError());
     if (k == next_check || k == g->max_niter) {
@@ -449,11 +521,17 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   Arena ar(g->workspace, g->workspace_bytes);
   SolveState<TV> S;
   TV* mx;
-  int rc = setup_state<TV>(g, 9, ar, S, &mx);
+  int rc = setup_state<TV>(g, 12, ar, S, &mx);
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
   op.apply = g->apply; op.apply_user = g->apply_user;
+  // right preconditioner (solve.py:276,282): y = P_r p, z = P_r s and x = h + omega z are the plain recurrences of the
+  // composed operator A o P_r on the iterate xt with x = P_r xt (applied once at the end); the residual is untouched
+  op.pre = g->precond_r; op.pre_user = g->precond_user; op.pre_tmp = S.ex[0];
+  // left preconditioner (solve.py:285-286): only omega = <K t, K s> / <K t, K t>
+  OpDesc pl{g->dtype, g->n, g->nbatch, g->ncols, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0};
+  pl.apply = g->precond_l; pl.apply_user = g->precond_user;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1); XT_LAUNCHED();
@@ -469,6 +547,12 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
     bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
     rc = apply_op<TV>(op, S.s, S.t, mx, S.s, S.dots, S.dots_gstride, done_flag, st, &napply);      // t = A s, t.s, t.t
     if (rc != XT_OK) return rc;
+    if (pl.apply != nullptr) {            // K s, then K t with <K s, K t> and <K t, K t> in place of t.s and t.t
+      rc = apply_op<TV>(pl, S.s, S.ex[1], mx, nullptr, nullptr, 0, done_flag, st, nullptr);
+      if (rc != XT_OK) return rc;
+      rc = apply_op<TV>(pl, S.t, S.ex[2], mx, S.ex[1], S.dots, S.dots_gstride, done_flag, st, nullptr);
+      if (rc != XT_OK) return rc;
+    }
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
       bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 3); XT_LAUNCHED();
@@ -487,7 +571,7 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
       if (done) break;
     }
   }
-  return finish<TV>(g, S, napply, st);
+  return finish<TV>(g, S, napply, st, g->precond_r);
 }
 
 size_t gmres_ws_bytes(size_t vs, int n, int nbatch, int ncols, int max_niter);   // gmres.cu
@@ -501,8 +585,8 @@ size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, in
   (void)has_M;
   const size_t vs = dtype == XT_F64 ? 8 : 4;
   if (method == nullptr) return 0;
-  if (strcmp(method, "cg") == 0) return xt::solve_ws_bytes(6, vs, n, nbatch, ncols);
-  if (strcmp(method, "bicgstab") == 0) return xt::solve_ws_bytes(9, vs, n, nbatch, ncols);
+  if (strcmp(method, "cg") == 0) return xt::solve_ws_bytes(7, vs, n, nbatch, ncols);
+  if (strcmp(method, "bicgstab") == 0) return xt::solve_ws_bytes(12, vs, n, nbatch, ncols);
   if (strcmp(method, "gmres") == 0) return xt::gmres_ws_bytes(vs, n, nbatch, ncols, max_niter);
   return 0;
 }

@@ -36,6 +36,8 @@ template <typename TV> struct SolveState {
   double *cta_max; int* cta_bad;   // [nbatch]
   SolveCtl* ctl;
   double eps;
+  TV* ex[3];             // bicgstab scratch: pre(X) | K s | K t   (preconditioners)
+  int precond;           // cg: z = P r comes from a separate operator application (the step kernel stops after the norms)
 };
 
 __device__ __forceinline__ double safedenom(double v, double eps) { return v == 0.0 ? eps : v; }
@@ -90,6 +92,9 @@ struct OpDesc {
   const void* E; int64_t e_bstride;
   void* apply = nullptr;        // matrix-free operator callback (xt_solve_args.apply)
   void* apply_user = nullptr;
+  void* pre = nullptr;          // right preconditioner callback: the operator applied is A o pre
+  void* pre_user = nullptr;
+  void* pre_tmp = nullptr;      // (nbatch, n, ncols) scratch for pre(X)
 };
 
 typedef void (*xt_apply_fn)(void* user, const void* X, void* Y, void* stream);
@@ -133,6 +138,13 @@ template <typename TV>
 static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const TV* U, double* dots, int64_t dots_gstride,
                     const int* done_flag, cudaStream_t st, int64_t* napply) {
   const int64_t len = (int64_t)op.n * op.ncols;
+  if (op.pre != nullptr) {
+    // composed operator A o pre: the preconditioned block goes through scratch, then the operator proper
+    reinterpret_cast<xt_apply_fn>(op.pre)(op.pre_user, X, op.pre_tmp, st);
+    OpDesc inner = op;
+    inner.pre = nullptr;
+    return apply_op<TV>(inner, static_cast<const TV*>(op.pre_tmp), Y, mx, U, dots, dots_gstride, done_flag, st, napply);
+  }
   if (op.apply != nullptr) {
     // matrix-free operator: the caller applies it, the dot products the dense path fuses into the matvec epilogue
     // come from one small kernel with the same per-tile layout
