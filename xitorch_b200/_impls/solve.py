@@ -229,11 +229,99 @@ def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef
     return X.reshape(*batch, n, ncols).to(out_dtype)
 
 
+# ----------------------------------------------------------------------------- complex systems
+def _to_real(x: torch.Tensor) -> torch.Tensor:
+    """(..., n, c) complex -> (..., 2n, c) real: real parts stacked over imaginary parts."""
+    return torch.cat([x.real, x.imag], dim=-2)
+
+
+def _to_cplx(x: torch.Tensor) -> torch.Tensor:
+    n = x.shape[-2] // 2
+    return torch.complex(x[..., :n, :].contiguous(), x[..., n:, :].contiguous())
+
+
+class _RealEquivalent(LinearOperator):
+    """the real 2n x 2n form ``[[Re, -Im], [Im, Re]]`` of a complex operator given by callables for the operator and
+    its adjoint; Hermitian complex <=> symmetric real, and the real inner product of stacked vectors is ``Re(x^H y)``,
+    which is all CG needs (the quantities it divides are real for Hermitian operators)."""
+
+    def __init__(self, fcn, fcn_adj, shape, is_hermitian, rdtype, device):
+        super().__init__(shape=shape, is_hermitian=is_hermitian, dtype=rdtype, device=device,
+                         _suppress_hermit_warning=True)
+        self._fcn, self._fcn_adj = fcn, fcn_adj
+
+    def _mv(self, x):
+        return self._mm(x.unsqueeze(-1)).squeeze(-1)
+
+    def _mm(self, x):
+        return _to_real(self._fcn(_to_cplx(x)))
+
+    def _rmv(self, x):
+        return self._rmm(x.unsqueeze(-1)).squeeze(-1)
+
+    def _rmm(self, x):
+        return _to_real(self._fcn_adj(_to_cplx(x)))
+
+    def _getparamnames(self, prefix=""):
+        return []
+
+
+def _run_complex(name, A, B, E, M, posdef, need_hermit, max_niter, rtol, atol, eps, resid_calc_every, check_every,
+                 info, precond_l, precond_r):
+    """Complex systems (the reference's cg / bicgstab are complex-correct through `_dot`'s conjugate,
+    solve.py:441-445) are solved in their real-equivalent form with the same real kernels: for cg the recurrences are
+    identical to the complex ones; bicgstab / gmres become the real-arithmetic method on the doubled system (same
+    solution at convergence, different iteration path)."""
+    cdt = A.dtype if A.dtype.is_complex else (torch.complex128 if B.dtype in (torch.float64, torch.complex128)
+                                              else torch.complex64)
+    rdt = torch.float64 if cdt == torch.complex128 else torch.float32
+    n = A.shape[-1]
+    Bc = B.to(cdt)
+    e_real = E is None or not E.is_complex()
+    if isinstance(A, MatrixLinearOperator) and A.mat.is_cuda and M is None and e_real and precond_l is None and \
+            precond_r is None:
+        # dense fast path: the doubled matrix goes through the block-matvec kernels like any real operator
+        Am = A.mat.to(cdt)
+        Ar = torch.cat([torch.cat([Am.real, -Am.imag], dim=-1), torch.cat([Am.imag, Am.real], dim=-1)], dim=-2)
+        opr = MatrixLinearOperator(Ar.contiguous(), is_hermitian=A.is_hermitian)
+        Er = None if E is None else E.to(rdt)
+        xr = _run_krylov(name, opr, _to_real(Bc), Er, None, posdef, need_hermit, max_niter, rtol, atol, eps,
+                         resid_calc_every, check_every, info)
+        return _to_cplx(xr)
+    Ec = None if E is None else E.to(cdt).unsqueeze(-2)
+
+    def fcn(x):
+        y = A.mm(x)
+        if Ec is not None:
+            y = y - (M.mm(x) if M is not None else x) * Ec
+        return y
+
+    def fcn_adj(x):
+        y = A.rmm(x)
+        if Ec is not None:
+            y = y - (M.rmm(x) if M is not None else x) * Ec.conj()
+        return y
+
+    hermit = A.is_hermitian and (E is None or (e_real and (M is None or M.is_hermitian)))
+    batch = get_batchdims(A, B, E, M)
+    opr = _RealEquivalent(fcn, fcn_adj, (*batch, 2 * n, 2 * n), hermit, rdt, B.device)
+    pcs = []
+    for pc in (precond_l, precond_r):
+        pcs.append(None if pc is None else
+                   _RealEquivalent(pc.mm, pc.rmm, (*pc.shape[:-2], 2 * n, 2 * n), pc.is_hermitian, rdt, B.device))
+    xr = _run_matrix_free(name, opr, _to_real(Bc), None, None, posdef, need_hermit, max_niter, rtol, atol, eps,
+                          resid_calc_every, info, pcs[0], pcs[1])
+    return _to_cplx(xr)
+
+
 def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, need_hermit: bool,
                 max_niter: int, rtol: float, atol: float, eps: float, resid_calc_every: int,
                 check_every: Optional[int], info: Optional[dict], precond_l=None, precond_r=None):
     _lib.require_cuda(B, "linalg.solve(method=%r)" % name)
     _check_precond(precond_l=precond_l, precond_r=precond_r)
+    if A.dtype.is_complex or B.is_complex() or (E is not None and E.is_complex()):
+        return _run_complex(name, A, B, E, M, posdef, need_hermit, max_niter, rtol, atol, eps, resid_calc_every,
+                            check_every, info, precond_l, precond_r)
     if not _is_dense(A) or (E is not None and not _is_dense(M)):
         return _run_matrix_free(name, A, B, E, M, posdef, need_hermit, max_niter, rtol, atol, eps,
                                 resid_calc_every, info, precond_l, precond_r)
