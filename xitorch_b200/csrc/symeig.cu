@@ -2,14 +2,19 @@
 // B200-native restatement of davidson (xitorch/_impls/linalg/symeig.py:100-227) and its orthogonaliser
 // tallqr (xitorch/_utils/tensor.py:8-19), plus the block-Lanczos variant ("lanczos", BASELINE.json C5).
 //
-// One iteration = one subspace expansion:
-//   1. W = A Q_j                      one pass over A (matvec.cu)                      [symeig.py:221]
-//   2. C = V^T W                      new block column of T = V^T A V (fp64 accumulate) [symeig.py:170, incremental]
-//   3. eigh(T), keep k extreme pairs  one-CTA cyclic Jacobi in fp64                      [symeig.py:174-175]
-//   4. X = V S, R = AV S - X Lambda,  max|R| -> stop test / best-pair bookkeeping        [symeig.py:178-199]
-//   5. expansion block Z: R (expansion=0, the reference's Davidson step, symeig.py:207) or W (expansion=1,
-//      block Lanczos: same Krylov space), orthogonalised against V by block classical Gram-Schmidt
-//      (twice for W) and orthonormalised by Cholesky-QR with an fp64 Gram matrix     [symeig.py:210-220, tensor.py:8-19]
+// One iteration = one subspace expansion.  With the Krylov expansion (the default) it is TWO launches on the main
+// stream plus one on a side stream:
+//   1. W = A Q_j                        one pass over A (matvec.cu)                                   [symeig.py:221]
+//   2. expand_fused_kernel (cooperative, one CTA per SM, two grid barriers):
+//        C = V^T W (new block column of T = V^T A V, fp64)                                           [symeig.py:170, incremental]
+//        W' = W - V C, C2 = V^T W', G = W'^T W'  (block classical Gram-Schmidt, twice)               [symeig.py:210-220]
+//        Q_{j+1} = (W' - V C2) chol(G)^-T        (Cholesky-QR, fp64 Gram matrix)                     [tensor.py:8-19]
+//        + the Ritz check that is due: X = V S, R = AV S - X Lambda, max|R| -> stop test / best pair [symeig.py:178-199]
+//   3. rr_kernel on a side stream (one CTA on an SM the matvec leaves free): the k extreme eigenpairs of T --
+//      register-resident Householder tridiagonalisation, Sturm multisection, inverse iteration, back-transformation
+//      (replaces torch.linalg.eigh of the whole T)                                                    [symeig.py:174-175]
+// The literal Davidson step (expansion = 0: append the Ritz residuals, symeig.py:207), restart iterations and
+// XT_NO_FUSE=1 use the multi-kernel path (subproj_kernel, orth_finish_kernel, ritz_kernel, t_update_kernel).
 // Differences from the reference, all result-preserving: T and the basis are updated incrementally (old
 // basis vectors are not re-orthonormalised every iteration), Gram/projection matrices are accumulated in
 // fp64 (the reference's fp32 tallqr breaks down), the subspace is thick-restarted when it
