@@ -25,6 +25,10 @@ class MathWarning(Warning):
     """Emitted when a mathematical requirement (e.g. degenerate-eigenvector gradients) is violated."""
 
 
+class GetSetParamsError(Exception):
+    """Raised by EditableModule.assertparams when a method changes the object's state or lists a non-float parameter."""
+
+
 def assert_runtime(cond: bool, msg: str = "") -> None:
     if not cond:
         raise RuntimeError(msg)
@@ -114,10 +118,27 @@ def set_attr(obj, path: str, val) -> None:
 
 
 def _set_module_attr(mod: torch.nn.Module, key: str, val) -> None:
-    if key in mod._parameters:
+    if isinstance(val, (torch.nn.Parameter, torch.nn.Module)):
+        mod.__dict__.pop(key, None)          # a plain tensor put there by an earlier substitution
+        setattr(mod, key, val)               # registers the parameter / submodule properly
+    elif key in mod._parameters:
         del mod._parameters[key]
         object.__setattr__(mod, key, val)
     elif key in mod._buffers:
         mod._buffers[key] = val
     else:
         object.__setattr__(mod, key, val)
+
+
+def del_attr(obj, path: str) -> None:
+    """delete the attribute / item at `path` (a list item is replaced by None so that the length is preserved)"""
+    toks = _parse_path(path)
+    for tok in toks[:-1]:
+        obj = _step(obj, tok)
+    kind, key = toks[-1]
+    if kind == "attr":
+        delattr(obj, key)
+    elif isinstance(obj, list):
+        obj[key] = None
+    else:
+        del obj[key]

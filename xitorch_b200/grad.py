@@ -6,15 +6,16 @@ These are the operators the rootfinder backward hands to `linalg.solve` (rootfin
 double-backward trick (one JVP per operator application), `rmv` one VJP.  With `xitorch_b200` the Krylov loop around
 them runs in the CUDA solver kernels and only these products are autograd calls (`xt_solve_args.apply`).
 
-Scope note: the function must be pure with respect to `params` (plain functions, closures, bound methods whose object
-state is constant).  The reference's object-parameter plumbing (`get_pure_function` over EditableModule / nn.Module
-state, xitorch/_core/pure_function.py) is outside the Krylov hot path and is not rebuilt here.
+`fcn` may be a function, a `torch.jit` script function, or a method of an `EditableModule` / `torch.nn.Module`: it is
+wrapped by `get_pure_function`, and the tensors hidden in the object (`objparams`) are operator parameters like the
+explicit ones, so derivatives with respect to them flow through `solve` / `symeig` backward.
 """
 from typing import Any, Callable, List, Sequence, Union
 
 import torch
 
 from xitorch_b200.linop import LinearOperator
+from xitorch_b200.pure_function import get_pure_function, make_sibling
 
 __all__ = ["jac", "hess"]
 
@@ -38,7 +39,8 @@ def jac(fcn: Callable[..., torch.Tensor], params: Sequence[Any],
         idxs: Union[None, int, Sequence[int]] = None) -> Union[LinearOperator, List[LinearOperator]]:
     """LinearOperator(s) of shape ``(nout, nin)`` acting as the Jacobian of ``fcn`` w.r.t. ``params[idx]``."""
     lst = _resolve_idxs(idxs, params)
-    res = [_Jac(fcn, params, i) for i in lst]
+    pfcn = get_pure_function(fcn)
+    res = [_Jac(pfcn, params, i) for i in lst]
     return res[0] if isinstance(idxs, int) else res
 
 
@@ -46,11 +48,13 @@ def hess(fcn: Callable[..., torch.Tensor], params: Sequence[Any],
          idxs: Union[None, int, Sequence[int]] = None) -> Union[LinearOperator, List[LinearOperator]]:
     """LinearOperator(s) of shape ``(nin, nin)`` acting as the Hessian of the scalar ``fcn`` w.r.t. ``params[idx]``."""
     lst = _resolve_idxs(idxs, params)
+    pfcn = get_pure_function(fcn)
 
     def grad_of(idx):
+        @make_sibling(pfcn)
         def gfcn(*prm):
             with torch.enable_grad():
-                z = fcn(*prm)
+                z = pfcn(*prm)
             (g,) = torch.autograd.grad(z, (prm[idx],), retain_graph=True, create_graph=torch.is_grad_enabled())
             return g
         return gfcn
@@ -71,7 +75,8 @@ class _Jac(LinearOperator):
     parameters are swapped (`uselinopparams`)."""
 
     def __init__(self, fcn, params: Sequence[Any], idx: int, is_hermitian: bool = False) -> None:
-        self.fcn = fcn
+        self.fcn = get_pure_function(fcn)
+        self.objparams = list(self.fcn.objparams())
         self.idx = idx
         self.params = list(params)
         self._tensor_pos = [i for i, p in enumerate(self.params) if isinstance(p, torch.Tensor)]
@@ -87,18 +92,19 @@ class _Jac(LinearOperator):
         for pos, t in zip(self._tensor_pos, self.params_tensor):
             self.params[pos] = t
         self.yparam = self.params[self.idx]
-        with torch.enable_grad():
+        with torch.enable_grad(), self.fcn.useobjparams(self.objparams):
             self.yout = self.fcn(*self.params)
             self.v = torch.ones_like(self.yout).requires_grad_()
             (self.dfdy,) = torch.autograd.grad(self.yout, (self.yparam,), grad_outputs=self.v, create_graph=True)
-        self._ids = [id(t) for t in self.params_tensor]
+        self._ids = [id(t) for t in self.params_tensor] + [id(t) for t in self.objparams]
 
     def _refresh(self):
-        if [id(t) for t in self.params_tensor] != self._ids:
+        if [id(t) for t in self.params_tensor] + [id(t) for t in self.objparams] != self._ids:
             self._linearise()
 
     def _getparamnames(self, prefix: str = "") -> List[str]:
-        return [prefix + ("params_tensor[%d]" % i) for i in range(len(self.params_tensor))]
+        return [prefix + ("params_tensor[%d]" % i) for i in range(len(self.params_tensor))] + \
+               [prefix + ("objparams[%d]" % i) for i in range(len(self.objparams))]
 
     def _mv(self, gy: torch.Tensor) -> torch.Tensor:
         # J g = d/dv <dfdy(v), g>   (dfdy is linear in the dummy cotangent v)
@@ -110,7 +116,7 @@ class _Jac(LinearOperator):
                                        retain_graph=True, create_graph=torch.is_grad_enabled())
             rows.append(r.reshape(1, self.nout))
         res = torch.cat(rows, dim=0).reshape(*gy.shape[:-1], self.nout)
-        return _tie(res, self.params_tensor)
+        return _tie(_tie(res, self.params_tensor), self.objparams)
 
     def _rmv(self, gout: torch.Tensor) -> torch.Tensor:
         # J^T g: one vector-Jacobian product per vector
@@ -122,4 +128,4 @@ class _Jac(LinearOperator):
                                        retain_graph=True, create_graph=torch.is_grad_enabled())
             rows.append(r.reshape(1, self.nin))
         res = torch.cat(rows, dim=0).reshape(*gout.shape[:-1], self.nin)
-        return _tie(res, self.params_tensor)
+        return _tie(_tie(res, self.params_tensor), self.objparams)

@@ -30,6 +30,7 @@ import torch
 
 from xitorch_b200 import _utils
 from xitorch_b200 import debug as _debug
+from xitorch_b200.editable_module import EditableModule
 
 __all__ = ["LinearOperator", "MatrixLinearOperator"]
 
@@ -39,7 +40,7 @@ def _indent(s: str, n: int) -> str:
     return ("\n" + pad).join(s.split("\n"))
 
 
-class LinearOperator(object):
+class LinearOperator(EditableModule):
     """Base class of (batched) linear operators of shape ``(*B, p, q)``."""
 
     _impl_flags_ready = False
@@ -228,28 +229,50 @@ class LinearOperator(object):
                                 matmat=lambda v: nn(self.mm(tt(v))), rmatmat=lambda v: nn(self.rmm(tt(v))))
 
     def check(self, warn: Optional[bool] = None) -> None:
-        """cheap self-consistency check (shape of mv/mm, adjoint identity, Hermiticity)."""
+        """Check that the operator behaves as a linear operator (contract of the reference's `check` / `checklinop`,
+        linop.py:492-521, 710-802): `mv` / `mm` (and `rmv` / `rmm` when implemented) are run on every input shape the
+        broadcasting rules allow; the output shapes, linearity (scaling by 1.25, zero input) and independence of an
+        extra leading batch dimension are asserted.  A failing operator call raises RuntimeError, a wrong result
+        AssertionError.  `warn=None` warns that the check is slow unless debug mode is on."""
         if warn is None:
-            warn = _debug.is_debug_enabled()
+            warn = not _debug.is_debug_enabled()
+        if warn:
+            warnings.warn("The linear operator check is performed. This might slow down your program.", stacklevel=2)
         p, q = self.shape[-2:]
-        x = torch.rand(q, dtype=self.dtype, device=self.device)
-        y = self.mv(x)
-        if list(y.shape) != [*self._batchshape, p]:
-            raise RuntimeError("mv returned shape %s, expected %s" % (tuple(y.shape), (*self._batchshape, p)))
-        X = torch.rand(q, 2, dtype=self.dtype, device=self.device)
-        Y = self.mm(X)
-        if list(Y.shape) != [*self._batchshape, p, 2]:
-            raise RuntimeError("mm returned shape %s" % (tuple(Y.shape),))
-        if not torch.allclose(Y[..., 0], self.mv(X[..., 0]), rtol=1e-4, atol=1e-6):
-            raise RuntimeError("mm and mv are inconsistent")
-        z = torch.rand(p, dtype=self.dtype, device=self.device)
-        lhs = (self.rmv(z).conj() * x).sum(-1)
-        rhs = (z.conj() * self.mv(x)).sum(-1)
-        if not torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-6):
-            msg = "rmv is not the adjoint of mv"
-            if self._is_hermitian:
-                msg = "The linear operator is marked Hermitian but <A^H z, x> != <z, A x>"
-            raise RuntimeError(msg)
+        batch = tuple(self._batchshape)
+
+        def expected(lead, nout):
+            # result batch shape: the operator's batch dims broadcast against the input's leading dims
+            return (*torch.broadcast_shapes(batch, lead), nout)
+
+        def probe(name, xshape, yshape):
+            fcn = getattr(self, name)
+            x = torch.rand(xshape, dtype=self.dtype, device=self.device)
+            try:
+                y = fcn(x)
+                y_scaled = fcn(1.25 * x)
+                y_zero = fcn(0 * x)
+                y_stacked = fcn(torch.stack((x, 1.25 * x), dim=0))
+            except Exception as exc:
+                raise RuntimeError("An error is raised from .%s with input shape: %s (linear operator shape: %s)\n%r"
+                                   % (name, tuple(xshape), tuple(self.shape), exc))
+            assert list(y.shape) == list(yshape), \
+                "The output shape of .%s is not correct. Input: %s, expected output: %s, output: %s\n%s" % \
+                (name, tuple(xshape), tuple(yshape), tuple(y.shape), self)
+            assert torch.allclose(y_scaled, 1.25 * y), "Linearity check fails\n%s\n" % self
+            assert torch.allclose(y_zero, y * 0), "Linearity check (with 0) fails\n%s" % self
+            assert torch.allclose(y_stacked[0], y) and torch.allclose(y_stacked[1], y_scaled), \
+                "Batched test fails (expanding batches changes the results)%s" % self
+
+        leads = [(), (1,), (1, 1), batch, (1, *batch)]
+        for lead in leads:
+            probe("mv", (*lead, q), expected(lead, p))
+            probe("mm", (*lead, q, 2), (*expected(lead, p), 2))
+        if self.is_rmv_implemented:
+            for lead in leads:
+                probe("rmv", (*lead, p), expected(lead, q))
+                probe("rmm", (*lead, p, 2), (*expected(lead, q), 2))
+        print("Check linear operator done")
 
     # ------------------------------------------------------------------ algebra
     @property

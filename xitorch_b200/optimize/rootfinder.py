@@ -9,8 +9,9 @@ parameter gradients through one more evaluation of ``fcn`` (:352-362).  With CUD
 the fused Krylov kernels (default for n > 5: "bicgstab") with the Jacobian applied through the operator callback of
 the C ABI.
 
-`fcn` must be pure with respect to `(y, *params)` (see `xitorch_b200.grad`); `minimize` is not part of the Krylov
-hot path and is not provided.
+`fcn` may be a function or a method of an `EditableModule` / `torch.nn.Module` (`get_pure_function`): the tensors hidden
+in the object travel through `torch.autograd.Function.apply` next to the explicit parameters, exactly as in the
+reference, so gradients reach them.  `minimize` is not part of the Krylov hot path and is not provided.
 """
 from typing import Any, Callable, Mapping, Sequence, Union
 
@@ -19,6 +20,7 @@ import torch
 from xitorch_b200._utils import get_method
 from xitorch_b200._impls.rootsolver import broyden1, broyden2, linearmixing
 from xitorch_b200.grad import jac
+from xitorch_b200.pure_function import get_pure_function, make_sibling
 from xitorch_b200.linalg.solve import solve
 
 __all__ = ["rootfinder", "equilibrium"]
@@ -35,58 +37,69 @@ def rootfinder(fcn: Callable[..., torch.Tensor], y0: torch.Tensor, params: Seque
     "linearmixing" | callable ``fcn_method(fcn, y0, params, **opts)``; ``bck_options``: options of the adjoint
     `linalg.solve` in backward (``method`` among them); ``**fwd_options``: options of the method.
     """
+    pfunc = get_pure_function(fcn)
     fwd_options["method"] = "broyden1" if method is None else method
-    return _RootFinder.apply(fcn, y0, fcn, fwd_options, bck_options, len(params), *params)
+    return _RootFinder.apply(pfunc, y0, pfunc, fwd_options, bck_options, len(params), *params, *pfunc.objparams())
 
 
 def equilibrium(fcn: Callable[..., torch.Tensor], y0: torch.Tensor, params: Sequence[Any] = [],
                 bck_options: Mapping[str, Any] = {}, method: Union[str, Callable, None] = None,
                 **fwd_options) -> torch.Tensor:
     r"""Solve :math:`\mathbf{y} = \mathbf{f}(\mathbf{y}, \theta)` for ``y`` (rootfinder on ``f(y) - y``)."""
+    pfunc = get_pure_function(fcn)
+
+    @make_sibling(pfunc)
     def resid(y, *prm):
-        return y - fcn(y, *prm)
+        return y - pfunc(y, *prm)
 
     fwd_options["method"] = "broyden1" if method is None else method
-    return _RootFinder.apply(resid, y0, resid, fwd_options, bck_options, len(params), *params)
+    return _RootFinder.apply(resid, y0, resid, fwd_options, bck_options, len(params), *params, *pfunc.objparams())
 
 
 class _RootFinder(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, fcn, y0, fwd_fcn, options, bck_options, nparams, *params):
+    def forward(ctx, fcn, y0, fwd_fcn, options, bck_options, nparams, *allparams):
         config = dict(options)
         ctx.bck_options = dict(bck_options)
+        params, objparams = allparams[:nparams], allparams[nparams:]
         method = config.pop("method")
         method_fcn = get_method("rootfinder", _RF_METHODS, method)
-        y = method_fcn(fwd_fcn, y0, params, **config)
+        with fwd_fcn.useobjparams(objparams):
+            y = method_fcn(fwd_fcn, y0, params, **config)
         ctx.fcn = fcn
-        ctx.is_tensor = [isinstance(p, torch.Tensor) for p in params]
-        ctx.nontensors = [p for p in params if not isinstance(p, torch.Tensor)]
-        ctx.save_for_backward(y, *[p for p in params if isinstance(p, torch.Tensor)])
+        ctx.nparams = nparams
+        ctx.is_tensor = [isinstance(p, torch.Tensor) for p in allparams]
+        ctx.nontensors = [p for p in allparams if not isinstance(p, torch.Tensor)]
+        ctx.save_for_backward(y, *[p for p in allparams if isinstance(p, torch.Tensor)])
         return y
 
     @staticmethod
     def backward(ctx, grad_yout):
         yout = ctx.saved_tensors[0]
         tensors = list(ctx.saved_tensors[1:])
-        fcn = ctx.fcn
+        fcn, nparams = ctx.fcn, ctx.nparams
 
         def rebuild(tens):
             it, jt = iter(tens), iter(ctx.nontensors)
             return [next(it) if flag else next(jt) for flag in ctx.is_tensor]
 
-        params = rebuild(tensors)
-        # dL/df: adjoint solve with the matrix-free Jacobian at the root
-        with torch.enable_grad():
-            y_lin = yout.detach().requires_grad_()
-        jac_dfdy = jac(fcn, params=(y_lin, *params), idxs=[0])[0]
-        gyfcn = solve(A=jac_dfdy.H, B=-grad_yout.reshape(-1, 1), bck_options=ctx.bck_options, **ctx.bck_options)
-        gyfcn = gyfcn.reshape(grad_yout.shape)
-        # gradients of the parameters through one more evaluation of fcn
-        with torch.enable_grad():
-            copies = [p.clone().requires_grad_() for p in tensors]
-            yfcn = fcn(yout, *rebuild(copies))
-        grads = torch.autograd.grad(yfcn, copies, grad_outputs=gyfcn, create_graph=torch.is_grad_enabled(),
-                                    allow_unused=True) if copies else ()
+        allparams = rebuild(tensors)
+        params, objparams = allparams[:nparams], allparams[nparams:]
+        with fcn.useobjparams(objparams):
+            # dL/df: adjoint solve with the matrix-free Jacobian at the root
+            with torch.enable_grad():
+                y_lin = yout.detach().requires_grad_()
+            jac_dfdy = jac(fcn, params=(y_lin, *params), idxs=[0])[0]
+            gyfcn = solve(A=jac_dfdy.H, B=-grad_yout.reshape(-1, 1), bck_options=ctx.bck_options, **ctx.bck_options)
+            gyfcn = gyfcn.reshape(grad_yout.shape)
+            # gradients of the (explicit and object) parameters through one more evaluation of fcn
+            with torch.enable_grad():
+                copies = [p.clone().requires_grad_() for p in tensors]
+                allcopy = rebuild(copies)
+                with fcn.useobjparams(allcopy[nparams:]):
+                    yfcn = fcn(yout, *allcopy[:nparams])
+            grads = torch.autograd.grad(yfcn, copies, grad_outputs=gyfcn, create_graph=torch.is_grad_enabled(),
+                                        allow_unused=True) if copies else ()
         it = iter(grads)
         grad_params = [next(it) if flag else None for flag in ctx.is_tensor]
         return (None, None, None, None, None, None, *grad_params)
