@@ -18,7 +18,7 @@ import torch
 
 from xitorch_b200._utils import ConvergenceWarning
 
-__all__ = ["broyden1", "broyden2", "linearmixing"]
+__all__ = ["newton", "broyden1", "broyden2", "linearmixing"]
 
 
 # ----------------------------------------------------------------------------- rank-r inverse Jacobian
@@ -130,6 +130,28 @@ class _Broyden(object):
 
 class _Broyden2(_Broyden):
     second = True
+
+
+class _Newton(object):
+    """exact Jacobian: each step solves ``J(x) s = f(x)`` with `linalg.solve` (_jacobian.py:26-49).  With a Krylov
+    `solver_method` on CUDA tensors this is Newton-Krylov: the linear solve runs in the CUDA solver kernels with the
+    matrix-free Jacobian applied through the operator callback."""
+
+    def __init__(self, solver_method="exactsolve", solver_kwargs=None):
+        self.solver_method = solver_method
+        self.solver_kwargs = {} if solver_kwargs is None else solver_kwargs
+
+    def setup(self, x0, y0, func):
+        self.x, self.func = x0, func
+
+    def solve(self, v, tol=0):
+        from xitorch_b200.grad import jac
+        from xitorch_b200.linalg import solve
+        J = jac(self.func, (self.x.clone().requires_grad_(),), idxs=0)
+        return solve(J, v.unsqueeze(-1), method=self.solver_method, **self.solver_kwargs).squeeze(-1)
+
+    def update(self, x, y):
+        self.x = x
 
 
 class _LinearMixing(object):
@@ -318,6 +340,20 @@ def _armijo(phi, phi0, derphi0, c1=1e-4, alpha0=1, amin=0, max_niter=20):
 
 
 # ----------------------------------------------------------------------------- methods
+def newton(fcn, x0, params=(), *, solver_method: str = "exactsolve", solver_kwargs: Optional[dict] = None, **kwargs):
+    """
+    Solve the root finder using the Newton method: ``x <- x - J(x)^{-1} f(x)`` with ``J`` the Jacobian of ``f``.
+
+    Keyword arguments
+    -----------------
+    solver_method: str
+        The `xitorch_b200.linalg.solve` method that solves with the Jacobian.
+    solver_kwargs: dict or None
+        The keyword arguments of that solve method.
+    """
+    return _nonlin_solver(fcn, x0, params, jacobian=_Newton(solver_method, solver_kwargs), **kwargs)
+
+
 def broyden1(fcn, x0, params=(), *, alpha: Optional[float] = None,
              uv0: Optional[Union[str, Tuple[torch.Tensor, torch.Tensor]]] = None,
              max_rank: Optional[int] = None, **kwargs):
@@ -371,5 +407,5 @@ def linearmixing(fcn, x0, params=(), *, alpha: Optional[float] = None, **kwargs)
     return _nonlin_solver(fcn, x0, params, jacobian=_LinearMixing(alpha=alpha), **kwargs)
 
 
-for _f in (broyden1, broyden2, linearmixing):
+for _f in (newton, broyden1, broyden2, linearmixing):
     _f.__doc__ += _nonlin_solver.__doc__

@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 from xitorch_b200 import _lib
-from xitorch_b200._utils import ConvergenceWarning, bcast_dims
+from xitorch_b200._utils import ConvergenceWarning, MathWarning, bcast_dims
+from xitorch_b200.debug import is_debug_enabled
 from xitorch_b200.linop import LinearOperator
 from xitorch_b200._impls.solve import _dense_of, _mat3
 
@@ -27,17 +28,60 @@ def _take(evals, evecs, neig, mode):
     return evals[..., -neig:], evecs[..., -neig:]
 
 
+class _EighDegenerate(torch.autograd.Function):
+    """`torch.linalg.eigh` whose backward stays finite at repeated eigenvalues.
+
+    The eigenvector cotangent enters the textbook formula through the gaps 1/(lambda_j - lambda_i); inside a
+    degenerate cluster that factor is dropped (its contribution vanishes whenever the loss does not depend on the
+    choice of basis inside the cluster, which is the only case where the derivative exists -- Kasim 2020,
+    arXiv:2011.04366).  Same contract as the reference's workaround (symeig.py:47-98): clusters are pairs closer than
+    eps**0.6, debug mode warns when the basis-independence requirement is violated, the result is Hermitian.
+    """
+
+    @staticmethod
+    def forward(ctx, A):
+        lam, U = torch.linalg.eigh(A)
+        ctx.save_for_backward(lam, U)
+        return lam, U
+
+    @staticmethod
+    def backward(ctx, glam, gU):
+        lam, U = ctx.saved_tensors
+        Uh = U.transpose(-2, -1).conj()
+        inner = None
+        if gU is not None:
+            gap = lam.unsqueeze(-2) - lam.unsqueeze(-1)                    # gap[i, j] = lam_j - lam_i
+            clustered = gap.abs() <= torch.finfo(lam.dtype).eps ** 0.6     # includes the diagonal
+            proj = torch.matmul(Uh, gU)
+            if is_debug_enabled():
+                skew = (proj - proj.transpose(-2, -1).conj())[clustered]
+                if not torch.allclose(skew, torch.zeros_like(skew)):
+                    warnings.warn(MathWarning(
+                        "Degeneracy appears but the loss function seem to depend strongly on the eigenvector. "
+                        "The gradient might be incorrect.\nEigenvalues:\n%s\nDegenerate map:\n%s\n"
+                        "Requirements (should be all 0s):\n%s" % (lam, clustered, skew)))
+            weight = torch.where(clustered, torch.zeros_like(gap), 1.0 / torch.where(clustered, torch.ones_like(gap), gap))
+            inner = weight * proj
+        if glam is not None:
+            d = torch.diag_embed(glam).to(U.dtype)
+            inner = d if inner is None else inner + d
+        if inner is None:
+            return torch.zeros_like(U)
+        gA = torch.matmul(U, torch.matmul(inner, Uh))
+        return 0.5 * (gA + gA.transpose(-2, -1).conj())
+
+
 def exacteig(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]):
     """full dense eigendecomposition then truncation (reference symeig.py:11-44); the generalized
-    problem is whitened with the Cholesky factor of M."""
+    problem is whitened with the Cholesky factor of M.  Differentiable also at degenerate spectra."""
     Amat = A.fullmatrix()
     if M is None:
-        evals, evecs = torch.linalg.eigh(Amat)
+        evals, evecs = _EighDegenerate.apply(Amat)
         return _take(evals, evecs, neig, mode)
     L = torch.linalg.cholesky(M.fullmatrix())
     Linv = torch.inverse(L)
     LinvT = Linv.transpose(-2, -1).conj()
-    evals, q = torch.linalg.eigh(torch.matmul(Linv, torch.matmul(Amat, LinvT)))
+    evals, q = _EighDegenerate.apply(torch.matmul(Linv, torch.matmul(Amat, LinvT)))
     evals, q = _take(evals, q, neig, mode)
     return evals, torch.matmul(LinvT, q)
 

@@ -1,3 +1,3 @@
-from xitorch_b200.optimize.rootfinder import rootfinder, equilibrium   # noqa: F401
+from xitorch_b200.optimize.rootfinder import rootfinder, equilibrium, minimize   # noqa: F401
 
-__all__ = ["rootfinder", "equilibrium"]
+__all__ = ["rootfinder", "equilibrium", "minimize"]
