@@ -179,6 +179,15 @@ typedef struct {
   int32_t world, rank;
   void* allgather;
   void* allgather_user;
+  /* matrix-free operator (any LinearOperator of the reference: user _mv, composite operators such as A^H A of svd,
+   * autograd Jacobians / Hessians; xitorch/_impls/linalg/symeig.py:155,165 call A.mm on whatever operator they get).
+   * When non-NULL, `A` is ignored and every block application is handed to the caller:
+   *   void apply(void* user, const void* X, void* Y, void* stream)      Y = A X,
+   * X and Y contiguous (n, neig) row-major blocks of the value type inside the workspace, ordered on `stream`.
+   * Everything else of the iteration stays in the library's kernels.  The stop flag cannot gate user code: up to three
+   * applications may run after convergence (their results are never read).  Needs nbatch = 1 and world <= 1. */
+  void* apply;
+  void* apply_user;
 } xt_symeig_args;
 
 size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);

@@ -16,8 +16,10 @@ import torch
 from xitorch_b200 import _lib
 from xitorch_b200._utils import ConvergenceWarning, MathWarning, bcast_dims
 from xitorch_b200.debug import is_debug_enabled
-from xitorch_b200.linop import LinearOperator
+from xitorch_b200.linop import LinearOperator, MatrixLinearOperator
 from xitorch_b200._impls.solve import _dense_of, _mat3
+
+_MATERIALISE_MAX_N = 16384      # composite / matrix-free operators up to this size are materialised by default
 
 __all__ = ["exacteig", "custom_exacteig", "davidson", "lanczos"]
 
@@ -117,14 +119,95 @@ def _start_block(kind, nb, n, neig, dtype, dev):
     return v
 
 
+def _use_callback(A: LinearOperator, M: Optional[LinearOperator], matrix_free: Optional[bool]) -> bool:
+    """matrix-free operators: dense ones never; others when asked for, or when they are too large to materialise
+    (None = automatic).  Batched matrix-free operators are always materialised (the engine solves batch items one
+    after another, an operator callback cannot be split per item)."""
+    if isinstance(A, MatrixLinearOperator) or matrix_free is False:
+        return False
+    batched = any(s != 1 for s in A.shape[:-2]) or (M is not None and any(s != 1 for s in M.shape[:-2]))
+    if batched:
+        if matrix_free:
+            raise RuntimeError("xitorch_b200: matrix_free=True needs an operator without batch dimensions")
+        return False
+    return bool(matrix_free) or A.shape[-1] > _MATERIALISE_MAX_N
+
+
+def _start(kind: str, nb: int, n: int, neig: int, vdt, dev):
+    # start block (the reference reseeds the GLOBAL RNG with 12421, symeig.py:236; a local generator with
+    # the same seed is used here so callers' random streams are left alone)
+    kind = kind.lower()
+    if kind == "eye":
+        return torch.eye(n, neig, dtype=vdt, device=dev).expand(nb, n, neig).contiguous()
+    if kind in ("randn", "rand", "random"):
+        return _start_block(kind, nb, n, neig, vdt, dev)
+    raise ValueError("Unknown v_init type: %s" % kind)
+
+
+def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps, max_basis, check_every, info, name):
+    """Krylov eigensolver on an operator that is only known through `A.mm` (user `_mv`, composite operators such as
+    ``A^H A`` of `svd`, autograd Hessians): the whole iteration stays in the engine's kernels, each block application
+    ``Y = A X`` comes back to Python through the `apply` hook of `xt_symeig_args` (one call per iteration, on the current
+    stream), as the reference calls `A.mm` on whatever operator it gets (symeig.py:155,165).  A generalized problem is
+    whitened with the dense Cholesky factor of M: the operator becomes ``X -> L^-1 A (L^-T X)``."""
+    n = A.shape[-1]
+    probe = torch.empty(0, dtype=A.dtype, device=A.device)
+    _lib.require_cuda(probe, "linalg.symeig(method=%r)" % name)
+    if A.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("xitorch_b200.%s: matrix-free operators must be float32 or float64 (got %s)" % (name, A.dtype))
+    vdt, dev = A.dtype, A.device
+    LinvT = None
+    op = A.mm
+    if M is not None:
+        with torch.no_grad():
+            L = torch.linalg.cholesky(_dense_of(M, "M").to(vdt).reshape(n, n))
+            Linv = torch.inverse(L)
+        LinvT = Linv.transpose(-2, -1)
+
+        def op(x):
+            return torch.matmul(Linv, A.mm(torch.matmul(LinvT, x)))
+
+    V0 = _start(v_init, 1, n, neig, vdt, dev)
+    failure = []
+
+    def make_apply(ws):
+        base, nbytes = ws.data_ptr(), n * neig * V0.element_size()
+
+        def _cb(user, xptr, yptr, stream):
+            try:
+                xv = ws[xptr - base: xptr - base + nbytes].view(vdt).view(n, neig)
+                yv = ws[yptr - base: yptr - base + nbytes].view(vdt).view(n, neig)
+                with torch.no_grad():
+                    yv.copy_(op(xv).reshape(n, neig))
+            except BaseException as exc:
+                if not failure:
+                    failure.append(exc)
+
+        return _lib.APPLY_FN(_cb)
+
+    evals, evecs = _call_engine(None, 0, 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis, check_every,
+                                min_eps, info, name, make_apply=make_apply)
+    if failure:
+        raise failure[0]
+    batch = tuple(A.shape[:-2])
+    evals = evals.reshape(*batch, neig)
+    evecs = evecs.reshape(*batch, n, neig)
+    if LinvT is not None:
+        evecs = torch.matmul(LinvT, evecs)
+    return evals, evecs
+
+
 def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator], expansion: int,
             max_niter: int, nguess: Optional[int], v_init: str, min_eps: float, max_basis: Optional[int],
-            check_every: Optional[int], info: Optional[dict], name: str):
+            check_every: Optional[int], info: Optional[dict], name: str, matrix_free: Optional[bool] = None):
     if nguess is not None and nguess != neig:
         raise RuntimeError("xitorch_b200.%s: nguess must equal neig (got %d vs %d)" % (name, nguess, neig))
     if mode not in ("lowest", "uppest"):
         raise RuntimeError("Unknown mode: %s" % mode)
     n = A.shape[-1]
+    if _use_callback(A, M, matrix_free):
+        return _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps, max_basis, check_every,
+                                   info, name)
     Amat = _dense_of(A, "A")
     _lib.require_cuda(Amat, "linalg.symeig(method=%r)" % name)
     if Amat.is_complex():
@@ -148,15 +231,7 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
         nb *= s
     vdt = Amat.dtype
 
-    # start block (the reference reseeds the GLOBAL RNG with 12421, symeig.py:236; a local generator with
-    # the same seed is used here so callers' random streams are left alone)
-    kind = v_init.lower()
-    if kind == "eye":
-        V0 = torch.eye(n, neig, dtype=vdt, device=dev).expand(nb, n, neig).contiguous()
-    elif kind in ("randn", "rand", "random"):
-        V0 = _start_block(kind, nb, n, neig, vdt, dev)
-    else:
-        raise ValueError("Unknown v_init type: %s" % v_init)
+    V0 = _start(v_init, nb, n, neig, vdt, dev)
 
     A3, a_bs, lda = _mat3(Amat, batch)
     evals, evecs = _call_engine(A3, lda, (a_bs if nb > 1 else 0), n, nb, neig, mode, expansion, V0, max_niter,
@@ -169,10 +244,11 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
 
 
 def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max_basis, check_every, min_eps,
-                 info, name, dist_ctx=None):
+                 info, name, dist_ctx=None, make_apply=None):
     """fill `xt_symeig_args` and run `xt_symeig_krylov`.  dist_ctx = (world, rank, group) for the row-partitioned
-    operator: A3 is then this rank's (n/world, n) row block and the per-iteration all-gather hook is installed."""
-    vdt, dev = A3.dtype, A3.device
+    operator: A3 is then this rank's (n/world, n) row block and the per-iteration all-gather hook is installed.
+    make_apply(workspace) -> APPLY_FN for a matrix-free operator (A3 is then None)."""
+    vdt, dev = V0.dtype, V0.device
     if max_basis is None:
         max_basis = _default_max_basis(n, neig)
     evals = torch.empty((nb, neig), dtype=vdt, device=dev)
@@ -183,14 +259,14 @@ def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max
     g.n, g.nbatch, g.neig = n, nb, neig
     g.mode = 0 if mode == "lowest" else 1
     g.expansion = expansion
-    g.A, g.lda, g.a_bstride = A3.data_ptr(), lda, a_bs
+    g.A, g.lda, g.a_bstride = (A3.data_ptr() if A3 is not None else None), lda, a_bs
     g.V0, g.ldv0, g.v0_bstride = V0.data_ptr(), neig, n * neig
     g.evals, g.evals_bstride = evals.data_ptr(), neig
     g.evecs, g.ldv, g.evecs_bstride = evecs.data_ptr(), neig, n * neig
     g.max_niter, g.max_basis = int(max_niter), int(max_basis)
     world = dist_ctx[0] if dist_ctx is not None else 1
     if check_every is None:
-        t_iter = max((n // world) * n * A3.element_size() / 6.0e12, 3e-5)
+        t_iter = max((n // world) * n * V0.element_size() / 6.0e12, 3e-5)
         check_every = max(4, min(16, int(1e-3 / t_iter)))
     g.check_every = int(check_every)
     g.min_eps = float(min_eps)
@@ -220,6 +296,10 @@ def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max
         keep.append(cb)
         g.world, g.rank = world, rank
         g.allgather = C.cast(cb, C.c_void_p)
+    if make_apply is not None:
+        acb = make_apply(ws)
+        keep.append(acb)
+        g.apply = C.cast(acb, C.c_void_p)
     with torch.cuda.device(dev):
         _lib.check(L_.xt_symeig_krylov(g), name)
     if info is not None:
@@ -252,7 +332,7 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
              max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
              max_addition: Optional[int] = None, min_eps: float = 1e-6, verbose: bool = False,
              max_basis: Optional[int] = None, check_every: Optional[int] = None,
-             info: Optional[dict] = None, expansion: str = "krylov", **unused):
+             info: Optional[dict] = None, expansion: str = "krylov", matrix_free: Optional[bool] = None, **unused):
     """
     Block Davidson (Rayleigh-Ritz on span{V0, r0, r1, ...}) on the B200.
 
@@ -283,17 +363,22 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
         longer waits for the Rayleigh-Ritz step, which then overlaps with the next matvec on the GPU.
         ``"residual"``: append the orthonormalised Ritz residuals literally as the reference does
         (symeig.py:207-220); Rayleigh-Ritz is then on the critical path of every iteration.
+    matrix_free: bool or None
+        How an operator that is not a dense matrix (user ``_mv``, ``A.H.matmul(A)``, Jacobians ...) is applied.
+        ``True``: through ``A.mm`` once per iteration, nothing is materialised.  ``False``: ``A.fullmatrix()`` is built
+        once and the dense kernels are used.  ``None``: materialise up to n = 16384, matrix-free beyond.
     """
     if expansion not in ("krylov", "residual"):
         raise RuntimeError("Unknown expansion: %s" % expansion)
     return _krylov(A, neig, mode, M, 1 if expansion == "krylov" else 0, max_niter, nguess, v_init, min_eps,
-                   max_basis, check_every, info, "davidson")
+                   max_basis, check_every, info, "davidson", matrix_free)
 
 
 def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
             max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
             min_eps: float = 1e-6, verbose: bool = False, max_basis: Optional[int] = None,
-            check_every: Optional[int] = None, info: Optional[dict] = None, **unused):
+            check_every: Optional[int] = None, info: Optional[dict] = None,
+            matrix_free: Optional[bool] = None, **unused):
     """
     Block Lanczos with full reorthogonalisation and Rayleigh-Ritz extraction on the B200: the same
     Krylov space as ``davidson`` (which has no preconditioner), expanded with the orthonormalised
@@ -311,8 +396,8 @@ def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
         Stop when the largest entry of the residual ``|A X - X E|`` is below this value
     verbose: bool
         Ignored
-    max_basis, check_every, info:
+    max_basis, check_every, info, matrix_free:
         As in :func:`davidson`
     """
     return _krylov(A, neig, mode, M, 1, max_niter, nguess, v_init, min_eps, max_basis, check_every, info,
-                   "lanczos")
+                   "lanczos", matrix_free)

@@ -78,6 +78,7 @@ class SymeigArgs(C.Structure):
         ("stream", C.c_void_p),
         ("world", C.c_int32), ("rank", C.c_int32),
         ("allgather", C.c_void_p), ("allgather_user", C.c_void_p),
+        ("apply", C.c_void_p), ("apply_user", C.c_void_p),
     ]
 
 

@@ -1841,6 +1841,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     XT_REQUIRE(g->allgather != nullptr && g->rank >= 0 && g->rank < world && g->nbatch == 1,
                "symeig: row-partitioned mode needs an all-gather hook, a valid rank and nbatch = 1");
   }
+  XT_REQUIRE(g->apply == nullptr || (!collective && g->nbatch == 1),
+             "symeig: a matrix-free operator needs nbatch = 1 and a single GPU");
   const int n_local = n / world;
   if (!carve(ar, W, sizeof(TV), n, k, mb, world)) {
     set_last_error("symeig: workspace too small (%zu needed, %zu given)", ar.off, ar.cap);
@@ -2029,7 +2031,14 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       // consecutive passes run in opposite column order: the tail of the previous pass is still in L2
       a.reverse = iter & 1;
       a.l2_keep_mb = MV_L2_KEEP_MB;
-      int rc = mv_launch(a, st);
+      int rc = XT_OK;
+      if (g->apply != nullptr) {
+        // matrix-free operator: the caller computes Y = A X on the stream (the rest of the iteration is unchanged)
+        typedef void (*apply_fn)(void*, const void*, void*, void*);
+        reinterpret_cast<apply_fn>(g->apply)(g->apply_user, a.X, a.Y, g->stream);
+      } else {
+        rc = mv_launch(a, st);
+      }
       if (rc != XT_OK) return rc;
       ++napply;
       if (collective) {
@@ -2268,7 +2277,7 @@ int xt_symeig_krylov(const xt_symeig_args* g) {
   XT_REQUIRE(g->neig >= 1 && g->neig <= xt::SE_MAXK, "symeig: neig=%d outside 1..%d", g->neig, xt::SE_MAXK);
   XT_REQUIRE(g->n >= 2 * g->neig, "symeig: n=%d too small for neig=%d", g->n, g->neig);
   XT_REQUIRE(g->dtype == XT_F32 || g->dtype == XT_F64, "symeig: only fp32 / fp64 operators are supported");
-  XT_REQUIRE(g->A && g->V0 && g->evals && g->evecs && g->workspace, "symeig: null pointer");
+  XT_REQUIRE((g->A || g->apply) && g->V0 && g->evals && g->evecs && g->workspace, "symeig: null pointer");
   XT_REQUIRE(g->mode == 0 || g->mode == 1, "symeig: mode must be 0 (lowest) or 1 (uppest)");
   XT_REQUIRE(g->max_basis <= 1024, "symeig: max_basis=%d exceeds 1024", g->max_basis);
   return g->dtype == XT_F64 ? xt::run_symeig<double>(g) : xt::run_symeig<float>(g);
