@@ -14,6 +14,7 @@ import functools
 import warnings
 from typing import Optional, Tuple, Union
 
+import numpy as np
 import torch
 
 from xitorch_b200._utils import ConvergenceWarning
@@ -179,18 +180,32 @@ def _svd_uv0(func, x0):
 
 
 # ----------------------------------------------------------------------------- outer loop
+def _host_scalars(*tensors):
+    """the values of several 0-dim tensors with ONE device -> host transfer, as numpy scalars of the tensors' dtype: the
+    control arithmetic done with them on the host (line-search interpolation, forcing terms, stop tests) rounds exactly
+    like the 0-dim tensor arithmetic of the reference, without a kernel launch per scalar operation."""
+    stacked = torch.stack([t if t.dim() == 0 else t.reshape(()) for t in tensors])
+    if stacked.dtype not in (torch.float32, torch.float64):
+        stacked = stacked.float()
+    arr = stacked.cpu().numpy()
+    return [arr[i] for i in range(len(tensors))]
+
+
 class TerminationCondition(object):
     def __init__(self, f_tol, f_rtol, f0_norm, x_tol, x_rtol):
         self.f_tol = 1e-6 if f_tol is None else f_tol
         self.f_rtol = float("inf") if f_rtol is None else f_rtol
         self.x_tol = 1e-6 if x_tol is None else x_tol
         self.x_rtol = float("inf") if x_rtol is None else x_rtol
-        self.f0_norm = f0_norm
+        self.f0_norm = _host_scalars(f0_norm)[0] if isinstance(f0_norm, torch.Tensor) else f0_norm
+
+    def check_norms(self, xnorm, ynorm, dxnorm) -> bool:
+        with np.errstate(all="ignore"):
+            return bool((dxnorm < self.x_tol) and (dxnorm < self.x_rtol * xnorm) and
+                        (ynorm < self.f_tol) and (ynorm < self.f_rtol * self.f0_norm))
 
     def check(self, x, y, dx) -> bool:
-        xnorm, ynorm, dxnorm = x.norm(), y.norm(), dx.norm()
-        return bool((dxnorm < self.x_tol) and (dxnorm < self.x_rtol * xnorm) and
-                    (ynorm < self.f_tol) and (ynorm < self.f_rtol * self.f0_norm))
+        return self.check_norms(*_host_scalars(x.norm(), y.norm(), dx.norm()))
 
 
 def _nonlin_solver(fcn, x0, params, jacobian, maxiter=None, f_tol=None, f_rtol=None, x_tol=None, x_rtol=None,
@@ -241,33 +256,39 @@ def _nonlin_solver(fcn, x0, params, jacobian, maxiter=None, f_tol=None, f_rtol=N
 
     x = ravel(x0)
     y = func(x)
-    y_norm = y.norm()
+    y_norm, x_norm = _host_scalars(y.norm(), x.norm())
     stop_cond = custom_terminator if custom_terminator is not None else \
         TerminationCondition(f_tol, f_rtol, y_norm, x_tol, x_rtol)
     if y_norm == 0:
         return x.reshape(xshape)
     jacobian.setup(x, y, func)
 
+    # All control decisions below are taken on host copies of the norms, fetched with one transfer per function
+    # evaluation (the reference syncs on every comparison of 0-dim tensors: ~4 per evaluation plus ~40 scalar kernels
+    # per line-search interpolation).
     gamma, eta_max, eta_threshold, eta = 0.9, 0.9999, 0.1, 1e-3     # forcing terms of the inexact Newton step
     converged = False
-    best_ynorm, best_x, best_dxnorm, best_iter = y_norm, x, x.norm(), 0
+    best_ynorm, best_x, best_dxnorm, best_iter = y_norm, x, x_norm, 0
     for i in range(maxiter):
-        tol = min(eta, eta * y_norm)
+        tol = float(min(eta, eta * y_norm))
         dx = -jacobian.solve(y, tol=tol)
-        dx_norm = dx.norm()
-        if dx_norm == 0:
-            raise ValueError("Jacobian inversion yielded zero vector. This indicates a bug in the Jacobian "
-                             "approximation.")
         if line_search:
-            s, xnew, ynew, y_norm_new = _line_search(func, x, y, dx, search_type=line_search)
+            s, xnew, ynew, (y_norm_new, x_norm_new, dx_norm) = _line_search(func, x, y, y_norm, dx,
+                                                                           search_type=line_search)
         else:
             xnew = x + dx
             ynew = func(xnew)
-            y_norm_new = ynew.norm()
+            y_norm_new, x_norm_new, dx_norm = _host_scalars(ynew.norm(), xnew.norm(), dx.norm())
+        if dx_norm == 0:
+            raise ValueError("Jacobian inversion yielded zero vector. This indicates a bug in the Jacobian "
+                             "approximation.")
         if y_norm_new < best_ynorm:
             best_x, best_dxnorm, best_ynorm, best_iter = xnew, dx_norm, y_norm_new, i + 1
-        jacobian.update(xnew.clone(), ynew)
-        to_stop = stop_cond.check(xnew, ynew, dx)
+        jacobian.update(xnew, ynew)
+        if custom_terminator is not None:
+            to_stop = stop_cond.check(xnew, ynew, dx)
+        else:
+            to_stop = stop_cond.check_norms(x_norm_new, y_norm_new, dx_norm)
         if verbose and (i < 10 or i % 10 == 0 or to_stop):
             print("%6d: |dx|=%.3e, |f|=%.3e" % (i, dx_norm, y_norm))
         if to_stop:
@@ -275,7 +296,9 @@ def _nonlin_solver(fcn, x0, params, jacobian, maxiter=None, f_tol=None, f_rtol=N
             # last step (|dx| < x_tol apart from xnew)
             converged = True
             break
-        eta_A = float(gamma * (y_norm_new / y_norm) ** 2)
+        with np.errstate(all="ignore"):
+            ratio = y_norm_new / y_norm
+            eta_A = float(gamma * (ratio * ratio))
         gamma_eta2 = gamma * eta * eta
         eta = min(eta_max, eta_A) if gamma_eta2 < eta_threshold else min(eta_max, max(eta_A, gamma_eta2))
         y_norm, x, y = y_norm_new, xnew, ynew
@@ -287,46 +310,61 @@ def _nonlin_solver(fcn, x0, params, jacobian, maxiter=None, f_tol=None, f_rtol=N
     return pack(x)
 
 
-def _line_search(func, x, y, dx, search_type="armijo", rdiff=1e-8, smin=1e-2):
-    cache_s, cache_y, cache_phi = [0], [y], [y.norm() ** 2]
+def _line_search(func, x, y, y_norm, dx, search_type="armijo", rdiff=1e-8, smin=1e-2):
+    """step length by backtracking on phi(s) = |f(x + s dx)|^2.  Returns ``(s, xnew, ynew, (|ynew|, |xnew|, |dx|))``, the
+    norms on the host: every evaluation of phi brings them along in its one transfer, so an accepted step needs no
+    further synchronisation."""
+    dx_norm_dev = dx.norm()
+    cache = {"s": 0, "phi": y_norm * y_norm, "x": x, "y": y, "norms": None}
 
-    def phi(s, store=True):
-        if s == cache_s[0]:
-            return cache_phi[0]
-        v = func(x + s * dx)
-        p = torch.dot(v.reshape(-1), v.reshape(-1))
-        if store:
-            cache_s[0], cache_phi[0], cache_y[0] = s, p, v
+    def phi(s):
+        if s == cache["s"]:
+            return cache["phi"]
+        xs = x + float(s) * dx
+        v = func(xs)
+        vf = v.reshape(-1)
+        p, vn, xn, dn = _host_scalars(torch.dot(vf, vf), v.norm(), xs.norm(), dx_norm_dev)
+        cache.update(s=s, phi=p, x=xs, y=v, norms=(vn, xn, dn))
         return p
 
     s = None
     if search_type == "armijo":
-        s, _ = _armijo(phi, cache_phi[0], -cache_phi[0], amin=smin)
+        with np.errstate(all="ignore"):
+            s, _ = _armijo(phi, cache["phi"], -cache["phi"], amin=smin)
     if s is None:
         s = 1.0                      # no acceptable step length: take the full step and hope for the best
-    xnew = x + s * dx
-    ynew = cache_y[0] if s == cache_s[0] else func(xnew)
-    return s, xnew, ynew, ynew.norm()
+    if s == cache["s"] and cache["norms"] is not None:
+        return s, cache["x"], cache["y"], cache["norms"]
+    xnew = x + float(s) * dx
+    ynew = func(xnew)
+    return s, xnew, ynew, tuple(_host_scalars(ynew.norm(), xnew.norm(), dx_norm_dev))
 
 
 def _armijo(phi, phi0, derphi0, c1=1e-4, alpha0=1, amin=0, max_niter=20):
-    # backtracking with quadratic, then cubic interpolation (scipy's scalar_search_armijo)
+    # backtracking with quadratic, then cubic interpolation (scipy's scalar_search_armijo) on host scalars of the
+    # problem's dtype; powers are written as products, which is what the tensor `**` of the reference evaluates
+    def sq(a):
+        return a * a
+
+    def cube(a):
+        return a * a * a
+
     phi_a0 = phi(alpha0)
     if phi_a0 <= phi0 + c1 * alpha0 * derphi0:
         return alpha0, phi_a0
-    alpha1 = -derphi0 * alpha0 ** 2 / 2.0 / (phi_a0 - phi0 - derphi0 * alpha0)
+    alpha1 = -derphi0 * sq(alpha0) / 2.0 / (phi_a0 - phi0 - derphi0 * alpha0)
     phi_a1 = phi(alpha1)
     if phi_a1 <= phi0 + c1 * alpha1 * derphi0:
         return alpha1, phi_a1
     niter = 0
     alpha2, phi_a2 = alpha1, phi_a1
     while alpha1 > amin and niter < max_niter:
-        factor = alpha0 ** 2 * alpha1 ** 2 * (alpha1 - alpha0)
-        a = alpha0 ** 2 * (phi_a1 - phi0 - derphi0 * alpha1) - alpha1 ** 2 * (phi_a0 - phi0 - derphi0 * alpha0)
+        factor = sq(alpha0) * sq(alpha1) * (alpha1 - alpha0)
+        a = sq(alpha0) * (phi_a1 - phi0 - derphi0 * alpha1) - sq(alpha1) * (phi_a0 - phi0 - derphi0 * alpha0)
         a = a / factor
-        b = -alpha0 ** 3 * (phi_a1 - phi0 - derphi0 * alpha1) + alpha1 ** 3 * (phi_a0 - phi0 - derphi0 * alpha0)
+        b = -cube(alpha0) * (phi_a1 - phi0 - derphi0 * alpha1) + cube(alpha1) * (phi_a0 - phi0 - derphi0 * alpha0)
         b = b / factor
-        alpha2 = (-b + torch.sqrt(torch.abs(b ** 2 - 3 * a * derphi0))) / (3.0 * a)
+        alpha2 = (-b + np.sqrt(np.abs(sq(b) - 3 * a * derphi0))) / (3.0 * a)
         phi_a2 = phi(alpha2)
         if phi_a2 <= phi0 + c1 * alpha2 * derphi0:
             return alpha2, phi_a2
