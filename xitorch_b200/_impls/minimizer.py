@@ -12,6 +12,8 @@ from typing import Callable, List, Optional
 
 import torch
 
+from xitorch_b200._impls.rootsolver import _host_scalars
+
 __all__ = ["gd", "adam"]
 
 
@@ -26,10 +28,10 @@ class _Progress(object):
         self.best = dict(f=float("inf"), x=None, dx=float("inf"), df=float("inf"))
 
     def step(self, i: int, x_new: torch.Tensor, x_old: torch.Tensor, f: torch.Tensor, f_old: torch.Tensor) -> bool:
-        dx = float((x_old - x_new).detach().norm())
-        df = float((f_old - f).detach().abs())
-        fval = float(f.detach())
-        hit = (dx < self.x_tol) or (dx < self.x_rtol * float(x_old.detach().norm())) or \
+        # one device -> host transfer per iteration; the differences are formed in the tensors' dtype as before
+        dx, xnorm, df, fval = (float(v) for v in _host_scalars(
+            (x_old - x_new).detach().norm(), x_old.detach().norm(), (f_old - f).detach().abs(), f.detach()))
+        hit = (dx < self.x_tol) or (dx < self.x_rtol * xnorm) or \
               (df < self.f_tol) or (df < self.f_rtol * abs(fval))
         if self.verbose:
             if i == 0:

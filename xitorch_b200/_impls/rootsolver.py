@@ -184,9 +184,13 @@ def _host_scalars(*tensors):
     """the values of several 0-dim tensors with ONE device -> host transfer, as numpy scalars of the tensors' dtype: the
     control arithmetic done with them on the host (line-search interpolation, forcing terms, stop tests) rounds exactly
     like the 0-dim tensor arithmetic of the reference, without a kernel launch per scalar operation."""
-    stacked = torch.stack([t if t.dim() == 0 else t.reshape(()) for t in tensors])
-    if stacked.dtype not in (torch.float32, torch.float64):
-        stacked = stacked.float()
+    items = [t if t.dim() == 0 else t.reshape(()) for t in tensors]
+    dt = items[0].dtype
+    if any(t.dtype != dt for t in items):
+        items = [t.double() for t in items]                    # mixed precisions: exact in fp64
+    elif dt not in (torch.float32, torch.float64):
+        items = [t.float() for t in items]                     # half / bfloat16 have no numpy scalar type
+    stacked = torch.stack(items)
     arr = stacked.cpu().numpy()
     return [arr[i] for i in range(len(tensors))]
 
