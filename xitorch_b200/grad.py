@@ -64,7 +64,10 @@ def hess(fcn: Callable[..., torch.Tensor], params: Sequence[Any],
 
 
 def _tie(out: torch.Tensor, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
-    # keeps `out` attached to the graph of every parameter (needed by create_graph consumers)
+    # keeps `out` attached to the graph of every parameter (needed by create_graph consumers); without a graph
+    # (the operator callback of the CUDA solvers runs under no_grad) it would only be launches that add zero
+    if not torch.is_grad_enabled():
+        return out
     for t in tensors:
         out = out + t.reshape(-1)[0] * 0
     return out
