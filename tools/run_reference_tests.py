@@ -1,13 +1,15 @@
 """
 Run the reference's OWN test files against this package (build container only: needs /root/reference).
 
-    python tools/run_reference_tests.py [pytest args]        e.g.  -k "not methods and not large"
+    python tools/run_reference_tests.py [--standin] [pytest args]        e.g.  -k "not methods and not large"
 
 The reference's test files are copied to a scratch directory (never into the repo), next to a conftest.py that calls
 `xitorch_b200.install_as_xitorch()` before anything imports `xitorch`, and that loads the reference's test helpers
 (`xitorch/_tests/utils.py`) under their original module name.  Everything the tests import as `xitorch.*` is then this
 package.  Cases that run a Krylov method on CPU tensors fail by construction (there is no CPU path): on a box without
-a GPU use  -k "not methods and not large"  for test_linop_fcns.py.
+a GPU use  -k "not methods and not large"  for test_linop_fcns.py -- or `--standin`, which replaces the CUDA library
+by tests/standin_engine.py (numpy on the argument structs) so that the Krylov `method=` cases exercise this package's
+host logic end to end on CPU tensors (the numerics inside the engine are then numpy's, not the kernels').
 """
 import os
 import shutil
@@ -28,6 +30,15 @@ xitorch_b200.install_as_xitorch()
 pkg = types.ModuleType("xitorch._tests"); pkg.__path__ = []; sys.modules["xitorch._tests"] = pkg
 spec = importlib.util.spec_from_file_location("xitorch._tests.utils", %r)
 mod = importlib.util.module_from_spec(spec); sys.modules["xitorch._tests.utils"] = mod; spec.loader.exec_module(mod)
+if %r:
+    sys.path.insert(0, %r)
+    import standin_engine
+
+    class _Patch(object):
+        def setattr(self, obj, name, value):
+            setattr(obj, name, value)
+
+    standin_engine.install(_Patch())
 '''
 
 
@@ -36,9 +47,14 @@ def main():
     try:
         for f in FILES:
             shutil.copy(os.path.join(REF, "xitorch", "_tests", f), scratch)
+        args = sys.argv[1:]
+        standin = "--standin" in args
+        if standin:
+            args.remove("--standin")
         with open(os.path.join(scratch, "conftest.py"), "w") as fh:
-            fh.write(CONFTEST % (ROOT, os.path.join(REF, "xitorch", "_tests", "utils.py")))
-        args = sys.argv[1:] or ["-q"]
+            fh.write(CONFTEST % (ROOT, os.path.join(REF, "xitorch", "_tests", "utils.py"), standin,
+                                 os.path.join(ROOT, "tests")))
+        args = args or ["-q"]
         return subprocess.call([sys.executable, "-m", "pytest", "-p", "no:cacheprovider", *args], cwd=scratch)
     finally:
         shutil.rmtree(scratch, ignore_errors=True)

@@ -206,12 +206,12 @@ def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef
     failure = []
     shape = (*batch, n, ncols)
     cb = _block_callback(op, ws, nbytes, vdt, shape, opdt, failure)
-    g.apply = C.cast(cb, C.c_void_p)
+    g.apply = _lib.fn_address(cb)
     keep = [cb]
     for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
         if pc is not None:
             pcb = _block_callback(pc.mm, ws, nbytes, vdt, shape, opdt, failure)
-            setattr(g, field, C.cast(pcb, C.c_void_p))
+            setattr(g, field, _lib.fn_address(pcb))
             keep.append(pcb)
     with torch.cuda.device(Bf.device):
         rc = getattr(L, "xt_" + name)(g)
@@ -416,7 +416,7 @@ def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, e
         for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
             if pc is not None:
                 pcb = _block_callback(pc.mm, ws, nbytes, vdt, (*batch, n, ncols), pc.dtype, failure)
-                setattr(g, field, C.cast(pcb, C.c_void_p))
+                setattr(g, field, _lib.fn_address(pcb))
                 keep.append(pcb)
         g.check_every = 1
     with torch.cuda.device(Bf.device):

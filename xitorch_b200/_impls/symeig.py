@@ -295,11 +295,11 @@ def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max
         cb = _lib.ALLGATHER_FN(_gather)
         keep.append(cb)
         g.world, g.rank = world, rank
-        g.allgather = C.cast(cb, C.c_void_p)
+        g.allgather = _lib.fn_address(cb)
     if make_apply is not None:
         acb = make_apply(ws)
         keep.append(acb)
-        g.apply = C.cast(acb, C.c_void_p)
+        g.apply = _lib.fn_address(acb)
     with torch.cuda.device(dev):
         _lib.check(L_.xt_symeig_krylov(g), name)
     if info is not None:

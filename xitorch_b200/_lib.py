@@ -84,6 +84,14 @@ class SymeigArgs(C.Structure):
 
 ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
 
+
+def fn_address(callback) -> int:
+    """address of a CFUNCTYPE callback for a `void*` struct field.  Not `ctypes.cast(callback, c_void_p)`: cast() makes
+    its result share the source's `_objects` dict and stores the source in it, i.e. the callback object then references
+    itself -- and everything its closure holds (the workspace tensor, the operator and its tensors) would stay alive
+    until the cyclic garbage collector runs.  The caller keeps `callback` alive for the duration of the library call."""
+    return C.c_void_p.from_address(C.addressof(callback)).value
+
 _lock = threading.Lock()
 _lib = None
 
