@@ -131,8 +131,33 @@ class StandInLibrary(object):
         self.log.append(rec)
         assert g.V0 and g.evals and g.evecs and g.workspace and (g.A or g.apply)
         napply = 0
+        world = g.world if g.world > 1 else 1
+        rec["world"] = world
         for b in range(nb):
-            if g.apply:
+            if world > 1:
+                # row-partitioned operator: the local row block times identity columns, one all-gather per application
+                # in the staging layout of the engine (chunk r = rank r's rows, plus one row carrying its stop flag)
+                assert g.allgather and nb == 1 and not g.apply and n % world == 0
+                n_local = n // world
+                per = (n_local + 1) * k
+                buf = _arr(g.workspace + 64, world * per, npdt)
+                Aloc = _matrix(g.A, n_local, n, g.lda, npdt).astype(np.float64)
+                A = np.zeros((n, n))
+                for c0 in range(0, n, k):
+                    X = np.zeros((n, k))
+                    for j in range(min(k, n - c0)):
+                        X[c0 + j, j] = 1
+                    buf[...] = np.nan
+                    mine = buf[g.rank * per:(g.rank + 1) * per]
+                    mine[:n_local * k] = (Aloc @ X).astype(npdt).ravel()
+                    mine[n_local * k:] = 0
+                    C.cast(g.allgather, _lib.ALLGATHER_FN)(None, g.workspace + 64, per, esz, None)
+                    napply += 1
+                    for r in range(world):
+                        blk = buf[r * per:r * per + n_local * k].reshape(n_local, k).astype(np.float64)
+                        A[r * n_local:(r + 1) * n_local, c0:c0 + k] = blk[:, :min(k, n - c0)]
+                        assert np.all(buf[r * per + n_local * k:(r + 1) * per] == 0)       # every rank's flag row arrived
+            elif g.apply:
                 assert nb == 1
                 woff = [64, 64 + ((n * k * esz + 63) // 64) * 64]
                 xblk = _arr(g.workspace + woff[0], n * k, npdt).reshape(n, k)

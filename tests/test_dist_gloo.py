@@ -72,6 +72,63 @@ def test_row_partitioned_operator_and_sharding_world2():
         assert r[6] >= 3          # mm, mv, fullmatrix each applied the operator (one all-gather each)
 
 
+def _worker_engine(rank, world, port, q):
+    """the row-partitioned eigensolver entry with the CUDA library replaced by the stand-in: checks the all-gather hook
+    the host installs (pointer arithmetic inside the workspace, in-place gather of `world` chunks) over gloo"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import standin_engine
+        from xitorch_b200 import dist as xd
+        import oracle
+
+        class _Patch(object):
+            def setattr(self, obj, name, value):
+                setattr(obj, name, value)
+
+        eng = standin_engine.install(_Patch())
+        n, k = 48, 4
+        A = oracle.make_herm(n, 2, torch.float64, seed=5)
+        lo, hi = xd.shard_range(n, rank, world)
+        info = {}
+        evals, evecs = xd.symeig_row_partitioned(A[lo:hi].contiguous(), n, k, info=info)
+        ref = torch.linalg.eigvalsh(A)[:k]
+        ok_vals = torch.allclose(evals, ref, atol=1e-10)
+        ok_vecs = torch.allclose(A @ evecs, evecs * evals, atol=1e-9)
+        eig_world = eng.log[-1]["world"]
+        # batch-sharded independent systems (BASELINE config 3): no data-path collective, reduced bookkeeping only
+        g = torch.Generator().manual_seed(11)
+        nbt, m = 5, 10
+        Ab = torch.eye(m, dtype=torch.float64) + 0.3 * torch.randn(nbt, m, m, generator=g, dtype=torch.float64) / m ** 0.5
+        Bb = torch.randn(nbt, m, 1, generator=g, dtype=torch.float64)
+        x_local, sinfo = xd.solve_batch_sharded(xd.shard_batch(Ab), xd.shard_batch(Bb), method="bicgstab")
+        ok_solve = torch.allclose(xd.shard_batch(Ab) @ x_local, xd.shard_batch(Bb), atol=1e-10)
+        ok_info = sinfo["all_converged"] and sinfo["niter_max"] >= 1 and eng.log[-1]["nbatch"] in (2, 3)
+        q.put((rank, ok_vals and ok_solve and ok_info, ok_vecs, eig_world, tuple(evecs.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_symeig_allgather_hook_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_engine, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] and r[2], r
+        assert r[3] == world and r[4] == (48, 4)
+
+
 def test_shard_range_properties():
     from xitorch_b200.dist import shard_range
     for n in (1, 7, 512, 513):
