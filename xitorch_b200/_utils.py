@@ -11,6 +11,7 @@ boundary relies on:
   * dotted/indexed attribute paths    (/root/reference/xitorch/_utils/attr.py:7-62)
 """
 import contextlib
+import functools
 import re
 from typing import Any, Callable, Dict, List, Mapping, Sequence, Union
 
@@ -74,6 +75,7 @@ def normalize_bcast_dims(*shapes) -> List[List[int]]:
 _TOKEN = re.compile(r"\.?([A-Za-z_][A-Za-z_0-9]*)|\[([^\]]+)\]")
 
 
+@functools.lru_cache(maxsize=4096)
 def _parse_path(path: str):
     pos, toks = 0, []
     while pos < len(path):
@@ -89,7 +91,7 @@ def _parse_path(path: str):
             else:
                 toks.append(("item", int(raw)))
         pos = m.end()
-    return toks
+    return tuple(toks)
 
 
 def _step(obj, tok):

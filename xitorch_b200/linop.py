@@ -142,7 +142,11 @@ class LinearOperator(EditableModule):
         if len(params) != len(uniq):
             raise RuntimeError("uselinopparams expects %d tensors, got %d" % (len(uniq), len(params)))
         originals = [(nm, _utils.get_attr(self, nm)) for nm in allnames]
-        by_id = {id(_utils.get_attr(self, nm)): p for nm, p in zip(uniq, params)}
+        current = [_utils.get_attr(self, nm) for nm in uniq]
+        if all(c is p for c, p in zip(current, params)):      # the operator's own tensors (every forward call): no-op
+            yield self
+            return
+        by_id = {id(c): p for c, p in zip(current, params)}
         try:
             for nm, orig in originals:
                 _utils.set_attr(self, nm, by_id[id(orig)])
