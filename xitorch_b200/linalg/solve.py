@@ -90,8 +90,24 @@ def solve(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None,
 
     params = A.getlinopparams()
     mparams = M.getlinopparams() if M is not None else []
+    needs_grad = torch.is_grad_enabled() and any(
+        isinstance(t, torch.Tensor) and t.requires_grad for t in (B, E, *params, *mparams))
+    if not needs_grad:
+        # nothing to differentiate: same result without the autograd-function round trip (host time per call)
+        with torch.no_grad():            # methods always run without grad, as inside the autograd function
+            return _forward(A, B, E, M, method, merged_options({}, fwd_options))
     return _SolveFunction.apply(A, B, E, M, method, fwd_options, bck_options,
                                 len(params), *params, *mparams)
+
+
+def _forward(A, B, E, M, method, config):
+    fcn = get_method("solve", _solve_methods(), method)
+    # a zero right-hand side is answered without calling the method (reference solve.py:176-180).  The library's own
+    # Krylov methods make that test themselves (|B| <= atol, one reduction) -- no second pass and synchronisation here
+    if getattr(fcn, "_checks_zero_rhs", False) or not torch.all(B == 0):
+        return fcn(A, B, E, M, **config)
+    dims = (*_impl.get_batchdims(A, B, E, M), *B.shape[-2:])
+    return torch.zeros(dims, dtype=B.dtype, device=B.device)
 
 
 class _SolveFunction(torch.autograd.Function):
@@ -101,13 +117,8 @@ class _SolveFunction(torch.autograd.Function):
         config = merged_options({}, fwd_options)
         ctx.bck_config = merged_options({}, bck_options)
 
-        if torch.all(B == 0):
-            dims = (*_impl.get_batchdims(A, B, E, M), *B.shape[-2:])
-            x = torch.zeros(dims, dtype=B.dtype, device=B.device)
-        else:
-            with A.uselinopparams(*params), (M.uselinopparams(*mparams) if M is not None else null_context()):
-                fcn = get_method("solve", _solve_methods(), method)
-                x = fcn(A, B, E, M, **config)
+        with A.uselinopparams(*params), (M.uselinopparams(*mparams) if M is not None else null_context()):
+            x = _forward(A, B, E, M, method, config)
 
         ctx.e_is_none = E is None
         ctx.A, ctx.M, ctx.na = A, M, na

@@ -88,7 +88,8 @@ def symeig(A: LinearOperator, neig: Optional[int] = None, mode: str = "lowest",
     mparams = M.getlinopparams() if M is not None else []
     if not (torch.is_grad_enabled() and any(p.requires_grad for p in (*params, *mparams))):
         # nothing to differentiate: same result without the autograd-function round trip (host time per call)
-        return get_method("symeig", _symeig_methods(), method)(A, neig, mode, M, **fwd_options)
+        with torch.no_grad():            # methods always run without grad, as inside the autograd function
+            return get_method("symeig", _symeig_methods(), method)(A, neig, mode, M, **fwd_options)
     fwd_options = dict(fwd_options)
     fwd_options["method"] = method
     return _SymeigFunction.apply(A, neig, mode, M, fwd_options, bck_options,
