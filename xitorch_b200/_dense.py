@@ -8,6 +8,7 @@ from typing import Optional, Tuple
 import torch
 
 from xitorch_b200 import _lib
+from xitorch_b200._utils import bcast_dims
 
 _SUPPORTED = (torch.float32, torch.bfloat16, torch.float64)
 
@@ -53,7 +54,7 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
     k = x.shape[-1]
     vdt = _lib.vec_dtype(mat.dtype)
     out_dtype = x.dtype
-    batch = tuple(torch.broadcast_shapes(mat.shape[:-2], x.shape[:-2]))
+    batch = tuple(bcast_dims(mat.shape[:-2], x.shape[:-2]))
     nb = 1
     for s in batch:
         nb *= s
