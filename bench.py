@@ -11,7 +11,8 @@ BASELINE configs[1] problem (make_herm, N=16384, fp32); an "iterat
 expansion (one block matvec over A + Rayleigh-Ritz + residual + orthogonalisation).
   value    = Davidson iterations / second with A resident in HBM (whole job, all ranks)
   e2e      = the same through the public API from PINNED HOST buffers: H2D of A every step + solve + D2H of
-             the eigenpairs, all inside the timed region
+             the eigenpairs, all inside the timed region, one step after the other (`e2e.value`);
+             `e2e.overlapped` repeats it with the copy of step i+1 in flight under the solve of step i
   roofline = the dominant kernel (block matvec, reads A once: 4*N^2 B per launch) timed in situ with CUDA
              events on its launch stream (xt_profile_*), against the measured HBM peak
   cpu_baseline = the oracle (bit-identical restatement of the reference's davidson, torch-CPU, all host
@@ -298,6 +299,61 @@ def main():
         dist.all_reduce(ie, op=dist.ReduceOp.SUM)
     e2e_value = ie.item() / te.item()
 
+    # ------------------------------------------------------------------ the same, copies overlapped with solves
+    # Two device buffers and a copy stream: the host -> device copy of step i+1 is in flight while step i is solved
+    # (every copy still starts and ends inside the timed region; results are read back every step).  Reported next
+    # to the serial number above; any error or result mismatch leaves only the serial one.
+    e2e_pipe = None
+    try:
+        ev_ref = ev_host.clone()
+        nstep = max(e2e_steps, 4)
+        bufs = [A2, torch.empty_like(A)]
+        main_stream = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue_copy(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[b])          # the solve that last read this buffer is done (no-op at first)
+                bufs[b].copy_(A_host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        barrier()
+        t0 = time.perf_counter()
+        issue_copy(0)
+        pipe_iters, pipe_ok = 0, True
+        for i in range(nstep):
+            b = i % 2
+            if i + 1 < nstep:
+                issue_copy(i + 1)
+            main_stream.wait_event(ready[b])
+            ev3, vec3, info3 = solve(xt.LinearOperator.m(bufs[b], is_hermitian=True))
+            free[b].record(main_stream)
+            ev_host.copy_(ev3, non_blocking=True)
+            vec_host.copy_(vec3, non_blocking=True)
+            main_stream.synchronize()
+            pipe_iters += info3["niter"]
+            pipe_ok = pipe_ok and bool(info3["converged"]) and bool(torch.allclose(ev_host, ev_ref, rtol=1e-5, atol=0))
+        torch.cuda.synchronize()
+        barrier()
+        pipe_dt = time.perf_counter() - t0
+        tp = torch.tensor([pipe_dt], dtype=torch.float64, device=dev)
+        ip = torch.tensor([float(pipe_iters), 1.0 if pipe_ok else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            okr = ip[1:].clone()
+            dist.all_reduce(ip[:1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(okr, op=dist.ReduceOp.MIN)
+            ip[1] = okr[0]
+        if ip[1].item() == 1.0:
+            e2e_pipe = {"value": ip[0].item() / tp.item(), "steps": nstep, "ms_per_step": tp.item() / nstep * 1e3}
+        del bufs
+    except Exception as exc:                                            # noqa: BLE001 -- keep the serial measurement
+        sys.stderr.write("bench: overlapped end-to-end pass skipped (%r)\n" % (exc,))
+        e2e_pipe = None
+
     if rank == 0:
         peak, peak_src = _peaks()
         bytes_per_launch = 4.0 * args.n * args.n
@@ -327,7 +383,10 @@ def main():
                          "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_launch),
                     "d2h_bytes_per_step": 4 * (args.neig + args.n * args.neig), "steps": e2e_steps,
-                    "ms_per_step": te.item() / e2e_steps * 1e3},
+                    "ms_per_step": te.item() / e2e_steps * 1e3,
+                    "mode": "serial: copy in, solve, copy out, synchronise, every step",
+                    # same work with the copy of step i+1 overlapped with the solve of step i (null: not measured)
+                    "overlapped": e2e_pipe},
             "gpu_launches": int(n_launch),
             "clocks": clocks,
         }
