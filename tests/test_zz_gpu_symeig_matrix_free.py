@@ -3,8 +3,8 @@ only through `_mv` must give the eigenpairs the dense kernels give for the same 
 only the operator application differs) and satisfy the residual identity in fp64.
 
 STATUS: this path was written after the round's GPU minutes were spent -- its host side is tested on CPU
-(tests/test_symeig_matrix_free_host.py), the engine change is a gated 8-line branch, but the first run on hardware is
-the driver's.  The file sorts last and is marked xfail(strict=False) for that reason only; the mark goes away with the
+(tests/test_symeig_matrix_free_host.py) and the engine branch itself by running the engine's source as a host build
+(tests/test_engine_emulation.py), but the first run on hardware is the driver's.  The file sorts last and is marked xfail(strict=False) for that reason only; the mark goes away with the
 first green run.
 """
 import pytest
