@@ -8,78 +8,31 @@ residual identity, orthonormality.  This is also the first execution of the matr
 
 TEST INFRASTRUCTURE: the emulated library is built in a temporary directory and never shipped; the product on a GPU
 box loads libxitorch_b200.so only."""
-import ctypes as C
 import os
-import shutil
-import subprocess
-import sys
 
 import pytest
 import torch
 
 import xitorch_b200 as xt
 from xitorch_b200 import _lib
-from xitorch_b200.linalg import symeig, svd
+from xitorch_b200.linalg import symeig, svd, solve
+
+import emu_engine_lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
-    if shutil.which("g++") is None:
+    lib = emu_engine_lib.build(str(tmp_path_factory.mktemp("emu_engine")))
+    if lib is None:
         pytest.skip("g++ not available")
-    d = str(tmp_path_factory.mktemp("emu_engine"))
-    sys.path.insert(0, os.path.join(ROOT, "tools", "emu_engine"))
-    try:
-        import preprocess
-    finally:
-        sys.path.pop(0)
-    src = open(os.path.join(ROOT, "xitorch_b200", "csrc", "symeig.cu")).read()
-    open(os.path.join(d, "symeig_host.cpp"), "w").write(preprocess.transform(src))
-    so = os.path.join(d, "libxt_emu.so")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
-                           "-I", os.path.join(ROOT, "tools", "emu_engine"), "-I", os.path.join(ROOT, "include"),
-                           "-o", so, os.path.join(d, "symeig_host.cpp")])
-    lib = C.CDLL(so)
-    lib.xt_symeig_workspace_bytes.argtypes = [C.c_int32] * 5
-    lib.xt_symeig_workspace_bytes.restype = C.c_size_t
-    lib.xt_symeig_krylov.argtypes = [C.POINTER(_lib.SymeigArgs)]
-    lib.xt_symeig_krylov.restype = C.c_int
-    lib.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_void_p]
-    lib.xt_small_eigh.restype = C.c_int
     return lib
-
-
-class _NoDevice(object):
-    def __init__(self, dev):
-        pass
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
 
 
 @pytest.fixture()
 def engine(emu_lib, monkeypatch):
-    class Hybrid(object):
-        def __getattr__(self, name):
-            return getattr(emu_lib, name)
-
-        def xt_last_error(self):
-            return b"emulated engine"
-
-    from xitorch_b200._impls import symeig as impl
-    monkeypatch.setattr(_lib, "lib", lambda: Hybrid())
-    monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
-    monkeypatch.setattr(_lib, "stream_ptr", lambda dev: 0)
-    monkeypatch.setattr(torch.cuda, "device", _NoDevice)
-    # the same start block the CUDA path draws (seed 12421, symeig.py:236), from the CPU generator
-    monkeypatch.setattr(impl, "_start_block",
-                        lambda kind, nb, n, neig, dtype, dev: (torch.randn if kind == "randn" else torch.rand)(
-                            (nb, n, neig), dtype=dtype, generator=torch.Generator().manual_seed(12421)))
+    emu_engine_lib.install(monkeypatch, emu_lib)
     return emu_lib
 
 
@@ -246,3 +199,70 @@ def test_small_eigh_entry(engine):
     assert rc == 0
     assert torch.allclose(w, torch.linalg.eigvalsh(T)[:nev], atol=1e-12)
     assert (T @ S - S * w).abs().max().item() <= 1e-11
+
+
+# ---------------------------------------------------------------------------------------------- linear solvers
+def _golden_solve(c):
+    A = xt.LinearOperator.m(c["A"], is_hermitian=c["herm"])
+    M = xt.LinearOperator.m(c["M"], is_hermitian=True) if c.get("M") is not None else None
+    info = {}
+    x = solve(A, c["B"], E=c.get("E"), M=M, method=c["method"], info=info, **c["opts"])
+    return x, info
+
+
+def test_golden_solve_cases(engine, golden):
+    """every committed output of the reference's cg / bicgstab / gmres (plain, batched, non-symmetric, normal equations,
+    E and M): the same solution, and the same number of iterations (cg exactly; bicgstab / gmres count the step that
+    detects convergence differently by one)"""
+    for c in golden["solve"]:
+        x, info = _golden_solve(c)
+        assert info["converged"], c["tag"]
+        rtol = c["opts"].get("rtol", 1e-6)
+        assert ((x - c["x"]).norm() / c["x"].norm()).item() <= 100 * rtol, (c["tag"], c["method"])
+        assert ((x - c["x_exact"]).norm() / c["x_exact"].norm()).item() <= 100 * rtol, (c["tag"], c["method"])
+        slack = 0 if c["method"] == "cg" else 1
+        assert abs(info["niter"] - c["oracle_niter"]) <= slack, (c["tag"], c["method"], info["niter"], c["oracle_niter"])
+
+
+def test_golden_preconditioned_cases(engine, golden):
+    for c in golden["solve_precond"]:
+        A = xt.LinearOperator.m(c["A"], is_hermitian=c["herm"])
+        pre = {k: xt.LinearOperator.m(v) for k, v in c["precond"].items()}
+        info = {}
+        x = solve(A, c["B"], method=c["method"], info=info, **pre, **c["opts"])
+        assert ((x - c["x_exact"]).norm() / c["x_exact"].norm()).item() <= 1e-7, c["tag"]
+        if c["oracle_niter"] < c["plain_niter"]:            # the preconditioner pays off exactly as in the reference
+            assert abs(info["niter"] - c["oracle_niter"]) <= 1, (c["tag"], info["niter"], c["oracle_niter"])
+
+
+def test_complex_and_float32_systems(engine):
+    g = torch.Generator().manual_seed(12)
+    n = 40
+    a = torch.randn(n, n, generator=g, dtype=torch.complex128)
+    A = a @ a.conj().T / n + 2 * torch.eye(n, dtype=torch.complex128)
+    B = torch.randn(n, 2, generator=g, dtype=torch.complex128)
+    x = solve(xt.LinearOperator.m(A, is_hermitian=True), B, method="cg", rtol=1e-10)
+    assert (A @ x - B).abs().max().item() <= 1e-8
+    Af = (A.real + torch.eye(n)).float()
+    Bf = B.real.float()
+    xf = solve(xt.LinearOperator.m(Af, is_hermitian=True), Bf, method="bicgstab", rtol=1e-6)
+    assert xf.dtype == torch.float32 and (Af @ xf - Bf).abs().max().item() <= 1e-4
+
+
+def test_rootfinder_backward_through_the_solver_engine(engine):
+    """BASELINE config 4 in small: Broyden forward, then the adjoint solve of the backward pass with the matrix-free
+    Jacobian driven by the bicgstab ENGINE through its operator callback; gradient against the exact implicit one"""
+    import oracle
+    from xitorch_b200.optimize import rootfinder
+
+    def fcn(y, A):
+        return torch.tanh(A @ y + 0.1) + y / 2.0
+
+    n = 24
+    A, _ = oracle.make_rootfinder_c4(n, dtype=torch.float64)
+    Ar = A.clone().requires_grad_()
+    y = rootfinder(fcn, torch.zeros(n, 1, dtype=torch.float64), params=(Ar,),
+                   bck_options={"method": "bicgstab", "rtol": 1e-10})
+    (g,) = torch.autograd.grad(y.sum(), Ar)
+    (g_exact,) = oracle.implicit_grad_dense(fcn, y.detach(), (A,), torch.ones_like(y))
+    assert (g - g_exact).abs().max().item() <= 1e-8 * max(1.0, g_exact.abs().max().item())

@@ -75,10 +75,11 @@ def _rewrite_launches(src: str) -> str:
 
 def _split_args(s: str):
     parts, depth, cur = [], 0, ""
-    for ch in s:
+    for i, ch in enumerate(s):
+        arrow = ch == ">" and i > 0 and s[i - 1] == "-"          # `->` is not a closing bracket
         if ch in "(<[":
             depth += 1
-        elif ch in ")>]":
+        elif ch in ")>]" and not arrow:
             depth -= 1
         if ch == "," and depth == 0:
             parts.append(cur)
@@ -89,16 +90,24 @@ def _split_args(s: str):
     return parts
 
 
-def transform(src: str) -> str:
+def transform(src: str, include_dir: str = None) -> str:
     src = src.replace('#include "matvec.cuh"', '#include "emu_cuda.h"')
+    m = re.search(r'#include "(solve_common\.cuh)"', src)
+    if m:                                                       # the solvers' shared header is inlined, rewritten too
+        import os
+        inc = open(os.path.join(include_dir, m.group(1))).read().replace("#pragma once", "")
+        src = src.replace(m.group(0), transform(inc, include_dir))
     for head in ("__device__ __forceinline__ unsigned long long gtimer() {",
                  "__device__ __forceinline__ void cp_async16(void* dst, const void* src) {",
                  "__device__ __forceinline__ void cp_async_wait_all() {",
                  "__device__ __forceinline__ double fast_rcp(double x) {"):
-        src = _drop_function(src, head)
+        if head in src:
+            src = _drop_function(src, head)
     src = src.replace('asm volatile("fence.acq_rel.gpu;" ::: "memory");', "emu_fence();")
     src = re.sub(r"extern __shared__ (?:__align__\(\d+\) )?(\w+(?: \w+)?) (\w+)\[\];",
                  r"\1* \2 = emu_dyn_smem<\1>();", src)
+    src = re.sub(r"__shared__ (\w+) (\w+)\[([^\]]+)\]\[([^\]]+)\];",
+                 r"\1 (*\2)[\4] = reinterpret_cast<\1 (*)[\4]>(emu_shared<\1>(__COUNTER__, (\3) * (\4)));", src)
     src = re.sub(r"__shared__ (\w+) (\w+)\[([^\]]+)\];", r"\1* \2 = emu_shared<\1>(__COUNTER__, \3);", src)
     src = re.sub(r"__shared__ (\w+) (\w+);", r"\1& \2 = *emu_shared<\1>(__COUNTER__, 1);", src)
     src = src.replace("cudaLaunchCooperativeKernel(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, po_smem, st)",
@@ -110,4 +119,5 @@ def transform(src: str) -> str:
 
 
 if __name__ == "__main__":
-    open(sys.argv[2], "w").write(transform(open(sys.argv[1]).read()))
+    import os
+    open(sys.argv[2], "w").write(transform(open(sys.argv[1]).read(), os.path.dirname(os.path.abspath(sys.argv[1]))))

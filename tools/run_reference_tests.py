@@ -1,7 +1,7 @@
 """
 Run the reference's OWN test files against this package (build container only: needs /root/reference).
 
-    python tools/run_reference_tests.py [--standin] [pytest args]        e.g.  -k "not methods and not large"
+    python tools/run_reference_tests.py [--standin | --emulated] [pytest args]        e.g.  -k "not methods and not large"
 
 The reference's test files are copied to a scratch directory (never into the repo), next to a conftest.py that calls
 `xitorch_b200.install_as_xitorch()` before anything imports `xitorch`, and that loads the reference's test helpers
@@ -10,6 +10,8 @@ package.  Cases that run a Krylov method on CPU tensors fail by construction (th
 a GPU use  -k "not methods and not large"  for test_linop_fcns.py -- or `--standin`, which replaces the CUDA library
 by tests/standin_engine.py (numpy on the argument structs) so that the Krylov `method=` cases exercise this package's
 host logic end to end on CPU tensors (the numerics inside the engine are then numpy's, not the kernels').
+`--emulated` goes one step further: the engines' own sources (csrc/{symeig,solve,gmres}.cu) as a host build
+(tools/emu_engine; only the block matvec is a stand-in), so the reference's method tests run the shipped algorithms.
 """
 import os
 import shutil
@@ -30,15 +32,20 @@ xitorch_b200.install_as_xitorch()
 pkg = types.ModuleType("xitorch._tests"); pkg.__path__ = []; sys.modules["xitorch._tests"] = pkg
 spec = importlib.util.spec_from_file_location("xitorch._tests.utils", %r)
 mod = importlib.util.module_from_spec(spec); sys.modules["xitorch._tests.utils"] = mod; spec.loader.exec_module(mod)
-if %r:
+mode = %r
+if mode:
     sys.path.insert(0, %r)
-    import standin_engine
 
     class _Patch(object):
         def setattr(self, obj, name, value):
             setattr(obj, name, value)
 
-    standin_engine.install(_Patch())
+    if mode == "standin":
+        import standin_engine
+        standin_engine.install(_Patch())
+    else:
+        import tempfile, emu_engine_lib
+        emu_engine_lib.install(_Patch(), emu_engine_lib.build(tempfile.mkdtemp(prefix="xt_emu_")))
 '''
 
 
@@ -48,9 +55,11 @@ def main():
         for f in FILES:
             shutil.copy(os.path.join(REF, "xitorch", "_tests", f), scratch)
         args = sys.argv[1:]
-        standin = "--standin" in args
-        if standin:
-            args.remove("--standin")
+        standin = ""
+        for flag in ("--standin", "--emulated"):
+            if flag in args:
+                args.remove(flag)
+                standin = flag[2:]
         with open(os.path.join(scratch, "conftest.py"), "w") as fh:
             fh.write(CONFTEST % (ROOT, os.path.join(REF, "xitorch", "_tests", "utils.py"), standin,
                                  os.path.join(ROOT, "tests")))
