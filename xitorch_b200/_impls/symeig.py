@@ -144,6 +144,27 @@ def _start(kind: str, nb: int, n: int, neig: int, vdt, dev):
     raise ValueError("Unknown v_init type: %s" % kind)
 
 
+def _space_exhausted(run: dict, n: int, neig: int, max_niter: int) -> bool:
+    """the engine grows the subspace in whole blocks of `neig` vectors and stops when the next block no longer fits
+    (m + neig > n).  The reference adds a PARTIAL block at that point, which makes the subspace the whole space and the
+    next Rayleigh-Ritz step exact (symeig.py:204-206, 209-211).  True when that is what happened: not converged, not
+    out of iterations, and no room left -- only possible for n below max_basis + neig (a few dozen rows)."""
+    if run.get("converged", True) or run.get("niter", 0) >= max_niter:
+        return False
+    mb = min(int(run.get("max_basis", n)), (n // neig) * neig)
+    return mb + neig > n
+
+
+def _full_space_pairs(Amat: torch.Tensor, neig: int, mode: str, run: dict):
+    """what the reference's last step computes once its basis spans everything: the eigenpairs of the projected
+    matrix, which then IS the operator in another basis (a dense `eigh` of an n x n matrix with n <= ~100)"""
+    w, S = torch.linalg.eigh(0.5 * (Amat + Amat.transpose(-2, -1)))
+    w, S = _take(w, S, neig, mode)
+    resid = (torch.matmul(Amat, S) - S * w.unsqueeze(-2)).abs().max().item()
+    run.update(converged=True, best_resid=resid, niter=run.get("niter", 0) + 1, completed_full_space=True)
+    return w.contiguous(), S.contiguous()
+
+
 def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps, max_basis, check_every, info, name):
     """Krylov eigensolver on an operator that is only known through `A.mm` (user `_mv`, composite operators such as
     ``A^H A`` of `svd`, autograd Hessians): the whole iteration stays in the engine's kernels, each block application
@@ -185,10 +206,15 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
 
         return _lib.APPLY_FN(_cb)
 
+    run = {} if info is None else info
     evals, evecs = _call_engine(None, 0, 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis, check_every,
-                                min_eps, info, name, make_apply=make_apply)
+                                min_eps, run, name, make_apply=make_apply)
     if failure:
         raise failure[0]
+    if _space_exhausted(run, n, neig, max_niter):
+        with torch.no_grad():
+            full = op(torch.eye(n, dtype=vdt, device=dev))
+        evals, evecs = _full_space_pairs(full.reshape(1, n, n), neig, mode, run)
     batch = tuple(A.shape[:-2])
     evals = evals.reshape(*batch, neig)
     evecs = evecs.reshape(*batch, n, neig)
@@ -234,8 +260,11 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     V0 = _start(v_init, nb, n, neig, vdt, dev)
 
     A3, a_bs, lda = _mat3(Amat, batch)
+    run = {} if info is None else info
     evals, evecs = _call_engine(A3, lda, (a_bs if nb > 1 else 0), n, nb, neig, mode, expansion, V0, max_niter,
-                                max_basis, check_every, min_eps, info, name)
+                                max_basis, check_every, min_eps, run, name)
+    if _space_exhausted(run, n, neig, max_niter):
+        evals, evecs = _full_space_pairs(Amat.reshape(nb, n, n), neig, mode, run)
     evals = evals.reshape(*batch, neig)
     evecs = evecs.reshape(*batch, n, neig)
     if LinvT is not None:
