@@ -324,3 +324,18 @@ def test_callbacks_do_not_keep_tensors_alive(eng):
         assert wr() is None
     finally:
         gc.enable()
+
+
+def test_symeig_with_fewer_than_two_blocks(eng):
+    # n < 2 neig: the reference's first expansion already spans the whole space -> exact pairs; no engine call
+    A = _spd(5, seed=60)
+    ncalls = len(eng.log)
+    info = {}
+    ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=3, method="davidson", info=info)
+    assert len(eng.log) == ncalls and info["converged"] and info["completed_full_space"]
+    assert torch.allclose(ev, torch.linalg.eigvalsh(A)[:3], atol=1e-12)
+    assert torch.allclose(A @ vec, vec * ev, atol=1e-12)
+    Mm = _spd(5, seed=61)
+    ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=4, mode="uppest",
+                     M=xt.LinearOperator.m(Mm, is_hermitian=True), method="lanczos")
+    assert torch.allclose(A @ vec, Mm @ vec * ev, atol=1e-10)

@@ -261,6 +261,12 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
 
     A3, a_bs, lda = _mat3(Amat, batch)
     run = {} if info is None else info
+    if n < 2 * neig:
+        # not even two blocks fit: the reference's first expansion already fills the whole space (symeig.py:209-211)
+        run.update(niter=0, converged=False, napply=0, max_basis=n)
+        evals, evecs = _full_space_pairs(Amat.reshape(nb, n, n).to(vdt), neig, mode, run)
+        evals, evecs = evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
+        return evals, (torch.matmul(LinvT, evecs) if LinvT is not None else evecs)
     evals, evecs = _call_engine(A3, lda, (a_bs if nb > 1 else 0), n, nb, neig, mode, expansion, V0, max_niter,
                                 max_basis, check_every, min_eps, run, name)
     if _space_exhausted(run, n, neig, max_niter):
