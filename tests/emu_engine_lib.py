@@ -37,7 +37,12 @@ def build(workdir: str):
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
                            "-I", os.path.join(ROOT, "tools", "emu_engine"), "-I", os.path.join(ROOT, "include"),
                            "-o", so] + cpps)
+    return load(so)
+
+
+def load(so: str):
     lib = C.CDLL(so)
+    lib.path = so
     lib.xt_symeig_workspace_bytes.argtypes = [C.c_int32] * 5
     lib.xt_symeig_workspace_bytes.restype = C.c_size_t
     lib.xt_symeig_krylov.argtypes = [C.POINTER(_lib.SymeigArgs)]

@@ -129,6 +129,62 @@ def test_row_partitioned_symeig_allgather_hook_world2():
         assert r[3] == world and r[4] == (48, 4)
 
 
+def _worker_emulated(rank, world, port, q, so_path):
+    """the row-partitioned path of the REAL engine (host build of csrc/symeig.cu, tools/emu_engine) on two gloo ranks:
+    local row block times the basis block, flag row packed behind it, one in-place all-gather per application, the
+    gathered image unpacked and the stop decision taken from the gathered flags -- on every rank identically"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import emu_engine_lib
+        from xitorch_b200 import dist as xd
+        import oracle
+
+        class _Patch(object):
+            def setattr(self, obj, name, value):
+                setattr(obj, name, value)
+
+        emu_engine_lib.install(_Patch(), emu_engine_lib.load(so_path))
+        n, k = 64, 4
+        A = oracle.make_herm(n, 2, torch.float64, seed=5)
+        lo, hi = xd.shard_range(n, rank, world)
+        info = {}
+        evals, evecs = xd.symeig_row_partitioned(A[lo:hi].contiguous(), n, k, min_eps=1e-8, info=info)
+        ref = torch.linalg.eigvalsh(A)[:k]
+        ok_vals = ((evals - ref).abs() / ref.abs()).max().item() <= 1e-9
+        ok_vecs = (A @ evecs - evecs * evals).abs().max().item() <= 2e-7
+        q.put((rank, ok_vals, ok_vecs, info["niter"], info["converged"], evals.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_engine_emulated_world2(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_engine_lib
+    lib = emu_engine_lib.build(str(tmp_path))
+    if lib is None:
+        pytest.skip("g++ not available")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_emulated, args=(r, world, port, q, lib.path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] and r[2] and r[4], r
+    assert res[0][3] == res[1][3]                    # both ranks stopped at the same iteration
+    assert res[0][5] == res[1][5]                    # ... with bit-identical eigenvalues (replicated small algebra)
+
+
 def test_shard_range_properties():
     from xitorch_b200.dist import shard_range
     for n in (1, 7, 512, 513):
