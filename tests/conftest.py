@@ -35,3 +35,14 @@ def _build_extension():
     if not os.path.exists(_lib.LIB_PATH):
         from xitorch_b200.csrc.build import build
         build()
+
+
+@pytest.fixture(scope="session")
+def emu_lib(tmp_path_factory):
+    """the engines' sources as a host build (tools/emu_engine), built once per test session"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu_engine_lib
+    lib = emu_engine_lib.build(str(tmp_path_factory.mktemp("emu_engine")))
+    if lib is None:
+        pytest.skip("g++ not available")
+    return lib

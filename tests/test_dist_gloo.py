@@ -161,13 +161,8 @@ def _worker_emulated(rank, world, port, q, so_path):
         dist.destroy_process_group()
 
 
-def test_row_partitioned_engine_emulated_world2(tmp_path):
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    import emu_engine_lib
-    lib = emu_engine_lib.build(str(tmp_path))
-    if lib is None:
-        pytest.skip("g++ not available")
+def test_row_partitioned_engine_emulated_world2(emu_lib):
+    lib = emu_lib
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -22,14 +22,6 @@ import emu_engine_lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emu_lib(tmp_path_factory):
-    lib = emu_engine_lib.build(str(tmp_path_factory.mktemp("emu_engine")))
-    if lib is None:
-        pytest.skip("g++ not available")
-    return lib
-
-
 @pytest.fixture()
 def engine(emu_lib, monkeypatch):
     emu_engine_lib.install(monkeypatch, emu_lib)
