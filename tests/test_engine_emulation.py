@@ -286,3 +286,27 @@ def test_batch_of_small_operators(engine):
     ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=3, method="davidson", min_eps=1e-8)
     assert (ev - torch.linalg.eigvalsh(A)[..., :3]).abs().max().item() <= 1e-9
     assert _residual(A, ev, vec) <= 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- engine code paths
+@pytest.mark.parametrize("env", [{"XT_LAG1_M": "128"}, {"XT_LAG1_M": "0"}, {"XT_NO_FUSE": "1"}, {"XT_PO_NOSTAGE": "1"},
+                                 {"XT_ROTATE_NAIVE": "1"}])
+def test_alternative_engine_paths_give_the_same_answer(engine, monkeypatch, env):
+    """the switches select code paths the default run at test sizes does not take: Ritz check lagging ONE iteration (what
+    the C2 benchmark runs: there the Rayleigh-Ritz kernel is faster than a matvec), the multi-kernel iteration without
+    the fused cooperative kernel, the basis read from L2 instead of staged in shared memory, the untiled restart
+    rotation.  Same eigenpairs, same iteration count; lag 1 costs exactly one application more than iterations."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    A = _herm(128, 4)
+    info = {}
+    kw = dict(max_basis=24) if "XT_ROTATE_NAIVE" in env else {}
+    ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=4, method="davidson", min_eps=1e-8, info=info, **kw)
+    ref = torch.linalg.eigvalsh(A)[:4]
+    assert info["converged"]
+    assert ((ev - ref).abs() / ref.abs()).max().item() <= 1e-9
+    assert _residual(A, ev, vec) <= 2e-7
+    if env.get("XT_LAG1_M") == "128":
+        assert info["napply"] == info["niter"] + 1
+    if env.get("XT_LAG1_M") == "0":
+        assert info["napply"] == info["niter"] + 2
