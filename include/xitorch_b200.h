@@ -200,6 +200,24 @@ int xt_symeig_krylov(const xt_symeig_args* args);
 int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out,
                   double* scratch, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Hermiticity check of a dense real operator in one pass over the matrix -- replaces
+ * torch.allclose(mat, mat.transpose(-2, -1).conj()) of LinearOperator.m (xitorch/_core/linop.py:96-103), with the same
+ * rule: |A_ij - A_ji| <= atol + rtol |A_ji| for every ordered pair, NaN never passes.
+ *   A: (nbatch, n, n) row-major, row stride lda, batch stride a_bstride (elements);
+ *   mismatch: device int32, zeroed by the caller; set to 1 when a violating pair is found.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;                              /* XT_F32 or XT_F64 */
+  int32_t n, nbatch;
+  const void* A; int64_t lda, a_bstride;
+  double rtol, atol;
+  int32_t* mismatch;
+  void* stream;
+} xt_hermcheck_args;
+
+int xt_hermitian_check(const xt_hermcheck_args* args);
+
 #ifdef __cplusplus
 }
 #endif

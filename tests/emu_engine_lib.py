@@ -1,5 +1,5 @@
 """
-Builds and installs the HOST BUILD of the engines (TEST INFRASTRUCTURE): csrc/{symeig,solve,gmres}.cu rewritten textually
+Builds and installs the HOST BUILD of the engines (TEST INFRASTRUCTURE): csrc/{symeig,solve,gmres,linop}.cu rewritten textually
 for a host compiler by tools/emu_engine (host threads for CUDA threads, a loop for the block matvec) into one shared
 library with the C ABI of include/xitorch_b200.h, loaded with ctypes and put in place of the CUDA library for the
 duration of a test.  Everything above the C ABI -- and everything below it except the matvec kernel -- is then the
@@ -16,7 +16,7 @@ import torch
 from xitorch_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SOURCES = ("symeig", "solve", "gmres")
+SOURCES = ("symeig", "solve", "gmres", "linop")
 
 
 def build(workdir: str):
@@ -55,6 +55,8 @@ def load(so: str):
     for nm in ("xt_cg", "xt_bicgstab", "xt_gmres"):
         getattr(lib, nm).argtypes = [C.POINTER(_lib.SolveArgs)]
         getattr(lib, nm).restype = C.c_int
+    lib.xt_hermitian_check.argtypes = [C.POINTER(_lib.HermCheckArgs)]
+    lib.xt_hermitian_check.restype = C.c_int
     return lib
 
 

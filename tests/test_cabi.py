@@ -28,7 +28,7 @@ def test_struct_layouts_match_header_field_order():
     hdr = open(os.path.join(ROOT, "include", "xitorch_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     for cname, cls in (("xt_matvec_args", _lib.MatvecArgs), ("xt_solve_args", _lib.SolveArgs),
-                       ("xt_symeig_args", _lib.SymeigArgs)):
+                       ("xt_symeig_args", _lib.SymeigArgs), ("xt_hermcheck_args", _lib.HermCheckArgs)):
         end = hdr.index("} %s;" % cname)
         body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
         fields = []

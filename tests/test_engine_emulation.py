@@ -310,3 +310,52 @@ def test_alternative_engine_paths_give_the_same_answer(engine, monkeypatch, env)
         assert info["napply"] == info["niter"] + 1
     if env.get("XT_LAG1_M") == "0":
         assert info["napply"] == info["niter"] + 2
+
+
+# ---------------------------------------------------------------------------------------------- Hermiticity check
+def test_hermitian_check_kernel_matches_allclose(engine):
+    """`xt_hermitian_check` (csrc/linop.cu, what LinearOperator.m runs on CUDA matrices) against torch.allclose(A, A^T):
+    symmetric matrices of awkward sizes, a single violating entry in every kind of tile position, the tolerance boundary
+    in both directions, NaN, batches, padded leading dimension, both precisions"""
+    from xitorch_b200 import _dense
+    g = torch.Generator().manual_seed(0)
+
+    def ref(m):
+        return bool(torch.allclose(m, m.transpose(-2, -1)))
+
+    for dtype in (torch.float32, torch.float64):
+        for n in (1, 5, 32, 33, 64, 70, 97):
+            a = torch.randn(n, n, generator=g, dtype=dtype)
+            sym = a + a.T
+            assert _dense.hermitian_check(sym) and ref(sym), (dtype, n)
+            for (i, j) in {(0, n - 1), (n - 1, 0), (n // 2, n // 3), (min(31, n - 1), min(32, n - 1)), (n - 1, n - 2)}:
+                if i == j or min(i, j) < 0:
+                    continue
+                bad = sym.clone()
+                bad[i, j] += 1e-2 * (1 + bad[i, j].abs())
+                assert _dense.hermitian_check(bad) == ref(bad) == False, (dtype, n, i, j)       # noqa: E712
+            if n > 1:
+                # inside the tolerance in both directions / outside in one
+                near = sym.clone()
+                near[0, 1] = near[1, 0] * (1 + 5e-6)
+                assert _dense.hermitian_check(near) == ref(near), (dtype, n)
+                tiny = sym.clone()
+                tiny[0, 1], tiny[1, 0] = 3e-9, -3e-9                 # |d| = 6e-9 <= atol = 1e-8
+                assert _dense.hermitian_check(tiny) == ref(tiny) == True      # noqa: E712
+                tiny[0, 1] = 3e-8
+                assert _dense.hermitian_check(tiny) == ref(tiny) == False     # noqa: E712
+                nan = sym.clone()
+                nan[1, 0] = nan[0, 1] = float("nan")
+                assert _dense.hermitian_check(nan) == ref(nan) == False       # noqa: E712
+    # batch: one bad item spoils the verdict; padded rows (lda > n)
+    a = torch.randn(3, 40, 40, generator=g, dtype=torch.float64)
+    sym = a + a.transpose(-2, -1)
+    assert _dense.hermitian_check(sym)
+    sym[2, 7, 30] += 1.0
+    assert not _dense.hermitian_check(sym)
+    big = torch.randn(64, 64, generator=g, dtype=torch.float32)
+    big = big + big.T
+    assert _dense.hermitian_check(big[:45, :45]) and not _dense.hermitian_check(big[:45, 1:46])
+    # and through the public entry: LinearOperator.m trusts / rejects the flag accordingly (CPU tensors take torch's test)
+    with pytest.raises(RuntimeError, match="hermitian"):
+        xt.LinearOperator.m(sym[2], is_hermitian=True)

@@ -118,3 +118,28 @@ def test_generalized_matrix_free():
                        matrix_free=True, min_eps=1e-7)
     assert (A @ X - Mm @ X * ev).abs().max().item() <= 1e-5
     assert (X.T @ Mm @ X - torch.eye(k, dtype=torch.float64, device="cuda")).abs().max().item() <= 1e-8
+
+
+def test_hermitian_check_kernel_on_hardware():
+    """`xt_hermitian_check` (csrc/linop.cu; logic verified on the host build, tests/test_engine_emulation.py) against
+    torch.allclose on the GPU, and LinearOperator.m through it"""
+    from xitorch_b200 import _dense
+    g = torch.Generator().manual_seed(1)
+    for dtype in (torch.float32, torch.float64):
+        for n in (1, 33, 1000, 4096):
+            a = torch.randn(n, n, generator=g, dtype=dtype).cuda()
+            sym = a + a.T
+            assert _dense.hermitian_check(sym)
+            if n > 1:
+                bad = sym.clone()
+                bad[n - 1, 0] += 1.0
+                assert not _dense.hermitian_check(bad)
+                assert _dense.hermitian_check(bad) == bool(torch.allclose(bad, bad.T))
+    batch = torch.randn(3, 200, 200, generator=g).cuda()
+    batch = batch + batch.transpose(-2, -1)
+    assert _dense.hermitian_check(batch)
+    batch[1, 5, 150] += 0.5
+    assert not _dense.hermitian_check(batch)
+    with pytest.raises(RuntimeError, match="hermitian"):
+        xt.LinearOperator.m(batch[1], is_hermitian=True)
+    assert xt.LinearOperator.m(batch[0]).is_hermitian

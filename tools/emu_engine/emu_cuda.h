@@ -63,9 +63,10 @@ inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_
 inline void emu_fence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline long long clock64() { return 0; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+constexpr size_t EMU_SLOT = 16384;      // bytes reserved per `__shared__` declaration site
 template <typename T> T* emu_shared(int id, size_t count) {
-  (void)count;
-  return reinterpret_cast<T*>(t_cta->stat.data() + 4096 * id);
+  if (count * sizeof(T) > EMU_SLOT || (size_t)id >= 64) { fprintf(stderr, "emu_shared: slot %d too small\n", id); abort(); }
+  return reinterpret_cast<T*>(t_cta->stat.data() + EMU_SLOT * id);
 }
 template <typename T> T* emu_dyn_smem() {
   return reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(t_cta->dyn.data()) + 15) & ~uintptr_t(15));
@@ -143,7 +144,7 @@ inline void emu_init_cta(EmuCta& cta, unsigned block, size_t smem) {
   cta.wbar.clear();
   for (unsigned w = 0; w < (block + 31) / 32; ++w)
     cta.wbar.push_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
-  cta.stat.assign(4096 * 64, 0);
+  cta.stat.assign(EMU_SLOT * 64, 0);
   cta.dyn.assign(smem + 64, 0);
   cta.wscr.assign(32 * ((block + 31) / 32), 0.0);
 }
@@ -155,12 +156,12 @@ template <typename F> void emu_launch(dim3 grid, dim3 block, size_t smem, F&& bo
   EmuCta cta;
   emu_init_cta(cta, block.x, smem);
   std::barrier<> cta_end(block.x);
-  const unsigned G = grid.x, B = block.x;
-  emu_parallel(B, [&cta, &cta_end, &body, G, B](unsigned t) {
+  const unsigned G = grid.x * grid.y * grid.z, B = block.x;
+  emu_parallel(B, [&cta, &cta_end, &body, G, B, grid](unsigned t) {
     t_cta = &cta;
-    threadIdx = {t, 0, 0}; blockDim = {B, 1, 1}; gridDim = {G, 1, 1};
+    threadIdx = {t, 0, 0}; blockDim = {B, 1, 1}; gridDim = {grid.x, grid.y, grid.z};
     for (unsigned c = 0; c < G; ++c) {
-      blockIdx = {c, 0, 0};
+      blockIdx = {c % grid.x, (c / grid.x) % grid.y, c / (grid.x * grid.y)};
       body();
       cta_end.arrive_and_wait();
     }

@@ -91,7 +91,8 @@ def _split_args(s: str):
 
 
 def transform(src: str, include_dir: str = None) -> str:
-    src = src.replace('#include "matvec.cuh"', '#include "emu_cuda.h"')
+    src = src.replace('#include "matvec.cuh"', '#include "emu_cuda.h"').replace('#include "common.cuh"',
+                                                                                 '#include "emu_cuda.h"')
     m = re.search(r'#include "(solve_common\.cuh)"', src)
     if m:                                                       # the solvers' shared header is inlined, rewritten too
         import os

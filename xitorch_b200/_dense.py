@@ -86,3 +86,29 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
         _lib.check(_lib.lib().xt_block_matvec(a), "block_matvec")
     y = y.reshape(*batch, p, k)
     return y if out_dtype == vdt else y.to(out_dtype)
+
+
+def hermitian_check(mat: torch.Tensor, rtol: float = 1e-5, atol: float = 1e-8) -> bool:
+    """``torch.allclose(mat, mat^T, rtol, atol)`` for a real CUDA matrix (or batch of matrices) in one pass over it
+    (`xt_hermitian_check`, csrc/linop.cu) instead of several elementwise kernels over the matrix and its strided
+    transpose plus their temporaries.  One device -> host read of the flag, like the library test."""
+    _lib.require_cuda(mat, "the Hermiticity check")
+    n = mat.shape[-1]
+    if mat.shape[-2] != n or mat.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("hermitian_check: square float32 / float64 matrices only")
+    batch = tuple(mat.shape[:-2])
+    m3, a_bstride, lda = flatten_batch(mat, batch)
+    nb = 1
+    for s_ in batch:
+        nb *= s_
+    flag = torch.zeros(1, dtype=torch.int32, device=mat.device)
+    a = _lib.HermCheckArgs()
+    a.dtype = _lib.dtype_code(mat.dtype)
+    a.n, a.nbatch = n, nb
+    a.A, a.lda, a.a_bstride = m3.data_ptr(), lda, a_bstride
+    a.rtol, a.atol = float(rtol), float(atol)
+    a.mismatch = flag.data_ptr()
+    a.stream = _lib.stream_ptr(mat.device)
+    with torch.cuda.device(mat.device):
+        _lib.check(_lib.lib().xt_hermitian_check(a), "hermitian_check")
+    return int(flag.item()) == 0

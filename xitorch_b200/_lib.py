@@ -22,7 +22,7 @@ _DTYPES = {torch.float32: XT_F32, torch.bfloat16: XT_BF16, torch.float64: XT_F64
 EXPORTS = [
     "xt_version", "xt_last_error", "xt_profile_reset", "xt_profile_read", "xt_block_matvec",
     "xt_solve_workspace_bytes", "xt_cg", "xt_bicgstab", "xt_gmres",
-    "xt_symeig_workspace_bytes", "xt_symeig_krylov", "xt_small_eigh",
+    "xt_symeig_workspace_bytes", "xt_symeig_krylov", "xt_small_eigh", "xt_hermitian_check",
 ]
 
 
@@ -82,6 +82,16 @@ class SymeigArgs(C.Structure):
     ]
 
 
+class HermCheckArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("n", C.c_int32), ("nbatch", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_bstride", C.c_int64),
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("mismatch", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
 ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
 
 
@@ -127,6 +137,8 @@ def lib():
         L.xt_solve_workspace_bytes.restype = C.c_size_t
         L.xt_symeig_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.xt_symeig_workspace_bytes.restype = C.c_size_t
+        L.xt_hermitian_check.argtypes = [C.POINTER(HermCheckArgs)]
+        L.xt_hermitian_check.restype = C.c_int
         L.xt_symeig_krylov.argtypes = [C.POINTER(SymeigArgs)]
         L.xt_symeig_krylov.restype = C.c_int
         L.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,0 +1,75 @@
+// Hermiticity check of a dense real operator, one pass over the matrix -- the test `LinearOperator.m(mat,
+// is_hermitian=True)` makes before it trusts the flag (reference: torch.allclose(mat, mat^H),
+// xitorch/_core/linop.py:96-103).  The library form of that test reads the matrix and its strided transpose through
+// several elementwise kernels and allocates 1-2 GiB of temporaries at N = 16384; on the end-to-end path of the
+// eigensolver (matrix copied in, operator built, solved) that is the second largest cost after the PCIe copy.
+// Here every pair of mirrored 32 x 32 tiles is loaded once with coalesced row reads, compared through shared memory
+// with the same rule in both directions (|a - b| <= atol + rtol |b| and |a - b| <= atol + rtol |a|; NaN never passes),
+// and a single flag records a violation.  HBM-bound: n^2 s bytes, nothing written.
+#include "common.cuh"
+
+namespace xt {
+
+constexpr int HC_TILE = 32;
+constexpr int HC_ROWS = 8;           // thread rows per CTA: 32 x 8 threads, 4 tile rows each
+
+template <typename T>
+__global__ void __launch_bounds__(HC_TILE * HC_ROWS)
+hermitian_check_kernel(const T* __restrict__ A, int n, int64_t lda, int64_t a_bstride, double rtol, double atol,
+                       int* mismatch) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;                                   // the pair (bj, bi) is handled by its mirror
+  if (*reinterpret_cast<volatile int*>(mismatch) != 0) return;
+  __shared__ T upper[HC_TILE][HC_TILE + 1];              // tile (bi, bj)
+  __shared__ T lower[HC_TILE][HC_TILE + 1];              // tile (bj, bi)
+  const T* Ab = A + (int64_t)blockIdx.z * a_bstride;
+  const int tx = threadIdx.x % HC_TILE, ty = threadIdx.x / HC_TILE;
+  for (int r = ty; r < HC_TILE; r += HC_ROWS) {
+    const int ru = bi * HC_TILE + r, cu = bj * HC_TILE + tx;
+    const int rl = bj * HC_TILE + r, cl = bi * HC_TILE + tx;
+    upper[r][tx] = (ru < n && cu < n) ? Ab[(int64_t)ru * lda + cu] : T(0);
+    lower[r][tx] = (rl < n && cl < n) ? Ab[(int64_t)rl * lda + cl] : T(0);
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int r = ty; r < HC_TILE; r += HC_ROWS) {
+    const int gi = bi * HC_TILE + r, gj = bj * HC_TILE + tx;
+    if (gi < n && gj < n) {
+      const double a = (double)upper[r][tx];             // A[gi][gj]
+      const double b = (double)lower[tx][r];             // A[gj][gi]
+      const double d = fabs(a - b);
+      // allclose(A, A^T) tests |A_ij - A_ji| <= atol + rtol |A_ji| for (i, j) AND for (j, i); exact equality always
+      // passes (it is how infinities compare equal in the library test as well)
+      const bool ok = (a == b) || (d <= atol + rtol * fabs(b) && d <= atol + rtol * fabs(a));
+      bad = bad || !ok;
+    }
+  }
+  if (bad) *mismatch = 1;
+}
+
+}  // namespace xt
+
+extern "C" {
+
+int xt_hermitian_check(const xt_hermcheck_args* g) {
+  XT_REQUIRE(g != nullptr && g->A != nullptr && g->mismatch != nullptr, "hermitian_check: null pointer");
+  XT_REQUIRE(g->n >= 1 && g->nbatch >= 1 && g->nbatch <= 65535, "hermitian_check: bad shape (n=%d, nbatch=%d)", g->n,
+             g->nbatch);
+  XT_REQUIRE(g->dtype == XT_F32 || g->dtype == XT_F64, "hermitian_check: only fp32 / fp64 matrices");
+  const int nt = (g->n + xt::HC_TILE - 1) / xt::HC_TILE;
+  XT_REQUIRE(nt <= 65535, "hermitian_check: n=%d too large for one launch", g->n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
+  const dim3 grid(nt, nt, g->nbatch), block(xt::HC_TILE * xt::HC_ROWS);
+  if (g->dtype == XT_F32) {
+    xt::hermitian_check_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(g->A), g->n, g->lda, g->a_bstride,
+                                                             g->rtol, g->atol, g->mismatch);
+  } else {
+    xt::hermitian_check_kernel<double><<<grid, block, 0, st>>>(static_cast<const double*>(g->A), g->n, g->lda,
+                                                              g->a_bstride, g->rtol, g->atol, g->mismatch);
+  }
+  XT_LAUNCHED();
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
+}  // extern "C"

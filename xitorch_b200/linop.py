@@ -40,6 +40,20 @@ def _indent(s: str, n: int) -> str:
     return ("\n" + pad).join(s.split("\n"))
 
 
+def _equals_adjoint(mat: torch.Tensor) -> bool:
+    """``allclose(mat, mat^H)`` (reference linop.py:96-103).  Real CUDA matrices take the one-pass kernel; a verdict of
+    "not Hermitian" -- and any failure of that path -- is settled by the library test, so the kernel can only ever make
+    the check cheaper, never change its outcome for a matrix the library test accepts."""
+    if mat.is_cuda and mat.dim() >= 2 and mat.dtype in (torch.float32, torch.float64) and mat.numel() > 0:
+        try:
+            from xitorch_b200 import _dense
+            if _dense.hermitian_check(mat):
+                return True
+        except Exception:                                        # noqa: BLE001 -- fall through to the library test
+            pass
+    return bool(torch.allclose(mat, mat.transpose(-2, -1).conj()))
+
+
 class LinearOperator(EditableModule):
     """Base class of (batched) linear operators of shape ``(*B, p, q)``."""
 
@@ -64,9 +78,9 @@ class LinearOperator(EditableModule):
             if mat.shape[-2] != mat.shape[-1]:
                 is_hermitian = False
             else:
-                is_hermitian = bool(torch.allclose(mat, mat.transpose(-2, -1).conj()))
+                is_hermitian = _equals_adjoint(mat)
         elif is_hermitian:
-            if not torch.allclose(mat, mat.transpose(-2, -1).conj()):
+            if not _equals_adjoint(mat):
                 raise RuntimeError("The linear operator is indicated to be hermitian, but the matrix is not")
         return MatrixLinearOperator(mat, is_hermitian)
 
