@@ -91,7 +91,7 @@ def test_lanczos_and_residual_expansion_agree(engine):
 def test_thick_restart(engine):
     # a basis cap far below what convergence needs: several restarts, still the right pairs
     g = torch.Generator().manual_seed(5)
-    n = 192
+    n = 128
     A = torch.randn(n, n, generator=g, dtype=torch.float64)
     A = (A + A.T) / (2 * n) ** 0.5 + torch.diag(torch.linspace(1, 3, n, dtype=torch.float64))
     info = {}
@@ -104,7 +104,7 @@ def test_thick_restart(engine):
 
 
 def test_uppest_float32_odd_size(engine):
-    A = _herm(150, 3, torch.float32, seed=9)                     # n not a multiple of the 64-row chunks
+    A = _herm(102, 3, torch.float32, seed=9)                     # n not a multiple of the 64-row chunks
     info = {}
     ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=3, mode="uppest", method="davidson",
                      min_eps=2e-4, info=info)
@@ -131,7 +131,7 @@ class UserOperator(xt.LinearOperator):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_matrix_free_hook_matches_dense_path(engine, dtype):
-    A = _herm(128, 4, dtype)
+    A = _herm(96, 4, dtype)
     eps = 1e-4 if dtype == torch.float32 else 1e-8
     info_d, info_f = {}, {}
     ev_d, vec_d = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=4, method="davidson", min_eps=eps, info=info_d)
@@ -298,7 +298,7 @@ def test_alternative_engine_paths_give_the_same_answer(engine, monkeypatch, env)
     rotation.  Same eigenpairs, same iteration count; lag 1 costs exactly one application more than iterations."""
     for k_, v_ in env.items():
         monkeypatch.setenv(k_, v_)
-    A = _herm(128, 4)
+    A = _herm(96, 4)
     info = {}
     kw = dict(max_basis=24) if "XT_ROTATE_NAIVE" in env else {}
     ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=4, method="davidson", min_eps=1e-8, info=info, **kw)
