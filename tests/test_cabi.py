@@ -59,3 +59,33 @@ def test_invalid_arguments_return_status_not_crash():
     g = _lib.SolveArgs()
     assert L.xt_cg(ctypes.byref(g)) != 0
     assert b"solve" in L.xt_last_error()
+
+
+def test_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
+    """the ctypes mirrors against what a C compiler makes of include/xitorch_b200.h: total size and the offset of every
+    field (catches a wrong field TYPE, which the name-order test above cannot)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    structs = (("xt_matvec_args", _lib.MatvecArgs), ("xt_solve_args", _lib.SolveArgs),
+               ("xt_symeig_args", _lib.SymeigArgs), ("xt_hermcheck_args", _lib.HermCheckArgs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "xitorch_b200.h"', 'int main(void) {']
+    for cname, cls in structs:
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    for (cname, cls), line in zip(structs, out):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == ctypes.sizeof(cls), cname
+        for (fname, _), off in zip(cls._fields_, parts[2:]):
+            assert int(off) == getattr(cls, fname).offset, (cname, fname)
