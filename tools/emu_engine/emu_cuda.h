@@ -281,7 +281,11 @@ struct MvArgs {
   const void* U; int64_t ldu, u_bstride;
   double* dot_out; int impl; const int* done_flag; int reserve_sms; int reverse; int l2_keep_mb;
 };
-struct emu_bf16 { uint16_t bits; explicit operator double() const { uint32_t u = (uint32_t)bits << 16; float f; std::memcpy(&f, &u, 4); return f; } };
+struct emu_bf16 {
+  uint16_t bits;
+  explicit operator float() const { uint32_t u = (uint32_t)bits << 16; float f; std::memcpy(&f, &u, 4); return f; }
+  explicit operator double() const { return (double)(float)*this; }
+};
 template <typename TA, typename TV> void emu_mv(const MvArgs& a) {
   const MvTiling til = mv_tiling(a.nbatch, a.nrows, a.reserve_sms);
   for (int b = 0; b < a.nbatch; ++b) {
