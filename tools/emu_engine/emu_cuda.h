@@ -214,6 +214,7 @@ inline void set_last_error(const char* fmt, ...) {
 #define XT_REQUIRE(cond, ...) do { if (!(cond)) { xt::set_last_error(__VA_ARGS__); return XT_ERR_INVALID; } } while (0)
 #define XT_LAUNCHED() ((void)0)
 inline int num_sms() { return g_emu_sms; }
+struct DeviceOnce { bool done = false; bool pending() { return !done; } void mark() { done = true; } };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Arena {
   char* base; size_t cap; size_t off;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <atomic>
 
 #include "../../include/xitorch_b200.h"
 
@@ -32,6 +33,23 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached)
+
+// One-time set-up that is PER DEVICE (cudaFuncSetAttribute applies to the current device only): a bit per device ordinal.
+// Two threads may both find the bit clear and both run the set-up -- it is idempotent -- but a launch never precedes it.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  int dev = -1;
+  bool pending() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    return (mask.load(std::memory_order_acquire) >> d & 1ull) == 0;
+  }
+  void mark() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return;
+    mask.fetch_or(1ull << d, std::memory_order_release);
+  }
+};
 
 // launch accounting / in-situ kernel timing (xt_profile_* in the C ABI)
 void note_launch(int n = 1);                        // every kernel launch site calls this

@@ -294,11 +294,11 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   const size_t smem_step =
       (size_t)((GM_JCHUNK + maxk + 3) * g->ncols + GM_JCHUNK * SV_THREADS + 64) * sizeof(double);
   const size_t smem_fin = (size_t)(maxk + 1) * g->ncols * sizeof(double) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     XT_CUDA_OK(cudaFuncSetAttribute(gm_step_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(gm_final_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_once.mark();
   }
   XT_REQUIRE(smem_step <= 200 * 1024 && smem_fin <= 200 * 1024,
              "gmres: max_niter*ncols = %d*%d too large for the on-chip Hessenberg state", maxk, g->ncols);

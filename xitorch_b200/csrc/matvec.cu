@@ -37,15 +37,18 @@ void set_last_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 // ---------------------------------------------------------------------------- launch accounting / profiling
+// Process-wide diagnostic state (xt_profile_* of the C ABI): two atomic launch counters, always on, and -- only while
+// bench.py has switched the in-situ timing on -- a mutex-protected list of CUDA event pairs around matvec launches.
 struct ProfState {
-  bool on = false;
+  std::atomic<bool> on{false};
+  std::mutex mu;                   // guards ev / used
   std::vector<cudaEvent_t> ev;     // pairs (begin, end); created once and reused across resets
   size_t used = 0;
-  int64_t launches = 0, mv_launches = 0;
+  std::atomic<int64_t> launches{0}, mv_launches{0};
 };
 static ProfState g_prof;
-void note_launch(int n) { g_prof.launches += n; }
-static void prof_record(cudaStream_t st) {
+void note_launch(int n) { g_prof.launches.fetch_add(n, std::memory_order_relaxed); }
+static void prof_record(cudaStream_t st) {          // caller holds g_prof.mu
   if (g_prof.used == g_prof.ev.size()) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -54,12 +57,15 @@ static void prof_record(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 void prof_mv_begin(cudaStream_t st) {
-  ++g_prof.mv_launches;
-  if (!g_prof.on) return;
+  g_prof.mv_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof.on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   prof_record(st);
 }
 void prof_mv_end(cudaStream_t st) {
-  if (!g_prof.on || (g_prof.used & 1) == 0) return;
+  if (!g_prof.on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  if ((g_prof.used & 1) == 0) return;
   prof_record(st);
 }
 
@@ -940,10 +946,10 @@ static int launch_tc(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cu
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
   dev.x_bulk = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     XT_CUDA_OK(cudaFuncSetAttribute(mv_tma_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_once.mark();
   }
   prof_mv_begin(st);
   mv_tma_tc_kernel<<<til.grid, 256 + 64, smem, st>>>(tm, dev);
@@ -1058,10 +1064,10 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   dev.x_bulk = x_bulk_ok<TV, K>(a) ? 1 : 0;
   dev.rows_pad = RP == 1 ? (til.tile_rows + 15) / 16 * 16 : ((til.tile_rows + RP - 1) / RP + 7) / 8 * 8;
   auto kern = mv_tma_kernel<TA, TV, K, NC, RP>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static DeviceOnce attr_once;   // per instantiation
+  if (attr_once.pending()) {
     XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_once.mark();
   }
   prof_mv_begin(st);
   kern<<<til.grid, NC + 64, smem, st>>>(tm, dev);
@@ -1092,10 +1098,10 @@ static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& t
   dev.a_batched = batched ? 1 : 0;
   dev.x_bulk = x_bulk_ok<float, K>(a) ? 1 : 0;
   auto kern = mv_tma_colslice_kernel<K>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_once.mark();
   }
   prof_mv_begin(st);
   kern<<<til.grid, 256 + 64, smem, st>>>(tm, dev);
@@ -1214,17 +1220,19 @@ extern "C" {
 int xt_version(void) { return 100; }
 
 void xt_profile_reset(int enable) {
+  std::lock_guard<std::mutex> lk(xt::g_prof.mu);
   xt::g_prof.used = 0;
-  xt::g_prof.on = enable != 0;
-  xt::g_prof.launches = 0;
-  xt::g_prof.mv_launches = 0;
+  xt::g_prof.on.store(enable != 0);
+  xt::g_prof.launches.store(0);
+  xt::g_prof.mv_launches.store(0);
 }
 
 int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_launches) {
-  // launches made after a solver's device-side `done` flag was raised return immediately: they are not counted
-  // as matvecs (duration below 20 % of the longest one)
+  // launches made after a solver's device-side `done` flag was raised return immediately (or abort part-way): they
+  // are not counted as matvecs (duration below 20 % of the longest one) but their time is reported in the total
+  std::lock_guard<std::mutex> lk(xt::g_prof.mu);
   double ms = 0.0;
-  int64_t eff = xt::g_prof.mv_launches;
+  int64_t eff = xt::g_prof.mv_launches.load();
   const size_t np = xt::g_prof.used / 2;
   if (np > 0) {
     XT_CUDA_OK(cudaEventSynchronize(xt::g_prof.ev[2 * np - 1]));
@@ -1240,7 +1248,7 @@ int xt_profile_read(double* matvec_ms, int64_t* matvec_launches, int64_t* total_
   }
   if (matvec_ms) *matvec_ms = ms;
   if (matvec_launches) *matvec_launches = eff;
-  if (total_launches) *total_launches = xt::g_prof.launches;
+  if (total_launches) *total_launches = xt::g_prof.launches.load();
   return XT_OK;
 }
 const char* xt_last_error(void) { return xt::last_error(); }

@@ -1861,8 +1861,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const size_t sp_smem = (size_t)(SE_ROWS * SE_MAXK + SE_GB * SE_MAXK * SE_MAXK) * sizeof(double) +
                          (size_t)SE_GB * SE_ROWS * k * sizeof(TV) + 64;
   const size_t rz_smem = (size_t)2 * SE_GB * SE_ROWS * k * sizeof(TV) + (size_t)SE_GB * k * k * sizeof(double) + 64;
-  static bool attrs_set = false;   // per TV instantiation
-  if (!attrs_set) {
+  static DeviceOnce attrs_once;   // per TV instantiation
+  if (attrs_once.pending()) {
     {
       cudaFuncAttributes fa;
       XT_CUDA_OK(cudaFuncGetAttributes(&fa, rr_kernel));
@@ -1876,7 +1876,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
     XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
     XT_CUDA_OK(cudaFuncSetAttribute(expand_fused_kernel<TV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
-    attrs_set = true;
+    attrs_once.mark();
   }
   // fused expansion step (one cooperative launch per iteration instead of ~8 stream operations): Krylov expansion on
   // one GPU, whenever this CTA's slice of the basis fits in shared memory
