@@ -289,13 +289,17 @@ def test_batch_of_small_operators(engine):
 
 
 # ---------------------------------------------------------------------------------------------- engine code paths
-@pytest.mark.parametrize("env", [{"XT_LAG1_M": "128"}, {"XT_LAG1_M": "0"}, {"XT_NO_FUSE": "1"}, {"XT_PO_NOSTAGE": "1"},
-                                 {"XT_ROTATE_NAIVE": "1"}])
+@pytest.mark.parametrize("env", [{}, {"XT_SYNC_CHECK": "1", "XT_LAG1_M": "128"}, {"XT_SYNC_CHECK": "1", "XT_LAG1_M": "0"},
+                                 {"XT_NO_FUSE": "1"}, {"XT_PO_NOSTAGE": "1"}, {"XT_ROTATE_NAIVE": "1"},
+                                 {"XT_SYNC_CHECK": "1", "XT_ROTATE_NAIVE": "1"}])
 def test_alternative_engine_paths_give_the_same_answer(engine, monkeypatch, env):
-    """the switches select code paths the default run at test sizes does not take: Ritz check lagging ONE iteration (what
-    the C2 benchmark runs: there the Rayleigh-Ritz kernel is faster than a matvec), the multi-kernel iteration without
-    the fused cooperative kernel, the basis read from L2 instead of staged in shared memory, the untiled restart
-    rotation.  Same eigenpairs, same iteration count; lag 1 costs exactly one application more than iterations."""
+    """the switches select code paths the default run at test sizes does not take: the in-stream Ritz checks (P0 of the
+    fused kernel) lagging one or two iterations instead of the asynchronous checks at the end of the Rayleigh-Ritz
+    kernels, the multi-kernel iteration without the fused cooperative kernel, the basis read from L2 instead of staged
+    in shared memory, the untiled restart rotation (with thick restarts, i.e. the hand-over between asynchronous checks
+    and the restart path).  Same eigenpairs, same iteration count.  On this host build every launch completes before the
+    next one starts, so an asynchronous check stops the solve with exactly one application per iteration; an in-stream
+    check lagging one (two) iterations costs exactly one (two) applications more."""
     for k_, v_ in env.items():
         monkeypatch.setenv(k_, v_)
     A = _herm(96, 4)
@@ -306,10 +310,46 @@ def test_alternative_engine_paths_give_the_same_answer(engine, monkeypatch, env)
     assert info["converged"]
     assert ((ev - ref).abs() / ref.abs()).max().item() <= 1e-9
     assert _residual(A, ev, vec) <= 2e-7
+    if not env:
+        assert info["napply"] == info["niter"]
     if env.get("XT_LAG1_M") == "128":
         assert info["napply"] == info["niter"] + 1
     if env.get("XT_LAG1_M") == "0":
         assert info["napply"] == info["niter"] + 2
+
+
+@pytest.mark.parametrize("dtype,mode,kw", [
+    (torch.float64, "lowest", dict(max_niter=5)),                 # stops unconverged: the best pair is returned
+    (torch.float32, "uppest", dict(max_niter=6)),
+    (torch.float64, "lowest", dict(max_basis=16)),                # thick restarts between asynchronous checks
+    (torch.float32, "lowest", dict(max_basis=24, max_niter=9)),   # restarts AND no convergence
+])
+def test_async_checks_match_in_stream_checks(engine, monkeypatch, dtype, mode, kw):
+    """The asynchronous Ritz check (Lanczos residual formula R = Q_{j+1} L^T S_last at the end of rr_kernel, best pair
+    kept as coefficients and turned into Ritz vectors once) against the in-stream check that forms X = V S and
+    R = AV S - X theta from the whole basis (XT_SYNC_CHECK=1): same iteration count, same stop decision, same residual
+    maximum to rounding, same eigenpairs -- also when the iteration limit ends the solve (best pair bookkeeping) and
+    across thick restarts (coefficients materialised before the basis is rotated)."""
+    A = _herm(96, 4, dtype=dtype)
+    out = {}
+    for sync in ("0", "1"):
+        if sync == "1":
+            monkeypatch.setenv("XT_SYNC_CHECK", "1")
+        else:
+            monkeypatch.delenv("XT_SYNC_CHECK", raising=False)
+        info = {}
+        ev, vec = symeig(xt.LinearOperator.m(A, is_hermitian=True), neig=4, mode=mode, method="davidson",
+                         min_eps=1e-9 if dtype == torch.float64 else 1e-5, info=info, **kw)
+        out[sync] = (ev, vec, info)
+    (ev0, vec0, i0), (ev1, vec1, i1) = out["0"], out["1"]
+    assert i0["niter"] == i1["niter"] and i0["converged"] == i1["converged"], (i0, i1)
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
+    assert (ev0 - ev1).abs().max().item() <= tol
+    assert (vec0.abs() - vec1.abs()).abs().max().item() <= (1e-8 if dtype == torch.float64 else 2e-4)
+    assert abs(i0["best_resid"] - i1["best_resid"]) <= 1e-3 * i1["best_resid"] + (1e-13 if dtype == torch.float64 else 2e-6)
+    # the reported residual maximum is the true one of the returned pair
+    true = _residual(A, ev0, vec0)
+    assert abs(true - i0["best_resid"]) <= 1e-3 * true + (1e-12 if dtype == torch.float64 else 1e-5)
 
 
 # ---------------------------------------------------------------------------------------------- Hermiticity check

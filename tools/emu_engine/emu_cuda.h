@@ -280,7 +280,7 @@ struct MvArgs {
   const void* E; int64_t e_bstride;
   const void* Z; int64_t ldz, z_bstride;
   const void* U; int64_t ldu, u_bstride;
-  double* dot_out; int impl; const int* done_flag; int reserve_sms; int reverse; int l2_keep_mb;
+  double* dot_out; int impl; const int* done_flag; const int* abort_flag; int reserve_sms; int reverse; int l2_keep_mb;
 };
 struct emu_bf16 {
   uint16_t bits;
@@ -319,6 +319,7 @@ template <typename TA, typename TV> void emu_mv(const MvArgs& a) {
 }
 inline int mv_launch(const MvArgs& a, cudaStream_t) {
   if (a.done_flag && *a.done_flag) return XT_OK;
+  if (a.abort_flag && *a.abort_flag) return XT_OK;
   if (a.dtype == XT_F32) emu_mv<float, float>(a);
   else if (a.dtype == XT_F64) emu_mv<double, double>(a);
   else if (a.dtype == XT_BF16) emu_mv<emu_bf16, float>(a);

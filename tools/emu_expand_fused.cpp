@@ -43,6 +43,7 @@ template <typename T> T* emu_shared(int id, int count) { (void)count; return rei
 static unsigned char* emu_dyn_smem() { return t_dyn_smem; }
 static double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 static unsigned int atomicAdd(unsigned int* p, unsigned int v) { return std::atomic_ref<unsigned int>(*p).fetch_add(v); }
+static int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
 static unsigned int atomicMax(unsigned int* p, unsigned int v) {
   std::atomic_ref<unsigned int> a(*p);
   unsigned int cur = a.load();

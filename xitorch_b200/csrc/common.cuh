@@ -114,6 +114,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// one probe of the barrier phase (the hardware suspends the thread for a bounded time before it reports failure)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// mbar_wait that gives up when `*abort_at` (shared memory, written by the CTA's TMA producer) says that chunk `seq`
+// will never be produced; returns false in that case
+__device__ __forceinline__ bool mbar_wait_abortable(uint64_t* bar, uint32_t parity, const int* abort_at, int seq) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (*reinterpret_cast<const volatile int*>(abort_at) <= seq) return false;
+  }
+  return true;
+}
+
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

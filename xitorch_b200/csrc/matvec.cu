@@ -174,6 +174,7 @@ struct MvDev {
   const void* U; int64_t ldu, u_bstride;
   double* dot_out;
   const int* done_flag;
+  const int* abort_flag;   // may be raised by another stream while the kernel runs (see MvArgs)
   int reverse;      // traverse the column chunks of A from the last to the first
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
@@ -292,9 +293,13 @@ constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 1
 
 // ---- roles shared by both consumer layouts -------------------------------------------------------------------
 // TMA producer (one elected lane): two boxes of tile_rows x 128 B per stage, L2 evict-first
+// `abort_at` (shared memory, kernels that support MvArgs.abort_flag; else nullptr): sequence number of the first chunk
+// that is NOT produced.  The producer is the only thread that looks at the global flag, so the decision is one per CTA:
+// everything before `*abort_at` is produced and consumed as usual (no TMA transfer is ever left in flight), every
+// waiter gives up at `*abort_at`.
 template <typename TA, typename TV, int K, int STAGE_BYTES>
 __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
-                                            uint64_t* empty, int NS, int nchunks) {
+                                            uint64_t* empty, int NS, int nchunks, int* abort_at = nullptr) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   const char* Xg = reinterpret_cast<const char*>(p.X);
@@ -302,13 +307,18 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
   const uint64_t pol_keep = l2_policy_evict_last();
   int s = 0;
   uint32_t ph = 0;
+  int seq = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int b = tile / p.tiles_per_batch;
     const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
     const int bA = p.a_batched ? b : 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
+    for (int ch = 0; ch < nchunks; ++ch, ++seq) {
       const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
       const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+      if (abort_at != nullptr && (seq & 7) == 0 && *reinterpret_cast<const volatile int*>(p.abort_flag) != 0) {
+        *reinterpret_cast<volatile int*>(abort_at) = seq;
+        return;
+      }
       mbar_wait(&empty[s], ph ^ 1);
       uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
       // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
@@ -333,7 +343,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
 // chunk ahead of the shared-memory slot becoming free, so their L2 latency overlaps the wait.
 template <typename TA, typename TV, int K, int STAGE_BYTES>
 __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty, int NS,
-                                           int nchunks, int lane) {
+                                           int nchunks, int lane, const int* abort_at = nullptr) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
@@ -352,16 +362,21 @@ __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, 
   };
   int s = 0;
   uint32_t ph = 0;
-  int tile = blockIdx.x, ch = 0;
+  int tile = blockIdx.x, ch = 0, seq = 0;
   if (tile < p.ntiles) load_chunk(tile, 0);
   while (tile < p.ntiles) {
-    mbar_wait(&empty[s], ph ^ 1);
+    if (abort_at != nullptr) {
+      if (!mbar_wait_abortable(&empty[s], ph ^ 1, abort_at, seq)) return;
+    } else {
+      mbar_wait(&empty[s], ph ^ 1);
+    }
     TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
 #pragma unroll
     for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[s]);
     if (++s == NS) { s = 0; ph ^= 1; }
+    ++seq;
     if (++ch == nchunks) { ch = 0; tile += gridDim.x; }
     if (tile < p.ntiles) load_chunk(tile, ch);
   }
@@ -407,6 +422,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;   // swizzle atoms need 1024-B aligned stages
 
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  __shared__ int abort_at_s;         // first chunk (sequence number) that is not produced; INT_MAX: none (see mv_producer)
+  int* abort_at = p.abort_flag != nullptr ? &abort_at_s : nullptr;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -427,6 +444,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     }
     fence_mbar_init();
     prefetch_tmap(&tmA);
+    // one thread decides for the whole CTA whether a flag that was already up at launch skips the pass
+    if (abort_at != nullptr) abort_at_s = (*reinterpret_cast<const volatile int*>(p.abort_flag) != 0) ? 0 : 0x7fffffff;
   }
   if (p.x_bulk) {   // X slots start as zeros: a ragged last chunk copies fewer bytes and must never expose NaN garbage
     for (int s = 0; s < NS; ++s) {
@@ -438,9 +457,10 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   __syncthreads();
 
   if (warp == 0) {
-    if (lane == 0) mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+    if (lane == 0 && (abort_at == nullptr || abort_at_s != 0))
+      mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks, abort_at);
   } else if (warp == 1) {
-    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane);
+    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane, abort_at);
   } else {
     // ------------------------------------------------------------------ consumers
     // thread <-> (row group r, k-slice q).  A thread owns RP rows: r, r + rows_pad, ... (rows_pad = ceil(tile_rows /
@@ -467,6 +487,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     const uint32_t x_q_off = (uint32_t)(q * nvec * EPV * K * (int)sizeof(TV));
     int s = 0;
     uint32_t ph = 0;
+    int seq = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_batch;
       const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
@@ -478,9 +499,15 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 #pragma unroll
         for (int i = 0; i < K; ++i) acc[h][i] = TV(0);
 
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = 0; ch < nchunks; ++ch, ++seq) {
         const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
-        mbar_wait(&full[s], ph);
+        if (abort_at != nullptr) {
+          // every consumer warp gives up at the same chunk (the first one the producer did not issue): the tile is
+          // dropped, no barrier below is entered by anyone
+          if (!mbar_wait_abortable(&full[s], ph, abort_at, seq)) return;
+        } else {
+          mbar_wait(&full[s], ph);
+        }
         if (active) {
           const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
           const uint32_t xs = a_s + MV_STAGE_A_BYTES + x_q_off;
@@ -1176,6 +1203,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.U = a.U; d.ldu = a.ldu; d.u_bstride = a.u_bstride;
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
+  d.abort_flag = a.abort_flag;
   d.reverse = a.reverse ? 1 : 0;
   {
     // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB
@@ -1192,6 +1220,8 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
     }
   }
 
+  if (a.abort_flag != nullptr && (a.impl == 4 || a.impl == 6 || a.impl == 2))
+    d.abort_flag = nullptr;               // only the row-slice TMA kernel polls it; the others run to completion
   const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5 || a.impl == 6);
   bool use_tma = forced_tma || (a.impl == 0 && mv_tma_ok(a));
   if (forced_tma && !mv_tma_ok(a)) {
@@ -1271,6 +1301,7 @@ int xt_block_matvec(const xt_matvec_args* g) {
     a.U = nullptr; a.ldu = 0; a.u_bstride = 0; a.dot_out = nullptr;
     a.impl = g->impl & 0xff;
     a.done_flag = nullptr;
+    a.abort_flag = nullptr;
     a.reserve_sms = 0;
     a.reverse = (g->impl >> 8) & 1;          // bit 8: last-to-first column traversal
     a.l2_keep_mb = (g->impl >> 16) & 0xff;   // bits 16..23: MB of the pass's tail to keep in L2 (see matvec.cuh)

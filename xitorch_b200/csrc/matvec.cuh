@@ -40,6 +40,10 @@ struct MvArgs {
   double* dot_out;                             // optional (needs U or self-dot), see above
   int impl;                                    // 0 auto, 1 TMA, 2 plain
   const int* done_flag;                        // optional device flag: kernel exits immediately when *done_flag != 0
+                                               // (only ever written by earlier work of the SAME stream)
+  const int* abort_flag;                       // optional device flag that may be raised ASYNCHRONOUSLY (another stream)
+                                               // while the kernel runs: the TMA producer polls it every few chunks, stops
+                                               // producing and the CTA drains and exits without storing its tile
   int reserve_sms;                             // leave this many SMs free (for kernels overlapped on another stream)
   int reverse;                                 // traverse A's column chunks last-to-first (alternate per call, see l2_keep_mb)
   int l2_keep_mb;                              // MB of the end of this pass to keep in L2 for the next, reversed pass

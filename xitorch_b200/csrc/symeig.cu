@@ -49,6 +49,11 @@ struct EigCtl {
   unsigned int resmax_bits;   // max |R| of the current iteration (float bits, atomicMax)
   float best_resid;
   unsigned int bar_count, bar_gen;   // grid barrier of the fused expansion kernel
+  int bar_abort;        // latched at a grid barrier: some CTA saw `done` (raised asynchronously by a side-stream check)
+  // asynchronous Ritz checks (rr_kernel on the side streams, see CheckArgs)
+  int best_in_S;        // 1: the best pair so far is held as coefficients (Sbest, best_m) w.r.t. the current basis
+  int best_m;
+  int check_done;       // ticket of the last check whose bookkeeping is complete (they are applied in launch order)
   int* host_done;       // host-mapped mirror of `done` (lets the host stop launching without draining the stream)
   unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
   unsigned long long ptrace[64][12]; // fused expansion kernel of iteration i (CTA 0): start and 10 phase stamps
@@ -104,7 +109,7 @@ __device__ __forceinline__ void stage_group(TV* dst, const TV* __restrict__ src,
 }
 
 // tiny k x k Cholesky-QR factor on one warp: Gs (k x k Gram, smem) -> Ri = R^-1 (upper, smem); returns 0 on breakdown
-__device__ int chol_inverse_warp(double* Gs, double* Ri, int k) {
+__device__ int chol_inverse_warp(double* Gs, double* Ri, int k, double* Lout = nullptr) {
   const int lane = threadIdx.x & 31;
   double scale = 0.0;
   for (int i = 0; i < k; ++i) scale = fmax(scale, Gs[i * k + i]);
@@ -124,6 +129,9 @@ __device__ int chol_inverse_warp(double* Gs, double* Ri, int k) {
     __syncwarp();
   }
   if (!ok) return 0;
+  if (Lout != nullptr) {                 // the factor itself (lower triangle, row-major), for the Lanczos residual formula
+    for (int e = lane; e < k * k; e += 32) Lout[e] = (e % k <= e / k) ? Gs[e] : 0.0;
+  }
   // Linv column c by forward substitution (lane c), stored as Ri[c][r] = Linv[r][c] = Rinv[c][r]
   for (int c = lane; c < k; c += 32) {
     for (int r = 0; r < k; ++r) {
@@ -141,7 +149,7 @@ __device__ int chol_inverse_warp(double* Gs, double* Ri, int k) {
 // G (row-major, k x k, shared) -> Ri[c*k + r] = (chol(G)^-T)[c][r] as chol_inverse_warp produces it.  rsqrt and
 // multiplications only.  Returns 0 on breakdown.
 template <int KP>
-__device__ __forceinline__ int chol_inverse_regs(const double* Gs, double* Ri, int k) {
+__device__ __forceinline__ int chol_inverse_regs(const double* Gs, double* Ri, int k, double* Lout = nullptr) {
   double L[KP][KP];
   double scale = 0.0;
 #pragma unroll
@@ -167,6 +175,14 @@ __device__ __forceinline__ int chol_inverse_regs(const double* Gs, double* Ri, i
       for (int c = j + 1; c <= i; ++c) L[i][c] = fma(-L[i][j], L[c][j], L[i][c]);
   }
   if (!ok) return 0;
+  if (Lout != nullptr && (threadIdx.x & 31) == 0) {
+    // the factor itself: strictly lower entries are final, the diagonal still holds L_jj^2 (L_jj = L_jj^2 / L_jj)
+#pragma unroll
+    for (int i = 0; i < KP; ++i)
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (i < k && j < k) Lout[i * k + j] = (j < i) ? L[i][j] : ((j == i) ? L[i][i] * rd[i] : 0.0);
+  }
   // X = L^-1 by forward substitution, column c: X[r][c] (r >= c)
   double X[KP][KP];
 #pragma unroll
@@ -474,16 +490,23 @@ struct PostArgs {
   int rz_m, rz_iter, rz_ld, rz_coff;          // pending Ritz check (rz_m == 0: none)
   const double* rz_S; const double* rz_theta;
   void* Xslots; double* evals_slots; float min_eps;
+  double* Lout;                               // optional: the Cholesky factor of the new block's Gram matrix (k x k, lower)
+  int async_stop;                             // 1: `done` may be raised by another stream while this kernel runs
 };
 
 // sense-reversing grid barrier; returns false (after raising `done`) if the other CTAs never arrive
+// With `async_stop` the barrier also takes the stop decision for the whole grid: `done` can be raised by a check on a
+// side stream at any moment, so the CTAs must not read it on their own (some would leave, the others would wait for
+// them).  Every CTA that has seen the flag when it arrives latches `bar_abort`; all arrivals precede the release, so
+// after it every CTA reads the same value and the grid leaves together (returns false).
 __device__ __forceinline__ bool grid_barrier(EigCtl* ctl, unsigned int nblocks, unsigned long long* tin = nullptr,
-                                             unsigned long long* tout = nullptr) {
+                                             unsigned long long* tout = nullptr, bool async_stop = false) {
   __shared__ int ok_s;
   __syncthreads();
   if (threadIdx.x == 0) {
     int ok = 1;
     if (tin) tin[blockIdx.x] = gtimer();
+    if (async_stop && *reinterpret_cast<volatile int*>(&ctl->done) != 0) atomicExch(&ctl->bar_abort, 1);
     const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&ctl->bar_gen);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     if (atomicAdd(&ctl->bar_count, 1u) == nblocks - 1) {
@@ -499,6 +522,7 @@ __device__ __forceinline__ bool grid_barrier(EigCtl* ctl, unsigned int nblocks, 
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     if (tout) tout[blockIdx.x] = gtimer();
     if (!ok) { ctl->breakdown = 2; ctl->local_done = 1; signal_done(ctl); }
+    if (async_stop && *reinterpret_cast<volatile int*>(&ctl->bar_abort) != 0) ok = 0;
     ok_s = ok;
   }
   __syncthreads();
@@ -647,7 +671,9 @@ template <typename TV, int KP>
 __global__ void __launch_bounds__(PO_THREADS)
 expand_fused_kernel(const PostArgs p) {
   EigCtl* ctl = p.ctl;
-  if (ctl->done) return;                 // written only by earlier launches of this stream: uniform over the grid
+  // `done` written only by earlier launches of this stream: uniform over the grid.  With asynchronous checks it is not,
+  // and the decision is taken at the first grid barrier instead (see grid_barrier).
+  if (!p.async_stop && ctl->done) return;
   extern __shared__ __align__(16) unsigned char po_raw[];
   const int tid = threadIdx.x;
   const int n = p.n, k = p.k, m = p.m, R = p.R;
@@ -750,7 +776,7 @@ expand_fused_kernel(const PostArgs p) {
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, false, part, accC);
   if (tr) ctl->ptrace[p.iter][3] = gtimer();
   const bool btr = (p.iter == 8 && gridDim.x <= 160);
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr)) return;
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr, p.async_stop != 0)) return;
   if (tr) ctl->ptrace[p.iter][4] = gtimer();
 
   if (rz_nblk > 0 && last_cta && tid == 0) {
@@ -798,7 +824,7 @@ expand_fused_kernel(const PostArgs p) {
   if (tr) ctl->ptrace[p.iter][5] = gtimer();
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, true, part, accC2);
   if (tr) ctl->ptrace[p.iter][6] = gtimer();
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr)) return;
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr, p.async_stop != 0)) return;
   if (tr) ctl->ptrace[p.iter][7] = gtimer();
 
   // ---- P3: Q = (W' - V C2) Rinv
@@ -831,8 +857,9 @@ expand_fused_kernel(const PostArgs p) {
   if (tr) ctl->ptrace[p.iter][8] = gtimer();
   if (tid < 32) {
     int ok;
-    if constexpr (KP <= 8) ok = chol_inverse_regs<KP>(Gs, Ri, k);      // 16 x 16 does not fit the register file
-    else ok = chol_inverse_warp(Gs, Ri, k);
+    double* Lout = (blockIdx.x == 0) ? p.Lout : nullptr;              // every CTA factorises the same G; one stores L
+    if constexpr (KP <= 8) ok = chol_inverse_regs<KP>(Gs, Ri, k, Lout);      // 16 x 16 does not fit the register file
+    else ok = chol_inverse_warp(Gs, Ri, k, Lout);
     if (tid == 0) chol_ok = ok;
   }
   po_subtract<TV, KP>(Vb, Cs, Zs, rows, vbs, k, nblk, 32);       // warps 1.. while warp 0 factorises
@@ -1661,41 +1688,177 @@ t_update_kernel(double* T, int ldt, const double* C, int m, int k, const EigCtl*
   }
 }
 
+// Asynchronous Ritz check riding at the end of rr_kernel (Krylov expansion, fused path).  With the expansion block
+// Q_{j+1} L^T = (I - V V^T) A Q_j  (L = Cholesky factor of the block's Gram matrix, stored by expand_fused_kernel) and
+// T = V^T A V, the residual of the Ritz pairs (X, theta) = (V S, theta) is
+//     R = A X - X theta = (A V - V T) S = Q_{j+1} (L^T S_last),        S_last = the last k rows of S,
+// because (I - V V^T) A Q_i = 0 for every earlier block (its expansion block is part of V) -- also after a thick restart,
+// whose kept Ritz vectors have their residuals in the span of the first block appended after it.  This is the
+// reference's R = AV S - X theta (symeig.py:178-188) read off n*k instead of 2*n*m numbers, so one CTA can do it
+// next to the running matvec: max|R| -> stop test / best pair (symeig.py:196-201) without a pass over the basis.  The
+// Ritz vectors themselves are formed once, by output_kernel, from the coefficients kept here.
+struct CheckArgs {
+  const void* Q;            // (n, k) row-major expansion block Q_{j+1}; nullptr: plain Rayleigh-Ritz, no check
+  const double* L;          // k x k lower factor
+  int n, is_f64;
+  double* Sbest;            // [max_basis][k] coefficients of the best pair so far
+  double* evals_best;       // [k]
+  float min_eps;
+  int seq;                  // checks apply their bookkeeping in launch order: this one waits for ticket seq - 1
+};
+
+// max |Q M| over all rows; M (k x k, row-major, shared memory).  fp32 arithmetic for fp32 blocks (the result is compared
+// with a threshold: 1e-6 relative is plenty), fp64 for fp64 blocks.  LH columns of M are held in registers per pass.
+template <typename TV, int K, int LH>
+__device__ __forceinline__ float lanczos_resid_max_k(const TV* __restrict__ Q, int n, const double* Ms) {
+  float lmax = 0.f;
+#pragma unroll 1
+  for (int l0 = 0; l0 < K; l0 += LH) {
+    TV mreg[K][LH];
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int l = 0; l < LH; ++l) mreg[c][l] = (TV)Ms[c * K + l0 + l];
+#pragma unroll 2
+    for (int row = threadIdx.x; row < n; row += blockDim.x) {
+      TV q[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) q[c] = Q[(int64_t)row * K + c];
+#pragma unroll
+      for (int l = 0; l < LH; ++l) {
+        TV acc = TV(0);
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc = fma(q[c], mreg[c][l], acc);
+        lmax = fmaxf(lmax, fabsf((float)acc));
+        if (!(acc == acc)) lmax = INFINITY;
+      }
+    }
+  }
+  return lmax;
+}
+template <typename TV>
+__device__ float lanczos_resid_max(const TV* __restrict__ Q, int n, int k, const double* Ms) {
+  constexpr bool F64 = sizeof(TV) == 8;
+  if (k == 8) return lanczos_resid_max_k<TV, 8, F64 ? 4 : 8>(Q, n, Ms);
+  if (k == 16) return lanczos_resid_max_k<TV, 16, F64 ? 4 : 8>(Q, n, Ms);
+  if (k == 4) return lanczos_resid_max_k<TV, 4, 4>(Q, n, Ms);
+  float lmax = 0.f;
+  for (int row = threadIdx.x; row < n; row += blockDim.x) {
+    for (int l = 0; l < k; ++l) {
+      TV acc = TV(0);
+      for (int c = 0; c < k; ++c) acc = fma(Q[(int64_t)row * k + c], (TV)Ms[c * k + l], acc);
+      lmax = fmaxf(lmax, fabsf((float)acc));
+      if (!(acc == acc)) lmax = INFINITY;
+    }
+  }
+  return lmax;
+}
+
 __global__ void __launch_bounds__(EIG_THREADS)
 rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw, double* Sk, double* theta, int mode,
-          int lds, int as_in_smem, int y_in_smem, int inv_slots, EigCtl* ctl, int iter) {
-  if (ctl->done) return;
+          int lds, int as_in_smem, int y_in_smem, int inv_slots, EigCtl* ctl, int iter, const CheckArgs chk) {
   extern __shared__ double dyn[];
+  __shared__ int flag_s;
+  __shared__ float redmax[32];
+  __shared__ double Ms[SE_MAXK * SE_MAXK];
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0 && iter < 64) ctl->trace[iter][0] = gtimer();
-  if (C != nullptr) {
-    const int c0 = m - k;
-    for (int e = tid; e < m * k; e += nt) {
-      const int i = e / k, j = e - i * k;
-      double v = C[e];
-      if (i >= c0) v = 0.5 * (C[e] + C[(int64_t)(c0 + j) * k + (i - c0)]);   // symmetrise the diagonal block
-      T[(int64_t)i * ldt + c0 + j] = v;
-      T[(int64_t)(c0 + j) * ldt + i] = v;
-    }
-    __syncthreads();
-  }
+  const bool checking = chk.Q != nullptr;
+  // `done` may be raised by a concurrent check: one thread reads it for the CTA
+  if (tid == 0) flag_s = *reinterpret_cast<volatile int*>(&ctl->done);
+  __syncthreads();
+  bool stale = flag_s != 0;
+  if (stale && !checking) return;
   double* lamv = dyn;                       // [nev]
   double* ysm = lamv + nev + (nev & 1);     // [m * nev] when it fits
   double* Y = y_in_smem ? ysm : Sk;
-  double* rest = y_in_smem ? ysm + (size_t)m * nev : ysm;
-  double* As = as_in_smem ? rest : Tw;
-  double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
-  for (int e = tid; e < m * m; e += nt) {
-    const int i = e / m, j = e - i * m;
-    As[(size_t)i * lds + j] = T[(int64_t)i * ldt + j];
+  if (!stale) {
+    if (tid == 0 && iter < 64) ctl->trace[iter][0] = gtimer();
+    if (C != nullptr) {
+      const int c0 = m - k;
+      for (int e = tid; e < m * k; e += nt) {
+        const int i = e / k, j = e - i * k;
+        double v = C[e];
+        if (i >= c0) v = 0.5 * (C[e] + C[(int64_t)(c0 + j) * k + (i - c0)]);   // symmetrise the diagonal block
+        T[(int64_t)i * ldt + c0 + j] = v;
+        T[(int64_t)(c0 + j) * ldt + i] = v;
+      }
+      __syncthreads();
+    }
+    double* rest = y_in_smem ? ysm + (size_t)m * nev : ysm;
+    double* As = as_in_smem ? rest : Tw;
+    double* sh = as_in_smem ? rest + (size_t)m * lds : rest;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = e / m, j = e - i * m;
+      As[(size_t)i * lds + j] = T[(int64_t)i * ldt + j];
+    }
+    __syncthreads();
+    eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y, nullptr, &ctl->done);
+    __syncthreads();
+    if (tid == 0) flag_s = *reinterpret_cast<volatile int*>(&ctl->done);
+    __syncthreads();
+    stale = flag_s != 0;                 // aborted or overtaken: results are not needed any more
+  }
+  if (!stale) {
+    if (y_in_smem)
+      for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
+    for (int j = tid; j < nev; j += nt) theta[j] = lamv[j];
+    if (tid == 0 && iter < 64) ctl->trace[iter][1] = gtimer();
+  }
+  if (!checking) return;
+
+  // ---- the Ritz check of this iteration (see CheckArgs)
+  const int coff = (mode == 0) ? 0 : (nev - k);
+  float rmax = INFINITY;
+  if (!stale) {
+    for (int e = tid; e < k * k; e += nt) {
+      const int c = e / k, l = e - c * k;
+      double acc = 0.0;
+      for (int i = c; i < k; ++i) acc = fma(chk.L[i * k + c], Y[(size_t)(m - k + i) * nev + coff + l], acc);
+      Ms[e] = acc;
+    }
+    __syncthreads();
+    const float lmax = chk.is_f64 ? lanczos_resid_max<double>(static_cast<const double*>(chk.Q), chk.n, k, Ms)
+                                  : lanczos_resid_max<float>(static_cast<const float*>(chk.Q), chk.n, k, Ms);
+    rmax = block_max(lmax, redmax);
+  }
+  // bookkeeping in launch order (two Rayleigh-Ritz kernels can be in flight on the two side streams)
+  if (tid == 0) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile int*>(&ctl->check_done) != chk.seq - 1) {
+      if (clock64() - t0 > 1000000000LL) break;       // never hang the device
+    }
+    __threadfence();
+    flag_s = (stale || *reinterpret_cast<volatile int*>(&ctl->converged) != 0) ? 0
+             : ((rmax < *reinterpret_cast<volatile float*>(&ctl->best_resid)) ? 2 : 1);
   }
   __syncthreads();
-  eig_extreme_device(As, lds, m, nev, mode, sh, inv_slots, lamv, Y, nullptr, &ctl->done);
-  if (ctl->done) return;               // aborted: results are not needed any more
-  if (y_in_smem)
-    for (int e = tid; e < m * nev; e += nt) Sk[e] = Y[e];
-  for (int j = tid; j < nev; j += nt) theta[j] = lamv[j];
-  if (tid == 0 && iter < 64) ctl->trace[iter][1] = gtimer();
+  const int act = flag_s;                // 0: ignore this check, 1: counted, 2: counted and the best pair so far
+  if (act == 2) {
+    for (int e = tid; e < m * k; e += nt) chk.Sbest[e] = Y[(size_t)(e / k) * nev + coff + (e % k)];
+    for (int j = tid; j < k; j += nt) chk.evals_best[j] = lamv[coff + j];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (act != 0) {
+      // the reference's bookkeeping (symeig.py:196-201)
+      ctl->niter = iter;
+      if (act == 2) {
+        ctl->best_resid = rmax;
+        ctl->best_m = m;
+        ctl->best_in_S = 1;
+      }
+      __threadfence();
+      if (rmax < chk.min_eps) {
+        ctl->converged = 1;
+        ctl->local_done = 1;
+        __threadfence();
+        if (!ctl->collective) signal_done(ctl);
+      }
+      if (iter < 64) ctl->trace[iter][3] = gtimer();
+    }
+    __threadfence();
+    *reinterpret_cast<volatile int*>(&ctl->check_done) = chk.seq;
+  }
 }
 
 __global__ void __launch_bounds__(EIG_THREADS)
@@ -1722,20 +1885,49 @@ small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double*
   for (int j = tid; j < nev; j += nt) w_out[j] = lamv[j];
 }
 
-// final copy of the best pair into the caller's tensors
+// The best pair -> the caller's tensors (to_slot = 0), or -> the spare slot of Xslots / evals_slots before a thick
+// restart rotates the basis (to_slot = 1; flip_best_kernel then makes that slot the best one).  The pair is either a
+// stored Ritz block (Xslots[best_slot], written by ritz_kernel / the fused P0 phase) or, after an asynchronous check,
+// coefficients w.r.t. the current basis: X = V[:, :best_m] Sbest is formed here, once per solve.
 template <typename TV>
-__global__ void output_kernel(const TV* Xslots, const double* evals_slots, int n, int k, TV* evecs, int64_t ldv,
-                              TV* evals, EigCtl* ctl) {
+__global__ void output_kernel(const TV* __restrict__ V, const TV* Xslots, const double* evals_slots,
+                              const double* __restrict__ Sbest, const double* evals_best, int n, int k, TV* evecs,
+                              int64_t ldv, TV* evals, int to_slot, EigCtl* ctl) {
   const int slot = ctl->best_slot;
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->trace[0][1] = gtimer();
+  const int in_S = ctl->best_in_S;
+  if (to_slot && !in_S) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !to_slot) ctl->trace[0][1] = gtimer();
+  TV* out = to_slot ? const_cast<TV*>(Xslots) + (int64_t)(1 - slot) * n * k : evecs;
+  const int64_t ldo = to_slot ? (int64_t)k : ldv;
   const TV* X = Xslots + (int64_t)slot * n * k;
+  const int nblk = in_S ? ctl->best_m / k : 0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n * k;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = e / k;
     const int j = (int)(e - row * k);
-    evecs[row * ldv + j] = X[e];
+    if (in_S) {
+      double acc = 0.0;
+      for (int b = 0; b < nblk; ++b) {
+        const TV* vr = V + ((int64_t)b * n + row) * k;
+        const double* sr = Sbest + (size_t)b * k * k + j;
+        for (int i = 0; i < k; ++i) acc = fma((double)vr[i], sr[i * k], acc);
+      }
+      out[row * ldo + j] = (TV)acc;
+    } else {
+      out[row * ldo + j] = X[e];
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x < k) evals[threadIdx.x] = (TV)evals_slots[slot * SE_MAXK + threadIdx.x];
+  if (blockIdx.x == 0 && (int)threadIdx.x < k) {
+    const double ev = in_S ? evals_best[threadIdx.x] : evals_slots[slot * SE_MAXK + threadIdx.x];
+    if (to_slot) const_cast<double*>(evals_slots)[(1 - slot) * SE_MAXK + threadIdx.x] = ev;
+    else evals[threadIdx.x] = (TV)ev;
+  }
+}
+__global__ void flip_best_kernel(EigCtl* ctl) {
+  if (threadIdx.x == 0 && ctl->best_in_S) {
+    ctl->best_slot = 1 - ctl->best_slot;
+    ctl->best_in_S = 0;
+  }
 }
 
 template <typename TV>
@@ -1781,7 +1973,8 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
-  ctl->bar_count = 0; ctl->bar_gen = 0;
+  ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0;
+  ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0;
   ctl->trace[0][0] = gtimer();
 }
 
@@ -1792,6 +1985,7 @@ struct EigWs {
   double *SkB, *thetaB, *CB;      // second and third slot for the overlapped Rayleigh-Ritz
   double *SkC, *thetaC, *CC, *TwB;
   double* Pacc;                   // accumulators of the fused expansion kernel
+  double *Lsave, *Sbest, *evals_best;   // asynchronous Ritz checks: Cholesky factors (one per slot), best coefficients
   EigCtl* ctl;
 };
 
@@ -1821,6 +2015,9 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
   W.Rinv = ar.take<double>(SE_MAXK * SE_MAXK);
   W.evals_slots = ar.take<double>(2 * SE_MAXK);
   W.Pacc = ar.take<double>((size_t)2 * PO_NCOPY * (size_t)(mb + SE_MAXK) * k);
+  W.Lsave = ar.take<double>((size_t)4 * SE_MAXK * SE_MAXK);
+  W.Sbest = ar.take<double>((size_t)mb * k);
+  W.evals_best = ar.take<double>(SE_MAXK);
   W.ctl = ar.take<EigCtl>(1);
   return ar.ok();
 }
@@ -1902,6 +2099,11 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     if (const char* lv = getenv("XT_LAG1_M")) lag1_m = atoi(lv);
   }
   const bool fuse_enabled = coop != 0 && g->expansion == 1 && num_sms() > 8 && getenv("XT_NO_FUSE") == nullptr;
+  // Asynchronous Ritz checks (one GPU): the check of iteration j rides at the end of its Rayleigh-Ritz kernel on a side
+  // stream (CheckArgs) and raises `done` from there; the main stream never waits for a Rayleigh-Ritz result, the matvec
+  // in flight when `done` goes up is abandoned part-way (MvArgs.abort_flag) and the fused kernel takes its stop
+  // decision at its first grid barrier.  XT_SYNC_CHECK=1 keeps the lagged in-stream checks (P0 of the fused kernel).
+  const bool async_check = fuse_enabled && !collective && getenv("XT_SYNC_CHECK") == nullptr;
 
   int64_t napply = 0;
   int all_conv = 1;
@@ -1983,6 +2185,20 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     Pending pendq[2] = {{false, 0, 0, 0, 0, 0}, {false, 0, 0, 0, 0, 0}};     // [0] = older
     bool ev_used[NSLOT] = {false, false, false};
     bool c_zero = false;        // W.C is known to be all zeros (left so by the fused expansion kernel)
+    int check_seq = 0;          // tickets of the asynchronous checks
+    bool async_inflight = false;
+    // before anything that changes the basis or reads the best pair from the slots: wait for the checks in flight and
+    // turn a best pair held as coefficients into a stored Ritz block
+    auto settle_async = [&]() -> int {
+      if (!async_inflight) return XT_OK;
+      for (int q = 0; q < NSLOT; ++q)
+        if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
+      output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n, k, nullptr, k,
+                                                   nullptr, 1, W.ctl); XT_LAUNCHED();
+      flip_best_kernel<<<1, 32, 0, st>>>(W.ctl); XT_LAUNCHED();
+      async_inflight = false;
+      return XT_OK;
+    };
     auto launch_ritz = [&](int par_, int m_, int iter_, int nev_, int coff_) -> int {
       if (overlap) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par_], 0));
       ritz_kernel<TV><<<grid_rows, SE_THREADS, rz_smem, st>>>(V, AV, n, k, m_, Skpar[par_], nev_, coff_, thpar[par_],
@@ -2023,7 +2239,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       const int64_t per = (int64_t)(n_local + 1) * k;
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
-      a.done_flag = &W.ctl->done;
+      a.done_flag = async_check ? nullptr : &W.ctl->done;
+      a.abort_flag = async_check ? &W.ctl->done : nullptr;
       // two free SMs, one per Rayleigh-Ritz kernel in flight (alternating side streams), so that no matvec CTA ever
       // waits for an SM.  Free: with two rows per consumer thread the k = 8 matvec runs at the same 6.26 TB/s for
       // any tile height 112..128 (tests/gpu_tile_sweep.py), i.e. on 145 SMs as well as on 147.
@@ -2055,7 +2272,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
           // the Ritz check that is due now (two iterations old) rides along when its AV slice fits as well
           // a Ritz check is due `lag` iterations after its Rayleigh-Ritz was launched: one while the projected problem
           // is small enough for rr_kernel to finish within a matvec, two beyond (a late result only stalls the stream)
-          const bool have_rz = pendq[0].valid && (iter - pendq[0].iter >= (pendq[0].m <= lag1_m ? 1 : 2));
+          const bool have_rz = !async_check && pendq[0].valid &&
+                               (iter - pendq[0].iter >= (pendq[0].m <= lag1_m ? 1 : 2));
           bool stage_v = true;
           size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m, have_rz ? pendq[0].m : 0, true);
           if (po_smem > (size_t)PO_SMEM_MAX || getenv("XT_PO_NOSTAGE") != nullptr) {       // large n: leave the basis in L2
@@ -2076,6 +2294,13 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
               pa.rz_m = q.m; pa.rz_iter = q.iter; pa.rz_ld = q.nev; pa.rz_coff = q.coff;
               pa.rz_S = Skpar[q.par]; pa.rz_theta = thpar[q.par];
             }
+            if (async_check) {
+              // slot `par` (Cholesky factor, Ritz coefficients) is free once the Rayleigh-Ritz kernel of iteration
+              // iter - NSLOT is through; this also bounds how far the side streams can fall behind
+              if (ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));
+              pa.Lout = W.Lsave + (size_t)par * SE_MAXK * SE_MAXK;
+              pa.async_stop = 1;
+            }
             if (!c_zero) XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)PO_NCOPY * (mb + SE_MAXK) * k, st));
             void* kargs[1] = {&pa};
             XT_CUDA_OK(cudaLaunchCooperativeKernel(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, po_smem, st));
@@ -2088,17 +2313,27 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
             cudaStream_t rsf = side[iter & 1];
             XT_CUDA_OK(cudaEventRecord(evC[par], st));
             XT_CUDA_OK(cudaStreamWaitEvent(rsf, evC[par], 0));
+            CheckArgs chk;
+            memset(&chk, 0, sizeof(chk));
+            if (async_check) {
+              chk.Q = pa.Qout; chk.L = pa.Lout; chk.n = n; chk.is_f64 = sizeof(TV) == 8 ? 1 : 0;
+              chk.Sbest = W.Sbest; chk.evals_best = W.evals_best; chk.min_eps = (float)g->min_eps;
+              chk.seq = ++check_seq;
+              async_inflight = true;
+            }
             rr_kernel<<<1, EIG_THREADS, plf.smem_bytes, rsf>>>(W.T, mb, nullptr, m, k, k, Twpar[iter & 1], Skpar[par],
                                                                thpar[par], g->mode, plf.lds, plf.as_in_smem,
-                                                               plf.y_in_smem, plf.inv_slots, W.ctl, iter); XT_LAUNCHED();
+                                                               plf.y_in_smem, plf.inv_slots, W.ctl, iter, chk); XT_LAUNCHED();
             XT_CUDA_OK(cudaEventRecord(evR[par], rsf));
             ev_used[par] = true;
-            if (pendq[0].valid && pendq[1].valid) {   // queue full (the lag just changed): the oldest check gets its own kernel
-              rc = flush_pending(1);
-              if (rc != XT_OK) return rc;
+            if (!async_check) {
+              if (pendq[0].valid && pendq[1].valid) {   // queue full (the lag just changed): the oldest check gets its own kernel
+                rc = flush_pending(1);
+                if (rc != XT_OK) return rc;
+              }
+              Pending pn = {true, par, m, iter, k, 0};
+              if (!pendq[0].valid) pendq[0] = pn; else pendq[1] = pn;
             }
-            Pending pn = {true, par, m, iter, k, 0};
-            if (!pendq[0].valid) pendq[0] = pn; else pendq[1] = pn;
             m += k;
             XT_CUDA_OK(cudaEventRecord(pool.it[iter % (LOOKAHEAD + 1)], st));
             XT_CUDA_OK(cudaGetLastError());
@@ -2107,6 +2342,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         }
       }
       // 2. C = V^T W  (new block column of T)
+      rc = settle_async();                       // restart / last iteration after asynchronous checks
+      if (rc != XT_OK) return rc;
       if (overlap && ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));   // rr of iteration iter-3 is done with C[par]
       XT_CUDA_OK(cudaMemsetAsync(Cpar[par], 0, sizeof(double) * (size_t)m * k, st));
       subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, m, AV + j * blk, nullptr, nullptr, Cpar[par],
@@ -2129,9 +2366,11 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         XT_CUDA_OK(cudaEventRecord(evC[par], st));
         XT_CUDA_OK(cudaStreamWaitEvent(rs, evC[par], 0));
       }
+      CheckArgs nochk;
+      memset(&nochk, 0, sizeof(nochk));
       rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, Crr, m, k, nev, Twpar[iter & 1], Skpar[par], thpar[par],
                                                         g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots,
-                                                        W.ctl, iter); XT_LAUNCHED();
+                                                        W.ctl, iter, nochk); XT_LAUNCHED();
       if (overlap) {
         XT_CUDA_OK(cudaEventRecord(evR[par], rs));
         ev_used[par] = true;
@@ -2212,9 +2451,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
     }
     // ---- output
-    output_kernel<TV><<<grid_rows, 256, 0, st>>>(Xslots, W.evals_slots, n, k,
+    output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n, k,
                                                  static_cast<TV*>(g->evecs) + (int64_t)b * g->evecs_bstride, g->ldv,
-                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, W.ctl); XT_LAUNCHED();
+                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, 0, W.ctl); XT_LAUNCHED();
     EigCtl h;
     const bool tracing = getenv("XT_TRACE") != nullptr;
     XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, tracing ? sizeof(h) : offsetof(EigCtl, trace), cudaMemcpyDeviceToHost, st));
