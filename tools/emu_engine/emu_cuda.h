@@ -44,6 +44,7 @@ inline thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 
 typedef int cudaError_t;
 constexpr int cudaSuccess = 0;
+constexpr int cudaErrorNotReady = 600;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
@@ -107,6 +108,7 @@ inline long long __double_as_longlong(double d) { long long l; std::memcpy(&l, &
 inline double __longlong_as_double(long long l) { double d; std::memcpy(&d, &l, 8); return d; }
 template <typename T> T __ldcg(const T* p) { return std::atomic_ref<T>(*const_cast<T*>(p)).load(); }
 inline unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
 using std::fma; using std::fabs; using std::fmax; using std::fmin; using std::sqrt; using std::min; using std::max;
 using std::ceil; using std::log2;
@@ -197,6 +199,7 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = reinterp
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { std::memmove(d, s, n); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memmove(d, s, n); return 0; }
@@ -230,6 +233,8 @@ struct Arena {
 inline unsigned long long gtimer() { return 0; }
 inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
 inline void cp_async_wait_all() {}
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
 inline double fast_rcp(double x) { return 1.0 / x; }
 template <typename T> T warp_sum(T v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

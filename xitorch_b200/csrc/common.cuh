@@ -51,6 +51,16 @@ struct DeviceOnce {
   }
 };
 
+// Opt a kernel in to the largest dynamic shared-memory size the device allows next to the kernel's own static shared
+// memory (227 KB per CTA on sm_100 in total; asking for 227 KB of dynamic memory on a kernel with any static
+// __shared__ variable is rejected with "invalid argument").
+template <typename K> static inline cudaError_t set_max_dyn_smem(K kern, int total = 227 * 1024) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, total - (int)fa.sharedSizeBytes);
+}
+
 // launch accounting / in-situ kernel timing (xt_profile_* in the C ABI)
 void note_launch(int n = 1);                        // every kernel launch site calls this
 void prof_mv_begin(cudaStream_t st);                // CUDA events around each block-matvec launch when enabled
@@ -97,6 +107,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// add to the pending transaction count of the current phase WITHOUT arriving (the arrival follows later)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Programmatic dependent launch (a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running): pdl_wait() returns once the predecessor has completed and its
+// writes are visible -- nothing the predecessor produces may be touched before it; pdl_trigger() lets the successor's
+// CTAs be scheduled as soon as this kernel's CTAs leave their SMs.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -178,6 +178,7 @@ struct MvDev {
   int reverse;      // traverse the column chunks of A from the last to the first
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
+  int pdl;          // launched as a programmatic dependent: see MvArgs.pdl
 };
 
 template <typename TA> struct ElemTraits;
@@ -299,7 +300,10 @@ constexpr int MV_STAGE_A_BYTES = MV_TILE_ROWS * 256;   // 128 rows x 2 boxes x 1
 // waiter gives up at `*abort_at`.
 template <typename TA, typename TV, int K, int STAGE_BYTES>
 __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
-                                            uint64_t* empty, int NS, int nchunks, int* abort_at = nullptr) {
+                                            uint64_t* empty, int NS, int nchunks, int* abort_at = nullptr,
+                                            int npre = 0) {
+  // npre: the A boxes of chunks 0 .. npre-1 (stages 0 .. npre-1, first phase) are already in flight with their byte
+  // counts registered (mv_preissue): only the arrival and the X chunk are still due for them
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   const char* Xg = reinterpret_cast<const char*>(p.X);
@@ -316,10 +320,15 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
       const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
       const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
       if (abort_at != nullptr && (seq & 7) == 0 && *reinterpret_cast<const volatile int*>(p.abort_flag) != 0) {
+        for (int q = seq; q < npre; ++q) {        // pre-issued A boxes must land before the CTA may leave
+          mbar_arrive_expect_tx(&full[q], 0u);
+          mbar_wait(&full[q], 0u);
+        }
         *reinterpret_cast<volatile int*>(abort_at) = seq;
         return;
       }
-      mbar_wait(&empty[s], ph ^ 1);
+      const bool pre = seq < npre;
+      if (!pre) mbar_wait(&empty[s], ph ^ 1);
       uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
       // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
       uint32_t xbytes = 0;
@@ -327,16 +336,46 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
         const int cols = min(KC, p.ncolsA - kc);
         xbytes = (uint32_t)(cols * K * (int)sizeof(TV));
       }
-      mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * p.tile_rows * 128) + xbytes);
-      for (int bx = 0; bx < nb; ++bx)
-        tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA,
-                    ch >= p.keep_from ? pol_keep : pol_first);
+      mbar_arrive_expect_tx(&full[s], (pre ? 0u : (uint32_t)(nb * p.tile_rows * 128)) + xbytes);
+      if (!pre) {
+        for (int bx = 0; bx < nb; ++bx)
+          tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA,
+                      ch >= p.keep_from ? pol_keep : pol_first);
+      }
       if (p.x_bulk)
         bulk_load_1d(dst + MV_STAGE_A_BYTES,
                      Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV), xbytes, &full[s]);
       if (++s == NS) { s = 0; ph ^= 1; }
     }
   }
+}
+
+// Programmatic dependent launch: the A boxes of the CTA's first chunks, issued before the predecessor kernel has
+// finished (A does not depend on it).  Byte counts are registered without an arrival; the producer completes the
+// stages (arrival + X chunk) after pdl_wait().  Returns the number of chunks issued.
+template <typename TA, typename TV, int K, int STAGE_BYTES>
+__device__ __forceinline__ int mv_preissue(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
+                                           int NS, int nchunks) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);
+  constexpr int KC = 2 * BOXC;
+  const int tile = blockIdx.x;
+  if (tile >= p.ntiles) return 0;
+  const uint64_t pol_first = l2_policy_evict_first();
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const int b = tile / p.tiles_per_batch;
+  const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+  const int bA = p.a_batched ? b : 0;
+  const int npre = min(NS, nchunks);
+  for (int ch = 0; ch < npre; ++ch) {
+    const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+    const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+    uint8_t* dst = stage_base + (size_t)ch * STAGE_BYTES;
+    mbar_expect_tx(&full[ch], (uint32_t)(nb * p.tile_rows * 128));
+    for (int bx = 0; bx < nb; ++bx)
+      tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[ch], kc + bx * BOXC, row0, bA,
+                  ch >= p.keep_from ? pol_keep : pol_first);
+  }
+  return npre;
 }
 
 // X staging warp: all loads of a chunk are issued back to back (KC*K/32 independent loads per lane) and one
@@ -421,10 +460,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
   constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;   // swizzle atoms need 1024-B aligned stages
 
-  if (p.done_flag != nullptr && *p.done_flag != 0) return;
-  __shared__ int abort_at_s;         // first chunk (sequence number) that is not produced; INT_MAX: none (see mv_producer)
-  int* abort_at = p.abort_flag != nullptr ? &abort_at_s : nullptr;
-
+  const bool pdl = p.pdl != 0;      // flags written by the predecessor may only be read after pdl_wait()
+  if (!pdl && p.done_flag != nullptr && *p.done_flag != 0) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.nstages;
@@ -433,6 +470,12 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   double* dscr = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(red) + NC * K * sizeof(TV));  // [NC/32][2][K]
   uint64_t* full = reinterpret_cast<uint64_t*>(dscr + (NC / 32) * 2 * K);
   uint64_t* empty = full + NS;
+  // first chunk (sequence number) that is not produced; INT_MAX: none (see mv_producer).  Lives in the dynamic region
+  // (slots 2*NS .. 15 of the 16 reserved mbarrier words are free: NS <= 6) so that the kernel has NO static shared
+  // memory and the full 227 KB can be requested as dynamic.
+  int& abort_at_s = *reinterpret_cast<int*>(full + 14);
+  int& skip_s = *reinterpret_cast<int*>(full + 15);
+  int* abort_at = p.abort_flag != nullptr ? &abort_at_s : nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = (p.ncolsA + KC - 1) / KC;
@@ -445,7 +488,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     fence_mbar_init();
     prefetch_tmap(&tmA);
     // one thread decides for the whole CTA whether a flag that was already up at launch skips the pass
-    if (abort_at != nullptr) abort_at_s = (*reinterpret_cast<const volatile int*>(p.abort_flag) != 0) ? 0 : 0x7fffffff;
+    if (!pdl && abort_at != nullptr)
+      abort_at_s = (*reinterpret_cast<const volatile int*>(p.abort_flag) != 0) ? 0 : 0x7fffffff;
   }
   if (p.x_bulk) {   // X slots start as zeros: a ragged last chunk copies fewer bytes and must never expose NaN garbage
     for (int s = 0; s < NS; ++s) {
@@ -456,9 +500,32 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   }
   __syncthreads();
 
+  int npre = 0;
+  if (pdl) {
+    if (warp == 0 && lane == 0) npre = mv_preissue<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, NS, nchunks);
+    pdl_wait();
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+      skip_s = (p.done_flag != nullptr && *p.done_flag != 0) ? 1 : 0;
+      if (abort_at != nullptr)
+        abort_at_s = (*reinterpret_cast<const volatile int*>(p.abort_flag) != 0) ? 0 : 0x7fffffff;
+    }
+    __syncthreads();
+    const bool skip = skip_s != 0 || (abort_at != nullptr && abort_at_s == 0);
+    if (skip) {
+      if (warp == 0 && lane == 0) {
+        for (int q = 0; q < npre; ++q) {          // the pre-issued A boxes must land before the CTA may leave
+          mbar_arrive_expect_tx(&full[q], 0u);
+          mbar_wait(&full[q], 0u);
+        }
+      }
+      return;
+    }
+  }
+
   if (warp == 0) {
     if (lane == 0 && (abort_at == nullptr || abort_at_s != 0))
-      mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks, abort_at);
+      mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks, abort_at, npre);
   } else if (warp == 1) {
     if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane, abort_at);
   } else {
@@ -975,7 +1042,7 @@ static int launch_tc(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cu
   dev.x_bulk = 0;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    XT_CUDA_OK(cudaFuncSetAttribute(mv_tma_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XT_CUDA_OK(set_max_dyn_smem(mv_tma_tc_kernel));
     attr_once.mark();
   }
   prof_mv_begin(st);
@@ -1093,11 +1160,30 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   auto kern = mv_tma_kernel<TA, TV, K, NC, RP>;
   static DeviceOnce attr_once;   // per instantiation
   if (attr_once.pending()) {
-    XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XT_CUDA_OK(set_max_dyn_smem(kern));
     attr_once.mark();
   }
   prof_mv_begin(st);
-  kern<<<til.grid, NC + 64, smem, st>>>(tm, dev);
+  static std::atomic<int> pdl_ok{1};
+  bool launched = false;
+  if (a.pdl && dev.x_bulk && pdl_ok.load(std::memory_order_relaxed)) {
+    dev.pdl = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(til.grid); cfg.blockDim = dim3(NC + 64); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tm, dev) == cudaSuccess) {
+      launched = true;
+    } else {
+      (void)cudaGetLastError();
+      pdl_ok.store(0);
+      dev.pdl = 0;
+    }
+  }
+  if (!launched) kern<<<til.grid, NC + 64, smem, st>>>(tm, dev);
   prof_mv_end(st);
   XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
@@ -1127,7 +1213,7 @@ static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& t
   auto kern = mv_tma_colslice_kernel<K>;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    XT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XT_CUDA_OK(set_max_dyn_smem(kern));
     attr_once.mark();
   }
   prof_mv_begin(st);
@@ -1204,6 +1290,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
   d.abort_flag = a.abort_flag;
+  d.pdl = 0;
   d.reverse = a.reverse ? 1 : 0;
   {
     // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB

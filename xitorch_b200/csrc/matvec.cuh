@@ -47,6 +47,10 @@ struct MvArgs {
   int reserve_sms;                             // leave this many SMs free (for kernels overlapped on another stream)
   int reverse;                                 // traverse A's column chunks last-to-first (alternate per call, see l2_keep_mb)
   int l2_keep_mb;                              // MB of the end of this pass to keep in L2 for the next, reversed pass
+  int pdl;                                     // 1: launch as a programmatic dependent of the previous kernel in the stream
+                                               // (row-slice TMA kernel with bulk X staging only; otherwise ignored): the
+                                               // first A tiles are in flight before the predecessor has finished, X / flags
+                                               // are only read after it has
 };
 
 // enqueue on `stream`; returns xt_status

@@ -50,6 +50,9 @@ struct EigCtl {
   float best_resid;
   unsigned int bar_count, bar_gen;   // grid barrier of the fused expansion kernel
   int bar_abort;        // latched at a grid barrier: some CTA saw `done` (raised asynchronously by a side-stream check)
+  int done_latched;     // set by the fused kernel that left through `bar_abort`: stream-ordered copy of `done`, uniform
+                        // for every later kernel of the main stream (which then returns at once instead of meeting at
+                        // a grid barrier / aborting a pass part-way)
   // asynchronous Ritz checks (rr_kernel on the side streams, see CheckArgs)
   int best_in_S;        // 1: the best pair so far is held as coefficients (Sbest, best_m) w.r.t. the current basis
   int best_m;
@@ -673,7 +676,7 @@ expand_fused_kernel(const PostArgs p) {
   EigCtl* ctl = p.ctl;
   // `done` written only by earlier launches of this stream: uniform over the grid.  With asynchronous checks it is not,
   // and the decision is taken at the first grid barrier instead (see grid_barrier).
-  if (!p.async_stop && ctl->done) return;
+  if (p.async_stop ? ctl->done_latched : ctl->done) return;
   extern __shared__ __align__(16) unsigned char po_raw[];
   const int tid = threadIdx.x;
   const int n = p.n, k = p.k, m = p.m, R = p.R;
@@ -701,6 +704,10 @@ expand_fused_kernel(const PostArgs p) {
   }
   // the basis slice as the phases below see it: staged copy (block stride R rows) or global memory (block stride n rows,
   // large n: the basis stays in the 126 MB L2 between the passes)
+  // Programmatic dependent launch: everything above only touches what kernels BEFORE the preceding matvec produced
+  // (the basis blocks, the control block); W, the matvec's output, is read below.  No-ops in an ordinary launch.
+  pdl_wait();
+  pdl_trigger();
   const TV* Vb = p.stage_v ? Vs : V + (int64_t)row0 * k;
   const TV* AVb = p.stage_v ? AVs : static_cast<const TV*>(p.AV) + (int64_t)row0 * k;
   const int64_t vbs = p.stage_v ? (int64_t)R : (int64_t)n;
@@ -776,7 +783,10 @@ expand_fused_kernel(const PostArgs p) {
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, false, part, accC);
   if (tr) ctl->ptrace[p.iter][3] = gtimer();
   const bool btr = (p.iter == 8 && gridDim.x <= 160);
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr, p.async_stop != 0)) return;
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr, p.async_stop != 0)) {
+    if (p.async_stop && blockIdx.x == 0 && tid == 0) ctl->done_latched = 1;
+    return;
+  }
   if (tr) ctl->ptrace[p.iter][4] = gtimer();
 
   if (rz_nblk > 0 && last_cta && tid == 0) {
@@ -824,7 +834,10 @@ expand_fused_kernel(const PostArgs p) {
   if (tr) ctl->ptrace[p.iter][5] = gtimer();
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, true, part, accC2);
   if (tr) ctl->ptrace[p.iter][6] = gtimer();
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr, p.async_stop != 0)) return;
+  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr, p.async_stop != 0)) {
+    if (p.async_stop && blockIdx.x == 0 && tid == 0) ctl->done_latched = 1;
+    return;
+  }
   if (tr) ctl->ptrace[p.iter][7] = gtimer();
 
   // ---- P3: Q = (W' - V C2) Rinv
@@ -1719,18 +1732,48 @@ __device__ __forceinline__ float lanczos_resid_max_k(const TV* __restrict__ Q, i
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int l = 0; l < LH; ++l) mreg[c][l] = (TV)Ms[c * K + l0 + l];
-#pragma unroll 2
-    for (int row = threadIdx.x; row < n; row += blockDim.x) {
-      TV q[K];
+    // RB rows per thread in flight: one CTA reads the whole block out of L2 next to a running matvec, so the loop is
+    // bound by load latency, not by bandwidth or arithmetic
+    constexpr int RB = 4;
+    constexpr int VW = 16 / (int)sizeof(TV);          // elements per 16-byte load
+    const int nt = blockDim.x;
+#pragma unroll 1
+    for (int row0 = threadIdx.x; row0 < n; row0 += RB * nt) {
+      TV q[RB][K];
 #pragma unroll
-      for (int c = 0; c < K; ++c) q[c] = Q[(int64_t)row * K + c];
+      for (int b = 0; b < RB; ++b) {
+        const int row = row0 + b * nt;
+        if (row < n) {
+          if constexpr (sizeof(TV) == 4) {
+            const float4* src = reinterpret_cast<const float4*>(Q + (int64_t)row * K);
 #pragma unroll
-      for (int l = 0; l < LH; ++l) {
-        TV acc = TV(0);
+            for (int v = 0; v < K / VW; ++v) {
+              const float4 f = src[v];
+              q[b][4 * v] = f.x; q[b][4 * v + 1] = f.y; q[b][4 * v + 2] = f.z; q[b][4 * v + 3] = f.w;
+            }
+          } else {
+            const double2* src = reinterpret_cast<const double2*>(Q + (int64_t)row * K);
 #pragma unroll
-        for (int c = 0; c < K; ++c) acc = fma(q[c], mreg[c][l], acc);
-        lmax = fmaxf(lmax, fabsf((float)acc));
-        if (!(acc == acc)) lmax = INFINITY;
+            for (int v = 0; v < K / VW; ++v) {
+              const double2 f = src[v];
+              q[b][2 * v] = f.x; q[b][2 * v + 1] = f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < K; ++c) q[b][c] = TV(0);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < RB; ++b) {
+#pragma unroll
+        for (int l = 0; l < LH; ++l) {
+          TV acc = TV(0);
+#pragma unroll
+          for (int c = 0; c < K; ++c) acc = fma(q[b][c], mreg[c][l], acc);
+          lmax = fmaxf(lmax, fabsf((float)acc));
+          if (!(acc == acc)) lmax = INFINITY;
+        }
       }
     }
   }
@@ -1892,7 +1935,16 @@ small_eigh_kernel(const double* T, int m, int nev, int mode, double* Tw, double*
 template <typename TV>
 __global__ void output_kernel(const TV* __restrict__ V, const TV* Xslots, const double* evals_slots,
                               const double* __restrict__ Sbest, const double* evals_best, int n, int k, TV* evecs,
-                              int64_t ldv, TV* evals, int to_slot, EigCtl* ctl) {
+                              int64_t ldv, TV* evals, int to_slot, EigCtl* ctl, int* host_res, int res_seq) {
+  if (host_res != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    // the solve's scalar results straight into host-mapped memory (they are final before this kernel starts): the
+    // host does not have to drain the stream or issue a copy to read them
+    volatile int* hr = host_res;
+    hr[1] = ctl->converged; hr[2] = ctl->niter; hr[3] = ctl->breakdown;
+    hr[4] = __float_as_int(ctl->best_resid);
+    __threadfence_system();
+    hr[0] = res_seq;
+  }
   const int slot = ctl->best_slot;
   const int in_S = ctl->best_in_S;
   if (to_slot && !in_S) return;
@@ -1973,7 +2025,7 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
-  ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0;
+  ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0; ctl->done_latched = 0;
   ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0;
   ctl->trace[0][0] = gtimer();
 }
@@ -2089,6 +2141,31 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   const int po_grid = (n + po_R - 1) / po_R;
   const void* po_fn = KP == 4 ? (const void*)expand_fused_kernel<TV, 4>
                               : (KP == 8 ? (const void*)expand_fused_kernel<TV, 8> : (const void*)expand_fused_kernel<TV, 16>);
+  // cooperative launch of the fused kernel, optionally as a programmatic dependent of the matvec before it
+  const bool want_pdl = getenv("XT_NO_PDL") == nullptr;
+  auto launch_po = [&](PostArgs& pa, size_t po_smem, bool pdl) -> int {
+    void* kargs[1] = {&pa};
+#ifdef __CUDACC__
+    static std::atomic<int> po_pdl_ok{1};
+    if (pdl && po_pdl_ok.load(std::memory_order_relaxed)) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(po_grid); cfg.blockDim = dim3(PO_THREADS); cfg.dynamicSmemBytes = po_smem; cfg.stream = st;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 2;
+      if (cudaLaunchKernelExC(&cfg, po_fn, kargs) == cudaSuccess) return XT_OK;
+      (void)cudaGetLastError();
+      po_pdl_ok.store(0);
+    }
+#endif
+    (void)pdl;
+    XT_CUDA_OK(cudaLaunchCooperativeKernel(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, po_smem, st));
+    return XT_OK;
+  };
   int lag1_m = 0;     // projected-problem size up to which the Ritz check lags ONE iteration (tuned on B200)
   {
     const double t_mv = (double)n_local * n * sizeof(TV) / 6.0e12;                 // one pass over A at ~6 TB/s
@@ -2118,8 +2195,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     cudaStream_t s[2] = {nullptr, nullptr};
     cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
     cudaEvent_t it[LOOKAHEAD + 1] = {nullptr, nullptr, nullptr, nullptr};   // end-of-iteration marks (run-ahead window)
-    volatile int* hflag = nullptr;      // pinned, mapped: the kernels mirror ctl->done here
+    volatile int* hflag = nullptr;      // pinned, mapped: the kernels mirror ctl->done here; words 8..12: result mirror
     int* hflag_dev = nullptr;
+    int res_seq = 0;                    // ticket of the last result mirror requested (see output_kernel)
     int dev = -1;
   };
   static thread_local SidePool pool;
@@ -2161,13 +2239,44 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     const auto host_t0 = std::chrono::steady_clock::now();
     init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
-    gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
-                                                       g->ldv0, n, k, Rblk); XT_LAUNCHED();
-    for (int pass = 0; pass < 2; ++pass) {
-      XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
-      subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, pass == 0 ? Rblk : V, nullptr, Zbuf,
-                                                                  nullptr, W.G, W.Rinv, 1, W.ctl); XT_LAUNCHED();
-      orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, Zbuf, W.C2, W.Rinv, V, W.ctl); XT_LAUNCHED();
+    bool c_zero = false;        // W.Pacc is known to be all zeros (left so by the fused expansion kernel)
+    bool start_done = false;
+    if (fuse_enabled && getenv("XT_START_UNFUSED") == nullptr) {
+      // two launches of the fused expansion kernel with an empty basis (m = 0: no projection, G = W^T W, Q = W chol(G)^-T)
+      // instead of gather + 2 x (memset, projection kernel, finish kernel)
+      const size_t st_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, 0, 0, true);
+      if (st_smem <= (size_t)PO_SMEM_MAX) {
+        const TV* src = static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride;
+        if (g->ldv0 != k) {
+          gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(src, g->ldv0, n, k, Rblk); XT_LAUNCHED();
+          src = Rblk;
+        }
+        XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)2 * PO_NCOPY * (mb + SE_MAXK) * k, st));
+        for (int pass = 0; pass < 2; ++pass) {
+          PostArgs pa;
+          memset(&pa, 0, sizeof(pa));
+          pa.V = V; pa.AV = AV; pa.W = pass == 0 ? src : V; pa.Qout = V;
+          pa.n = n; pa.k = k; pa.m = 0; pa.R = po_R;
+          pa.acc = W.Pacc; pa.acc_stride = (mb + SE_MAXK) * k; pa.T = W.T; pa.ldt = mb;
+          pa.ctl = W.ctl; pa.iter = 0; pa.stage_v = 1;
+          pa.Xslots = Xslots; pa.evals_slots = W.evals_slots; pa.min_eps = (float)g->min_eps;
+          const int lrc = launch_po(pa, st_smem, false);
+          if (lrc != XT_OK) return lrc;
+          XT_LAUNCHED();
+        }
+        c_zero = true;
+        start_done = true;
+      }
+    }
+    if (!start_done) {
+      gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride,
+                                                         g->ldv0, n, k, Rblk); XT_LAUNCHED();
+      for (int pass = 0; pass < 2; ++pass) {
+        XT_CUDA_OK(cudaMemsetAsync(W.G, 0, sizeof(double) * SE_MAXK * SE_MAXK, st));
+        subproj_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, pass == 0 ? Rblk : V, nullptr, Zbuf,
+                                                                    nullptr, W.G, W.Rinv, 1, W.ctl); XT_LAUNCHED();
+        orth_finish_kernel<TV><<<grid_rows, SE_THREADS, sp_smem, st>>>(V, n, k, 0, Zbuf, W.C2, W.Rinv, V, W.ctl); XT_LAUNCHED();
+      }
     }
     XT_CUDA_OK(cudaGetLastError());
 
@@ -2184,7 +2293,6 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     struct Pending { bool valid; int par, m, iter, nev, coff; };
     Pending pendq[2] = {{false, 0, 0, 0, 0, 0}, {false, 0, 0, 0, 0, 0}};     // [0] = older
     bool ev_used[NSLOT] = {false, false, false};
-    bool c_zero = false;        // W.C is known to be all zeros (left so by the fused expansion kernel)
     int check_seq = 0;          // tickets of the asynchronous checks
     bool async_inflight = false;
     // before anything that changes the basis or reads the best pair from the slots: wait for the checks in flight and
@@ -2194,7 +2302,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       for (int q = 0; q < NSLOT; ++q)
         if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
       output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n, k, nullptr, k,
-                                                   nullptr, 1, W.ctl); XT_LAUNCHED();
+                                                   nullptr, 1, W.ctl, nullptr, 0); XT_LAUNCHED();
       flip_best_kernel<<<1, 32, 0, st>>>(W.ctl); XT_LAUNCHED();
       async_inflight = false;
       return XT_OK;
@@ -2239,7 +2347,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       const int64_t per = (int64_t)(n_local + 1) * k;
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
       a.ldy = k; a.y_bstride = 0;
-      a.done_flag = async_check ? nullptr : &W.ctl->done;
+      a.done_flag = async_check ? &W.ctl->done_latched : &W.ctl->done;
       a.abort_flag = async_check ? &W.ctl->done : nullptr;
       // two free SMs, one per Rayleigh-Ritz kernel in flight (alternating side streams), so that no matvec CTA ever
       // waits for an SM.  Free: with two rows per consumer thread the k = 8 matvec runs at the same 6.26 TB/s for
@@ -2248,6 +2356,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       // consecutive passes run in opposite column order: the tail of the previous pass is still in L2
       a.reverse = iter & 1;
       a.l2_keep_mb = MV_L2_KEEP_MB;
+      a.pdl = (want_pdl && fuse_enabled && !collective) ? 1 : 0;
       int rc = XT_OK;
       if (g->apply != nullptr) {
         // matrix-free operator: the caller computes Y = A X on the stream (the rest of the iteration is unchanged)
@@ -2302,8 +2411,8 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
               pa.async_stop = 1;
             }
             if (!c_zero) XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)PO_NCOPY * (mb + SE_MAXK) * k, st));
-            void* kargs[1] = {&pa};
-            XT_CUDA_OK(cudaLaunchCooperativeKernel(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, po_smem, st));
+            rc = launch_po(pa, po_smem, want_pdl && g->apply == nullptr && !collective);
+            if (rc != XT_OK) return rc;
             XT_LAUNCHED();
             c_zero = true;                           // the kernel leaves C cleared for the next launch
             if (have_rz) { pendq[0] = pendq[1]; pendq[1].valid = false; }
@@ -2453,11 +2562,32 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     // ---- output
     output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n, k,
                                                  static_cast<TV*>(g->evecs) + (int64_t)b * g->evecs_bstride, g->ldv,
-                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, 0, W.ctl); XT_LAUNCHED();
+                                                 static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, 0, W.ctl,
+                                                 pool.hflag_dev + 8, ++pool.res_seq); XT_LAUNCHED();
     EigCtl h;
     const bool tracing = getenv("XT_TRACE") != nullptr;
-    XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, tracing ? sizeof(h) : offsetof(EigCtl, trace), cudaMemcpyDeviceToHost, st));
-    XT_CUDA_OK(cudaStreamSynchronize(st));
+    bool have_res = false;
+    if (!tracing) {
+      // wait for the result mirror written by output_kernel (a few microseconds after the last kernel starts) instead
+      // of a device-to-host copy into pageable memory plus a stream synchronisation
+      volatile int* hr = pool.hflag + 8;
+      const auto w0 = std::chrono::steady_clock::now();
+      while (true) {
+        if (hr[0] == pool.res_seq) { have_res = true; break; }
+        if (std::chrono::steady_clock::now() - w0 > std::chrono::milliseconds(2)) {
+          if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == pool.res_seq); break; }
+        }
+      }
+      if (have_res) {
+        h.converged = hr[1]; h.niter = hr[2]; h.breakdown = hr[3];
+        int bits = hr[4];
+        memcpy(&h.best_resid, &bits, sizeof(float));
+      }
+    }
+    if (!have_res) {
+      XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, tracing ? sizeof(h) : offsetof(EigCtl, trace), cudaMemcpyDeviceToHost, st));
+      XT_CUDA_OK(cudaStreamSynchronize(st));
+    }
     if (getenv("XT_TRACE") != nullptr) {
       const unsigned long long t0 = h.trace[0][0];
       fprintf(stderr, "xt-trace device span %.1f us, host span %.1f us, %d iterations enqueued\n",
