@@ -190,10 +190,39 @@ typedef struct {
    * applications may run after convergence (their results are never read).  Needs nbatch = 1 and world <= 1. */
   void* apply;
   void* apply_user;
+  /* row-SHARDED engine over peer memory (world >= 1, expansion = 1, nbatch = 1; takes precedence over `allgather`).
+   * `peers[r]` is the address, in THIS process, of rank r's exchange region of xt_symeig_peer_bytes(...) bytes
+   * (peers[rank] is this rank's own region; the others are CUDA-IPC mappings, see xt_peer_*).  Every rank keeps only
+   * its n/world rows of the basis and of A*basis; per iteration the kernels exchange two small partial-sum blocks
+   * (projection coefficients, Gram matrix) and all-gather the new n x neig basis block by direct stores into the
+   * peers' regions -- no collective library call and no host round trip inside the iteration.  All ranks take the
+   * same stop decision at the same iteration (bit-identical projected matrices).  `evecs` then receives this rank's
+   * rows only: (n/world, neig).  `epoch` must be the same on all ranks and increase by one per call using the same
+   * regions (the regions must be zero when first used).  restart_keep: Ritz vectors kept at a thick restart
+   * (0 = 2*neig). */
+  const void* const* peers;
+  uint32_t epoch;
+  int32_t restart_keep;
 } xt_symeig_args;
 
 size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);
 int xt_symeig_krylov(const xt_symeig_args* args);
+
+/* workspace / exchange-region sizes of the row-sharded engine (0 = unsupported arguments) */
+size_t xt_symeig_sharded_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);
+size_t xt_symeig_peer_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);
+
+/* Peer-visible device memory for the exchange regions (the one place where the library allocates: CUDA IPC needs
+ * whole cudaMalloc allocations, which a caching allocator's sub-blocks are not).  xt_peer_alloc: cudaMalloc + zero,
+ * `handle_out` receives the 64-byte cudaIpcMemHandle_t to be sent to the other ranks (any transport);
+ * xt_peer_open maps another rank's handle into this process (device = current device, peer access enabled lazily);
+ * xt_peer_close / xt_peer_free undo them. */
+#define XT_PEER_HANDLE_BYTES 64
+#define XT_MAX_WORLD 8
+int xt_peer_alloc(size_t bytes, void** ptr_out, void* handle_out);
+int xt_peer_open(const void* handle, void** ptr_out);
+int xt_peer_close(void* ptr);
+int xt_peer_free(void* ptr);
 
 /* small dense symmetric eigensolver used for the projected problem (device, one CTA; replaces torch.linalg.eigh
  * at xitorch/_impls/linalg/symeig.py:174): the nev lowest (mode 0) or highest (mode 1) eigenpairs of the m x m

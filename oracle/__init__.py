@@ -31,5 +31,5 @@ from oracle.krylov import (  # noqa: F401
 )
 from oracle.rootfinder import broyden1_root, implicit_grad_dense  # noqa: F401
 from oracle.problems import (  # noqa: F401
-    make_herm, make_slow_herm, make_spd_c1, make_nonsym_c3, make_rootfinder_c4,
+    make_herm, make_slow_herm, make_spd_c1, make_nonsym_c3, make_rootfinder_c4, make_herm_row_block,
 )

@@ -62,3 +62,30 @@ def make_rootfinder_c4(n: int = 8192, seed: int = 0, dtype=torch.float32):
     """C4: f(y, A) = tanh(A @ y + 0.1) + y / 2 with A = 0.1*randn(n,n)/sqrt(n), y0 = zeros(n,1)."""
     A = 0.1 * torch.randn(n, n, generator=_gen(seed), dtype=torch.float32) / math.sqrt(n)
     return A.to(dtype), torch.zeros(n, 1, dtype=dtype)
+
+
+def make_herm_row_block(n: int, neig: int, lo: int, hi: int, device, bs: int = 2048) -> torch.Tensor:
+    """rows [lo, hi) of a make_herm-like matrix of order n (C5: 16 GiB at n = 65536, never assembled in one place),
+    generated on `device` from per-block-pair seeds so that every rank of a row partition draws a consistent,
+    symmetric-by-construction matrix:  G = U + U^T with the (bi, bj) block (bi <= bj) of U from seed 1000003*bi + bj."""
+    dev = torch.device(device)
+    out = torch.empty(hi - lo, n, dtype=torch.float32, device=dev)
+    for bi in range(lo // bs, (hi + bs - 1) // bs):
+        r0, r1 = max(lo, bi * bs), min(hi, (bi + 1) * bs)
+        for bj in range((n + bs - 1) // bs):
+            c0, c1 = bj * bs, min(n, (bj + 1) * bs)
+            a, b = min(bi, bj), max(bi, bj)
+            g = torch.Generator(device=dev)
+            g.manual_seed(1000003 * a + b)
+            blk = torch.randn(bs, bs, generator=g, device=dev)
+            if bi == bj:
+                blk = blk + blk.t()
+            elif bi > bj:
+                blk = blk.t()
+            sub = blk[r0 - bi * bs: r1 - bi * bs, : c1 - c0]
+            out[r0 - lo: r1 - lo, c0:c1] = sub * (0.05 / (2.0 * n) ** 0.5) * (1.0 if bi == bj else 2.0 ** 0.5)
+    d = 20.0 + 10.0 * torch.linspace(0, 1, n, device=dev)
+    d[:2 * neig] = 1.0 + torch.arange(2 * neig, device=dev, dtype=torch.float32)
+    idx = torch.arange(lo, hi, device=dev)
+    out[idx - lo, idx] += d[lo:hi]
+    return out

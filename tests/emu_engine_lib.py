@@ -47,6 +47,10 @@ def load(so: str):
     lib.xt_symeig_workspace_bytes.restype = C.c_size_t
     lib.xt_symeig_krylov.argtypes = [C.POINTER(_lib.SymeigArgs)]
     lib.xt_symeig_krylov.restype = C.c_int
+    lib.xt_symeig_sharded_workspace_bytes.argtypes = [C.c_int32] * 5
+    lib.xt_symeig_sharded_workspace_bytes.restype = C.c_size_t
+    lib.xt_symeig_peer_bytes.argtypes = [C.c_int32] * 5
+    lib.xt_symeig_peer_bytes.restype = C.c_size_t
     lib.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
     lib.xt_small_eigh.restype = C.c_int

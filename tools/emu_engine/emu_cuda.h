@@ -200,6 +200,7 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return 0; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { std::memmove(d, s, n); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memmove(d, s, n); return 0; }
@@ -217,6 +218,7 @@ inline void set_last_error(const char* fmt, ...) {
 #define XT_REQUIRE(cond, ...) do { if (!(cond)) { xt::set_last_error(__VA_ARGS__); return XT_ERR_INVALID; } } while (0)
 #define XT_LAUNCHED() ((void)0)
 inline int num_sms() { return g_emu_sms; }
+template <typename K> inline cudaError_t set_max_dyn_smem(K, int = 0) { return 0; }
 struct DeviceOnce { bool done = false; bool pending() { return !done; } void mark() { done = true; } };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Arena {
@@ -233,6 +235,18 @@ struct Arena {
 inline unsigned long long gtimer() { return 0; }
 inline void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
 inline void cp_async_wait_all() {}
+inline void sys_store_release(unsigned long long* p, unsigned long long v) {
+  std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release);
+}
+inline unsigned long long sys_load_acquire(const unsigned long long* p) {
+  return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_acquire);
+}
+inline void sys_red_add_release(unsigned int* p, unsigned int v) {
+  std::atomic_ref<unsigned int>(*p).fetch_add(v, std::memory_order_release);
+}
+inline unsigned int sys_load_acquire_u32(const unsigned int* p) {
+  return std::atomic_ref<unsigned int>(*const_cast<unsigned int*>(p)).load(std::memory_order_acquire);
+}
 inline void pdl_wait() {}
 inline void pdl_trigger() {}
 inline double fast_rcp(double x) { return 1.0 / x; }
@@ -285,7 +299,7 @@ struct MvArgs {
   const void* E; int64_t e_bstride;
   const void* Z; int64_t ldz, z_bstride;
   const void* U; int64_t ldu, u_bstride;
-  double* dot_out; int impl; const int* done_flag; const int* abort_flag; int reserve_sms; int reverse; int l2_keep_mb;
+  double* dot_out; int impl; const int* done_flag; const int* abort_flag; int reserve_sms; int reverse; int l2_keep_mb; int pdl;
 };
 struct emu_bf16 {
   uint16_t bits;

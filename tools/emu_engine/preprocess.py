@@ -113,6 +113,8 @@ def transform(src: str, include_dir: str = None) -> str:
     src = re.sub(r"__shared__ (\w+) (\w+);", r"\1& \2 = *emu_shared<\1>(__COUNTER__, 1);", src)
     src = re.sub(r"cudaLaunchCooperativeKernel\(po_fn, dim3\(po_grid\), dim3\(PO_THREADS\), kargs, (\w+), st\)",
                  r"emu_coop<PostArgs>(po_fn, dim3(po_grid), dim3(PO_THREADS), kargs, \1)", src)
+    src = re.sub(r"cudaLaunchCooperativeKernel\(sh_fn, dim3\(sh_grid\), dim3\(PO_THREADS\), kargs, (\w+), st\)",
+                 r"emu_coop<ShardArgs>(sh_fn, dim3(sh_grid), dim3(PO_THREADS), kargs, \1)", src)
     src = _rewrite_launches(src)
     assert "asm" not in re.sub(r"//.*", "", src), "PTX left in the host source"
     assert "__shared__" not in src and "<<<" not in src

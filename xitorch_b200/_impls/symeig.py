@@ -363,6 +363,86 @@ def _krylov_row_partitioned(A_local, n, neig, mode, expansion, group, min_eps, m
     return evals[0], evecs[0]
 
 
+def _sharded_applies(A_local, n, neig, max_basis, group) -> bool:
+    """the row-sharded engine takes fp32 / fp64 CUDA blocks, n divisible by the world size and at least twice the basis cap"""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if not A_local.is_cuda or A_local.dtype not in (torch.float32, torch.float64) or world > 8 or n % world != 0:
+        return False
+    mb = _default_max_basis(n, neig) if max_basis is None else max_basis
+    return _lib.lib().xt_symeig_peer_bytes(_lib.dtype_code(A_local.dtype), n, neig, int(mb), world) > 0
+
+
+def _krylov_row_sharded(A_local, n, neig, mode, group, min_eps, max_niter, max_basis, info, regions, restart_keep,
+                        gather=True):
+    """row-sharded block Lanczos (BASELINE config 5): `xt_symeig_krylov` with `peers` set."""
+    import torch.distributed as dist
+    _lib.require_cuda(A_local, "symeig on a row-partitioned operator")
+    if A_local.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("row-partitioned symeig supports float32 / float64 operators")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if n % world != 0 or tuple(A_local.shape) != (n // world, n):
+        raise RuntimeError("expected a local row block of shape %s, got %s" % ((n // world, n), tuple(A_local.shape)))
+    if mode not in ("lowest", "uppest"):
+        raise RuntimeError("Unknown mode: %s" % mode)
+    A_local = A_local.contiguous()
+    vdt, dev = A_local.dtype, A_local.device
+    n_loc = n // world
+    if max_basis is None:
+        max_basis = _default_max_basis(n, neig)
+    L_ = _lib.lib()
+    dcode = _lib.dtype_code(vdt)
+    pbytes = L_.xt_symeig_peer_bytes(dcode, n, neig, int(max_basis), world)
+    wsb = L_.xt_symeig_sharded_workspace_bytes(dcode, n, neig, int(max_basis), world)
+    if pbytes == 0 or wsb == 0:
+        raise RuntimeError("xitorch_b200.lanczos (sharded): unsupported sizes n=%d neig=%d max_basis=%d world=%d "
+                           "(need n %% world == 0, max_basis >= 4*neig, n >= 2*max_basis, world <= 8)"
+                           % (n, neig, max_basis, world))
+    if regions is None:
+        from xitorch_b200.dist import _regions_for
+        regions = _regions_for(pbytes, group)
+    if regions.nbytes < pbytes or regions.world != world:
+        raise RuntimeError("exchange regions too small or made for another world size")
+    regions.epoch += 1
+    V0 = _start_block("randn", 1, n, neig, vdt, dev)                 # same start block on every rank
+    evals = torch.empty((neig,), dtype=vdt, device=dev)
+    evecs_loc = torch.empty((n_loc, neig), dtype=vdt, device=dev)
+    g = _lib.SymeigArgs()
+    g.dtype = dcode
+    g.n, g.nbatch, g.neig = n, 1, neig
+    g.mode = 0 if mode == "lowest" else 1
+    g.expansion = 1
+    g.A, g.lda, g.a_bstride = A_local.data_ptr(), A_local.stride(0), 0
+    g.V0, g.ldv0, g.v0_bstride = V0.data_ptr(), neig, n * neig
+    g.evals, g.evals_bstride = evals.data_ptr(), neig
+    g.evecs, g.ldv, g.evecs_bstride = evecs_loc.data_ptr(), neig, n_loc * neig
+    g.max_niter, g.max_basis, g.check_every = int(max_niter), int(max_basis), 1
+    g.min_eps = float(min_eps)
+    niter, conv, best, napply = C.c_int32(0), C.c_int32(0), C.c_double(0.0), C.c_int64(0)
+    g.niter_out, g.converged_out = C.pointer(niter), C.pointer(conv)
+    g.best_resid_out, g.napply_out = C.pointer(best), C.pointer(napply)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    g.workspace, g.workspace_bytes = ws.data_ptr(), wsb
+    g.stream = _lib.stream_ptr(dev)
+    g.world, g.rank = world, rank
+    parr = (C.c_void_p * world)(*regions.ptrs)
+    g.peers = C.cast(parr, C.POINTER(C.c_void_p))
+    g.epoch = regions.epoch
+    g.restart_keep = int(restart_keep or 0)
+    with torch.cuda.device(dev):
+        _lib.check(L_.xt_symeig_krylov(g), "lanczos (sharded)")
+    if info is not None:
+        info.update(niter=niter.value, converged=bool(conv.value), best_resid=best.value, napply=napply.value,
+                    max_basis=int(max_basis), engine="sharded")
+    del parr
+    if not gather or world == 1:
+        return evals, evecs_loc
+    evecs = torch.empty((n, neig), dtype=vdt, device=dev)
+    dist.all_gather_into_tensor(evecs, evecs_loc, group=group)      # once per solve, outside the iteration
+    return evals, evecs
+
+
 def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
              max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
              max_addition: Optional[int] = None, min_eps: float = 1e-6, verbose: bool = False,

@@ -23,6 +23,8 @@ EXPORTS = [
     "xt_version", "xt_last_error", "xt_profile_reset", "xt_profile_read", "xt_block_matvec",
     "xt_solve_workspace_bytes", "xt_cg", "xt_bicgstab", "xt_gmres",
     "xt_symeig_workspace_bytes", "xt_symeig_krylov", "xt_small_eigh", "xt_hermitian_check",
+    "xt_symeig_sharded_workspace_bytes", "xt_symeig_peer_bytes",
+    "xt_peer_alloc", "xt_peer_open", "xt_peer_close", "xt_peer_free",
 ]
 
 
@@ -79,6 +81,7 @@ class SymeigArgs(C.Structure):
         ("world", C.c_int32), ("rank", C.c_int32),
         ("allgather", C.c_void_p), ("allgather_user", C.c_void_p),
         ("apply", C.c_void_p), ("apply_user", C.c_void_p),
+        ("peers", C.POINTER(C.c_void_p)), ("epoch", C.c_uint32), ("restart_keep", C.c_int32),
     ]
 
 
@@ -141,6 +144,18 @@ def lib():
         L.xt_hermitian_check.restype = C.c_int
         L.xt_symeig_krylov.argtypes = [C.POINTER(SymeigArgs)]
         L.xt_symeig_krylov.restype = C.c_int
+        L.xt_symeig_sharded_workspace_bytes.argtypes = [C.c_int32] * 5
+        L.xt_symeig_sharded_workspace_bytes.restype = C.c_size_t
+        L.xt_symeig_peer_bytes.argtypes = [C.c_int32] * 5
+        L.xt_symeig_peer_bytes.restype = C.c_size_t
+        L.xt_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+        L.xt_peer_alloc.restype = C.c_int
+        L.xt_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.xt_peer_open.restype = C.c_int
+        L.xt_peer_close.argtypes = [C.c_void_p]
+        L.xt_peer_close.restype = C.c_int
+        L.xt_peer_free.argtypes = [C.c_void_p]
+        L.xt_peer_free.restype = C.c_int
         L.xt_small_eigh.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
         L.xt_small_eigh.restype = C.c_int

@@ -57,6 +57,7 @@ struct EigCtl {
   int best_in_S;        // 1: the best pair so far is held as coefficients (Sbest, best_m) w.r.t. the current basis
   int best_m;
   int check_done;       // ticket of the last check whose bookkeeping is complete (they are applied in launch order)
+  int stop_iter;        // first iteration whose check met min_eps (0: none yet); checks are applied in launch order
   int* host_done;       // host-mapped mirror of `done` (lets the host stop launching without draining the stream)
   unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
   unsigned long long ptrace[64][12]; // fused expansion kernel of iteration i (CTA 0): start and 10 phase stamps
@@ -1734,7 +1735,7 @@ __device__ __forceinline__ float lanczos_resid_max_k(const TV* __restrict__ Q, i
       for (int l = 0; l < LH; ++l) mreg[c][l] = (TV)Ms[c * K + l0 + l];
     // RB rows per thread in flight: one CTA reads the whole block out of L2 next to a running matvec, so the loop is
     // bound by load latency, not by bandwidth or arithmetic
-    constexpr int RB = 4;
+    constexpr int RB = ((sizeof(TV) == 4 ? 64 : 32) / K) > 8 ? 8 : (((sizeof(TV) == 4 ? 64 : 32) / K) < 2 ? 2 : ((sizeof(TV) == 4 ? 64 : 32) / K));
     constexpr int VW = 16 / (int)sizeof(TV);          // elements per 16-byte load
     const int nt = blockDim.x;
 #pragma unroll 1
@@ -1894,6 +1895,7 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
       if (rmax < chk.min_eps) {
         ctl->converged = 1;
         ctl->local_done = 1;
+        if (ctl->stop_iter == 0) ctl->stop_iter = iter;
         __threadfence();
         if (!ctl->collective) signal_done(ctl);
       }
@@ -2026,7 +2028,7 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
   ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0; ctl->done_latched = 0;
-  ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0;
+  ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0; ctl->stop_iter = 0;
   ctl->trace[0][0] = gtimer();
 }
 
@@ -2072,6 +2074,49 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
   W.evals_best = ar.take<double>(SE_MAXK);
   W.ctl = ar.take<EigCtl>(1);
   return ar.ok();
+}
+
+constexpr int LOOKAHEAD = 3; // the host enqueues at most this many iterations beyond the last one known complete
+constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
+// side streams / events are host-side handles: created once per device and thread, reused by every call
+struct SidePool {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
+  cudaEvent_t it[LOOKAHEAD + 1] = {nullptr, nullptr, nullptr, nullptr};   // end-of-iteration marks (run-ahead window)
+  volatile int* hflag = nullptr;      // pinned, mapped: the kernels mirror ctl->done here; words 8..12: result mirror
+  int* hflag_dev = nullptr;
+  int res_seq = 0;                    // ticket of the last result mirror requested (see output_kernel)
+  int dev = -1;
+};
+static int side_pool_get(SidePool** out) {
+  static thread_local SidePool pool;
+  int dev = 0;
+  XT_CUDA_OK(cudaGetDevice(&dev));
+  if (pool.dev != dev) {
+    for (int i = 0; i < 2; ++i) { if (pool.s[i]) cudaStreamDestroy(pool.s[i]); pool.s[i] = nullptr; }
+    for (int i = 0; i < NSLOT; ++i) {
+      if (pool.c[i]) cudaEventDestroy(pool.c[i]);
+      if (pool.r[i]) cudaEventDestroy(pool.r[i]);
+      pool.c[i] = pool.r[i] = nullptr;
+    }
+    for (int i = 0; i <= LOOKAHEAD; ++i) {
+      if (pool.it[i]) cudaEventDestroy(pool.it[i]);
+      XT_CUDA_OK(cudaEventCreateWithFlags(&pool.it[i], cudaEventDisableTiming));
+    }
+    if (pool.hflag) cudaFreeHost(const_cast<int*>(pool.hflag));
+    void* hp = nullptr;
+    XT_CUDA_OK(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    pool.hflag = static_cast<volatile int*>(hp);
+    XT_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pool.hflag_dev), hp, 0));
+    for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
+    for (int i = 0; i < NSLOT; ++i) {
+      XT_CUDA_OK(cudaEventCreateWithFlags(&pool.c[i], cudaEventDisableTiming));
+      XT_CUDA_OK(cudaEventCreateWithFlags(&pool.r[i], cudaEventDisableTiming));
+    }
+    pool.dev = dev;
+  }
+  *out = &pool;
+  return XT_OK;
 }
 
 template <typename TV> static int run_symeig(const xt_symeig_args* g) {
@@ -2188,49 +2233,15 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   int last_niter = 0;
 
   const bool overlap = (g->expansion == 1) && (num_sms() > 8);
-  constexpr int LOOKAHEAD = 3; // the host enqueues at most this many iterations beyond the last one known complete
-  constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
-  // side streams / events are host-side handles: created once per device and thread, reused by every call
-  struct SidePool {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
-    cudaEvent_t it[LOOKAHEAD + 1] = {nullptr, nullptr, nullptr, nullptr};   // end-of-iteration marks (run-ahead window)
-    volatile int* hflag = nullptr;      // pinned, mapped: the kernels mirror ctl->done here; words 8..12: result mirror
-    int* hflag_dev = nullptr;
-    int res_seq = 0;                    // ticket of the last result mirror requested (see output_kernel)
-    int dev = -1;
-  };
-  static thread_local SidePool pool;
+  SidePool* pool_p = nullptr;
+  {
+    const int prc = side_pool_get(&pool_p);
+    if (prc != XT_OK) return prc;
+  }
+  SidePool& pool = *pool_p;
   cudaStream_t* side = pool.s;
   cudaEvent_t* evC = pool.c;
   cudaEvent_t* evR = pool.r;
-  {
-    int dev = 0;
-    XT_CUDA_OK(cudaGetDevice(&dev));
-    if (pool.dev != dev) {
-      for (int i = 0; i < 2; ++i) { if (pool.s[i]) cudaStreamDestroy(pool.s[i]); pool.s[i] = nullptr; }
-      for (int i = 0; i < NSLOT; ++i) {
-        if (pool.c[i]) cudaEventDestroy(pool.c[i]);
-        if (pool.r[i]) cudaEventDestroy(pool.r[i]);
-        pool.c[i] = pool.r[i] = nullptr;
-      }
-      for (int i = 0; i <= LOOKAHEAD; ++i) {
-        if (pool.it[i]) cudaEventDestroy(pool.it[i]);
-        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.it[i], cudaEventDisableTiming));
-      }
-      if (pool.hflag) cudaFreeHost(const_cast<int*>(pool.hflag));
-      void* hp = nullptr;
-      XT_CUDA_OK(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
-      pool.hflag = static_cast<volatile int*>(hp);
-      XT_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pool.hflag_dev), hp, 0));
-      for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
-      for (int i = 0; i < NSLOT; ++i) {
-        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.c[i], cudaEventDisableTiming));
-        XT_CUDA_OK(cudaEventCreateWithFlags(&pool.r[i], cudaEventDisableTiming));
-      }
-      pool.dev = dev;
-    }
-  }
 
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
@@ -2331,7 +2342,14 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         // run-ahead window instead of polling: wait (normally not at all) until iteration iter-LOOKAHEAD has
         // finished on the device, then look at the host mirror of the stop flag.  The stream is never drained and
         // at most LOOKAHEAD iterations of no-op kernels are enqueued after convergence.
-        XT_CUDA_OK(cudaEventSynchronize(pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)]));
+        // (polled, not cudaEventSynchronize: a blocking wait wakes the host 10-20 us late, which is pure idle time of
+        // the GPU at the end of a solve; the stop flag itself is visible here the moment a kernel raises it)
+        cudaEvent_t evw = pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)];
+        while (!*pool.hflag) {
+          const cudaError_t qe = cudaEventQuery(evw);
+          if (qe == cudaSuccess) break;
+          if (qe != cudaErrorNotReady) { XT_CUDA_OK(qe); }
+        }
         if (*pool.hflag) { --iter; break; }
       }
       const int j = m / k - 1;     // newest block
@@ -2625,6 +2643,564 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   return XT_OK;
 }
 
+// ============================================================================ row-sharded engine over peer memory
+// One large operator, rows split over `world` GPUs (BASELINE config 5).  Rank p keeps rows
+// [p n/P, (p+1) n/P) of A, of the basis V and of A V; the only replicated vector data is the newest basis block (n x k),
+// which every rank needs in full as the matvec operand.  Per iteration:
+//   1. W_p = A_p Q_j                             block matvec over the local rows (matvec.cu), Q_j from the exchange region
+//   2. expand_sharded_kernel (cooperative):
+//        P1  partial C_p = V_p^T W_p  -> grid barrier -> pushed to every rank's region -> all ranks sum the P partials
+//            in rank order (bit-identical C, hence bit-identical T, Ritz pairs and stop decisions everywhere)
+//        P2  W' = W - V C; partial C2, G -> same exchange
+//        P3  Q_{j+1} rows = (W' - V C2) chol(G)^-T -> own basis AND directly into every peer's copy of Q_{j+1}
+//            (peer stores over NVLink + one arrival counter per rank: the all-gather costs no launch and no host call)
+//   3. rr_kernel on a side stream, replicated: Rayleigh-Ritz of T plus the stop test by the Lanczos residual formula on
+//      the full Q_{j+1} every rank holds.  Its verdict is consumed ONE iteration later at a fixed point of the main
+//      stream (latch_kernel), so that all ranks leave the iteration together.
+// Thick restart (basis full): Rayleigh-Ritz for `keep` pairs on the main stream, the rotation of V_p / A V_p is local.
+constexpr unsigned long long SH_TIMEOUT_CLK = 3000000000ull;      // ~1.5 s: a lost peer never hangs the device
+
+struct PeerLayout {
+  size_t qfull[2];      // two copies of the newest basis block, (n, k) row-major value type
+  size_t xbuf;          // [2 phases][world][xcap] doubles: partial sums pushed by each rank
+  size_t xflag;         // [2 phases][world] u64: (epoch << 32 | sequence) of the partial last pushed by each rank
+  size_t qcount;        // [4] u32, 64 B apart: arrivals of Q rows (one per CTA and launch), counter epoch & 3 in use
+  size_t startflag;     // [world] u64: start-of-solve barrier
+  size_t xcap;          // doubles per partial
+  size_t total;
+};
+static PeerLayout peer_layout(size_t vs, int n, int k, int mb, int world) {
+  PeerLayout L;
+  size_t off = 0;
+  for (int b = 0; b < 2; ++b) { L.qfull[b] = off; off += align_up((size_t)n * k * vs, 1024); }
+  L.xcap = align_up((size_t)(mb + SE_MAXK) * k + 8, 16);
+  L.xbuf = off; off += align_up((size_t)2 * world * L.xcap * sizeof(double), 1024);
+  L.xflag = off; off += align_up((size_t)2 * world * sizeof(unsigned long long), 256);
+  L.qcount = off; off += 4 * 64;
+  L.startflag = off; off += align_up((size_t)world * sizeof(unsigned long long), 256);
+  L.total = align_up(off, 4096);
+  return L;
+}
+
+struct ShardArgs {
+  const void* V; const void* W; void* Qout;   // local basis [block][n_loc][k], local W (n_loc, k), local output block
+  int n_loc, k, m, R;
+  double* acc; int acc_stride;                // local accumulators, as PostArgs
+  double* T; int ldt; int update_T;
+  EigCtl* ctl;
+  int iter, stage_v;
+  double* Lout;
+  int world, rank;
+  char* peer[XT_MAX_WORLD];                   // exchange regions as mapped in this process (peer[rank]: own)
+  PeerLayout lay;
+  int qbuf;                                   // which copy of Qfull receives the new block
+  unsigned long long flag[2];                 // values of the two partial-sum flags of this launch
+  unsigned int qtarget; int qslot;            // arrival counter value once every rank's launch has delivered
+};
+
+__device__ __forceinline__ double* sh_xbuf(const ShardArgs& p, int owner, int phase, int src) {
+  return reinterpret_cast<double*>(p.peer[owner] + p.lay.xbuf) + ((size_t)phase * p.world + src) * p.lay.xcap;
+}
+__device__ __forceinline__ unsigned long long* sh_xflag(const ShardArgs& p, int owner, int phase, int src) {
+  return reinterpret_cast<unsigned long long*>(p.peer[owner] + p.lay.xflag) + (size_t)phase * p.world + src;
+}
+__device__ __forceinline__ unsigned int* sh_qcount(const ShardArgs& p, int owner, int slot) {
+  return reinterpret_cast<unsigned int*>(p.peer[owner] + p.lay.qcount + (size_t)slot * 64);
+}
+__device__ __forceinline__ void sh_fail(EigCtl* ctl) {
+  ctl->breakdown = 2;
+  ctl->done_latched = 1;
+  ctl->local_done = 1;
+  signal_done(ctl);
+}
+
+// Grid barrier + all-reduce over the ranks of `count` doubles accumulated in set `set` of p.acc: the last CTA to arrive
+// folds the accumulator copies, pushes the partial into every rank's region (its own included) and raises this rank's
+// flag there; every CTA then waits for all `world` flags in its OWN region.  Returns false on a timeout.  The caller
+// sums the partials sh_xbuf(p, rank, phase, 0 .. world-1) in rank order.
+__device__ __forceinline__ bool shard_exchange(const ShardArgs& p, int phase, int set, int count) {
+  __shared__ int role_s;
+  __shared__ int ok_s;
+  EigCtl* ctl = p.ctl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const unsigned int old = atomicAdd(&ctl->bar_count, 1u);
+    role_s = (old == gridDim.x - 1) ? 1 : 0;
+    if (role_s) {
+      ctl->bar_count = 0;
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    ok_s = 1;
+  }
+  __syncthreads();
+  if (role_s) {
+    const double* src = p.acc + (size_t)set * PO_NCOPY * p.acc_stride;
+    for (int e = threadIdx.x; e < count; e += PO_THREADS) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < PO_NCOPY; ++c) v += __ldcg(&src[(size_t)c * p.acc_stride + e]);
+      for (int q = 0; q < p.world; ++q) sh_xbuf(p, q, phase, p.rank)[e] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.world) sys_store_release(sh_xflag(p, threadIdx.x, phase, p.rank), p.flag[phase]);
+  }
+  if ((int)threadIdx.x < p.world) {
+    const unsigned long long* f = sh_xflag(p, p.rank, phase, threadIdx.x);
+    const long long t0 = clock64();
+    while (sys_load_acquire(f) < p.flag[phase]) {
+      if ((unsigned long long)(clock64() - t0) > SH_TIMEOUT_CLK) { ok_s = 0; break; }
+    }
+  }
+  __syncthreads();
+  if (!ok_s && blockIdx.x == 0 && threadIdx.x == 0) sh_fail(ctl);
+  return ok_s != 0;
+}
+
+template <typename TV, int KP>
+__global__ void __launch_bounds__(PO_THREADS)
+expand_sharded_kernel(const ShardArgs p) {
+  EigCtl* ctl = p.ctl;
+  if (ctl->done_latched) return;              // stream-ordered and identical on every rank
+  extern __shared__ __align__(16) unsigned char po_raw[];
+  const int tid = threadIdx.x;
+  const int n = p.n_loc, k = p.k, m = p.m, R = p.R;
+  const int nblk = m / k;
+  const int row0 = blockIdx.x * R;
+  const int rows = max(0, min(R, n - row0));
+  const bool last_cta = (blockIdx.x == gridDim.x - 1);
+  double* Zs = reinterpret_cast<double*>(po_raw);              // [R][KP]
+  double* Cs = Zs + (size_t)R * KP;                            // [m][KP]
+  double* part = Cs + (size_t)m * KP;                          // [3][m + k][KP]
+  double* Gs = part + (size_t)3 * (m + KP) * KP;               // [k][k]
+  double* Ri = Gs + KP * KP;                                   // [k][k]
+  TV* Vs = reinterpret_cast<TV*>(Ri + KP * KP);                // [nblk][R][k]
+  __shared__ int chol_ok;
+  const TV* V = static_cast<const TV*>(p.V);
+  const TV* W = static_cast<const TV*>(p.W);
+  if (p.stage_v) po_stage<TV>(Vs, V, n, k, row0, rows, R, nblk);
+  const TV* Vb = p.stage_v ? Vs : V + (int64_t)row0 * k;
+  const int64_t vbs = p.stage_v ? (int64_t)R : (int64_t)n;
+  for (int e = tid; e < R * KP; e += PO_THREADS) {
+    const int r = e / KP, j = e - r * KP;
+    Zs[e] = (r < rows && j < k) ? (double)W[((int64_t)row0 + r) * k + j] : 0.0;
+  }
+  double* accC = p.acc + (size_t)(blockIdx.x % PO_NCOPY) * p.acc_stride;
+  double* accC2 = p.acc + (size_t)(PO_NCOPY + blockIdx.x % PO_NCOPY) * p.acc_stride;
+  {                                      // clear set 1 (the previous launch is done with it)
+    double* set1 = p.acc + (size_t)PO_NCOPY * p.acc_stride;
+    const int tot = PO_NCOPY * p.acc_stride;
+    for (int e = blockIdx.x * PO_THREADS + tid; e < tot; e += gridDim.x * PO_THREADS) set1[e] = 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  if (m > 0) {
+    // ---- P1: C = V^T W, summed over the CTAs of this rank and then over the ranks
+    po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, false, part, accC);
+    if (!shard_exchange(p, 0, 0, m * k)) return;
+    const double* xb = sh_xbuf(p, p.rank, 0, 0);
+    for (int e = tid; e < m * KP; e += PO_THREADS) {
+      const int i = e / KP, j = e - i * KP;
+      double v = 0.0;
+      if (j < k)
+        for (int q = 0; q < p.world; ++q) v += __ldcg(&xb[(size_t)q * p.lay.xcap + (size_t)i * k + j]);
+      Cs[e] = v;
+    }
+    __syncthreads();
+    // ---- P2: W' = W - V C;  T[:, new block] = C
+    po_subtract<TV, KP>(Vb, Cs, Zs, rows, vbs, k, nblk);
+    if (last_cta && p.update_T) {
+      const int c0 = m - k;
+      for (int e = tid; e < m * k; e += PO_THREADS) {
+        const int i = e / k, j = e - i * k;
+        double v = Cs[(size_t)i * KP + j];
+        if (i >= c0) v = 0.5 * (v + Cs[(size_t)(c0 + j) * KP + (i - c0)]);     // symmetrise the diagonal block
+        p.T[(int64_t)i * p.ldt + c0 + j] = v;
+        p.T[(int64_t)(c0 + j) * p.ldt + i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  // C2 = V^T W', G = W'^T W'
+  po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, true, part, accC2);
+  if (!shard_exchange(p, 1, 1, (m + k) * k)) return;
+  {
+    const double* xb = sh_xbuf(p, p.rank, 1, 0);
+    for (int e = tid; e < m * KP; e += PO_THREADS) {
+      const int i = e / KP, j = e - i * KP;
+      double v = 0.0;
+      if (j < k)
+        for (int q = 0; q < p.world; ++q) v += __ldcg(&xb[(size_t)q * p.lay.xcap + (size_t)i * k + j]);
+      Cs[e] = v;
+    }
+    for (int e = tid; e < k * k; e += PO_THREADS) {
+      const int i = e / k, j = e - i * k;
+      double v = 0.0;
+      for (int q = 0; q < p.world; ++q)
+        v += __ldcg(&xb[(size_t)q * p.lay.xcap + (size_t)(m + i) * k + j]) +
+             __ldcg(&xb[(size_t)q * p.lay.xcap + (size_t)(m + j) * k + i]);
+      Gs[e] = 0.5 * v;
+    }
+    // every CTA of this rank is past the first exchange: set 0 can be cleared for the next launch
+    const int tot = PO_NCOPY * p.acc_stride;
+    for (int e = blockIdx.x * PO_THREADS + tid; e < tot; e += gridDim.x * PO_THREADS) p.acc[e] = 0.0;
+  }
+  __syncthreads();
+  // ---- P3: Q = (W' - V C2) chol(G)^-T
+  if (tid < 32) {
+    int ok;
+    double* Lout = (blockIdx.x == 0) ? p.Lout : nullptr;
+    if constexpr (KP <= 8) ok = chol_inverse_regs<KP>(Gs, Ri, k, Lout);
+    else ok = chol_inverse_warp(Gs, Ri, k, Lout);
+    if (tid == 0) chol_ok = ok;
+  }
+  po_subtract<TV, KP>(Vb, Cs, Zs, rows, vbs, k, nblk, 32);
+  __syncthreads();
+  TV* Q = static_cast<TV*>(p.Qout);
+  const int64_t grow0 = (int64_t)p.rank * n + row0;           // global index of this CTA's first row
+  for (int e = tid; e < rows * k; e += PO_THREADS) {
+    const int r = e / k, j = e - r * k;
+    double acc = 0.0;
+    if (chol_ok)
+      for (int i = 0; i <= j; ++i) acc = fma(Zs[(size_t)r * KP + i], Ri[i * k + j], acc);
+    const TV qv = (TV)acc;                                      // breakdown: a zero block keeps later kernels defined
+    Q[(int64_t)row0 * k + e] = qv;
+    for (int q = 0; q < p.world; ++q)
+      reinterpret_cast<TV*>(p.peer[q] + p.lay.qfull[p.qbuf])[grow0 * k + e] = qv;
+  }
+  if (!chol_ok && last_cta && tid == 0) {                       // the same G on every rank: all ranks stop here
+    ctl->breakdown = 1;
+    ctl->local_done = 1;
+    ctl->done_latched = 1;
+    signal_done(ctl);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < p.world) sys_red_add_release(sh_qcount(p, tid, p.qslot), 1u);
+  if (blockIdx.x == 0 && tid == 0) {
+    // the kernel (hence the stream) does not complete before every rank's rows of the new block have arrived here
+    const unsigned int* qc = sh_qcount(p, p.rank, p.qslot);
+    const long long t0 = clock64();
+    while (sys_load_acquire_u32(qc) < p.qtarget) {
+      if ((unsigned long long)(clock64() - t0) > SH_TIMEOUT_CLK) { sh_fail(ctl); break; }
+    }
+  }
+}
+
+// start-of-solve barrier over the ranks (no rank touches a peer's region before that peer has finished its previous
+// solve) + reset of the arrival counter that will be used two solves from now
+__global__ void peer_start_kernel(ShardArgs p, unsigned long long value, int clear_slot) {
+  const int tid = threadIdx.x;
+  if (tid == 0) *sh_qcount(p, p.rank, clear_slot) = 0u;
+  __threadfence_system();
+  __syncthreads();
+  if (tid < p.world) {
+    sys_store_release(reinterpret_cast<unsigned long long*>(p.peer[tid] + p.lay.startflag) + p.rank, value);
+    const unsigned long long* f = reinterpret_cast<unsigned long long*>(p.peer[p.rank] + p.lay.startflag) + tid;
+    const long long t0 = clock64();
+    while (sys_load_acquire(f) < value) {
+      if ((unsigned long long)(clock64() - t0) > 4 * SH_TIMEOUT_CLK) { sh_fail(p.ctl); break; }
+    }
+  }
+}
+
+// consume the verdicts of all checks up to iteration `upto` at a fixed point of the main stream
+__global__ void latch_kernel(EigCtl* ctl, int upto) {
+  if (threadIdx.x != 0) return;
+  const int si = *reinterpret_cast<volatile int*>(&ctl->stop_iter);
+  if ((si != 0 && si <= upto) || ctl->breakdown) {
+    ctl->done_latched = 1;
+    signal_done(ctl);
+  }
+}
+
+struct ShardWs {
+  void *V, *AV, *Vtmp, *Xslots, *Rblk;
+  double *T, *Tw[2], *Sk[NSLOT], *theta[NSLOT], *Pacc, *Lsave, *Sbest, *evals_best, *evals_slots;
+  EigCtl* ctl;
+};
+static bool carve_sharded(Arena& ar, ShardWs& W, size_t vs, int n_loc, int k, int mb) {
+  const size_t blk = (size_t)n_loc * k * vs;
+  const int nb = mb / k;
+  W.V = ar.take<char>((size_t)(nb + 1) * blk);
+  W.AV = ar.take<char>((size_t)(nb + 1) * blk);
+  W.Vtmp = ar.take<char>((size_t)(nb + 1) * blk);
+  W.Xslots = ar.take<char>(2 * blk);
+  W.Rblk = ar.take<char>(blk);
+  W.T = ar.take<double>((size_t)mb * mb);
+  for (int i = 0; i < 2; ++i) W.Tw[i] = ar.take<double>((size_t)mb * (mb | 1));
+  for (int i = 0; i < NSLOT; ++i) { W.Sk[i] = ar.take<double>((size_t)mb * mb); W.theta[i] = ar.take<double>(mb); }
+  W.Pacc = ar.take<double>((size_t)2 * PO_NCOPY * (size_t)(mb + SE_MAXK) * k);
+  W.Lsave = ar.take<double>((size_t)4 * SE_MAXK * SE_MAXK);
+  W.Sbest = ar.take<double>((size_t)mb * k);
+  W.evals_best = ar.take<double>(SE_MAXK);
+  W.evals_slots = ar.take<double>(2 * SE_MAXK);
+  W.ctl = ar.take<EigCtl>(1);
+  return ar.ok();
+}
+
+template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
+  const int n = g->n, k = g->neig;
+  const int world = g->world > 1 ? g->world : 1;
+  const int rank = world > 1 ? g->rank : 0;
+  XT_REQUIRE(world <= XT_MAX_WORLD && rank >= 0 && rank < world, "symeig(sharded): world=%d rank=%d", world, g->rank);
+  XT_REQUIRE(n % world == 0, "symeig(sharded): n=%d is not divisible by the world size %d", n, world);
+  XT_REQUIRE(g->nbatch == 1 && g->expansion == 1 && g->apply == nullptr,
+             "symeig(sharded): needs nbatch = 1, the Krylov expansion and a dense operator");
+  const int n_loc = n / world;
+  int mb = g->max_basis;
+  if (mb > 128) mb = 128;                       // the on-chip Rayleigh-Ritz kernel
+  mb = (mb / k) * k;
+  XT_REQUIRE(mb >= 4 * k && n >= 2 * mb, "symeig(sharded): max_basis=%d too small for neig=%d, or n=%d too small", mb, k, n);
+  int keep = g->restart_keep > 0 ? g->restart_keep : 2 * k;
+  keep = (keep / k) * k;
+  if (keep < k) keep = k;
+  if (keep > mb - 2 * k) keep = mb - 2 * k;
+  Arena ar(g->workspace, g->workspace_bytes);
+  ShardWs W;
+  if (!carve_sharded(ar, W, sizeof(TV), n_loc, k, mb)) {
+    set_last_error("symeig(sharded): workspace too small (%zu needed, %zu given)", ar.off, ar.cap);
+    return XT_ERR_WORKSPACE;
+  }
+  TV* V = static_cast<TV*>(W.V);
+  TV* AV = static_cast<TV*>(W.AV);
+  TV* Vtmp = static_cast<TV*>(W.Vtmp);
+  TV* Xslots = static_cast<TV*>(W.Xslots);
+  const int64_t blk = (int64_t)n_loc * k;
+  const int grid_rows = (n_loc + SE_ROWS - 1) / SE_ROWS;
+  int coop = 0;
+  {
+    int dev = 0;
+    XT_CUDA_OK(cudaGetDevice(&dev));
+    XT_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  }
+  XT_REQUIRE(coop != 0 && num_sms() > 8, "symeig(sharded): needs cooperative launches");
+  static DeviceOnce attrs_once;   // per TV instantiation
+  if (attrs_once.pending()) {
+    XT_CUDA_OK(set_max_dyn_smem(rr_kernel));
+    XT_CUDA_OK(cudaFuncSetAttribute(rotate_tiled_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_sharded_kernel<TV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_sharded_kernel<TV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
+    XT_CUDA_OK(cudaFuncSetAttribute(expand_sharded_kernel<TV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PO_SMEM_MAX));
+    attrs_once.mark();
+  }
+  const int KP = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
+  const int po_gmax = num_sms() - 2;
+  const int po_R = (n_loc + po_gmax - 1) / po_gmax;
+  const int sh_grid = (n_loc + po_R - 1) / po_R;
+  const void* sh_fn = KP == 4 ? (const void*)expand_sharded_kernel<TV, 4>
+                              : (KP == 8 ? (const void*)expand_sharded_kernel<TV, 8> : (const void*)expand_sharded_kernel<TV, 16>);
+  SidePool* pool_p = nullptr;
+  {
+    const int prc = side_pool_get(&pool_p);
+    if (prc != XT_OK) return prc;
+  }
+  SidePool& pool = *pool_p;
+  cudaStream_t* side = pool.s;
+  cudaEvent_t* evC = pool.c;
+  cudaEvent_t* evR = pool.r;
+
+  ShardArgs base;
+  memset(&base, 0, sizeof(base));
+  base.lay = peer_layout(sizeof(TV), n, k, mb, world);
+  base.world = world; base.rank = rank;
+  for (int q = 0; q < world; ++q) {
+    base.peer[q] = static_cast<char*>(const_cast<void*>(g->peers[q]));
+    XT_REQUIRE(base.peer[q] != nullptr, "symeig(sharded): peers[%d] is NULL", q);
+  }
+  base.V = V; base.n_loc = n_loc; base.k = k; base.R = po_R;
+  base.acc = W.Pacc; base.acc_stride = (mb + SE_MAXK) * k; base.T = W.T; base.ldt = mb;
+  base.ctl = W.ctl; base.qslot = (int)(g->epoch & 3u);
+  const unsigned long long etag = (unsigned long long)g->epoch << 32;
+  unsigned long long xseq = 0;         // partial-sum exchanges so far
+  unsigned int qlaunches = 0;          // launches of the sharded kernel so far (each delivers world * sh_grid arrivals)
+  TV* Qfull[2] = {reinterpret_cast<TV*>(base.peer[rank] + base.lay.qfull[0]),
+                  reinterpret_cast<TV*>(base.peer[rank] + base.lay.qfull[1])};
+
+  auto launch_sh = [&](int m_, const TV* Wsrc, TV* Qout, int qbuf, int update_T, double* Lout, int iter_) -> int {
+    ShardArgs sa = base;
+    sa.m = m_; sa.W = Wsrc; sa.Qout = Qout; sa.qbuf = qbuf; sa.update_T = update_T; sa.Lout = Lout; sa.iter = iter_;
+    sa.stage_v = 1;
+    size_t po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m_, 0, true);
+    if (po_smem > (size_t)PO_SMEM_MAX) {
+      sa.stage_v = 0;
+      po_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, m_, 0, false);
+    }
+    XT_REQUIRE(po_smem <= (size_t)PO_SMEM_MAX, "symeig(sharded): %d local rows per CTA do not fit in shared memory", po_R);
+    if (m_ > 0) sa.flag[0] = etag | ++xseq;
+    sa.flag[1] = etag | ++xseq;
+    if (getenv("XT_SH_DEBUG")) fprintf(stderr, "[sharded r%d] launch m=%d iter=%d qbuf=%d grid=%d smem=%zu\n", rank, m_, iter_, qbuf, sh_grid, po_smem);
+    sa.qtarget = ++qlaunches * (unsigned int)(world * sh_grid);
+    void* kargs[1] = {&sa};
+    XT_CUDA_OK(cudaLaunchCooperativeKernel(sh_fn, dim3(sh_grid), dim3(PO_THREADS), kargs, po_smem, st));
+    XT_LAUNCHED();
+    return XT_OK;
+  };
+
+  *pool.hflag = 0;
+  init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, 2, pool.hflag_dev); XT_LAUNCHED();
+  peer_start_kernel<<<1, 32, 0, st>>>(base, etag | 1ull, (int)((g->epoch + 2u) & 3u)); XT_LAUNCHED();
+  XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)2 * PO_NCOPY * (mb + SE_MAXK) * k, st));
+  // ---- start block: Cholesky-QR twice on the row-sharded block (tensor.py:8-19 / symeig.py:249-252)
+  {
+    const TV* src = static_cast<const TV*>(g->V0) + (int64_t)rank * n_loc * g->ldv0;
+    if (g->ldv0 != k) {
+      gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(src, g->ldv0, n_loc, k, static_cast<TV*>(W.Rblk)); XT_LAUNCHED();
+      src = static_cast<const TV*>(W.Rblk);
+    }
+    int rc = launch_sh(0, src, V, 1, 0, nullptr, 0);
+    if (rc != XT_OK) return rc;
+    rc = launch_sh(0, V, V, 0, 0, nullptr, 0);
+    if (rc != XT_OK) return rc;
+  }
+  int m = k, iter = 0, cur = 0;
+  int64_t napply = 0;
+  bool ev_used[NSLOT] = {false, false, false};
+  int check_seq = 0;
+  int latched_upto = 0;
+  // before anything that changes the basis: all checks done, a best pair held as coefficients becomes a stored block
+  auto settle = [&]() -> int {
+    for (int q = 0; q < NSLOT; ++q)
+      if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
+    output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n_loc, k, nullptr, k,
+                                                 nullptr, 1, W.ctl, nullptr, 0); XT_LAUNCHED();
+    flip_best_kernel<<<1, 32, 0, st>>>(W.ctl); XT_LAUNCHED();
+    return XT_OK;
+  };
+  while (true) {
+    ++iter;
+    if (iter > LOOKAHEAD) {
+      cudaEvent_t evw = pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)];
+      while (!*pool.hflag) {
+        const cudaError_t qe = cudaEventQuery(evw);
+        if (qe == cudaSuccess) break;
+        if (qe != cudaErrorNotReady) { XT_CUDA_OK(qe); }
+      }
+      if (*pool.hflag) { --iter; break; }
+    }
+    const int j = m / k - 1;
+    const int par = iter % NSLOT;
+    // 1. W = A_p Q_j
+    MvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dtype = g->dtype;
+    a.nbatch = 1; a.nrows = n_loc; a.ncolsA = n; a.k = k;
+    a.A = g->A; a.lda = g->lda; a.a_bstride = 0;
+    a.X = Qfull[cur]; a.ldx = k; a.x_bstride = 0;
+    a.Y = AV + j * blk; a.ldy = k; a.y_bstride = 0;
+    a.done_flag = &W.ctl->done_latched;
+    a.reserve_sms = 2;
+    a.reverse = iter & 1;
+    a.l2_keep_mb = MV_L2_KEEP_MB;
+    int rc = mv_launch(a, st);
+    if (rc != XT_OK) return rc;
+    ++napply;
+    // 2. the verdict of the previous iteration's check, consumed here on every rank (its Rayleigh-Ritz ran next to
+    //    the matvec above)
+    if (iter > 1) {
+      const int pp = (iter - 1) % NSLOT;
+      if (ev_used[pp]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[pp], 0));
+      latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter - 1); XT_LAUNCHED();
+      latched_upto = iter - 1;
+    }
+    // 3. expansion (the basis has room for one block beyond max_basis)
+    if (ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));     // slot `par` (Lsave, Sk, theta) is free
+    double* Lout = W.Lsave + (size_t)par * SE_MAXK * SE_MAXK;
+    rc = launch_sh(m, AV + j * blk, V + (int64_t)(m / k) * blk, cur ^ 1, 1, Lout, iter);
+    if (rc != XT_OK) return rc;
+    // 4. Rayleigh-Ritz + stop test of this iteration (replicated; side stream unless a restart needs it now)
+    const bool last = iter >= g->max_niter;
+    const bool restart = !last && (m + k > mb);
+    const int nev = restart ? keep : k;
+    const EigPlan pl = eig_plan(m, nev);
+    XT_REQUIRE(pl.inv_slots >= 1, "symeig(sharded): projected problem %d x %d (nev=%d) exceeds the on-chip eigensolver", m, m, nev);
+    cudaStream_t rs = side[iter & 1];
+    XT_CUDA_OK(cudaEventRecord(evC[par], st));
+    XT_CUDA_OK(cudaStreamWaitEvent(rs, evC[par], 0));
+    CheckArgs chk;
+    memset(&chk, 0, sizeof(chk));
+    chk.Q = Qfull[cur ^ 1]; chk.L = Lout; chk.n = n; chk.is_f64 = sizeof(TV) == 8 ? 1 : 0;
+    chk.Sbest = W.Sbest; chk.evals_best = W.evals_best; chk.min_eps = (float)g->min_eps;
+    chk.seq = ++check_seq;
+    rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, nullptr, m, k, nev, W.Tw[iter & 1], W.Sk[par], W.theta[par],
+                                                      g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots, W.ctl,
+                                                      iter, chk); XT_LAUNCHED();
+    XT_CUDA_OK(cudaEventRecord(evR[par], rs));
+    ev_used[par] = true;
+    XT_CUDA_OK(cudaGetLastError());
+    if (last) break;
+    if (restart) {
+      // thick restart: this iteration's Ritz pairs are needed now.  Everything below acts on local rows only.
+      rc = settle();
+      if (rc != XT_OK) return rc;
+      latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter); XT_LAUNCHED();
+      latched_upto = iter;
+      const size_t rt_smem = (size_t)RT_ROWS * m * sizeof(double);
+      const int rtg = (n_loc + RT_ROWS - 1) / RT_ROWS;
+      const int64_t tot = (int64_t)n_loc * keep;
+      for (int which = 0; which < 2; ++which) {
+        TV* arr = which == 0 ? V : AV;
+        if (rt_smem <= 200 * 1024) {
+          rotate_tiled_kernel<TV><<<rtg, 256, rt_smem, st>>>(arr, n_loc, k, m, W.Sk[par], keep, Vtmp, W.ctl);
+        } else {
+          rotate_kernel<TV><<<(int)((tot + SE_THREADS - 1) / SE_THREADS), SE_THREADS, 0, st>>>(arr, n_loc, k, m, W.Sk[par],
+                                                                                               keep, Vtmp, W.ctl);
+        }
+        XT_LAUNCHED();
+        XT_CUDA_OK(cudaMemcpyAsync(arr, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
+      }
+      restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.theta[par], keep, W.ctl); XT_LAUNCHED();
+      XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, V + (int64_t)(m / k) * blk, (size_t)blk * sizeof(TV),
+                                 cudaMemcpyDeviceToDevice, st));
+      m = keep + k;
+    } else {
+      m += k;
+    }
+    cur ^= 1;
+    XT_CUDA_OK(cudaEventRecord(pool.it[iter % (LOOKAHEAD + 1)], st));
+    XT_CUDA_OK(cudaGetLastError());
+  }
+  for (int q = 0; q < NSLOT; ++q)
+    if (ev_used[q]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[q], 0));
+  (void)latched_upto;
+  output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n_loc, k,
+                                               static_cast<TV*>(g->evecs), g->ldv, static_cast<TV*>(g->evals), 0, W.ctl,
+                                               pool.hflag_dev + 8, ++pool.res_seq); XT_LAUNCHED();
+  EigCtl h;
+  bool have_res = false;
+  {
+    volatile int* hr = pool.hflag + 8;
+    const auto w0 = std::chrono::steady_clock::now();
+    while (true) {
+      if (hr[0] == pool.res_seq) { have_res = true; break; }
+      if (std::chrono::steady_clock::now() - w0 > std::chrono::milliseconds(2)) {
+        if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == pool.res_seq); break; }
+      }
+    }
+    if (have_res) {
+      h.converged = hr[1]; h.niter = hr[2]; h.breakdown = hr[3];
+      int bits = hr[4];
+      memcpy(&h.best_resid, &bits, sizeof(float));
+    }
+  }
+  if (!have_res) {
+    XT_CUDA_OK(cudaMemcpyAsync(&h, W.ctl, offsetof(EigCtl, trace), cudaMemcpyDeviceToHost, st));
+    XT_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  if (h.breakdown == 2) {
+    set_last_error("symeig(sharded): a peer did not answer within the time-out (rank %d of %d)", rank, world);
+    return XT_ERR_CUDA;
+  }
+  if (g->niter_out) *g->niter_out = h.niter;
+  if (g->converged_out) *g->converged_out = h.converged ? 1 : 0;
+  if (g->best_resid_out) *g->best_resid_out = h.best_resid;
+  if (g->napply_out) *g->napply_out = napply;
+  return XT_OK;
+}
+
 }  // namespace xt
 
 extern "C" {
@@ -2649,7 +3225,32 @@ int xt_symeig_krylov(const xt_symeig_args* g) {
   XT_REQUIRE((g->A || g->apply) && g->V0 && g->evals && g->evecs && g->workspace, "symeig: null pointer");
   XT_REQUIRE(g->mode == 0 || g->mode == 1, "symeig: mode must be 0 (lowest) or 1 (uppest)");
   XT_REQUIRE(g->max_basis <= 1024, "symeig: max_basis=%d exceeds 1024", g->max_basis);
+  if (g->peers != nullptr)
+    return g->dtype == XT_F64 ? xt::run_symeig_sharded<double>(g) : xt::run_symeig_sharded<float>(g);
   return g->dtype == XT_F64 ? xt::run_symeig<double>(g) : xt::run_symeig<float>(g);
+}
+
+static bool sharded_dims(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world, int* mb_out) {
+  if (dtype != XT_F32 && dtype != XT_F64) return false;
+  if (neig < 1 || neig > xt::SE_MAXK || world < 1 || world > XT_MAX_WORLD || n < 1 || n % world != 0) return false;
+  int mb = max_basis > 128 ? 128 : max_basis;
+  mb = (mb / neig) * neig;
+  if (mb < 4 * neig || n < 2 * mb) return false;
+  *mb_out = mb;
+  return true;
+}
+size_t xt_symeig_sharded_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world) {
+  int mb = 0;
+  if (!sharded_dims(dtype, n, neig, max_basis, world, &mb)) return 0;
+  xt::Arena ar(nullptr, 0);
+  xt::ShardWs W;
+  xt::carve_sharded(ar, W, dtype == XT_F64 ? 8 : 4, n / world, neig, mb);
+  return ar.off + 256;
+}
+size_t xt_symeig_peer_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world) {
+  int mb = 0;
+  if (!sharded_dims(dtype, n, neig, max_basis, world, &mb)) return 0;
+  return xt::peer_layout(dtype == XT_F64 ? 8 : 4, n, neig, mb, world).total;
 }
 
 int xt_small_eigh(const double* T, int32_t m, int32_t nev, int32_t mode, double* w_out, double* S_out, double* scratch,

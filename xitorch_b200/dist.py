@@ -12,7 +12,12 @@ One process per GPU, `torch.distributed` (NCCL over NVLink on the GPU box, gloo 
   `A_p = A[rows_p, :]`; every rank computes `Y_p = A_p X` with the block-matvec kernel from a replicated `X`
   and ONE all-gather per operator application assembles `Y` (N*k*s bytes: 4 MiB at N = 65536, k = 16).  The
   O(N m) subspace algebra is replicated on every rank (deterministic, no further collectives).
-  `symeig_row_partitioned` runs the block-Lanczos/Davidson engine on top of it.
+  `symeig_row_partitioned` runs the block-Lanczos/Davidson engine on top of it.  Two engines:
+  - "sharded" (default on CUDA): every rank keeps only its rows of the basis; the kernels exchange two small partial
+    sums and the new basis block per iteration by direct stores into the peers' memory (`PeerRegions`: cudaMalloc'ed
+    regions mapped into every rank with CUDA IPC) -- no collective call and no host round trip inside the iteration;
+  - "allgather": the whole O(N m) subspace algebra replicated, one NCCL all-gather per application issued from a
+    host callback (round-1 path, kept for comparison and for process groups without peer access).
 """
 from typing import Optional, Tuple
 
@@ -103,12 +108,98 @@ class RowPartitionedOperator(LinearOperator):
         return [prefix + "A_local"]
 
 
+class PeerRegions(object):
+    """one exchange region per rank, each mapped into every rank's address space.
+
+    `ptrs[r]` is the address in THIS process of rank r's region.  `create` allocates this rank's region with
+    `xt_peer_alloc` (cudaMalloc, zeroed), exchanges the CUDA IPC handles over the process group and opens the others.
+    `epoch` counts the solves that used the regions (the engine tags its flags with it; same on all ranks)."""
+
+    def __init__(self, ptrs, nbytes, rank, world, owner=None):
+        self.ptrs, self.nbytes, self.rank, self.world = list(ptrs), int(nbytes), rank, world
+        self.epoch = 0
+        self._owner = owner          # (own pointer, [opened peer pointers]) when created through xt_peer_*
+
+    @classmethod
+    def create(cls, nbytes: int, group=None):
+        import ctypes as C
+        from xitorch_b200 import _lib
+        rank, world = _world(group)
+        L = _lib.lib()
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(L.xt_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs, opened = [], []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own.value)
+                continue
+            pp = C.c_void_p()
+            _lib.check(L.xt_peer_open(C.create_string_buffer(handles[r], 64), C.byref(pp)), "peer_open")
+            ptrs.append(pp.value)
+            opened.append(pp.value)
+        if world > 1:
+            dist.barrier(group=group)
+        return cls(ptrs, nbytes, rank, world, owner=(own.value, opened))
+
+    def close(self, group=None):
+        if self._owner is None:
+            return
+        from xitorch_b200 import _lib
+        L = _lib.lib()
+        own, opened = self._owner
+        self._owner = None
+        torch.cuda.synchronize()
+        for pp in opened:
+            L.xt_peer_close(pp)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=group)           # nobody frees a region a peer still has mapped
+        L.xt_peer_free(own)
+
+
+_REGIONS = {}
+
+
+def _regions_for(nbytes: int, group=None) -> PeerRegions:
+    """exchange regions are allocated once per (group, size class) and reused by every solve"""
+    key = (id(group), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    reg = _REGIONS.get(key)
+    if reg is None or reg.nbytes < nbytes:
+        if reg is not None:
+            reg.close(group)
+        reg = PeerRegions.create(nbytes, group)
+        _REGIONS[key] = reg
+    return reg
+
+
+def release_regions(group=None):
+    """free the cached exchange regions (collective: call on every rank, before destroy_process_group)"""
+    for key in list(_REGIONS):
+        _REGIONS.pop(key).close(group)
+
+
 def symeig_row_partitioned(A_local: torch.Tensor, n: int, neig: int, mode: str = "lowest", method: str = "lanczos",
                            group=None, min_eps: float = 1e-6, max_niter: int = 1000,
                            max_basis: Optional[int] = None, check_every: Optional[int] = None,
-                           info: Optional[dict] = None):
-    """`neig` extreme eigenpairs of the row-partitioned operator; every rank returns the same result.
-    On CUDA this drives `xt_symeig_krylov` with its per-iteration all-gather hook."""
-    from xitorch_b200._impls.symeig import _krylov_row_partitioned
+                           info: Optional[dict] = None, engine: Optional[str] = None,
+                           regions: Optional[PeerRegions] = None, restart_keep: Optional[int] = None,
+                           gather: bool = True):
+    """`neig` extreme eigenpairs of the row-partitioned operator; every rank returns the same eigenvalues.
+
+    engine: "sharded" (row-sharded subspace algebra, in-kernel exchange over peer memory; needs method="lanczos") or
+            "allgather" (replicated algebra, one NCCL all-gather per application); None = sharded whenever it applies.
+    gather: with the sharded engine, all-gather the eigenvectors at the end (one collective per solve) so that every
+            rank returns the full (n, neig) block; False returns this rank's rows only."""
+    from xitorch_b200._impls.symeig import _krylov_row_partitioned, _krylov_row_sharded, _sharded_applies
+    if engine is None:
+        engine = "sharded" if (method == "lanczos" and _sharded_applies(A_local, n, neig, max_basis, group)) else "allgather"
+    if engine == "sharded":
+        return _krylov_row_sharded(A_local, n, neig, mode, group, min_eps, max_niter, max_basis, info, regions,
+                                   restart_keep, gather)
+    if engine != "allgather":
+        raise RuntimeError("Unknown engine: %s" % engine)
     return _krylov_row_partitioned(A_local, n, neig, mode, 1 if method == "lanczos" else 0, group, min_eps,
                                    max_niter, max_basis, check_every, info)
