@@ -238,13 +238,16 @@ inline void cp_async_wait_all() {}
 inline void sys_store_release(unsigned long long* p, unsigned long long v) {
   std::atomic_ref<unsigned long long>(*p).store(v, std::memory_order_release);
 }
+// (the loads below sit in spin loops: yield, or a few thousand emulated threads starve the one being waited for)
 inline unsigned long long sys_load_acquire(const unsigned long long* p) {
+  std::this_thread::yield();
   return std::atomic_ref<unsigned long long>(*const_cast<unsigned long long*>(p)).load(std::memory_order_acquire);
 }
 inline void sys_red_add_release(unsigned int* p, unsigned int v) {
   std::atomic_ref<unsigned int>(*p).fetch_add(v, std::memory_order_release);
 }
 inline unsigned int sys_load_acquire_u32(const unsigned int* p) {
+  std::this_thread::yield();
   return std::atomic_ref<unsigned int>(*const_cast<unsigned int*>(p)).load(std::memory_order_acquire);
 }
 inline void pdl_wait() {}

@@ -1719,6 +1719,11 @@ struct CheckArgs {
   double* evals_best;       // [k]
   float min_eps;
   int seq;                  // checks apply their bookkeeping in launch order: this one waits for ticket seq - 1
+  // row-sharded engine: Q / n are this rank's rows only and the maximum is completed over the ranks through the
+  // exchange regions: every rank stores (tag << 32 | float bits of its maximum) into slot seq & 3 of every region
+  int world, rank;
+  unsigned long long* vbuf[XT_MAX_WORLD];    // vbuf[q]: rank q's [4][world] verdict slots as mapped here (world > 1)
+  unsigned int tag;
 };
 
 // max |Q M| over all rows; M (k x k, row-major, shared memory).  fp32 arithmetic for fp32 blocks (the result is compared
@@ -1811,6 +1816,7 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
   if (tid == 0) flag_s = *reinterpret_cast<volatile int*>(&ctl->done);
   __syncthreads();
   bool stale = flag_s != 0;
+  __syncthreads();                       // flag_s is rewritten below (by thread 0) -- not before everybody has read it
   if (stale && !checking) return;
   double* lamv = dyn;                       // [nev]
   double* ysm = lamv + nev + (nev & 1);     // [m * nev] when it fits
@@ -1841,6 +1847,7 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
     if (tid == 0) flag_s = *reinterpret_cast<volatile int*>(&ctl->done);
     __syncthreads();
     stale = flag_s != 0;                 // aborted or overtaken: results are not needed any more
+    __syncthreads();                     // (same hazard as above)
   }
   if (!stale) {
     if (y_in_smem)
@@ -1864,6 +1871,31 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
     const float lmax = chk.is_f64 ? lanczos_resid_max<double>(static_cast<const double*>(chk.Q), chk.n, k, Ms)
                                   : lanczos_resid_max<float>(static_cast<const float*>(chk.Q), chk.n, k, Ms);
     rmax = block_max(lmax, redmax);
+    if (chk.world > 1) {
+      // every rank runs this kernel for the same iterations in the same state (the row-sharded driver consumes
+      // verdicts at fixed points of the main stream), so all of them arrive here
+      __shared__ float vmax_s[XT_MAX_WORLD];
+      const int slot = chk.seq & 3;
+      if (tid < chk.world) {
+        const unsigned long long mine = ((unsigned long long)chk.tag << 32) | (unsigned long long)__float_as_uint(rmax);
+        sys_store_release(chk.vbuf[tid] + (size_t)slot * chk.world + chk.rank, mine);
+        const unsigned long long* f = chk.vbuf[chk.rank] + (size_t)slot * chk.world + tid;
+        const long long t0 = clock64();
+        unsigned long long v = sys_load_acquire(f);
+        while ((unsigned int)(v >> 32) != chk.tag) {
+          if ((unsigned long long)(clock64() - t0) > 3000000000ull) { v = (unsigned long long)__float_as_uint(INFINITY); break; }
+          v = sys_load_acquire(f);
+        }
+        vmax_s[tid] = __uint_as_float((unsigned int)(v & 0xffffffffull));
+      }
+      __syncthreads();
+      float gm = 0.f;
+      for (int q = 0; q < chk.world; ++q) {
+        const float vq = vmax_s[q];
+        gm = (vq == vq) ? fmaxf(gm, vq) : INFINITY;
+      }
+      rmax = gm;
+    }
   }
   // bookkeeping in launch order (two Rayleigh-Ritz kernels can be in flight on the two side streams)
   if (tid == 0) {
@@ -2666,6 +2698,7 @@ struct PeerLayout {
   size_t xflag;         // [2 phases][world] u64: (epoch << 32 | sequence) of the partial last pushed by each rank
   size_t qcount;        // [4] u32, 64 B apart: arrivals of Q rows (one per CTA and launch), counter epoch & 3 in use
   size_t startflag;     // [world] u64: start-of-solve barrier
+  size_t vbuf;          // [4][world] u64: residual maxima of the row-sharded stop test (tag << 32 | float bits)
   size_t xcap;          // doubles per partial
   size_t total;
 };
@@ -2678,6 +2711,7 @@ static PeerLayout peer_layout(size_t vs, int n, int k, int mb, int world) {
   L.xflag = off; off += align_up((size_t)2 * world * sizeof(unsigned long long), 256);
   L.qcount = off; off += 4 * 64;
   L.startflag = off; off += align_up((size_t)world * sizeof(unsigned long long), 256);
+  L.vbuf = off; off += align_up((size_t)4 * world * sizeof(unsigned long long), 256);
   L.total = align_up(off, 4096);
   return L;
 }
@@ -3032,7 +3066,6 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     XT_REQUIRE(po_smem <= (size_t)PO_SMEM_MAX, "symeig(sharded): %d local rows per CTA do not fit in shared memory", po_R);
     if (m_ > 0) sa.flag[0] = etag | ++xseq;
     sa.flag[1] = etag | ++xseq;
-    if (getenv("XT_SH_DEBUG")) fprintf(stderr, "[sharded r%d] launch m=%d iter=%d qbuf=%d grid=%d smem=%zu\n", rank, m_, iter_, qbuf, sh_grid, po_smem);
     sa.qtarget = ++qlaunches * (unsigned int)(world * sh_grid);
     void* kargs[1] = {&sa};
     XT_CUDA_OK(cudaLaunchCooperativeKernel(sh_fn, dim3(sh_grid), dim3(PO_THREADS), kargs, po_smem, st));
@@ -3061,6 +3094,11 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
   bool ev_used[NSLOT] = {false, false, false};
   int check_seq = 0;
   int latched_upto = 0;
+  const int nbk = mb / k;                 // block index of the spare slot of V / AV
+  // thick restart, deferred by one matvec: the iteration that fills the basis only requests `keep` Ritz pairs from its
+  // Rayleigh-Ritz kernel (side stream); the next iteration's matvec -- it needs nothing but the new block -- runs
+  // meanwhile, writing into the spare block, and the rotation follows it.  restart_m / restart_par: pending restart.
+  int restart_m = 0, restart_par = 0;
   // before anything that changes the basis: all checks done, a best pair held as coefficients becomes a stored block
   auto settle = [&]() -> int {
     for (int q = 0; q < NSLOT; ++q)
@@ -3081,16 +3119,16 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
       }
       if (*pool.hflag) { --iter; break; }
     }
-    const int j = m / k - 1;
     const int par = iter % NSLOT;
-    // 1. W = A_p Q_j
+    // 1. W = A_p Q_j  (into the spare block while a restart is pending: block j itself is about to be rotated away)
+    const int jw = restart_m ? nbk : m / k - 1;
     MvArgs a;
     memset(&a, 0, sizeof(a));
     a.dtype = g->dtype;
     a.nbatch = 1; a.nrows = n_loc; a.ncolsA = n; a.k = k;
     a.A = g->A; a.lda = g->lda; a.a_bstride = 0;
     a.X = Qfull[cur]; a.ldx = k; a.x_bstride = 0;
-    a.Y = AV + j * blk; a.ldy = k; a.y_bstride = 0;
+    a.Y = AV + jw * blk; a.ldy = k; a.y_bstride = 0;
     a.done_flag = &W.ctl->done_latched;
     a.reserve_sms = 2;
     a.reverse = iter & 1;
@@ -3106,12 +3144,41 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
       latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter - 1); XT_LAUNCHED();
       latched_upto = iter - 1;
     }
+    if (restart_m) {
+      // 2b. the pending thick restart (local rows only; every kernel returns at once if the solve has just stopped)
+      const int mo = restart_m;
+      rc = settle();
+      if (rc != XT_OK) return rc;
+      const size_t rt_smem = (size_t)RT_ROWS * mo * sizeof(double);
+      const int rtg = (n_loc + RT_ROWS - 1) / RT_ROWS;
+      const int64_t tot = (int64_t)n_loc * keep;
+      for (int which = 0; which < 2; ++which) {
+        TV* arr = which == 0 ? V : AV;
+        if (rt_smem <= 200 * 1024) {
+          rotate_tiled_kernel<TV><<<rtg, 256, rt_smem, st>>>(arr, n_loc, k, mo, W.Sk[restart_par], keep, Vtmp, W.ctl);
+        } else {
+          rotate_kernel<TV><<<(int)((tot + SE_THREADS - 1) / SE_THREADS), SE_THREADS, 0, st>>>(arr, n_loc, k, mo,
+                                                                                               W.Sk[restart_par], keep, Vtmp, W.ctl);
+        }
+        XT_LAUNCHED();
+        XT_CUDA_OK(cudaMemcpyAsync(arr, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
+      }
+      restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.theta[restart_par], keep, W.ctl); XT_LAUNCHED();
+      XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, V + (int64_t)(mo / k) * blk, (size_t)blk * sizeof(TV),
+                                 cudaMemcpyDeviceToDevice, st));
+      XT_CUDA_OK(cudaMemcpyAsync(AV + (int64_t)(keep / k) * blk, AV + (int64_t)nbk * blk, (size_t)blk * sizeof(TV),
+                                 cudaMemcpyDeviceToDevice, st));
+      m = keep + k;
+      restart_m = 0;
+    }
+    const int j = m / k - 1;
     // 3. expansion (the basis has room for one block beyond max_basis)
     if (ev_used[par]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[par], 0));     // slot `par` (Lsave, Sk, theta) is free
     double* Lout = W.Lsave + (size_t)par * SE_MAXK * SE_MAXK;
     rc = launch_sh(m, AV + j * blk, V + (int64_t)(m / k) * blk, cur ^ 1, 1, Lout, iter);
     if (rc != XT_OK) return rc;
-    // 4. Rayleigh-Ritz + stop test of this iteration (replicated; side stream unless a restart needs it now)
+    // 4. Rayleigh-Ritz + stop test of this iteration on a side stream: replicated small algebra on bit-identical T,
+    //    the residual maximum over this rank's rows of Q_{j+1} completed over the ranks inside the kernel
     const bool last = iter >= g->max_niter;
     const bool restart = !last && (m + k > mb);
     const int nev = restart ? keep : k;
@@ -3122,9 +3189,13 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     XT_CUDA_OK(cudaStreamWaitEvent(rs, evC[par], 0));
     CheckArgs chk;
     memset(&chk, 0, sizeof(chk));
-    chk.Q = Qfull[cur ^ 1]; chk.L = Lout; chk.n = n; chk.is_f64 = sizeof(TV) == 8 ? 1 : 0;
+    chk.Q = Qfull[cur ^ 1] + (int64_t)rank * n_loc * k; chk.L = Lout; chk.n = n_loc; chk.is_f64 = sizeof(TV) == 8 ? 1 : 0;
     chk.Sbest = W.Sbest; chk.evals_best = W.evals_best; chk.min_eps = (float)g->min_eps;
     chk.seq = ++check_seq;
+    chk.world = world; chk.rank = rank;
+    for (int q = 0; q < world; ++q) chk.vbuf[q] = reinterpret_cast<unsigned long long*>(base.peer[q] + base.lay.vbuf);
+    chk.tag = ((g->epoch & 0xffffu) << 16) | ((unsigned int)check_seq & 0xffffu);
+    if (chk.tag == 0u) chk.tag = 0x10000u;
     rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, nullptr, m, k, nev, W.Tw[iter & 1], W.Sk[par], W.theta[par],
                                                       g->mode, pl.lds, pl.as_in_smem, pl.y_in_smem, pl.inv_slots, W.ctl,
                                                       iter, chk); XT_LAUNCHED();
@@ -3133,29 +3204,8 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     XT_CUDA_OK(cudaGetLastError());
     if (last) break;
     if (restart) {
-      // thick restart: this iteration's Ritz pairs are needed now.  Everything below acts on local rows only.
-      rc = settle();
-      if (rc != XT_OK) return rc;
-      latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter); XT_LAUNCHED();
-      latched_upto = iter;
-      const size_t rt_smem = (size_t)RT_ROWS * m * sizeof(double);
-      const int rtg = (n_loc + RT_ROWS - 1) / RT_ROWS;
-      const int64_t tot = (int64_t)n_loc * keep;
-      for (int which = 0; which < 2; ++which) {
-        TV* arr = which == 0 ? V : AV;
-        if (rt_smem <= 200 * 1024) {
-          rotate_tiled_kernel<TV><<<rtg, 256, rt_smem, st>>>(arr, n_loc, k, m, W.Sk[par], keep, Vtmp, W.ctl);
-        } else {
-          rotate_kernel<TV><<<(int)((tot + SE_THREADS - 1) / SE_THREADS), SE_THREADS, 0, st>>>(arr, n_loc, k, m, W.Sk[par],
-                                                                                               keep, Vtmp, W.ctl);
-        }
-        XT_LAUNCHED();
-        XT_CUDA_OK(cudaMemcpyAsync(arr, Vtmp, (size_t)tot * sizeof(TV), cudaMemcpyDeviceToDevice, st));
-      }
-      restart_T_kernel<<<1, 256, 0, st>>>(W.T, mb, W.theta[par], keep, W.ctl); XT_LAUNCHED();
-      XT_CUDA_OK(cudaMemcpyAsync(V + (int64_t)(keep / k) * blk, V + (int64_t)(m / k) * blk, (size_t)blk * sizeof(TV),
-                                 cudaMemcpyDeviceToDevice, st));
-      m = keep + k;
+      restart_m = m;                      // carried out after the next matvec
+      restart_par = par;
     } else {
       m += k;
     }
