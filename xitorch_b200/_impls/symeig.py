@@ -401,7 +401,7 @@ def _krylov_row_sharded(A_local, n, neig, mode, group, min_eps, max_niter, max_b
                            % (n, neig, max_basis, world))
     if regions is None:
         from xitorch_b200.dist import _regions_for
-        regions = _regions_for(pbytes, group)
+        regions = _regions_for(pbytes, group, signature=(str(vdt), n, neig, int(max_basis)))
     if regions.nbytes < pbytes or regions.world != world:
         raise RuntimeError("exchange regions too small or made for another world size")
     regions.epoch += 1

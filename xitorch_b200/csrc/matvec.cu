@@ -1053,6 +1053,365 @@ static int launch_tc(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cu
   return XT_OK;
 }
 
+// ---------------------------------------------------------------------------- tcgen05 layout (fp32, k = 16)
+// The genuine tall-skinny GEMM of the path (block Lanczos with neig = 16, BASELINE config 5) on the fifth-generation
+// tensor cores.  The SIMT layouts are bound by FP32 issue at k = 16 (4.3 TB/s); here the products run as
+// error-compensated TF32 (the 3xTF32 scheme) with the accumulators in tensor memory:
+//     A = A_hi + A_lo,  X = X_hi + X_lo   (hi = the 19 leading bits the tensor core reads, lo = the exact remainder)
+//     Y ~= A_hi X_hi + (A_hi X_lo + A_lo X_hi)          (A_lo X_lo is below fp32 rounding)
+//   * A_hi costs nothing: kind::tf32 ignores the 13 low mantissa bits, so the RAW TMA tile (tile_rows x 32 floats per
+//     box, SWIZZLE_128B, 1024-byte aligned = the canonical K-major SW128 operand layout) is the A operand of
+//     D1 (+)= A_hi [X_hi | X_lo]   -- one tcgen05.mma M128 N32 K8 per k-step, A from shared memory (SS);
+//   * A_lo = A - trunc(A) is formed by four conversion warps (thread = row: 16 conflict-free LDS.128 of its row, AND +
+//     FSUB, one tcgen05.st of 64 columns) straight into TENSOR MEMORY and used as the A operand of
+//     D2 (+)= A_lo X_hi            -- M128 N16 K8, A from tensor memory (TS): it never touches shared memory again;
+//   * B = [X_hi | X_lo]^T (32 x 64 per stage, K-major SW128) is written by one warp from the bulk-copied X chunk;
+//   * the tensor core accumulates in fp32 with truncation, so D1 / D2 only ever hold MV5_FLUSH stages: four epilogue
+//     warps (thread = row) drain them with tcgen05.ld into round-to-nearest fp32 running sums while the issuer fills the
+//     other accumulator pair, and apply the common row epilogue (shift, store, partial dots) at tile end.
+// Roles (12 warps): 0 TMA producer, 1 TMEM allocation + MMA issue (one thread), 2 B staging, 4-7 A_lo conversion,
+// 8-11 epilogue (warp % 4 selects the 32 TMEM lanes a warp may touch).  mbarriers: full (TMA), bready (B tile), aready
+// (A_lo in TMEM), empty (tcgen05.commit: stage and A_lo slot reusable), accfull / accempty (accumulator pair hand-over).
+constexpr int MV5_XRAW = 64 * 16 * 4;                                  // raw X chunk: 64 k-rows x 16 columns fp32
+constexpr int MV5_BTILE = 2 * 32 * 128;                                // [2 k-slabs][32 rows (hi | lo)][128 B]
+constexpr int MV5_STAGE_BYTES = MV_STAGE_A_BYTES + MV5_XRAW + MV5_BTILE;   // 45056 = 44 * 1024
+constexpr int MV5_FLUSH = 2;                                           // stages per accumulator window
+constexpr int MV5_THREADS = 384;
+static_assert(MV5_STAGE_BYTES % 1024 == 0, "stage alignment");
+
+__device__ __forceinline__ uint64_t mv5_smem_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B canonical layout: rows 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (= 1),
+  // descriptor version 1 (Blackwell), layout type 2
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ constexpr uint32_t mv5_idesc(int n) {
+  // D = F32, A = B = TF32, both K-major, M = 128
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mv5_mma_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc),
+      "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mv5_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db),
+      "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mv5_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mv5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mv5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define MV5_R16(a, o) "=r"(a[o + 0]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), \
+                      "=r"(a[o + 6]), "=r"(a[o + 7]), "=r"(a[o + 8]), "=r"(a[o + 9]), "=r"(a[o + 10]), "=r"(a[o + 11]), \
+                      "=r"(a[o + 12]), "=r"(a[o + 13]), "=r"(a[o + 14]), "=r"(a[o + 15])
+#define MV5_W16(a, o) "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), \
+                      "r"(a[o + 6]), "r"(a[o + 7]), "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), \
+                      "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]), "r"(a[o + 15])
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void mv5_ld16(uint32_t taddr, uint32_t (&v)[48], int o) {
+  if (o == 0)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : MV5_R16(v, 0) : "r"(taddr) : "memory");
+  else if (o == 16)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : MV5_R16(v, 16) : "r"(taddr) : "memory");
+  else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : MV5_R16(v, 32) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void mv5_st16(uint32_t taddr, const uint32_t (&v)[64], int o) {
+#define MV5_ST(O)                                                                                                     \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), MV5_W16(v, O) : "memory")
+  if (o == 0) MV5_ST(0);
+  else if (o == 16) MV5_ST(16);
+  else if (o == 32) MV5_ST(32);
+  else MV5_ST(48);
+#undef MV5_ST
+}
+
+__global__ void __launch_bounds__(MV5_THREADS, 1)
+mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
+  using TA = float;
+  using TV = float;
+  constexpr int K = 16, BOXC = 32, KC = 64;
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * MV5_STAGE_BYTES);
+  uint64_t* full = bars;                 // [NS]
+  uint64_t* empty = full + NS;           // [NS]
+  uint64_t* bready = empty + NS;         // [NS]
+  uint64_t* aready = bready + NS;        // [NS]
+  uint64_t* accfull = aready + NS;       // [2]
+  uint64_t* accempty = accfull + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+  double* dscr = reinterpret_cast<double*>(tmem_slot + 4);      // [4 warps][2][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.ncolsA + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);           // one tcgen05.commit
+      mbar_init(&bready[s], 1);
+      mbar_init(&aready[s], 4);          // one arrival per conversion warp
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&accfull[b], 1);
+      mbar_init(&accempty[b], 4);        // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+  }
+  for (int s = 0; s < NS; ++s) {         // X slots start as zeros (ragged last chunk copies fewer bytes)
+    uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * MV5_STAGE_BYTES + MV_STAGE_A_BYTES);
+    for (int i = threadIdx.x; i < MV5_XRAW / 4; i += blockDim.x) xz[i] = 0u;
+  }
+  fence_proxy_async();
+  if (warp == 1) {                       // 512 TMEM columns: 2 x (32 + 16) accumulators, then NS x 64 of A_lo
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  mv5_fence_before();
+  __syncthreads();
+  mv5_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tm_acc = tmem_base;                 // + buf * 48: D1 (32 columns), + 32: D2 (16 columns)
+  const uint32_t tm_alo = tmem_base + 96;            // + slot * 64
+
+  if (warp == 0) {
+    if (lane == 0) mv_producer<TA, TV, K, MV5_STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t id32 = mv5_idesc(32), id16 = mv5_idesc(16);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t win = 0;                  // accumulator windows so far (pair = win & 1)
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int in_win = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const uint32_t buf = win & 1u;
+          if (in_win == 0) {
+            mbar_wait(&accempty[buf], ((win >> 1) & 1u) ^ 1u);      // the epilogue has drained this pair
+            mv5_fence_after();
+          }
+          mbar_wait(&full[s], ph);
+          mbar_wait(&bready[s], ph);
+          mbar_wait(&aready[s], ph);
+          mv5_fence_after();
+          const uint32_t a_s = smem_u32(stage_base + (size_t)s * MV5_STAGE_BYTES);
+          const uint32_t b_s = a_s + MV_STAGE_A_BYTES + MV5_XRAW;
+          const uint32_t d1 = tm_acc + buf * 48u, d2 = d1 + 32u;
+          const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+          const int nks = min(8, (p.ncolsA - kc + 7) / 8);          // k-steps of this chunk (ragged last chunk)
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t koff = (uint32_t)(ks >> 2) * (MV_TILE_ROWS * 128) + (uint32_t)(ks & 3) * 32u;
+            const uint32_t boff = (uint32_t)(ks >> 2) * (32 * 128) + (uint32_t)(ks & 3) * 32u;
+            const uint64_t da = mv5_smem_desc(a_s + koff);
+            const uint64_t db = mv5_smem_desc(b_s + boff);
+            const uint32_t acc = (in_win > 0 || ks > 0) ? 1u : 0u;
+            mv5_mma_ss(d1, da, db, id32, acc);                                        // A_hi [X_hi | X_lo]
+            mv5_mma_ts(d2, tm_alo + (uint32_t)s * 64u + (uint32_t)ks * 8u, db, id16, acc);   // A_lo X_hi
+          }
+          mv5_commit(&empty[s]);                                    // stage + A_lo slot reusable once these MMAs are done
+          ++in_win;
+          if (in_win == MV5_FLUSH || ch == nchunks - 1) {
+            mv5_commit(&accfull[buf]);
+            in_win = 0;
+            ++win;
+          }
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ B staging: X chunk -> [X_hi | X_lo]^T, K-major SW128
+    int s = 0;
+    uint32_t ph = 0;
+    const int n = lane & 15, kh = lane >> 4;               // column of X, parity of the k-row
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nchunks; ++ch) {
+        mbar_wait(&full[s], ph);                           // X chunk landed (the slot was free when the producer issued it)
+        uint8_t* st = stage_base + (size_t)s * MV5_STAGE_BYTES;
+        const float* xr = reinterpret_cast<const float*>(st + MV_STAGE_A_BYTES);
+        uint8_t* bt = st + MV_STAGE_A_BYTES + MV5_XRAW;
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) {                   // 16-byte chunk pairs: this lane does chunks 2 c2 + kh
+          const int c = 2 * c2 + kh;                       // chunk = 4 consecutive k-rows, 0..15 over the stage
+          float hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x = xr[(4 * c + q) * K + n];
+            const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            hi[q] = h;
+            lo[q] = x - h;
+          }
+          const int slab = c >> 3, cc = c & 7;
+          uint8_t* rowh = bt + slab * (32 * 128) + n * 128 + ((cc ^ (n & 7)) << 4);
+          uint8_t* rowl = rowh + 16 * 128;                 // rows 16..31 (same swizzle phase: (n + 16) & 7 == n & 7)
+          *reinterpret_cast<float4*>(rowh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(rowl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bready[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ A_lo conversion: thread = row
+    const int r = (warp - 4) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
+    const uint32_t sw = (uint32_t)(r & 7);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int ch = 0; ch < nchunks; ++ch) {
+        mbar_wait(&full[s], ph);
+        const uint32_t a_s = smem_u32(stage_base + (size_t)s * MV5_STAGE_BYTES) + (uint32_t)r * 128u;
+        uint32_t lo[64];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float4 v = lds128(a_s + (uint32_t)(c >> 3) * (MV_TILE_ROWS * 128) + ((((uint32_t)c & 7u) ^ sw) << 4));
+          const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float h = __uint_as_float(__float_as_uint(f[q]) & 0xffffe000u);
+            const float l = f[q] - h;
+            // rows past the tile hold stale bits (possibly NaN / Inf patterns): their products stay in their own
+            // accumulator rows, which are never stored
+            lo[4 * c + q] = __float_as_uint(l);
+          }
+        }
+        // (the TMEM slot s was released together with the shared-memory stage: the producer's wait on empty[s] precedes
+        //  the TMA issue that completed full[s])
+        const uint32_t t = tm_alo + (uint32_t)s * 64u + lane_addr;
+        mv5_st16(t, lo, 0);
+        mv5_st16(t + 16, lo, 16);
+        mv5_st16(t + 32, lo, 32);
+        mv5_st16(t + 48, lo, 48);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        mv5_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aready[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue: thread = row
+    const int ew = warp - 8;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    uint32_t win = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+      const int rows = min(p.tile_rows, p.nrows - row0);
+      float y[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) y[i] = 0.f;
+      const int nwin = (nchunks + MV5_FLUSH - 1) / MV5_FLUSH;
+      for (int w = 0; w < nwin; ++w, ++win) {
+        const uint32_t buf = win & 1u;
+        mbar_wait(&accfull[buf], (win >> 1) & 1u);
+        mv5_fence_after();
+        uint32_t v[48];
+        const uint32_t t = tm_acc + buf * 48u + lane_addr;
+        mv5_ld16(t, v, 0);
+        mv5_ld16(t + 16, v, 16);
+        mv5_ld16(t + 32, v, 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        mv5_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&accempty[buf]);
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          y[i] += __uint_as_float(v[i]) + (__uint_as_float(v[16 + i]) + __uint_as_float(v[32 + i]));   // round to nearest
+      }
+      double d0[K], d1[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) { d0[i] = 0.0; d1[i] = 0.0; }
+      if (r < rows) row_epilogue<TV, K>(p, b, (int64_t)row0 + r, y, d0, d1);
+      if (p.dot_out != nullptr) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          d0[i] = warp_sum(d0[i]);
+          d1[i] = warp_sum(d1[i]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            dscr[(ew * 2 + 0) * K + i] = d0[i];
+            dscr[(ew * 2 + 1) * K + i] = d1[i];
+          }
+        }
+        named_bar_sync(1, 128);
+        const int tc = ew * 32 + lane;
+        if (tc < 2 * K) {
+          const int which = tc / K, i = tc - which * K;
+          double sum = 0.0;
+          for (int q = 0; q < 4; ++q) sum += dscr[(q * 2 + which) * K + i];
+          p.dot_out[((size_t)tile * 2 + which) * MV_MAXK + i] = sum;
+        }
+        named_bar_sync(1, 128);
+      }
+    }
+  }
+  // ---- teardown: every role is done with tensor memory
+  mv5_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    mv5_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+static int launch_tc5(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
+  const size_t fixed = (size_t)(4 * 8 + 4) * sizeof(uint64_t) + 16 + 4 * 2 * 16 * sizeof(double) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / MV5_STAGE_BYTES);
+  if (ns > 5) ns = 5;
+  if (ns > 6) ns = 6;                    // A_lo slots: 96 + 64 ns <= 512 columns
+  if (ns < 2) {
+    set_last_error("matvec: not enough shared memory for 2 stages");
+    return XT_ERR_INVALID;
+  }
+  const size_t smem = (size_t)ns * MV5_STAGE_BYTES + fixed;
+  MvDev dev = dev0;
+  dev.nstages = ns;
+  CUtensorMap tm;
+  bool batched = false;
+  int rc = make_tmap(a, til.tile_rows, &tm, &batched);
+  if (rc != XT_OK) return rc;
+  dev.a_batched = batched ? 1 : 0;
+  dev.x_bulk = 1;
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
+    XT_CUDA_OK(set_max_dyn_smem(mv_tma_tc5_kernel));
+    attr_once.mark();
+  }
+  prof_mv_begin(st);
+  mv_tma_tc5_kernel<<<til.grid, MV5_THREADS, smem, st>>>(tm, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
 // ---------------------------------------------------------------------------- plain-load kernel
 // one CTA per tile (same tiling => same dot layout), one warp per row, lanes stride the columns.
 template <typename TA, typename TV>
@@ -1240,6 +1599,17 @@ static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cu
       return XT_ERR_INVALID;
     }
     if (a.impl == 6) return launch_tc(a, dev, til, st);
+    // impl == 7: tcgen05 / TMEM form of the same 3xTF32 scheme (k = 16, contiguous X); XT_MV_TC5=1 makes it the default
+    // for such blocks
+    {
+      static const int tc5_default = (getenv("XT_MV_TC5") != nullptr && atoi(getenv("XT_MV_TC5")) != 0) ? 1 : 0;
+      const bool tc5_ok = a.k == 16 && x_bulk_ok<float, 16>(a);
+      if (a.impl == 7 && !tc5_ok) {
+        set_last_error("matvec: the tcgen05 layout takes k = 16 with a contiguous, 16-byte aligned X");
+        return XT_ERR_INVALID;
+      }
+      if (a.impl == 7 || (a.impl == 0 && tc5_default && tc5_ok)) return launch_tc5(a, dev, til, st);
+    }
     if (a.impl == 4 && a.k > 4) {
       if (a.k <= 8) return launch_colslice<8>(a, dev, til, st);
       return launch_colslice<16>(a, dev, til, st);

@@ -160,16 +160,23 @@ class PeerRegions(object):
         L.xt_peer_free(own)
 
 
-_REGIONS = {}
+_REGIONS = {}          # (group, device, layout signature) -> PeerRegions, at most _REGIONS_MAX of them
 
 
-def _regions_for(nbytes: int, group=None) -> PeerRegions:
-    """exchange regions are allocated once per (group, size class) and reused by every solve"""
-    key = (id(group), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+_REGIONS_MAX = 4
+
+
+def _regions_for(nbytes: int, group=None, signature=()) -> PeerRegions:
+    """exchange regions are allocated once per (group, device, problem signature) and reused by every solve with that
+    signature.  The signature (dtype, n, neig, max_basis) fixes the LAYOUT of a region: its flags are monotone counters
+    that are never reset, so a region must not be reinterpreted with another layout.  Collective: every rank calls this
+    with the same arguments in the same order (creation and eviction contain barriers)."""
+    key = (id(group), torch.cuda.current_device() if torch.cuda.is_available() else -1, tuple(signature))
     reg = _REGIONS.get(key)
-    if reg is None or reg.nbytes < nbytes:
-        if reg is not None:
-            reg.close(group)
+    if reg is None:
+        if len(_REGIONS) >= _REGIONS_MAX:
+            oldest = next(iter(_REGIONS))
+            _REGIONS.pop(oldest).close(group)
         reg = PeerRegions.create(nbytes, group)
         _REGIONS[key] = reg
     return reg
