@@ -144,3 +144,24 @@ def test_matvec_tensor_core_layout(n, rows, k):
     refs = A.double() @ Xs.double()
     rel = ((ys.double().cpu() - refs).abs() / (A.double().abs() @ Xs.double().abs())).max().item()
     assert rel <= 2e-6, rel
+
+
+@pytest.mark.parametrize("nr,nc", [(128, 64), (1000, 1000), (4096, 4096), (148 * 128 + 5, 2048 + 40), (8192, 16384)])
+def test_matvec_k16_tcgen05(nr, nc):
+    """fp32 k = 16 on the fifth-generation tensor cores (impl = 7: tcgen05.mma kind::tf32, operands and accumulators in
+    tensor memory, error-compensated 3xTF32): the SIMT kernels' tolerance, ragged tiles and ragged last chunk, shift and
+    fused dots through the common row epilogue."""
+    g = torch.Generator().manual_seed(nr + nc)
+    A = torch.randn(nr, nc, generator=g)
+    X = torch.randn(nc, 16, generator=g)
+    y = _dense.block_matvec(A.to(DEV), X.to(DEV), impl=7)
+    ref = A.double() @ X.double()
+    bound = A.double().abs() @ X.double().abs()
+    assert ((y.cpu().double() - ref).abs() / bound).max().item() <= 2e-6
+    y3 = _dense.block_matvec(A.to(DEV), X.to(DEV), impl=3)
+    assert ((y.cpu().double() - y3.cpu().double()).abs() / bound).max().item() <= 2e-6
+    if nr == nc:
+        E = torch.randn(16, generator=g)
+        ye = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), impl=7)
+        refe = ref - X.double() * E.double()
+        assert ((ye.cpu().double() - refe).abs() / (bound + (X.double() * E.double()).abs())).max().item() <= 2e-6

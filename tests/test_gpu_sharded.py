@@ -35,9 +35,10 @@ def test_sharded_world1_matches_dense_engine(n, neig, dtype, eps):
     assert ((ev.double() - ev1.double()).abs() / ref.abs()).max().item() <= 1e-5
     assert (A.double() @ vec.double() - vec.double() * ev.double()).abs().max().item() <= 20 * eps
     assert (vec.double().t() @ vec.double() - torch.eye(neig, device="cuda", dtype=torch.float64)).abs().max().item() <= 1e-5
-    # a second solve on the same exchange regions (next epoch) reproduces the first bit for bit
+    # a second solve on the same exchange regions (next epoch) reproduces the first (up to the summation order of the
+    # fp64 atomics inside one rank; ACROSS ranks the values are bit-identical, see the world-2 test)
     ev2, _ = xd.symeig_row_partitioned(A, n, neig, min_eps=eps, engine="sharded")
-    assert torch.equal(ev, ev2)
+    assert ((ev.double() - ev2.double()).abs() / ref.abs()).max().item() <= 1e-6 * (1 if dtype == torch.float32 else 1e-4)
 
 
 def test_sharded_restart_keeps_converging():

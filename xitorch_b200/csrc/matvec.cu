@@ -179,6 +179,7 @@ struct MvDev {
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
   int pdl;          // launched as a programmatic dependent: see MvArgs.pdl
+  int dbg;          // tcgen05 kernel: XT_TC5_DBG bit mask that switches single roles off (timing experiments only)
 };
 
 template <typename TA> struct ElemTraits;
@@ -1055,29 +1056,29 @@ static int launch_tc(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cu
 
 // ---------------------------------------------------------------------------- tcgen05 layout (fp32, k = 16)
 // The genuine tall-skinny GEMM of the path (block Lanczos with neig = 16, BASELINE config 5) on the fifth-generation
-// tensor cores.  The SIMT layouts are bound by FP32 issue at k = 16 (4.3 TB/s); here the products run as
-// error-compensated TF32 (the 3xTF32 scheme) with the accumulators in tensor memory:
+// tensor cores.  The SIMT layouts are bound by FP32 issue at k = 16 (4.2 TB/s); here the products run as
+// error-compensated TF32 (the 3xTF32 scheme) with operands AND accumulators in tensor memory:
 //     A = A_hi + A_lo,  X = X_hi + X_lo   (hi = the 19 leading bits the tensor core reads, lo = the exact remainder)
 //     Y ~= A_hi X_hi + (A_hi X_lo + A_lo X_hi)          (A_lo X_lo is below fp32 rounding)
-//   * A_hi costs nothing: kind::tf32 ignores the 13 low mantissa bits, so the RAW TMA tile (tile_rows x 32 floats per
-//     box, SWIZZLE_128B, 1024-byte aligned = the canonical K-major SW128 operand layout) is the A operand of
-//     D1 (+)= A_hi [X_hi | X_lo]   -- one tcgen05.mma M128 N32 K8 per k-step, A from shared memory (SS);
-//   * A_lo = A - trunc(A) is formed by four conversion warps (thread = row: 16 conflict-free LDS.128 of its row, AND +
-//     FSUB, one tcgen05.st of 64 columns) straight into TENSOR MEMORY and used as the A operand of
-//     D2 (+)= A_lo X_hi            -- M128 N16 K8, A from tensor memory (TS): it never touches shared memory again;
-//   * B = [X_hi | X_lo]^T (32 x 64 per stage, K-major SW128) is written by one warp from the bulk-copied X chunk;
-//   * the tensor core accumulates in fp32 with truncation, so D1 / D2 only ever hold MV5_FLUSH stages: four epilogue
+//   * four conversion warps (thread = row) read the TMA tile (tile_rows x 32 floats per box, SWIZZLE_128B: 16 conflict-
+//     free LDS.128 per row and stage) and write the RAW row (kind::tf32 ignores the 13 low mantissa bits: that is A_hi) and
+//     A_lo = A - trunc(A) into TENSOR MEMORY with tcgen05.st -- the shared-memory stage is free again as soon as they
+//     are through, the tensor core never reads A from shared memory;
+//   * B = [X_hi | X_lo]^T (32 x 64 per chunk, K-major SW128) is written by one warp from the bulk-copied X chunk into a
+//     small ring of its own;
+//   * one thread issues, per 8 columns of A:  D1 (+)= A_hi [X_hi | X_lo]  (M128 N32 K8)  and  D2 (+)= A_lo X_hi  (M128
+//     N16 K8), both with A from tensor memory;
+//   * the tensor core accumulates in fp32 with truncation, so D1 / D2 only ever hold MV5_FLUSH chunks: four epilogue
 //     warps (thread = row) drain them with tcgen05.ld into round-to-nearest fp32 running sums while the issuer fills the
 //     other accumulator pair, and apply the common row epilogue (shift, store, partial dots) at tile end.
-// Roles (12 warps): 0 TMA producer, 1 TMEM allocation + MMA issue (one thread), 2 B staging, 4-7 A_lo conversion,
-// 8-11 epilogue (warp % 4 selects the 32 TMEM lanes a warp may touch).  mbarriers: full (TMA), bready (B tile), aready
-// (A_lo in TMEM), empty (tcgen05.commit: stage and A_lo slot reusable), accfull / accempty (accumulator pair hand-over).
+// Two rings: NS shared-memory stages (TMA -> conversion / B staging) and MV5_NT tensor-memory operand slots + B tiles
+// (conversion / B staging -> MMA).  Roles (12 warps): 0 TMA producer, 1 TMEM allocation + MMA issue (one thread),
+// 2 B staging, 4-7 conversion, 8-11 epilogue (warp % 4 selects the 32 TMEM lanes a warp may touch).
 constexpr int MV5_XRAW = 64 * 16 * 4;                                  // raw X chunk: 64 k-rows x 16 columns fp32
 constexpr int MV5_BTILE = 2 * 32 * 128;                                // [2 k-slabs][32 rows (hi | lo)][128 B]
-constexpr int MV5_STAGE_BYTES = MV_STAGE_A_BYTES + MV5_XRAW + MV5_BTILE;   // 45056 = 44 * 1024
-constexpr int MV5_FLUSH = 2;                                           // stages per accumulator window
+constexpr int MV5_NT = 3;                                              // operand slots: 96 + 3 x 128 TMEM columns
+constexpr int MV5_FLUSH = 2;                                           // chunks per accumulator window
 constexpr int MV5_THREADS = 384;
-static_assert(MV5_STAGE_BYTES % 1024 == 0, "stage alignment");
 
 __device__ __forceinline__ uint64_t mv5_smem_desc(uint32_t saddr) {
   // K-major, SWIZZLE_128B canonical layout: rows 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (= 1),
@@ -1141,20 +1142,24 @@ __device__ __forceinline__ void mv5_st16(uint32_t taddr, const uint32_t (&v)[64]
 
 __global__ void __launch_bounds__(MV5_THREADS, 1)
 mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
-  using TA = float;
   using TV = float;
-  constexpr int K = 16, BOXC = 32, KC = 64;
+  constexpr int K = 16, BOXC = 32, KC = 64, NT = MV5_NT;
+#define MV5_WAIT(bar, par) mbar_wait(bar, par)
   if (p.done_flag != nullptr && *p.done_flag != 0) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.nstages;
+  const uint32_t box_tx = (uint32_t)p.tile_rows * 128u;                 // bytes one TMA box delivers
+  const uint32_t box_bytes = ((uint32_t)p.tile_rows + 7u) / 8u * 1024u; // its slot: whole 8-row swizzle atoms (1024-byte aligned)
+  const uint32_t stage_bytes = 2u * box_bytes + MV5_XRAW;
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * MV5_STAGE_BYTES);
-  uint64_t* full = bars;                 // [NS]
-  uint64_t* empty = full + NS;           // [NS]
-  uint64_t* bready = empty + NS;         // [NS]
-  uint64_t* aready = bready + NS;        // [NS]
-  uint64_t* accfull = aready + NS;       // [2]
+  uint8_t* bring = smem + (size_t)NS * stage_bytes;                    // [NT][MV5_BTILE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + (size_t)NT * MV5_BTILE);
+  uint64_t* full = bars;                 // [NS]  TMA landed
+  uint64_t* empty = full + 8;            // [NS]  stage read by the 4 conversion warps + the B warp
+  uint64_t* tready = empty + 8;          // [NT]  operand slot written (4 conversion warps + B warp)
+  uint64_t* tfree = tready + 4;          // [NT]  operand slot consumed (tcgen05.commit)
+  uint64_t* accfull = tfree + 4;         // [2]
   uint64_t* accempty = accfull + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   double* dscr = reinterpret_cast<double*>(tmem_slot + 4);      // [4 warps][2][K]
@@ -1164,9 +1169,11 @@ mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);           // one tcgen05.commit
-      mbar_init(&bready[s], 1);
-      mbar_init(&aready[s], 4);          // one arrival per conversion warp
+      mbar_init(&empty[s], 5);
+    }
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(&tready[t], 5);
+      mbar_init(&tfree[t], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&accfull[b], 1);
@@ -1175,12 +1182,12 @@ mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     fence_mbar_init();
     prefetch_tmap(&tmA);
   }
-  for (int s = 0; s < NS; ++s) {         // X slots start as zeros (ragged last chunk copies fewer bytes)
-    uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * MV5_STAGE_BYTES + MV_STAGE_A_BYTES);
+  for (int s = 0; s < NS; ++s) {         // X slots start as zeros (a ragged last chunk copies fewer bytes)
+    uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * stage_bytes + 2u * box_bytes);
     for (int i = threadIdx.x; i < MV5_XRAW / 4; i += blockDim.x) xz[i] = 0u;
   }
   fence_proxy_async();
-  if (warp == 1) {                       // 512 TMEM columns: 2 x (32 + 16) accumulators, then NS x 64 of A_lo
+  if (warp == 1) {                       // 512 TMEM columns: 2 x (32 + 16) accumulators, then NT x (64 A_hi + 64 A_lo)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -1189,126 +1196,162 @@ mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   mv5_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   const uint32_t tm_acc = tmem_base;                 // + buf * 48: D1 (32 columns), + 32: D2 (16 columns)
-  const uint32_t tm_alo = tmem_base + 96;            // + slot * 64
+  const uint32_t tm_op = tmem_base + 96;             // + slot * 128: A_hi (64 columns), + 64: A_lo
 
   if (warp == 0) {
-    if (lane == 0) mv_producer<TA, TV, K, MV5_STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks);
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      const char* Xg = reinterpret_cast<const char*>(p.X);
+      const uint64_t pol_first = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_batch;
+        const int row0 = (tile - b * p.tiles_per_batch) * p.tile_rows;
+        const int bA = p.a_batched ? b : 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
+          const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+          MV5_WAIT(&empty[s], ph ^ 1);
+          uint8_t* dst = stage_base + (size_t)s * stage_bytes;
+          const int cols = min(KC, p.ncolsA - kc);
+          const uint32_t xbytes = (uint32_t)(cols * K * (int)sizeof(TV));
+          mbar_arrive_expect_tx(&full[s], (uint32_t)nb * box_tx + xbytes);
+          for (int bx = 0; bx < nb; ++bx)
+            tma_load_3d(dst + (size_t)bx * box_bytes, &tmA, &full[s], kc + bx * BOXC, row0, bA,
+                        ch >= p.keep_from ? pol_keep : pol_first);
+          bulk_load_1d(dst + 2u * box_bytes, Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV),
+                       xbytes, &full[s]);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t id32 = mv5_idesc(32), id16 = mv5_idesc(16);
-      int s = 0;
-      uint32_t ph = 0;
+      const int flush = ((p.dbg >> 8) & 0xff) ? ((p.dbg >> 8) & 0xff) : MV5_FLUSH;
+      int t = 0;
+      uint32_t pt = 0;
       uint32_t win = 0;                  // accumulator windows so far (pair = win & 1)
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int in_win = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
           const uint32_t buf = win & 1u;
-          if (in_win == 0) {
-            mbar_wait(&accempty[buf], ((win >> 1) & 1u) ^ 1u);      // the epilogue has drained this pair
-            mv5_fence_after();
-          }
-          mbar_wait(&full[s], ph);
-          mbar_wait(&bready[s], ph);
-          mbar_wait(&aready[s], ph);
+          if (in_win == 0) MV5_WAIT(&accempty[buf], ((win >> 1) & 1u) ^ 1u);      // the epilogue has drained this pair
+          MV5_WAIT(&tready[t], pt);
           mv5_fence_after();
-          const uint32_t a_s = smem_u32(stage_base + (size_t)s * MV5_STAGE_BYTES);
-          const uint32_t b_s = a_s + MV_STAGE_A_BYTES + MV5_XRAW;
+          const uint32_t b_s = smem_u32(bring + (size_t)t * MV5_BTILE);
           const uint32_t d1 = tm_acc + buf * 48u, d2 = d1 + 32u;
+          const uint32_t ahi = tm_op + (uint32_t)t * 128u, alo = ahi + 64u;
           const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
           const int nks = min(8, (p.ncolsA - kc + 7) / 8);          // k-steps of this chunk (ragged last chunk)
 #pragma unroll 1
           for (int ks = 0; ks < nks; ++ks) {
-            const uint32_t koff = (uint32_t)(ks >> 2) * (MV_TILE_ROWS * 128) + (uint32_t)(ks & 3) * 32u;
             const uint32_t boff = (uint32_t)(ks >> 2) * (32 * 128) + (uint32_t)(ks & 3) * 32u;
-            const uint64_t da = mv5_smem_desc(a_s + koff);
             const uint64_t db = mv5_smem_desc(b_s + boff);
             const uint32_t acc = (in_win > 0 || ks > 0) ? 1u : 0u;
-            mv5_mma_ss(d1, da, db, id32, acc);                                        // A_hi [X_hi | X_lo]
-            mv5_mma_ts(d2, tm_alo + (uint32_t)s * 64u + (uint32_t)ks * 8u, db, id16, acc);   // A_lo X_hi
+            if (!(p.dbg & 2)) mv5_mma_ts(d1, ahi + (uint32_t)ks * 8u, db, id32, acc);      // A_hi [X_hi | X_lo]
+            if (!(p.dbg & 1)) mv5_mma_ts(d2, alo + (uint32_t)ks * 8u, db, id16, acc);      // A_lo X_hi
           }
-          mv5_commit(&empty[s]);                                    // stage + A_lo slot reusable once these MMAs are done
+          mv5_commit(&tfree[t]);                                    // operand slot + B tile reusable once these MMAs are done
           ++in_win;
-          if (in_win == MV5_FLUSH || ch == nchunks - 1) {
+          if (in_win == flush || ch == nchunks - 1) {
             mv5_commit(&accfull[buf]);
             in_win = 0;
             ++win;
           }
-          if (++s == NS) { s = 0; ph ^= 1; }
+          if (++t == NT) { t = 0; pt ^= 1; }
         }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ B staging: X chunk -> [X_hi | X_lo]^T, K-major SW128
-    int s = 0;
-    uint32_t ph = 0;
-    const int n = lane & 15, kh = lane >> 4;               // column of X, parity of the k-row
+    int s = 0, t = 0;
+    uint32_t ph = 0, pt = 0;
+    const int n = lane & 15, kh = lane >> 4;               // column of X, parity of the 16-byte chunk
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch) {
-        mbar_wait(&full[s], ph);                           // X chunk landed (the slot was free when the producer issued it)
-        uint8_t* st = stage_base + (size_t)s * MV5_STAGE_BYTES;
-        const float* xr = reinterpret_cast<const float*>(st + MV_STAGE_A_BYTES);
-        uint8_t* bt = st + MV_STAGE_A_BYTES + MV5_XRAW;
+        MV5_WAIT(&full[s], ph);
+        MV5_WAIT(&tfree[t], pt ^ 1);
+        const float* xr = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes + 2u * box_bytes);
+        uint8_t* bt = bring + (size_t)t * MV5_BTILE;
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) {                   // 16-byte chunk pairs: this lane does chunks 2 c2 + kh
-          const int c = 2 * c2 + kh;                       // chunk = 4 consecutive k-rows, 0..15 over the stage
-          float hi[4], lo[4];
+          for (int c2 = 0; c2 < 8; ++c2) {
+            const int c = 2 * c2 + kh;                     // chunk = 4 consecutive k-rows, 0..15 over the stage
+            float hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x = xr[(4 * c + q) * K + n];
-            const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-            hi[q] = h;
-            lo[q] = x - h;
+            for (int q = 0; q < 4; ++q) {
+              const float x = xr[(4 * c + q) * K + n];
+              const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+              hi[q] = h;
+              lo[q] = x - h;
+            }
+            const int slab = c >> 3, cc = c & 7;
+            uint8_t* rowh = bt + slab * (32 * 128) + n * 128 + ((cc ^ (n & 7)) << 4);
+            uint8_t* rowl = rowh + 16 * 128;               // rows 16..31 (same swizzle phase: (n + 16) & 7 == n & 7)
+            *reinterpret_cast<float4*>(rowh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(rowl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
-          const int slab = c >> 3, cc = c & 7;
-          uint8_t* rowh = bt + slab * (32 * 128) + n * 128 + ((cc ^ (n & 7)) << 4);
-          uint8_t* rowl = rowh + 16 * 128;                 // rows 16..31 (same swizzle phase: (n + 16) & 7 == n & 7)
-          *reinterpret_cast<float4*>(rowh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(rowl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bready[s]);
+        if (lane == 0) {
+          mbar_arrive(&tready[t]);
+          mbar_arrive(&empty[s]);
+        }
         if (++s == NS) { s = 0; ph ^= 1; }
+        if (++t == NT) { t = 0; pt ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ A_lo conversion: thread = row
+    // ------------------------------------------------------------------ conversion: thread = row, A_hi / A_lo -> TMEM
     const int r = (warp - 4) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
     const uint32_t sw = (uint32_t)(r & 7);
-    int s = 0;
-    uint32_t ph = 0;
+    const bool live = r < p.tile_rows;                     // rows past the tile: their TMEM lanes may hold anything
+    int s = 0, t = 0;
+    uint32_t ph = 0, pt = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       for (int ch = 0; ch < nchunks; ++ch) {
-        mbar_wait(&full[s], ph);
-        const uint32_t a_s = smem_u32(stage_base + (size_t)s * MV5_STAGE_BYTES) + (uint32_t)r * 128u;
-        uint32_t lo[64];
+        MV5_WAIT(&full[s], ph);
+        MV5_WAIT(&tfree[t], pt ^ 1);
+        mv5_fence_after();
+        const uint32_t a_s = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)r * 128u;
+        const uint32_t tdst = tm_op + (uint32_t)t * 128u + lane_addr;
+        if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float4 v = lds128(a_s + (uint32_t)(c >> 3) * (MV_TILE_ROWS * 128) + ((((uint32_t)c & 7u) ^ sw) << 4));
-          const float f[4] = {v.x, v.y, v.z, v.w};
+          for (int half = 0; half < 2; ++half) {           // one TMA box (32 columns of A) at a time
+            uint32_t hi[64], lo[64];                       // only [0, 32) used per half (the helpers take 64-wide arrays)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float h = __uint_as_float(__float_as_uint(f[q]) & 0xffffe000u);
-            const float l = f[q] - h;
-            // rows past the tile hold stale bits (possibly NaN / Inf patterns): their products stay in their own
-            // accumulator rows, which are never stored
-            lo[4 * c + q] = __float_as_uint(l);
+            for (int c = 0; c < 8; ++c) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) v = lds128(a_s + (uint32_t)half * box_bytes + ((((uint32_t)c) ^ sw) << 4));
+              const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t raw = __float_as_uint(f[q]);
+                hi[4 * c + q] = raw;                                                       // the tensor core truncates
+                lo[4 * c + q] = __float_as_uint(f[q] - __uint_as_float(raw & 0xffffe000u));
+              }
+            }
+            mv5_st16(tdst + (uint32_t)half * 32u, hi, 0);
+            mv5_st16(tdst + (uint32_t)half * 32u + 16u, hi, 16);
+            mv5_st16(tdst + 64u + (uint32_t)half * 32u, lo, 0);
+            mv5_st16(tdst + 64u + (uint32_t)half * 32u + 16u, lo, 16);
           }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        // (the TMEM slot s was released together with the shared-memory stage: the producer's wait on empty[s] precedes
-        //  the TMA issue that completed full[s])
-        const uint32_t t = tm_alo + (uint32_t)s * 64u + lane_addr;
-        mv5_st16(t, lo, 0);
-        mv5_st16(t + 16, lo, 16);
-        mv5_st16(t + 32, lo, 32);
-        mv5_st16(t + 48, lo, 48);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         mv5_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&aready[s]);
+        if (lane == 0) {
+          mbar_arrive(&tready[t]);
+          mbar_arrive(&empty[s]);
+        }
         if (++s == NS) { s = 0; ph ^= 1; }
+        if (++t == NT) { t = 0; pt ^= 1; }
       }
     }
   } else if (warp >= 8) {
@@ -1324,17 +1367,23 @@ mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
       float y[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) y[i] = 0.f;
-      const int nwin = (nchunks + MV5_FLUSH - 1) / MV5_FLUSH;
+      const int flush = ((p.dbg >> 8) & 0xff) ? ((p.dbg >> 8) & 0xff) : MV5_FLUSH;
+      const int nwin = (nchunks + flush - 1) / flush;
       for (int w = 0; w < nwin; ++w, ++win) {
         const uint32_t buf = win & 1u;
-        mbar_wait(&accfull[buf], (win >> 1) & 1u);
+        MV5_WAIT(&accfull[buf], (win >> 1) & 1u);
         mv5_fence_after();
         uint32_t v[48];
         const uint32_t t = tm_acc + buf * 48u + lane_addr;
-        mv5_ld16(t, v, 0);
-        mv5_ld16(t + 16, v, 16);
-        mv5_ld16(t + 32, v, 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!(p.dbg & 16)) {
+          mv5_ld16(t, v, 0);
+          mv5_ld16(t + 16, v, 16);
+          mv5_ld16(t + 32, v, 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 48; ++i) v[i] = 0u;
+        }
         mv5_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&accempty[buf]);
@@ -1381,16 +1430,19 @@ mv_tma_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   }
 }
 
+#undef MV5_WAIT
+
 static int launch_tc5(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
-  const size_t fixed = (size_t)(4 * 8 + 4) * sizeof(uint64_t) + 16 + 4 * 2 * 16 * sizeof(double) + 1024 + 64;
-  int ns = (int)((227 * 1024 - fixed) / MV5_STAGE_BYTES);
-  if (ns > 5) ns = 5;
-  if (ns > 6) ns = 6;                    // A_lo slots: 96 + 64 ns <= 512 columns
+  const size_t fixed = (size_t)MV5_NT * MV5_BTILE + (size_t)(8 + 8 + 4 + 4 + 2 + 2) * sizeof(uint64_t) + 16 +
+                       4 * 2 * 16 * sizeof(double) + 1024 + 64;
+  const size_t stage_bytes = (size_t)((til.tile_rows + 7) / 8) * 2048 + MV5_XRAW;
+  int ns = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (ns > 8) ns = 8;
   if (ns < 2) {
-    set_last_error("matvec: not enough shared memory for 2 stages");
+    set_last_error("matvec: tcgen05 layout: tile of %d rows does not fit", til.tile_rows);
     return XT_ERR_INVALID;
   }
-  const size_t smem = (size_t)ns * MV5_STAGE_BYTES + fixed;
+  const size_t smem = (size_t)ns * stage_bytes + fixed;
   MvDev dev = dev0;
   dev.nstages = ns;
   CUtensorMap tm;
@@ -1399,6 +1451,7 @@ static int launch_tc5(const MvArgs& a, const MvDev& dev0, const MvTiling& til, c
   if (rc != XT_OK) return rc;
   dev.a_batched = batched ? 1 : 0;
   dev.x_bulk = 1;
+  dev.dbg = getenv("XT_TC5_DBG") ? atoi(getenv("XT_TC5_DBG")) : 0;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
     XT_CUDA_OK(set_max_dyn_smem(mv_tma_tc5_kernel));
@@ -1661,6 +1714,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.done_flag = a.done_flag;
   d.abort_flag = a.abort_flag;
   d.pdl = 0;
+  d.dbg = 0;
   d.reverse = a.reverse ? 1 : 0;
   {
     // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB
@@ -1677,9 +1731,9 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
     }
   }
 
-  if (a.abort_flag != nullptr && (a.impl == 4 || a.impl == 6 || a.impl == 2))
+  if (a.abort_flag != nullptr && (a.impl == 4 || a.impl == 6 || a.impl == 7 || a.impl == 2))
     d.abort_flag = nullptr;               // only the row-slice TMA kernel polls it; the others run to completion
-  const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5 || a.impl == 6);
+  const bool forced_tma = (a.impl == 1 || a.impl == 3 || a.impl == 4 || a.impl == 5 || a.impl == 6 || a.impl == 7);
   bool use_tma = forced_tma || (a.impl == 0 && mv_tma_ok(a));
   if (forced_tma && !mv_tma_ok(a)) {
     set_last_error("matvec: TMA kernel forced but A is not 16-byte aligned / strided (lda=%lld)", (long long)a.lda);
