@@ -179,6 +179,8 @@ struct MvDev {
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
   int pdl;          // launched as a programmatic dependent: see MvArgs.pdl
+  uint32_t box_stride;    // bytes between the two TMA boxes of a stage (shared-memory slot of one box)
+  uint32_t stage_stride;  // bytes between stages; the X chunk of a stage sits at 2 * box_stride
   int dbg;          // tcgen05 kernel: XT_TC5_DBG bit mask that switches single roles off (timing experiments only)
 };
 
@@ -330,7 +332,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
       }
       const bool pre = seq < npre;
       if (!pre) mbar_wait(&empty[s], ph ^ 1);
-      uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
+      uint8_t* dst = stage_base + (size_t)s * p.stage_stride;
       // one box = tile_rows x 128 B (rows past the end of the matrix are zero-filled by the TMA unit)
       uint32_t xbytes = 0;
       if (p.x_bulk) {
@@ -340,11 +342,11 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
       mbar_arrive_expect_tx(&full[s], (pre ? 0u : (uint32_t)(nb * p.tile_rows * 128)) + xbytes);
       if (!pre) {
         for (int bx = 0; bx < nb; ++bx)
-          tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[s], kc + bx * BOXC, row0, bA,
+          tma_load_3d(dst + (size_t)bx * p.box_stride, tmA, &full[s], kc + bx * BOXC, row0, bA,
                       ch >= p.keep_from ? pol_keep : pol_first);
       }
       if (p.x_bulk)
-        bulk_load_1d(dst + MV_STAGE_A_BYTES,
+        bulk_load_1d(dst + 2u * p.box_stride,
                      Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV), xbytes, &full[s]);
       if (++s == NS) { s = 0; ph ^= 1; }
     }
@@ -370,10 +372,10 @@ __device__ __forceinline__ int mv_preissue(const CUtensorMap* tmA, const MvDev& 
   for (int ch = 0; ch < npre; ++ch) {
     const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
     const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
-    uint8_t* dst = stage_base + (size_t)ch * STAGE_BYTES;
+    uint8_t* dst = stage_base + (size_t)ch * p.stage_stride;
     mbar_expect_tx(&full[ch], (uint32_t)(nb * p.tile_rows * 128));
     for (int bx = 0; bx < nb; ++bx)
-      tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), tmA, &full[ch], kc + bx * BOXC, row0, bA,
+      tma_load_3d(dst + (size_t)bx * p.box_stride, tmA, &full[ch], kc + bx * BOXC, row0, bA,
                   ch >= p.keep_from ? pol_keep : pol_first);
   }
   return npre;
@@ -410,7 +412,7 @@ __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, 
     } else {
       mbar_wait(&empty[s], ph ^ 1);
     }
-    TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+    TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * p.stage_stride + 2u * p.box_stride);
 #pragma unroll
     for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
     __syncwarp();
@@ -467,15 +469,15 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NS = p.nstages;
   uint8_t* stage_base = smem;
-  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);                 // [NC][K]
+  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * p.stage_stride);              // [NC][K]
   double* dscr = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(red) + NC * K * sizeof(TV));  // [NC/32][2][K]
   uint64_t* full = reinterpret_cast<uint64_t*>(dscr + (NC / 32) * 2 * K);
-  uint64_t* empty = full + NS;
+  uint64_t* empty = full + 16;
   // first chunk (sequence number) that is not produced; INT_MAX: none (see mv_producer).  Lives in the dynamic region
-  // (slots 2*NS .. 15 of the 16 reserved mbarrier words are free: NS <= 6) so that the kernel has NO static shared
-  // memory and the full 227 KB can be requested as dynamic.
-  int& abort_at_s = *reinterpret_cast<int*>(full + 14);
-  int& skip_s = *reinterpret_cast<int*>(full + 15);
+  // (32 mbarrier words are reserved: full[0..15], empty[16..29] for NS <= 14, these two at 30 / 31) so that the kernel
+  // has NO static shared memory and the full 227 KB can be requested as dynamic.
+  int& abort_at_s = *reinterpret_cast<int*>(full + 30);
+  int& skip_s = *reinterpret_cast<int*>(full + 31);
   int* abort_at = p.abort_flag != nullptr ? &abort_at_s : nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -494,7 +496,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   }
   if (p.x_bulk) {   // X slots start as zeros: a ragged last chunk copies fewer bytes and must never expose NaN garbage
     for (int s = 0; s < NS; ++s) {
-      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * p.stage_stride + 2u * p.box_stride);
       for (int i = threadIdx.x; i < XBYTES / 4; i += blockDim.x) xz[i] = 0u;
     }
     fence_proxy_async();
@@ -550,7 +552,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
       const int gv = q * nvec + (v < nvec ? v : 0);
-      aoff[v] = (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off + ((((uint32_t)gv & 7u) ^ sw) << 4);
+      aoff[v] = (uint32_t)(gv >> 3) * p.box_stride + a_row_off + ((((uint32_t)gv & 7u) ^ sw) << 4);
     }
     const uint32_t x_q_off = (uint32_t)(q * nvec * EPV * K * (int)sizeof(TV));
     int s = 0;
@@ -577,8 +579,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
           mbar_wait(&full[s], ph);
         }
         if (active) {
-          const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
-          const uint32_t xs = a_s + MV_STAGE_A_BYTES + x_q_off;
+          const uint32_t a_s = smem_u32(stage_base + (size_t)s * p.stage_stride);
+          const uint32_t xs = a_s + 2u * p.box_stride + x_q_off;
           if (kc + KC <= p.ncolsA) {
             // full chunk: every vector of this thread is in bounds (rows past the tile read stale, finite-or-not
             // shared memory into accumulators that are never stored)
@@ -591,7 +593,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
             for (int v = 0; v < nvec; ++v) {
               const int gv = q * nvec + v;
               if (kc + (gv >> 3) * BOXC < p.ncolsA) {
-                const uint32_t off = (uint32_t)((gv >> 3) * (MV_TILE_ROWS * 128)) + a_row_off +
+                const uint32_t off = (uint32_t)(gv >> 3) * p.box_stride + a_row_off +
                                      ((((uint32_t)gv & 7u) ^ sw) << 4);
                 TV a[RP][EPV];
 #pragma unroll
@@ -1551,17 +1553,25 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   constexpr int BOXC = 128 / (int)sizeof(TA);
   constexpr int KC = 2 * BOXC;
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
-  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
-  const size_t fixed = NC * K * sizeof(TV) + (NC / 32) * 2 * K * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 1024 + 64;
-  int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
-  if (ns > 6) ns = 6;
+  // compact stages: a TMA box of tile_rows rows occupies whole 8-row swizzle atoms only, so that short tiles (few rows
+  // per SM: row-partitioned operators, small matrices) get MORE stages instead of half-empty ones -- the bytes in flight
+  // per SM stay the same (8192 x 65536 fp32, 56-row tiles: 6 stages x 14 KB before)
+  const uint32_t box_stride = (uint32_t)((til.tile_rows + 7) / 8) * 1024u;
+  const uint32_t stage_stride = (2u * box_stride + (uint32_t)XBYTES + 1023u) / 1024u * 1024u;
+  const size_t fixed = NC * K * sizeof(TV) + (NC / 32) * 2 * K * sizeof(double) + 32 * sizeof(uint64_t) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / stage_stride);
+  const int ns_cap = getenv("XT_MV_MAXSTAGES") ? atoi(getenv("XT_MV_MAXSTAGES")) : 14;
+  if (ns > ns_cap) ns = ns_cap;
+  if (ns > 14) ns = 14;
   if (ns < 2) {
     set_last_error("matvec: not enough shared memory for 2 stages");
     return XT_ERR_INVALID;
   }
-  const size_t smem = (size_t)ns * STAGE_BYTES + fixed;
+  const size_t smem = (size_t)ns * stage_stride + fixed;
   MvDev dev = dev0;
   dev.nstages = ns;
+  dev.box_stride = box_stride;
+  dev.stage_stride = stage_stride;
   CUtensorMap tm;
   bool batched = false;
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
@@ -1616,6 +1626,8 @@ static int launch_colslice(const MvArgs& a, const MvDev& dev0, const MvTiling& t
   const size_t smem = (size_t)ns * STAGE_BYTES + fixed;
   MvDev dev = dev0;
   dev.nstages = ns;
+  dev.box_stride = MV_TILE_ROWS * 128;
+  dev.stage_stride = STAGE_BYTES;
   CUtensorMap tm;
   bool batched = false;
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
@@ -1715,6 +1727,8 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.abort_flag = a.abort_flag;
   d.pdl = 0;
   d.dbg = 0;
+  d.box_stride = MV_TILE_ROWS * 128;
+  d.stage_stride = 0;          // set by the launcher
   d.reverse = a.reverse ? 1 : 0;
   {
     // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB
