@@ -523,7 +523,9 @@ def gmres(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, 
     posdef: bool or None
         ``False`` switches to the normal equations; ``None`` means True.
     max_niter: int or None
-        Maximum number of iterations (= Krylov dimension). If None, ``min(A.shape[-1], 256)``.
+        Maximum number of iterations. If None, ``A.shape[-1]`` (as the reference, solve.py:357).  One Krylov cycle holds
+        at most 256 vectors (the Hessenberg matrix lives on chip); beyond that the method restarts from the current
+        iterate (GMRES(256)) until ``max_niter`` iterations have been spent.
     rtol, atol: float
         Stop when every column satisfies ``||r|| < max(rtol * ||b||, atol)``.
     eps: float
@@ -535,8 +537,40 @@ def gmres(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None, 
         raise RuntimeError("gmres does not support E (neither does the reference method: "
                            "xitorch/_impls/linalg/solve.py:386-398)")
     if max_niter is None:
-        max_niter = min(int(A.shape[-1]), 256)
-    return _run_krylov("gmres", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, 0, check_every, info)
+        max_niter = int(A.shape[-1])
+    cycle = 256
+    if max_niter <= cycle:
+        return _run_krylov("gmres", A, B, E, M, posdef, False, max_niter, rtol, atol, eps, 0, check_every, info)
+    # restarted cycles: solve A dx = r for the current residual, with the ABSOLUTE target of the original problem
+    run = {}
+    X = _run_krylov("gmres", A, B, E, M, posdef, False, cycle, rtol, atol, eps, 0, check_every, run)
+    spent = int(run.get("niter", cycle))
+    if not run.get("converged", True):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", ConvergenceWarning)
+            bnorm = B.norm(dim=-2, keepdim=True)
+            target = torch.clamp(rtol * bnorm, min=atol)
+            while spent < max_niter:
+                R = B - A.mm(X)
+                if bool((R.norm(dim=-2, keepdim=True) < target).all()):
+                    run["converged"] = True
+                    break
+                run = {}
+                dX = _run_krylov("gmres", A, R, None, M, posdef, False, min(cycle, max_niter - spent), 0.0,
+                                 float(target.min().item()), eps, 0, check_every, run)
+                X = X + dX
+                spent += int(run.get("niter", cycle))
+        if not run.get("converged", True):
+            R = B - A.mm(X)
+            if not bool((R.norm(dim=-2, keepdim=True) < target).all()):
+                warnings.warn(ConvergenceWarning("Convergence is not achieved after %d iterations. Max norm of best "
+                                                 "resid: %.3e" % (spent, R.norm(dim=-2).max().item())))
+            else:
+                run["converged"] = True
+    if info is not None:
+        info.update(run)
+        info["niter"] = spent
+    return X
 
 
 def broyden1_solve(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor] = None,

@@ -188,6 +188,17 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
         def op(x):
             return torch.matmul(Linv, A.mm(torch.matmul(LinvT, x)))
 
+    if n < 2 * neig:
+        # not even two blocks fit: the reference's first expansion already fills the whole space (symeig.py:209-211);
+        # same shortcut as the dense path (a tiny operator, e.g. the A^H A of `svd` of a thin matrix)
+        run = {} if info is None else info
+        run.update(niter=0, converged=False, napply=1, max_basis=n)
+        with torch.no_grad():
+            full = op(torch.eye(n, dtype=vdt, device=dev))
+        evals, evecs = _full_space_pairs(full.reshape(1, n, n), neig, mode, run)
+        batch = tuple(A.shape[:-2])
+        evals, evecs = evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
+        return evals, (torch.matmul(LinvT, evecs) if LinvT is not None else evecs)
     V0 = _start(v_init, 1, n, neig, vdt, dev)
     failure = []
 

@@ -179,6 +179,7 @@ struct MvDev {
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
   int pdl;          // launched as a programmatic dependent: see MvArgs.pdl
+  int y_atomic;           // Y += (atomicAdd) instead of Y =: the two column halves of a split pass (see mv_launch)
   uint32_t box_stride;    // bytes between the two TMA boxes of a stage (shared-memory slot of one box)
   uint32_t stage_stride;  // bytes between stages; the X chunk of a stage sits at 2 * box_stride
   int dbg;          // tcgen05 kernel: XT_TC5_DBG bit mask that switches single roles off (timing experiments only)
@@ -437,9 +438,16 @@ __device__ __forceinline__ void row_epilogue(const MvDev& p, int b, int64_t row,
       if (i < p.kvalid) y[i] -= Eb[i] * Zr[i];
   }
   TV* Yr = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride + row * p.ldy;
+  if (p.y_atomic) {
+    // column-split pass: exactly two partial sums land on a zeroed Y, fl(a + b) either way round (deterministic)
 #pragma unroll
-  for (int i = 0; i < K; ++i)
-    if (i < p.kvalid) Yr[i] = y[i];
+    for (int i = 0; i < K; ++i)
+      if (i < p.kvalid) atomicAdd(&Yr[i], y[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+      if (i < p.kvalid) Yr[i] = y[i];
+  }
   if (p.dot_out != nullptr) {
     const TV* Ur = (p.U != nullptr) ? reinterpret_cast<const TV*>(p.U) + (int64_t)b * p.u_bstride + row * p.ldu
                                     : nullptr;
@@ -1705,12 +1713,42 @@ static int launch_plain(const MvArgs& a, const MvDev& dev, const MvTiling& til, 
   return XT_OK;
 }
 
-int mv_launch(const MvArgs& a, cudaStream_t st) {
-  XT_REQUIRE(a.k >= 1 && a.k <= MV_MAXK, "matvec: k=%d outside 1..%d", a.k, MV_MAXK);
-  XT_REQUIRE(a.nbatch >= 1 && a.nrows >= 1 && a.ncolsA >= 1, "matvec: empty problem (%d,%d,%d)", a.nbatch, a.nrows,
-             a.ncolsA);
-  XT_REQUIRE(a.A && a.X && a.Y, "matvec: null pointer");
-  XT_REQUIRE(a.E == nullptr || a.Z != nullptr || a.nrows == a.ncolsA, "matvec: shift with Z = X needs a square A");
+int mv_launch(const MvArgs& a0, cudaStream_t st) {
+  XT_REQUIRE(a0.k >= 1 && a0.k <= MV_MAXK, "matvec: k=%d outside 1..%d", a0.k, MV_MAXK);
+  XT_REQUIRE(a0.nbatch >= 1 && a0.nrows >= 1 && a0.ncolsA >= 1, "matvec: empty problem (%d,%d,%d)", a0.nbatch, a0.nrows,
+             a0.ncolsA);
+  XT_REQUIRE(a0.A && a0.X && a0.Y, "matvec: null pointer");
+  XT_REQUIRE(a0.E == nullptr || a0.Z != nullptr || a0.nrows == a0.ncolsA, "matvec: shift with Z = X needs a square A");
+  MvArgs a = a0;
+  int y_atomic = 0;
+  {
+    // Column split for wide, short operators (a row block of a row-partitioned matrix: 8192 x 65536 per GPU at 8 GPUs).
+    // One wave of row tiles would be only ~56 rows high there, and the consumer layouts lose a quarter of their speed on
+    // such flat tiles (3.2 instead of 4.1 TB/s at k = 16).  Instead the pass runs as TWO virtual batch items -- the left
+    // and the right half of the columns (A: batch stride = half a row; X: its lower half) -- over tiles of twice the
+    // height, both adding into a zeroed Y.
+    const int64_t es = a.dtype == XT_F64 ? 8 : (a.dtype == XT_BF16 ? 2 : 4);
+    const int64_t vs = a.dtype == XT_F64 ? 8 : 4;
+    const int64_t kc_cols = 2 * (128 / es);
+    const MvTiling t1 = mv_tiling(1, a.nrows, a.reserve_sms);
+    const bool want = a.nbatch == 1 && a.impl == 0 && a.E == nullptr && a.dot_out == nullptr && a.abort_flag == nullptr &&
+                      !a.pdl && t1.tile_rows <= 80 && a.nrows >= 8 * MV_BOX_ROWS && a.ncolsA >= 4096 &&
+                      a.ncolsA % (2 * kc_cols) == 0 && mv_tma_ok(a) && getenv("XT_MV_NO_CSPLIT") == nullptr;
+    if (want) {
+      const int64_t half = a.ncolsA / 2;
+      if (a.ldy == a.k) {
+        XT_CUDA_OK(cudaMemsetAsync(a.Y, 0, (size_t)a.nrows * a.k * vs, st));
+      } else {
+        XT_CUDA_OK(cudaMemset2DAsync(a.Y, (size_t)a.ldy * vs, 0, (size_t)a.k * vs, (size_t)a.nrows, st));
+      }
+      a.nbatch = 2;
+      a.ncolsA = (int)half;
+      a.a_bstride = half;
+      a.x_bstride = half * a.ldx;
+      a.y_bstride = 0;
+      y_atomic = 1;
+    }
+  }
   const MvTiling til = mv_tiling(a.nbatch, a.nrows, a.reserve_sms);
   MvDev d;
   d.nbatch = a.nbatch; d.nrows = a.nrows; d.ncolsA = a.ncolsA; d.kvalid = a.k;
@@ -1727,6 +1765,7 @@ int mv_launch(const MvArgs& a, cudaStream_t st) {
   d.abort_flag = a.abort_flag;
   d.pdl = 0;
   d.dbg = 0;
+  d.y_atomic = y_atomic;
   d.box_stride = MV_TILE_ROWS * 128;
   d.stage_stride = 0;          // set by the launcher
   d.reverse = a.reverse ? 1 : 0;
@@ -1815,6 +1854,7 @@ int xt_block_matvec(const xt_matvec_args* g) {
   // column groups of <= 16: one pass over A per group
   for (int c0 = 0; c0 < g->k; c0 += xt::MV_MAXK) {
     xt::MvArgs a;
+    memset(&a, 0, sizeof(a));
     a.dtype = g->dtype;
     a.nbatch = g->nbatch; a.nrows = g->nrows; a.ncolsA = g->ncolsA;
     a.k = (g->k - c0 < xt::MV_MAXK) ? (g->k - c0) : xt::MV_MAXK;
