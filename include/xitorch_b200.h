@@ -86,6 +86,11 @@ typedef struct {
   const void* Z; int64_t ldz, z_bstride;
   int32_t impl;
   void* stream;
+  /* trans != 0:  Y_b = A_b^T X_b  with X: (nbatch, nrows, k), Y: (nbatch, ncolsA, k) -- replaces the `mat^H @ x` of
+   * MatrixLinearOperator._rmm/_rmv (xitorch/_core/linop.py:698-702) and the A^H (A x) of the normal equations
+   * (xitorch/_impls/linalg/solve.py:637-643) without materialising the transpose: A is read once, by column strips.
+   * fp32 / fp64, E must be NULL, A 16-byte aligned with a 16-byte multiple row stride. */
+  int32_t trans;
 } xt_matvec_args;
 
 int xt_block_matvec(const xt_matvec_args* args);

@@ -165,3 +165,41 @@ def test_matvec_k16_tcgen05(nr, nc):
         ye = _dense.block_matvec(A.to(DEV), X.to(DEV), E=E.to(DEV), impl=7)
         refe = ref - X.double() * E.double()
         assert ((ye.cpu().double() - refe).abs() / (bound + (X.double() * E.double()).abs())).max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("nr,nc,k", [(128, 64, 1), (300, 200, 3), (1000, 1000, 8), (4096, 2048, 16), (777, 4100, 5),
+                                     (2048, 4096, 20)])
+def test_matvec_transposed_access(dtype, nr, nc, k):
+    """Y = A^T X by column strips (trans = 1): no transposed copy of A (reference linop.py:698-702 materialises mat^H)"""
+    g = torch.Generator().manual_seed(nr * 7 + nc + k)
+    A = torch.randn(nr, nc, generator=g, dtype=dtype)
+    X = torch.randn(nr, k, generator=g, dtype=dtype)
+    if (nc * A.element_size()) % 16 != 0:
+        pytest.skip("row stride not a 16-byte multiple: the wrapper materialises the transpose")
+    Ad, Xd = A.to(DEV), X.to(DEV)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    y = _dense.block_matvec(Ad, Xd, adjoint=True)
+    torch.cuda.synchronize()
+    assert torch.cuda.max_memory_allocated() - base < nr * nc * A.element_size() // 2      # no copy of A
+    ref = A.double().t() @ X.double()
+    bound = A.double().abs().t() @ X.double().abs()
+    tol = 2e-6 if dtype == torch.float32 else 1e-13
+    assert ((y.cpu().double() - ref).abs() / bound).max().item() <= tol
+
+
+def test_matvec_transposed_batched_and_rmm():
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(3, 512, 384, generator=g)
+    X = torch.randn(3, 512, 4, generator=g)
+    y = _dense.block_matvec(A.to(DEV), X.to(DEV), adjoint=True)
+    assert torch.allclose(y.cpu(), A.transpose(-2, -1) @ X, rtol=1e-4, atol=1e-4)
+    import xitorch_b200 as xt
+    M = torch.randn(640, 640, generator=g)
+    op = xt.LinearOperator.m(M.to(DEV), is_hermitian=False)
+    V = torch.randn(640, 7, generator=g)
+    assert torch.allclose(op.rmm(V.to(DEV)).cpu(), M.t() @ V, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(op.H.mm(V.to(DEV)).cpu(), M.t() @ V, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(op.rmv(V[:, 0].to(DEV)).cpu(), M.t() @ V[:, 0], rtol=1e-4, atol=1e-4)

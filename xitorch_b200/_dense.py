@@ -46,11 +46,17 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
                  impl: int = 0) -> torch.Tensor:
     """``mat @ x`` (or ``mat^T @ x``), optionally ``- Z * E`` with ``E (*B, k)``, ``Z (*B, p, k)`` (default x)."""
     _lib.require_cuda(mat, "the dense block matvec")
-    if adjoint:
-        mat = mat.transpose(-2, -1).contiguous()     # materialised, like the reference's `.H` for dense operators
-    p, q = mat.shape[-2:]
-    if x.shape[-2] != q:
-        raise RuntimeError("block_matvec: shape mismatch %s @ %s" % (tuple(mat.shape), tuple(x.shape)))
+    # mat^T @ x: the transposed-access kernel reads mat once, by column strips (fp32 / fp64, no shift); anything else
+    # materialises the transpose as the reference's `.H` does for dense operators (linop.py:390-391)
+    trans = bool(adjoint and E is None and mat.dtype in (torch.float32, torch.float64)
+                 and (mat.shape[-1] * mat.element_size()) % 16 == 0)
+    if adjoint and not trans:
+        mat = mat.transpose(-2, -1).contiguous()
+    p, q = mat.shape[-2:]                       # the stored matrix: p rows, q columns
+    nin, nout = (p, q) if trans else (q, p)     # rows of x / of the result
+    if x.shape[-2] != nin:
+        raise RuntimeError("block_matvec: shape mismatch %s%s @ %s" % (tuple(mat.shape), "^T" if trans else "",
+                                                                       tuple(x.shape)))
     k = x.shape[-1]
     vdt = _lib.vec_dtype(mat.dtype)
     out_dtype = x.dtype
@@ -59,18 +65,23 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
     for s in batch:
         nb *= s
     if nb == 0:
-        return torch.empty((*batch, p, k), dtype=out_dtype, device=x.device)
+        return torch.empty((*batch, nout, k), dtype=out_dtype, device=x.device)
     m3, a_bstride, lda = flatten_batch(mat, batch)
     if m3.data_ptr() % 16 != 0:
         m3 = m3.clone()
-    xx = x.to(vdt).expand(*batch, q, k).reshape(nb, q, k).contiguous()
-    y = torch.empty((nb, p, k), dtype=vdt, device=x.device)
+    if trans and (lda * m3.element_size()) % 16 != 0:
+        m3 = m3.contiguous()
+        lda = m3.stride(-2)
+        a_bstride = m3.stride(0) if (m3.dim() == 3 and a_bstride != 0) else a_bstride
+    xx = x.to(vdt).expand(*batch, nin, k).reshape(nb, nin, k).contiguous()
+    y = torch.empty((nb, nout, k), dtype=vdt, device=x.device)
     a = _lib.MatvecArgs()
     a.dtype = _lib.dtype_code(mat.dtype)
     a.nbatch, a.nrows, a.ncolsA, a.k = nb, p, q, k
     a.A, a.lda, a.a_bstride = m3.data_ptr(), lda, a_bstride
-    a.X, a.ldx, a.x_bstride = xx.data_ptr(), k, q * k
-    a.Y, a.ldy, a.y_bstride = y.data_ptr(), k, p * k
+    a.X, a.ldx, a.x_bstride = xx.data_ptr(), k, nin * k
+    a.Y, a.ldy, a.y_bstride = y.data_ptr(), k, nout * k
+    a.trans = 1 if trans else 0
     keep = [m3, xx, y]
     if E is not None:
         ee = E.to(vdt).expand(*batch, k).reshape(nb, k).contiguous()
@@ -84,7 +95,7 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
     a.stream = _lib.stream_ptr(x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().xt_block_matvec(a), "block_matvec")
-    y = y.reshape(*batch, p, k)
+    y = y.reshape(*batch, nout, k)
     return y if out_dtype == vdt else y.to(out_dtype)
 
 

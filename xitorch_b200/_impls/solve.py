@@ -355,25 +355,12 @@ def _run_krylov(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef, nee
 
     Bv = B
     if not posdef:
-        # normal equations (solve.py:637-643):  (A-EM)^H (A-EM) x = (A-EM)^H b, built densely per column
-        if E is not None:
-            Ec = E.reshape(*([1] * (len(batch) - E.dim() + 1)), *E.shape) if E.dim() - 1 < len(batch) else E
-            eye = torch.eye(n, dtype=Amat.dtype, device=Amat.device) if Mmat is None else Mmat
-            Afull = Amat.expand(*batch, n, n).unsqueeze(-3) - \
-                Ec.to(Amat.dtype).expand(*batch, ncols)[..., None, None] * eye.expand(*batch, n, n).unsqueeze(-3)
-            # (*batch, ncols, n, n): every column becomes its own batch item with one right-hand side
-            AT = Afull.transpose(-2, -1)
-            Amat = torch.matmul(AT, Afull)
-            Bcol = B.expand(*batch, n, ncols).transpose(-2, -1).unsqueeze(-1).to(Amat.dtype)   # (*batch, ncols, n, 1)
-            Bv = torch.matmul(AT, Bcol)
-            if precond_l is not None or precond_r is not None:
-                raise RuntimeError("xitorch_b200: preconditioners together with E and the normal equations are not supported")
-            x = _call(name, Amat, None, None, Bv, (*batch, ncols), n, 1, vdt, max_niter, rtol, atol, eps,
-                      resid_calc_every, check_every, info)
-            return x.squeeze(-1).transpose(-2, -1).to(out_dtype)
-        AT = Amat.transpose(-2, -1)
-        Bv = torch.matmul(AT.to(vdt), B.to(vdt))
-        Amat = torch.matmul(AT, Amat)
+        # normal equations (solve.py:637-643), MATRIX-FREE as in the reference: the operator is x -> F^H (F x) with
+        # F x = A x - (M x) E, two (three with M) dense passes per application -- the forward block matvec and the
+        # transposed-access one (`xt_block_matvec`, trans = 1), which reads A once without materialising A^T.  No
+        # N x N product is formed: nothing is squared in storage precision and the E case needs no matrix per column.
+        return _run_matrix_free(name, A, B, E, M, False, need_hermit, max_niter, rtol, atol, eps, resid_calc_every,
+                                info, precond_l, precond_r)
     x = _call(name, Amat, Mmat, E, Bv, batch, n, ncols, vdt, max_niter, rtol, atol, eps, resid_calc_every,
               check_every, info, precond_l, precond_r)
     return x.to(out_dtype)

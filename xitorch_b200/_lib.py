@@ -38,6 +38,7 @@ class MatvecArgs(C.Structure):
         ("Z", C.c_void_p), ("ldz", C.c_int64), ("z_bstride", C.c_int64),
         ("impl", C.c_int32),
         ("stream", C.c_void_p),
+        ("trans", C.c_int32),
     ]
 
 

@@ -1475,6 +1475,231 @@ static int launch_tc5(const MvArgs& a, const MvDev& dev0, const MvTiling& til, c
   return XT_OK;
 }
 
+// ---------------------------------------------------------------------------- transposed access  Y = A^T X
+// rmm / rmv of a non-Hermitian dense operator and the A^H (A x) of the normal equations (reference linop.py:698-702,
+// solve.py:637-643) WITHOUT materialising A^T: a CTA owns a strip of 2 TMA boxes = 64 (fp32) / 32 (fp64) columns of A and
+// streams ALL rows through the same SWIZZLE_128B box ring as the forward kernels (box = 128 rows x 128 B), so A is
+// read once, in full 128-byte row segments.  Consumers: a warp takes one box and every fourth row pair, a lane two
+// adjacent columns (one LDS.64 of A per row -- a 128-byte row of the box is conflict-free under the swizzle -- plus
+// K/4 broadcast LDS.128 of the X row) and keeps 2 x K accumulators; the row groups are summed through shared memory
+// at the end of the strip.  X rows are staged by one warp with plain loads (any row stride, rows past the end as
+// zeros; TMA zero-fills the rows of A past the end).
+constexpr int MVT_ROWS = 128;                 // rows of A per stage
+constexpr int MVT_NCW = 8;                    // consumer warps: 2 boxes x 4 row groups
+
+template <typename TA, typename TV, int K>
+__global__ void __launch_bounds__(MVT_NCW * 32 + 64, 1)
+mv_tma_t_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);           // columns per box
+  constexpr int STRIP = 2 * BOXC;
+  constexpr int CPL = BOXC / 16;                        // columns per lane: 2 (4-byte elements) or 1 (8-byte)
+  constexpr int XBYTES = MVT_ROWS * K * (int)sizeof(TV);
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
+  static_assert(sizeof(TA) == sizeof(TV), "transposed kernel: A and the vectors share one element type");
+  if (p.done_flag != nullptr && *p.done_flag != 0) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int NS = p.nstages;
+  uint8_t* stage_base = smem;
+  TV* red = reinterpret_cast<TV*>(smem + (size_t)NS * STAGE_BYTES);          // [4 row groups][STRIP][K]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * STRIP * K);
+  uint64_t* empty = full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrchunks = (p.nrows + MVT_ROWS - 1) / MVT_ROWS;
+  const int strips_per_batch = (p.ncolsA + STRIP - 1) / STRIP;
+  const int nstrips = strips_per_batch * p.nbatch;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 2);                 // TMA lane (expect_tx) + X staging warp
+      mbar_init(&empty[s], MVT_NCW);
+    }
+    fence_mbar_init();
+    prefetch_tmap(&tmA);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const int b = strip / strips_per_batch;
+        const int c0 = (strip - b * strips_per_batch) * STRIP;
+        const int bA = p.a_batched ? b : 0;
+        const int nb = (c0 + BOXC < p.ncolsA) ? 2 : 1;
+        for (int rc = 0; rc < nrchunks; ++rc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* dst = stage_base + (size_t)s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * MVT_ROWS * 128));
+          for (int bx = 0; bx < nb; ++bx)
+            tma_load_3d(dst + bx * (MV_TILE_ROWS * 128), &tmA, &full[s], c0 + bx * BOXC, rc * MVT_ROWS, bA, pol);
+          if (++s == NS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // X staging: rows [rc * 128, +128) of X_b, K values each, zero rows past the end
+    constexpr int NPL = MVT_ROWS * K / 32;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+      const int b = strip / strips_per_batch;
+      const TV* Xb = reinterpret_cast<const TV*>(p.X) + (int64_t)b * p.x_bstride;
+      for (int rc = 0; rc < nrchunks; ++rc) {
+        TV vals[NPL];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int idx = lane + 32 * i;
+          const int r = idx / K, v = idx - r * K;
+          const int row = rc * MVT_ROWS + r;
+          vals[i] = (row < p.nrows && v < p.kvalid) ? Xb[(int64_t)row * p.ldx + v] : TV(0);
+        }
+        mbar_wait(&empty[s], ph ^ 1);
+        TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * STAGE_BYTES + MV_STAGE_A_BYTES);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int cw = warp - 2;                  // consumer warp 0..7
+    const int box = cw & 1, rg = cw >> 1;     // its box of the stage, its row group
+    const int half = lane >> 4, cl = lane & 15;
+    // byte offset of this lane's columns inside a 128-byte box row: 16-byte chunk (cl * CPL * sizeof / 16), swizzled per row
+    const uint32_t chunk = (uint32_t)(cl * CPL * (int)sizeof(TA)) >> 4;
+    const uint32_t within = (uint32_t)(cl * CPL * (int)sizeof(TA)) & 15u;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+      const int b = strip / strips_per_batch;
+      const int c0 = (strip - b * strips_per_batch) * STRIP;
+      TV acc[CPL][K];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc[c][i] = TV(0);
+      const bool box_live = c0 + box * BOXC < p.ncolsA;
+      for (int rc = 0; rc < nrchunks; ++rc) {
+        mbar_wait(&full[s], ph);
+        if (box_live) {
+          const uint32_t a_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES) + (uint32_t)box * (MV_TILE_ROWS * 128);
+          const uint32_t x_s = smem_u32(stage_base + (size_t)s * STAGE_BYTES) + MV_STAGE_A_BYTES;
+#pragma unroll 4
+          for (int j = 0; j < MVT_ROWS / 8; ++j) {
+            const int r = 8 * j + 2 * rg + half;
+            const uint32_t aaddr = a_s + (uint32_t)r * 128u + (((chunk ^ (uint32_t)(r & 7)) << 4) | within);
+            TV av[CPL];
+            if constexpr (sizeof(TA) == 4) {
+              float2 t;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(aaddr));
+              av[0] = t.x; av[1] = t.y;
+            } else {
+              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av[0]) : "r"(aaddr));
+            }
+            TV x[K];
+            load_xrow<K>(x_s + (uint32_t)(r * K * (int)sizeof(TV)), x);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) fma_row<K>(av[c], x, acc[c]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NS) { s = 0; ph ^= 1; }
+      }
+      // the two row parities of a warp (lanes l and l + 16 hold the same columns), then the 4 row groups
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc[c][i] += __shfl_xor_sync(0xffffffffu, acc[c][i], 16);
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+          for (int i = 0; i < K; ++i) red[((size_t)rg * STRIP + box * BOXC + cl * CPL + c) * K + i] = acc[c][i];
+      }
+      named_bar_sync(1, MVT_NCW * 32);
+      TV* Yb = reinterpret_cast<TV*>(p.Y) + (int64_t)b * p.y_bstride;
+      for (int e = cw * 32 + lane; e < STRIP * K; e += MVT_NCW * 32) {
+        const int c = e / K, i = e - c * K;
+        if (c0 + c < p.ncolsA && i < p.kvalid) {
+          const TV sum = (red[(size_t)(0 * STRIP + c) * K + i] + red[(size_t)(1 * STRIP + c) * K + i]) +
+                         (red[(size_t)(2 * STRIP + c) * K + i] + red[(size_t)(3 * STRIP + c) * K + i]);
+          Yb[(int64_t)(c0 + c) * p.ldy + i] = sum;
+        }
+      }
+      named_bar_sync(1, MVT_NCW * 32);       // red[] is reused by the next strip
+    }
+  }
+}
+
+template <typename TA, typename TV, int K>
+static int launch_tma_t_k(const MvArgs& a, const MvDev& dev0, cudaStream_t st) {
+  constexpr int BOXC = 128 / (int)sizeof(TA);
+  constexpr int STRIP = 2 * BOXC;
+  constexpr int XBYTES = MVT_ROWS * K * (int)sizeof(TV);
+  constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;
+  const size_t fixed = (size_t)4 * STRIP * K * sizeof(TV) + 16 * sizeof(uint64_t) + 1024 + 64;
+  int ns = (int)((227 * 1024 - fixed) / STAGE_BYTES);
+  if (ns > 8) ns = 8;
+  if (ns < 2) {
+    set_last_error("matvec (transposed): not enough shared memory for 2 stages");
+    return XT_ERR_INVALID;
+  }
+  const size_t smem = (size_t)ns * STAGE_BYTES + fixed;
+  MvDev dev = dev0;
+  dev.nstages = ns;
+  CUtensorMap tm;
+  bool batched = false;
+  int rc = make_tmap(a, MVT_ROWS, &tm, &batched);
+  if (rc != XT_OK) return rc;
+  dev.a_batched = batched ? 1 : 0;
+  auto kern = mv_tma_t_kernel<TA, TV, K>;
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
+    XT_CUDA_OK(set_max_dyn_smem(kern));
+    attr_once.mark();
+  }
+  const int nstrips = ((a.ncolsA + STRIP - 1) / STRIP) * a.nbatch;
+  int G = num_sms() - a.reserve_sms;
+  if (G < 1) G = 1;
+  const int grid = nstrips < G ? nstrips : G;
+  prof_mv_begin(st);
+  kern<<<grid, MVT_NCW * 32 + 64, smem, st>>>(tm, dev);
+  prof_mv_end(st);
+  XT_LAUNCHED();
+  XT_CUDA_OK(cudaGetLastError());
+  return XT_OK;
+}
+
+// Y_b = A_b^T X_b  (A: nrows x ncolsA, X: nrows x k, Y: ncolsA x k); fp32 / fp64, TMA-able A only
+int mv_launch_t(const MvArgs& a, cudaStream_t st) {
+  XT_REQUIRE(a.k >= 1 && a.k <= MV_MAXK, "matvec^T: k=%d outside 1..%d", a.k, MV_MAXK);
+  XT_REQUIRE(a.nbatch >= 1 && a.nrows >= 1 && a.ncolsA >= 1 && a.A && a.X && a.Y, "matvec^T: bad arguments");
+  XT_REQUIRE(a.E == nullptr && a.dot_out == nullptr, "matvec^T: plain products only (no shift, no fused dots)");
+  XT_REQUIRE(a.dtype == XT_F32 || a.dtype == XT_F64, "matvec^T: fp32 / fp64 operators only");
+  XT_REQUIRE(mv_tma_ok(a), "matvec^T: A must be 16-byte aligned with a 16-byte multiple row stride");
+  MvDev d;
+  memset(&d, 0, sizeof(d));
+  d.nbatch = a.nbatch; d.nrows = a.nrows; d.ncolsA = a.ncolsA; d.kvalid = a.k;
+  d.X = a.X; d.ldx = a.ldx; d.x_bstride = a.x_bstride;
+  d.Y = a.Y; d.ldy = a.ldy; d.y_bstride = a.y_bstride;
+  d.done_flag = a.done_flag;
+  if (a.dtype == XT_F32) {
+    if (a.k <= 1) return launch_tma_t_k<float, float, 1>(a, d, st);
+    if (a.k <= 2) return launch_tma_t_k<float, float, 2>(a, d, st);
+    if (a.k <= 4) return launch_tma_t_k<float, float, 4>(a, d, st);
+    if (a.k <= 8) return launch_tma_t_k<float, float, 8>(a, d, st);
+    return launch_tma_t_k<float, float, 16>(a, d, st);
+  }
+  if (a.k <= 1) return launch_tma_t_k<double, double, 1>(a, d, st);
+  if (a.k <= 2) return launch_tma_t_k<double, double, 2>(a, d, st);
+  if (a.k <= 4) return launch_tma_t_k<double, double, 4>(a, d, st);
+  if (a.k <= 8) return launch_tma_t_k<double, double, 8>(a, d, st);
+  return launch_tma_t_k<double, double, 16>(a, d, st);
+}
+
 // ---------------------------------------------------------------------------- plain-load kernel
 // one CTA per tile (same tiling => same dot layout), one warp per row, lanes stride the columns.
 template <typename TA, typename TV>
@@ -1851,6 +2076,26 @@ int xt_block_matvec(const xt_matvec_args* g) {
   if (g == nullptr) return XT_ERR_INVALID;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
   const size_t vs = (g->dtype == XT_F64) ? 8 : 4;
+  if (g->trans) {
+    // Y = A^T X without materialising the transpose (rmm / rmv, normal equations)
+    for (int c0 = 0; c0 < g->k; c0 += xt::MV_MAXK) {
+      xt::MvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.dtype = g->dtype;
+      a.nbatch = g->nbatch; a.nrows = g->nrows; a.ncolsA = g->ncolsA;
+      a.k = (g->k - c0 < xt::MV_MAXK) ? (g->k - c0) : xt::MV_MAXK;
+      a.A = g->A; a.lda = g->lda; a.a_bstride = g->a_bstride;
+      a.X = static_cast<const char*>(g->X) + c0 * vs; a.ldx = g->ldx; a.x_bstride = g->x_bstride;
+      a.Y = static_cast<char*>(g->Y) + c0 * vs; a.ldy = g->ldy; a.y_bstride = g->y_bstride;
+      if (g->E != nullptr) {
+        xt::set_last_error("matvec: the transposed pass takes no shift");
+        return XT_ERR_INVALID;
+      }
+      int rc = xt::mv_launch_t(a, st);
+      if (rc != XT_OK) return rc;
+    }
+    return XT_OK;
+  }
   // column groups of <= 16: one pass over A per group
   for (int c0 = 0; c0 < g->k; c0 += xt::MV_MAXK) {
     xt::MvArgs a;

@@ -56,6 +56,9 @@ struct MvArgs {
 // enqueue on `stream`; returns xt_status
 int mv_launch(const MvArgs& a, cudaStream_t stream);
 
+// Y_b = A_b^T X_b without a transposed copy (A: nrows x ncolsA, X: nrows x k, Y: ncolsA x k; fp32 / fp64, plain product)
+int mv_launch_t(const MvArgs& a, cudaStream_t stream);
+
 // true when the TMA kernel can take these arguments (alignment / stride rules)
 bool mv_tma_ok(const MvArgs& a);
 
