@@ -61,6 +61,7 @@ inline void __syncthreads() { t_cta->bar->arrive_and_wait(); }
 inline void __syncwarp() { t_cta->wbar[threadIdx.x >> 5]->arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void emu_fence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline long long clock64() { return 0; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

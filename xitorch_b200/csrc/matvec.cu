@@ -180,8 +180,9 @@ struct MvDev {
                     // oppositely ordered pass finds the tail of this one in L2
   int pdl;          // launched as a programmatic dependent: see MvArgs.pdl
   int y_atomic;           // Y += (atomicAdd) instead of Y =: the two column halves of a split pass (see mv_launch)
-  uint32_t box_stride;    // bytes between the two TMA boxes of a stage (shared-memory slot of one box)
-  uint32_t stage_stride;  // bytes between stages; the X chunk of a stage sits at 2 * box_stride
+  uint32_t box_stride;    // bytes between the TMA boxes of a stage (shared-memory slot of one box)
+  uint32_t stage_stride;  // bytes between stages; the X chunk of a stage sits at nbx * box_stride
+  int nbx;                // TMA boxes (128 bytes of every row each) per stage: 2, or 4 in the wide-chunk row-slice variant
   int dbg;          // tcgen05 kernel: XT_TC5_DBG bit mask that switches single roles off (timing experiments only)
 };
 
@@ -309,7 +310,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
   // npre: the A boxes of chunks 0 .. npre-1 (stages 0 .. npre-1, first phase) are already in flight with their byte
   // counts registered (mv_preissue): only the arrival and the X chunk are still due for them
   constexpr int BOXC = 128 / (int)sizeof(TA);
-  constexpr int KC = 2 * BOXC;
+  const int KC = p.nbx * BOXC;
   const char* Xg = reinterpret_cast<const char*>(p.X);
   const uint64_t pol_first = l2_policy_evict_first();
   const uint64_t pol_keep = l2_policy_evict_last();
@@ -322,7 +323,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
     const int bA = p.a_batched ? b : 0;
     for (int ch = 0; ch < nchunks; ++ch, ++seq) {
       const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
-      const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+      const int nb = min(p.nbx, (p.ncolsA - kc + BOXC - 1) / BOXC);
       if (abort_at != nullptr && (seq & 7) == 0 && *reinterpret_cast<const volatile int*>(p.abort_flag) != 0) {
         for (int q = seq; q < npre; ++q) {        // pre-issued A boxes must land before the CTA may leave
           mbar_arrive_expect_tx(&full[q], 0u);
@@ -347,7 +348,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
                       ch >= p.keep_from ? pol_keep : pol_first);
       }
       if (p.x_bulk)
-        bulk_load_1d(dst + 2u * p.box_stride,
+        bulk_load_1d(dst + (uint32_t)p.nbx * p.box_stride,
                      Xg + ((int64_t)b * p.x_bstride + (int64_t)kc * K) * (int64_t)sizeof(TV), xbytes, &full[s]);
       if (++s == NS) { s = 0; ph ^= 1; }
     }
@@ -361,7 +362,7 @@ template <typename TA, typename TV, int K, int STAGE_BYTES>
 __device__ __forceinline__ int mv_preissue(const CUtensorMap* tmA, const MvDev& p, uint8_t* stage_base, uint64_t* full,
                                            int NS, int nchunks) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
-  constexpr int KC = 2 * BOXC;
+  const int KC = p.nbx * BOXC;
   const int tile = blockIdx.x;
   if (tile >= p.ntiles) return 0;
   const uint64_t pol_first = l2_policy_evict_first();
@@ -372,7 +373,7 @@ __device__ __forceinline__ int mv_preissue(const CUtensorMap* tmA, const MvDev& 
   const int npre = min(NS, nchunks);
   for (int ch = 0; ch < npre; ++ch) {
     const int kc = (p.reverse ? nchunks - 1 - ch : ch) * KC;
-    const int nb = (kc + BOXC < p.ncolsA) ? 2 : 1;
+    const int nb = min(p.nbx, (p.ncolsA - kc + BOXC - 1) / BOXC);
     uint8_t* dst = stage_base + (size_t)ch * p.stage_stride;
     mbar_expect_tx(&full[ch], (uint32_t)(nb * p.tile_rows * 128));
     for (int bx = 0; bx < nb; ++bx)
@@ -384,11 +385,11 @@ __device__ __forceinline__ int mv_preissue(const CUtensorMap* tmA, const MvDev& 
 
 // X staging warp: all loads of a chunk are issued back to back (KC*K/32 independent loads per lane) and one
 // chunk ahead of the shared-memory slot becoming free, so their L2 latency overlaps the wait.
-template <typename TA, typename TV, int K, int STAGE_BYTES>
+template <typename TA, typename TV, int K, int STAGE_BYTES, int NBX = 2>
 __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, uint64_t* full, uint64_t* empty, int NS,
                                            int nchunks, int lane, const int* abort_at = nullptr) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
-  constexpr int KC = 2 * BOXC;
+  constexpr int KC = NBX * BOXC;
   const TV* __restrict__ Xg = reinterpret_cast<const TV*>(p.X);
   constexpr int NPL = KC * K / 32;
   TV vals[NPL];
@@ -413,7 +414,7 @@ __device__ __forceinline__ void mv_xstager(const MvDev& p, uint8_t* stage_base, 
     } else {
       mbar_wait(&empty[s], ph ^ 1);
     }
-    TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * p.stage_stride + 2u * p.box_stride);
+    TV* xs = reinterpret_cast<TV*>(stage_base + (size_t)s * p.stage_stride + (uint32_t)p.nbx * p.box_stride);
 #pragma unroll
     for (int i = 0; i < NPL; ++i) xs[lane + 32 * i] = vals[i];
     __syncwarp();
@@ -461,13 +462,14 @@ __device__ __forceinline__ void row_epilogue(const MvDev& p, int b, int64_t row,
   }
 }
 
-template <typename TA, typename TV, int K, int NC, int RP>
+template <typename TA, typename TV, int K, int NC, int RP, int NBX = 2>
 __global__ void __launch_bounds__(NC + 64, 1)
 mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   using Tr = ElemTraits<TA>;
   constexpr int EPV = Tr::EPV;
   constexpr int BOXC = 128 / (int)sizeof(TA);   // columns per box
-  constexpr int KC = 2 * BOXC;                  // columns per stage
+  constexpr int KC = NBX * BOXC;                // columns per stage (NBX boxes of 128 bytes per row)
+  constexpr int VPR = NBX * 8;                  // 16-byte vectors of a row per stage
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
   constexpr int STAGE_BYTES = (MV_STAGE_A_BYTES + XBYTES + 1023) / 1024 * 1024;   // swizzle atoms need 1024-B aligned stages
 
@@ -504,7 +506,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   }
   if (p.x_bulk) {   // X slots start as zeros: a ragged last chunk copies fewer bytes and must never expose NaN garbage
     for (int s = 0; s < NS; ++s) {
-      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * p.stage_stride + 2u * p.box_stride);
+      uint32_t* xz = reinterpret_cast<uint32_t*>(stage_base + (size_t)s * p.stage_stride + (uint32_t)NBX * p.box_stride);
       for (int i = threadIdx.x; i < XBYTES / 4; i += blockDim.x) xz[i] = 0u;
     }
     fence_proxy_async();
@@ -538,7 +540,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     if (lane == 0 && (abort_at == nullptr || abort_at_s != 0))
       mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks, abort_at, npre);
   } else if (warp == 1) {
-    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES>(p, stage_base, full, empty, NS, nchunks, lane, abort_at);
+    if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES, NBX>(p, stage_base, full, empty, NS, nchunks, lane, abort_at);
   } else {
     // ------------------------------------------------------------------ consumers
     // thread <-> (row group r, k-slice q).  A thread owns RP rows: r, r + rows_pad, ... (rows_pad = ceil(tile_rows /
@@ -550,7 +552,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     const int q = tc / p.rows_pad;
     int ksplit = 16;
     while (ksplit * p.rows_pad > NC) ksplit >>= 1;
-    const int nvec = 16 / ksplit;
+    const int nvec = VPR / ksplit;        // <= 8 (the launcher picks NBX accordingly)
     const int cw = warp - 2;
     const uint32_t a_row_off = (uint32_t)(r * 128);
     const uint32_t hoff = (uint32_t)(p.rows_pad * 128);
@@ -588,7 +590,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
         }
         if (active) {
           const uint32_t a_s = smem_u32(stage_base + (size_t)s * p.stage_stride);
-          const uint32_t xs = a_s + 2u * p.box_stride + x_q_off;
+          const uint32_t xs = a_s + (uint32_t)NBX * p.box_stride + x_q_off;
           if (kc + KC <= p.ncolsA) {
             // full chunk: every vector of this thread is in bounds (rows past the tile read stale, finite-or-not
             // shared memory into accumulators that are never stored)
@@ -1781,16 +1783,16 @@ template <typename TV, int K> static bool x_bulk_ok(const MvArgs& a) {
   return true;
 }
 
-template <typename TA, typename TV, int K, int NC, int RP>
+template <typename TA, typename TV, int K, int NC, int RP, int NBX = 2>
 static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til, cudaStream_t st) {
   constexpr int BOXC = 128 / (int)sizeof(TA);
-  constexpr int KC = 2 * BOXC;
+  constexpr int KC = NBX * BOXC;
   constexpr int XBYTES = KC * K * (int)sizeof(TV);
   // compact stages: a TMA box of tile_rows rows occupies whole 8-row swizzle atoms only, so that short tiles (few rows
   // per SM: row-partitioned operators, small matrices) get MORE stages instead of half-empty ones -- the bytes in flight
   // per SM stay the same (8192 x 65536 fp32, 56-row tiles: 6 stages x 14 KB before)
   const uint32_t box_stride = (uint32_t)((til.tile_rows + 7) / 8) * 1024u;
-  const uint32_t stage_stride = (2u * box_stride + (uint32_t)XBYTES + 1023u) / 1024u * 1024u;
+  const uint32_t stage_stride = ((uint32_t)NBX * box_stride + (uint32_t)XBYTES + 1023u) / 1024u * 1024u;
   const size_t fixed = NC * K * sizeof(TV) + (NC / 32) * 2 * K * sizeof(double) + 32 * sizeof(uint64_t) + 1024 + 64;
   int ns = (int)((227 * 1024 - fixed) / stage_stride);
   const int ns_cap = getenv("XT_MV_MAXSTAGES") ? atoi(getenv("XT_MV_MAXSTAGES")) : 14;
@@ -1805,6 +1807,8 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   dev.nstages = ns;
   dev.box_stride = box_stride;
   dev.stage_stride = stage_stride;
+  dev.nbx = NBX;
+  if (NBX != 2) dev.keep_from = dev0.keep_from * 2 / NBX;      // mv_launch counted chunks of 2 boxes
   CUtensorMap tm;
   bool batched = false;
   int rc = make_tmap(a, til.tile_rows, &tm, &batched);
@@ -1812,7 +1816,7 @@ static int launch_tma_k(const MvArgs& a, const MvDev& dev0, const MvTiling& til,
   dev.a_batched = batched ? 1 : 0;
   dev.x_bulk = x_bulk_ok<TV, K>(a) ? 1 : 0;
   dev.rows_pad = RP == 1 ? (til.tile_rows + 15) / 16 * 16 : ((til.tile_rows + RP - 1) / RP + 7) / 8 * 8;
-  auto kern = mv_tma_kernel<TA, TV, K, NC, RP>;
+  auto kern = mv_tma_kernel<TA, TV, K, NC, RP, NBX>;
   static DeviceOnce attr_once;   // per instantiation
   if (attr_once.pending()) {
     XT_CUDA_OK(set_max_dyn_smem(kern));
@@ -1921,6 +1925,13 @@ static int launch_tma(const MvArgs& a, const MvDev& dev, const MvTiling& til, cu
   // k = 8: two rows per thread (impl == 5 keeps the one-row form for comparison)
   if (a.k <= 8) {
     if (a.impl == 5) return launch_tma_k<TA, TV, 8, NCW, 1>(a, dev, til, st);
+    if constexpr (std::is_same<TA, float>::value) {
+      // wide chunks (4 boxes = 512 bytes of every row per stage): half as many DRAM row activations per byte.  Needs
+      // at most 8 vectors per thread and stage: ksplit >= 4, i.e. two-row groups of <= 128 consumer threads
+      static const int nbx = getenv("XT_MV_NBX") ? atoi(getenv("XT_MV_NBX")) : 4;   // 4: measured +4 % (6.15 -> 6.39 TB/s in situ)
+      const int rows_pad2 = ((til.tile_rows + 1) / 2 + 7) / 8 * 8;
+      if (nbx == 4 && 4 * rows_pad2 <= NCW && a.ncolsA >= 1024) return launch_tma_k<TA, TV, 8, NCW, 2, 4>(a, dev, til, st);
+    }
     return launch_tma_k<TA, TV, 8, NCW, 2>(a, dev, til, st);
   }
   if (a.impl == 5) return launch_tma_k<TA, TV, 16, 256, 1>(a, dev, til, st);
@@ -1993,6 +2004,7 @@ int mv_launch(const MvArgs& a0, cudaStream_t st) {
   d.y_atomic = y_atomic;
   d.box_stride = MV_TILE_ROWS * 128;
   d.stage_stride = 0;          // set by the launcher
+  d.nbx = 2;
   d.reverse = a.reverse ? 1 : 0;
   {
     // L2 carry-over between oppositely ordered passes (single-wave launches only): keep the last `keep` MB

@@ -59,6 +59,8 @@ struct EigCtl {
   int check_done;       // ticket of the last check whose bookkeeping is complete (they are applied in launch order)
   int stop_iter;        // first iteration whose check met min_eps (0: none yet); checks are applied in launch order
   int* host_done;       // host-mapped mirror of `done` (lets the host stop launching without draining the stream)
+  int host_epoch;       // what is written there: the solve's ticket, so that a straggler of the previous solve on this
+                        // thread's pool can never stop the next one
   unsigned long long trace[64][4];   // XT_TRACE=1: globaltimer stamps [iteration][rr start, rr end, ritz start, ritz end]
   unsigned long long ptrace[64][12]; // fused expansion kernel of iteration i (CTA 0): start and 10 phase stamps
   unsigned long long barr[4][160];   // iteration 8: per-CTA arrival / release stamps of the two grid barriers
@@ -67,7 +69,7 @@ struct EigCtl {
 __device__ __forceinline__ void signal_done(EigCtl* ctl) {
   ctl->done = 1;
   if (ctl->host_done) {
-    *reinterpret_cast<volatile int*>(ctl->host_done) = 1;
+    *reinterpret_cast<volatile int*>(ctl->host_done) = ctl->host_epoch;
     __threadfence_system();
   }
 }
@@ -496,6 +498,8 @@ struct PostArgs {
   void* Xslots; double* evals_slots; float min_eps;
   double* Lout;                               // optional: the Cholesky factor of the new block's Gram matrix (k x k, lower)
   int async_stop;                             // 1: `done` may be raised by another stream while this kernel runs
+  const double* w_scale;                      // optional k x k (row-major): W <- W * w_scale first, written back to p.W
+                                              // (first iteration: the matvec ran on the RAW start block, see start_block_kernel)
 };
 
 // sense-reversing grid barrier; returns false (after raising `done`) if the other CTAs never arrive
@@ -712,9 +716,28 @@ expand_fused_kernel(const PostArgs p) {
   const TV* Vb = p.stage_v ? Vs : V + (int64_t)row0 * k;
   const TV* AVb = p.stage_v ? AVs : static_cast<const TV*>(p.AV) + (int64_t)row0 * k;
   const int64_t vbs = p.stage_v ? (int64_t)R : (int64_t)n;
-  for (int e = tid; e < R * KP; e += PO_THREADS) {
-    const int r = e / KP, j = e - r * KP;
-    Zs[e] = (r < rows && j < k) ? (double)W[((int64_t)row0 + r) * k + j] : 0.0;
+  if (p.w_scale == nullptr) {
+    for (int e = tid; e < R * KP; e += PO_THREADS) {
+      const int r = e / KP, j = e - r * KP;
+      Zs[e] = (r < rows && j < k) ? (double)W[((int64_t)row0 + r) * k + j] : 0.0;
+    }
+  } else {
+    // W = (A V0_raw) * Rtot, Rtot = the upper-triangular factor that orthonormalises the raw start block
+    for (int e = tid; e < k * k; e += PO_THREADS) Gs[e] = p.w_scale[e];
+    __syncthreads();
+    for (int e = tid; e < R * KP; e += PO_THREADS) {
+      const int r = e / KP, j = e - r * KP;
+      double v = 0.0;
+      if (r < rows && j < k)
+        for (int i = 0; i <= j; ++i) v = fma((double)W[((int64_t)row0 + r) * k + i], Gs[i * k + j], v);
+      Zs[e] = v;
+    }
+    __syncthreads();                        // every raw row has been read: write the corrected block back in place
+    TV* Wout = const_cast<TV*>(W);
+    for (int e = tid; e < rows * k; e += PO_THREADS) {
+      const int r = e / k, j = e - r * k;
+      Wout[((int64_t)row0 + r) * k + j] = (TV)Zs[(size_t)r * KP + j];
+    }
   }
   const int slot = 1 - ctl->best_slot;
   if (rz_nblk > 0) {
@@ -1719,6 +1742,8 @@ struct CheckArgs {
   double* evals_best;       // [k]
   float min_eps;
   int seq;                  // checks apply their bookkeeping in launch order: this one waits for ticket seq - 1
+  int* host_res;            // optional host-mapped result mirror (see output_kernel): filled by the check that converges,
+  int res_seq;              // so that the host has niter / best_resid the moment it sees the stop flag
   // row-sharded engine: Q / n are this rank's rows only and the maximum is completed over the ranks through the
   // exchange regions: every rank stores (tag << 32 | float bits of its maximum) into slot seq & 3 of every region
   int world, rank;
@@ -1929,7 +1954,16 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
         ctl->local_done = 1;
         if (ctl->stop_iter == 0) ctl->stop_iter = iter;
         __threadfence();
-        if (!ctl->collective) signal_done(ctl);
+        if (!ctl->collective) {
+          if (chk.host_res != nullptr) {
+            volatile int* hr = chk.host_res;
+            hr[1] = 1; hr[2] = ctl->niter; hr[3] = ctl->breakdown;
+            hr[4] = __float_as_int(ctl->best_resid);
+            __threadfence_system();
+            hr[0] = chk.res_seq;
+          }
+          signal_done(ctl);
+        }
       }
       if (iter < 64) ctl->trace[iter][3] = gtimer();
     }
@@ -2046,7 +2080,7 @@ __global__ void unpack_gathered_kernel(const TV* __restrict__ Wg, int world, int
   }
 }
 
-__global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
+__global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done, int host_epoch) {
   unsigned long long* tr = &ctl->trace[0][0];
   unsigned long long* pt = &ctl->ptrace[0][0];
   unsigned long long* br = &ctl->barr[0][0];
@@ -2056,12 +2090,135 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done) {
   __syncthreads();
   if (threadIdx.x != 0) return;
   ctl->host_done = host_done;
+  ctl->host_epoch = host_epoch;
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
   ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0; ctl->done_latched = 0;
   ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0; ctl->stop_iter = 0;
   ctl->trace[0][0] = gtimer();
+}
+
+// Cholesky-QR twice of the (n, k) start block on ONE CTA (tensor.py:8-19 / symeig.py:249-252), so that it can run on a
+// side stream -- on one of the two SMs the matvec grid leaves free -- while the first matvec already streams A against
+// the RAW block:  A Q_0 = (A V_0) Rtot  with  Q_0 = V_0 Rtot,  Rtot = R_1^-1 R_2^-1 (upper triangular, written to `Rtot`
+// for the first fused kernel).  Gram matrices in fp64; thread <-> (4 x 4 block of the Gram matrix, row slice) with one
+// 16-byte load per operand and row, warp-shuffle + shared-memory reduction.
+template <typename TV>
+__global__ void __launch_bounds__(1024)
+start_block_kernel(const TV* __restrict__ V0, int64_t ld, int n, int k, TV* Q, double* Rtot, EigCtl* ctl) {
+  __shared__ double Gs[SE_MAXK * SE_MAXK];
+  __shared__ double Ri1[SE_MAXK * SE_MAXK];
+  __shared__ double Ri2[SE_MAXK * SE_MAXK];
+  __shared__ double part[32][16];
+  __shared__ int ok_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kb = (k + 3) / 4;                     // 4 x 4 blocks per side
+  const int nblk = kb * kb;                       // <= 16
+  const int S = (1024 / nblk) / 32 * 32;          // row slices per block (a multiple of 32: warps never mix blocks)
+  const int blk = tid / S, slice = tid - blk * S;
+  const int bi = blk / kb, bj = blk - bi * kb;
+  auto gram = [&](const TV* X, int64_t ldx) {
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    if (blk < nblk && bj <= bi) {                 // lower triangle of blocks
+      for (int row = slice; row < n; row += S) {
+        const TV* xr = X + (int64_t)row * ldx;
+        double u[4], v[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          u[a] = (4 * bi + a < k) ? (double)xr[4 * bi + a] : 0.0;
+          v[a] = (4 * bj + a < k) ? (double)xr[4 * bj + a] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] = fma(u[a], v[c], acc[a][c]);
+      }
+    }
+    for (int rr = 0; rr < nblk; ++rr) {           // one block of the Gram matrix per round through part[][]
+      if (blk == rr) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double w = warp_sum(acc[a][c]);
+            if (lane == 0) part[warp - rr * (S / 32)][4 * a + c] = w;
+          }
+      }
+      __syncthreads();
+      if (tid < 16) {
+        const int rbi = rr / kb, rbj = rr - rbi * kb;
+        if (rbj <= rbi) {
+          double sum = 0.0;
+          for (int w = 0; w < S / 32; ++w) sum += part[w][tid];
+          const int gi = 4 * rbi + tid / 4, gj = 4 * rbj + (tid & 3);
+          if (gi < k && gj < k) { Gs[gi * k + gj] = sum; Gs[gj * k + gi] = sum; }
+        }
+      }
+      __syncthreads();
+    }
+  };
+  // ---- pass 1: G = V0^T V0, R1
+  gram(V0, ld);
+  if (warp == 0) {
+    const int ok = chol_inverse_warp(Gs, Ri1, k, nullptr);
+    if (lane == 0) ok_s = ok;
+  }
+  __syncthreads();
+  // Q1 = V0 R1^-1 (a thread owns whole rows)
+  if (ok_s) {
+    for (int row = tid; row < n; row += 1024) {
+      double q[SE_MAXK];
+      for (int i = 0; i < k; ++i) q[i] = (double)V0[(int64_t)row * ld + i];
+      for (int j = 0; j < k; ++j) {
+        double acc = 0.0;
+        for (int i = 0; i <= j; ++i) acc = fma(q[i], Ri1[i * k + j], acc);
+        Q[(int64_t)row * k + j] = (TV)acc;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- pass 2: G = Q1^T Q1, R2, Q = Q1 R2^-1 (in place: a thread owns whole rows)
+  if (ok_s) {
+    gram(Q, k);
+    if (warp == 0) {
+      const int ok = chol_inverse_warp(Gs, Ri2, k, nullptr);
+      if (lane == 0) ok_s = ok;
+    }
+    __syncthreads();
+  }
+  if (ok_s) {
+    for (int row = tid; row < n; row += 1024) {
+      double q[SE_MAXK];
+      for (int i = 0; i < k; ++i) q[i] = (double)Q[(int64_t)row * k + i];
+      for (int j = k - 1; j >= 0; --j) {
+        double acc = 0.0;
+        for (int i = 0; i <= j; ++i) acc = fma(q[i], Ri2[i * k + j], acc);
+        Q[(int64_t)row * k + j] = (TV)acc;
+      }
+    }
+    for (int e = tid; e < k * k; e += 1024) {
+      const int i = e / k, j = e - i * k;
+      double acc = 0.0;
+      for (int t = i; t <= j; ++t) acc = fma(Ri1[i * k + t], Ri2[t * k + j], acc);
+      Rtot[e] = acc;
+    }
+  } else {
+    // rank-deficient start block: stop (zero block and zero factor keep the later kernels well defined)
+    for (int e = tid; e < n * k; e += 1024) Q[e] = TV(0);
+    for (int e = tid; e < k * k; e += 1024) Rtot[e] = 0.0;
+    if (tid == 0) {
+      ctl->breakdown = 1;
+      ctl->local_done = 1;
+      ctl->done_latched = 1;
+      signal_done(ctl);
+    }
+  }
 }
 
 // ============================================================================ host driver
@@ -2138,6 +2295,7 @@ static int side_pool_get(SidePool** out) {
     if (pool.hflag) cudaFreeHost(const_cast<int*>(pool.hflag));
     void* hp = nullptr;
     XT_CUDA_OK(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    memset(hp, 0, 64);
     pool.hflag = static_cast<volatile int*>(hp);
     XT_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pool.hflag_dev), hp, 0));
     for (int i = 0; i < 2; ++i) XT_CUDA_OK(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
@@ -2278,13 +2436,38 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
   for (int b = 0; b < g->nbatch; ++b) {
     const void* Ab = static_cast<const char*>(g->A) +
                      (size_t)b * g->a_bstride * (g->dtype == XT_F32 ? 4 : (g->dtype == XT_BF16 ? 2 : 8));
-    *pool.hflag = 0;
+    const int my_seq = ++pool.res_seq;          // this solve's ticket: stop flag value and result-mirror tag
+    if (my_seq == 0x7fffffff) pool.res_seq = 0;
     const auto host_t0 = std::chrono::steady_clock::now();
-    init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev); XT_LAUNCHED();
+    init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, collective ? 1 : 0, pool.hflag_dev, my_seq); XT_LAUNCHED();
     // ---- orthonormalise the start block (Cholesky-QR twice; tensor.py:8-19 / symeig.py:249-252)
     bool c_zero = false;        // W.Pacc is known to be all zeros (left so by the fused expansion kernel)
     bool start_done = false;
-    if (fuse_enabled && getenv("XT_START_UNFUSED") == nullptr) {
+    const TV* raw_start = nullptr;        // non-null: the first matvec runs on the RAW start block (see start_block_kernel)
+    // (only when iteration 1 is certain to take the fused expansion kernel, which applies the start block's factor)
+    const bool first_fused = overlap && g->max_niter > 1 && 2 * k <= n && 2 * k <= mb &&
+                             (po_smem_bytes(sizeof(TV), KP, po_R, k, k, 0, true) <= (size_t)PO_SMEM_MAX ||
+                              po_smem_bytes(sizeof(TV), KP, po_R, k, k, 0, false) <= (size_t)PO_SMEM_MAX);
+    // (opt-in, XT_START_OVERLAP=1: measured on B200 the one-CTA Cholesky-QR is latency-bound -- ~340 us next to a running
+    //  matvec for a 16384 x 8 block, longer than the matvec it hides behind -- so the serial start below is the default)
+    if (fuse_enabled && async_check && first_fused && g->apply == nullptr && getenv("XT_START_OVERLAP") != nullptr &&
+        getenv("XT_START_UNFUSED") == nullptr) {
+      const TV* src = static_cast<const TV*>(g->V0) + (int64_t)b * g->v0_bstride;
+      if (g->ldv0 != k || (reinterpret_cast<uintptr_t>(src) & 15) != 0) {
+        gather_block_kernel<TV><<<grid_rows, 256, 0, st>>>(src, g->ldv0, n, k, Rblk); XT_LAUNCHED();
+        src = Rblk;
+      }
+      XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)2 * PO_NCOPY * (mb + SE_MAXK) * k, st));
+      c_zero = true;
+      // Cholesky-QR of the start block on a side stream, next to the first matvec
+      XT_CUDA_OK(cudaEventRecord(evC[0], st));
+      XT_CUDA_OK(cudaStreamWaitEvent(side[0], evC[0], 0));
+      start_block_kernel<TV><<<1, 1024, 0, side[0]>>>(src, k, n, k, V, W.Rinv, W.ctl); XT_LAUNCHED();
+      XT_CUDA_OK(cudaEventRecord(evR[0], side[0]));
+      raw_start = src;
+      start_done = true;
+    }
+    if (!start_done && fuse_enabled && getenv("XT_START_UNFUSED") == nullptr) {
       // two launches of the fused expansion kernel with an empty basis (m = 0: no projection, G = W^T W, Q = W chol(G)^-T)
       // instead of gather + 2 x (memset, projection kernel, finish kernel)
       const size_t st_smem = po_smem_bytes(sizeof(TV), KP, po_R, k, 0, 0, true);
@@ -2377,12 +2560,12 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         // (polled, not cudaEventSynchronize: a blocking wait wakes the host 10-20 us late, which is pure idle time of
         // the GPU at the end of a solve; the stop flag itself is visible here the moment a kernel raises it)
         cudaEvent_t evw = pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)];
-        while (!*pool.hflag) {
+        while (*pool.hflag != my_seq) {
           const cudaError_t qe = cudaEventQuery(evw);
           if (qe == cudaSuccess) break;
           if (qe != cudaErrorNotReady) { XT_CUDA_OK(qe); }
         }
-        if (*pool.hflag) { --iter; break; }
+        if (*pool.hflag == my_seq) { --iter; break; }
       }
       const int j = m / k - 1;     // newest block
       const int par = overlap ? (iter % NSLOT) : 0;
@@ -2392,7 +2575,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.dtype = g->dtype;
       a.nbatch = 1; a.nrows = n_local; a.ncolsA = n; a.k = k;
       a.A = Ab; a.lda = g->lda; a.a_bstride = 0;
-      a.X = V + j * blk; a.ldx = k; a.x_bstride = 0;
+      a.X = (raw_start != nullptr && iter == 1) ? raw_start : V + j * blk; a.ldx = k; a.x_bstride = 0;
       TV* Wg = static_cast<TV*>(W.Wg);
       const int64_t per = (int64_t)(n_local + 1) * k;
       a.Y = collective ? Wg + (int64_t)g->rank * per : AV + j * blk;
@@ -2453,6 +2636,12 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
               pa.rz_m = q.m; pa.rz_iter = q.iter; pa.rz_ld = q.nev; pa.rz_coff = q.coff;
               pa.rz_S = Skpar[q.par]; pa.rz_theta = thpar[q.par];
             }
+            if (raw_start != nullptr && iter == 1) {
+              // the start block's Cholesky-QR (side stream) is needed from here on: Q_0 in the basis, its factor to
+              // turn A V0_raw into A Q_0
+              XT_CUDA_OK(cudaStreamWaitEvent(st, evR[0], 0));
+              pa.w_scale = W.Rinv;
+            }
             if (async_check) {
               // slot `par` (Cholesky factor, Ritz coefficients) is free once the Rayleigh-Ritz kernel of iteration
               // iter - NSLOT is through; this also bounds how far the side streams can fall behind
@@ -2478,6 +2667,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
               chk.Q = pa.Qout; chk.L = pa.Lout; chk.n = n; chk.is_f64 = sizeof(TV) == 8 ? 1 : 0;
               chk.Sbest = W.Sbest; chk.evals_best = W.evals_best; chk.min_eps = (float)g->min_eps;
               chk.seq = ++check_seq;
+              chk.host_res = pool.hflag_dev + 8; chk.res_seq = my_seq;
               async_inflight = true;
             }
             rr_kernel<<<1, EIG_THREADS, plf.smem_bytes, rsf>>>(W.T, mb, nullptr, m, k, k, Twpar[iter & 1], Skpar[par],
@@ -2500,6 +2690,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
           }
         }
       }
+      XT_REQUIRE(!(raw_start != nullptr && iter == 1), "symeig: internal error (raw start block outside the fused path)");
       // 2. C = V^T W  (new block column of T)
       rc = settle_async();                       // restart / last iteration after asynchronous checks
       if (rc != XT_OK) return rc;
@@ -2613,7 +2804,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
     output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n, k,
                                                  static_cast<TV*>(g->evecs) + (int64_t)b * g->evecs_bstride, g->ldv,
                                                  static_cast<TV*>(g->evals) + (int64_t)b * g->evals_bstride, 0, W.ctl,
-                                                 pool.hflag_dev + 8, ++pool.res_seq); XT_LAUNCHED();
+                                                 pool.hflag_dev + 8, my_seq); XT_LAUNCHED();
     EigCtl h;
     const bool tracing = getenv("XT_TRACE") != nullptr;
     bool have_res = false;
@@ -2623,9 +2814,9 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       volatile int* hr = pool.hflag + 8;
       const auto w0 = std::chrono::steady_clock::now();
       while (true) {
-        if (hr[0] == pool.res_seq) { have_res = true; break; }
+        if (hr[0] == my_seq) { have_res = true; break; }
         if (std::chrono::steady_clock::now() - w0 > std::chrono::milliseconds(2)) {
-          if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == pool.res_seq); break; }
+          if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == my_seq); break; }
         }
       }
       if (have_res) {
@@ -3073,8 +3264,9 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     return XT_OK;
   };
 
-  *pool.hflag = 0;
-  init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, 2, pool.hflag_dev); XT_LAUNCHED();
+  const int my_seq = ++pool.res_seq;            // this solve's ticket: stop flag value and result-mirror tag
+  if (my_seq == 0x7fffffff) pool.res_seq = 0;
+  init_ctl_kernel<<<1, 256, 0, st>>>(W.ctl, 2, pool.hflag_dev, my_seq); XT_LAUNCHED();
   peer_start_kernel<<<1, 32, 0, st>>>(base, etag | 1ull, (int)((g->epoch + 2u) & 3u)); XT_LAUNCHED();
   XT_CUDA_OK(cudaMemsetAsync(W.Pacc, 0, sizeof(double) * (size_t)2 * PO_NCOPY * (mb + SE_MAXK) * k, st));
   // ---- start block: Cholesky-QR twice on the row-sharded block (tensor.py:8-19 / symeig.py:249-252)
@@ -3112,12 +3304,12 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     ++iter;
     if (iter > LOOKAHEAD) {
       cudaEvent_t evw = pool.it[(iter - LOOKAHEAD) % (LOOKAHEAD + 1)];
-      while (!*pool.hflag) {
+      while (*pool.hflag != my_seq) {
         const cudaError_t qe = cudaEventQuery(evw);
         if (qe == cudaSuccess) break;
         if (qe != cudaErrorNotReady) { XT_CUDA_OK(qe); }
       }
-      if (*pool.hflag) { --iter; break; }
+      if (*pool.hflag == my_seq) { --iter; break; }
     }
     const int par = iter % NSLOT;
     // 1. W = A_p Q_j  (into the spare block while a restart is pending: block j itself is about to be rotated away)
@@ -3218,16 +3410,16 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
   (void)latched_upto;
   output_kernel<TV><<<grid_rows, 256, 0, st>>>(V, Xslots, W.evals_slots, W.Sbest, W.evals_best, n_loc, k,
                                                static_cast<TV*>(g->evecs), g->ldv, static_cast<TV*>(g->evals), 0, W.ctl,
-                                               pool.hflag_dev + 8, ++pool.res_seq); XT_LAUNCHED();
+                                               pool.hflag_dev + 8, my_seq); XT_LAUNCHED();
   EigCtl h;
   bool have_res = false;
   {
     volatile int* hr = pool.hflag + 8;
     const auto w0 = std::chrono::steady_clock::now();
     while (true) {
-      if (hr[0] == pool.res_seq) { have_res = true; break; }
+      if (hr[0] == my_seq) { have_res = true; break; }
       if (std::chrono::steady_clock::now() - w0 > std::chrono::milliseconds(2)) {
-        if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == pool.res_seq); break; }
+        if (cudaStreamQuery(st) != cudaErrorNotReady) { have_res = (hr[0] == my_seq); break; }
       }
     }
     if (have_res) {
