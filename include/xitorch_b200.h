@@ -47,7 +47,8 @@ typedef enum {
   XT_ERR_INVALID = -1,     /* bad argument / unsupported shape or alignment */
   XT_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
   XT_ERR_WORKSPACE = -3,   /* workspace too small */
-  XT_ERR_BREAKDOWN = -4    /* numerical breakdown that cannot be recovered (e.g. non-finite input) */
+  XT_ERR_BREAKDOWN = -4,   /* numerical breakdown that cannot be recovered (e.g. non-finite input) */
+  XT_ERR_ABORTED = -5      /* a callback asked to stop through `abort` (e.g. user code raised): nothing else is called */
 } xt_status;
 
 int xt_version(void);
@@ -139,6 +140,9 @@ typedef struct {
   void* precond_l;
   void* precond_r;
   void* precond_user;
+  /* optional HOST flag a callback may set non-zero (user code failed): the library then returns XT_ERR_ABORTED right
+   * after that callback instead of iterating on garbage until max_niter */
+  const int32_t* abort;
 } xt_solve_args;
 
 size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, int32_t nbatch,
@@ -208,6 +212,7 @@ typedef struct {
   const void* const* peers;
   uint32_t epoch;
   int32_t restart_keep;
+  const int32_t* abort;                       /* optional host flag set by the `apply` callback: see xt_solve_args.abort */
 } xt_symeig_args;
 
 size_t xt_symeig_workspace_bytes(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world);

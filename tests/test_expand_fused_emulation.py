@@ -106,7 +106,7 @@ def _check(r):
     k, m, V, W, Q, eps = r["k"], r["m"], r["V"], r["W"], r["Q"], r["eps"]
     n = V.shape[0]
     tol = 50 * eps * max(1.0, np.abs(W).max()) * np.sqrt(n)
-    assert r["ctl"]["breakdown"] == 0 and r["ctl"]["bar_count"] == 0
+    assert r["ctl"]["breakdown"] == 0 and r["ctl"]["bar_count"] > 0 and r["ctl"]["bar_count"] % 2 == 0   # monotone: 2 barriers x CTAs
     # new block column of the projected matrix (diagonal block symmetrised)
     C = V.T @ W
     c0 = m - k

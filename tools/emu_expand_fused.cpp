@@ -55,6 +55,8 @@ static unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &
 static float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
 static void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
 static void cp_async_wait_all() {}
+static void pdl_wait() {}
+static void pdl_trigger() {}
 template <typename T> T block_max(T v, T*) {
   t_red[threadIdx.x] = (float)v;
   t_cta_bar->arrive_and_wait();

@@ -99,6 +99,8 @@ def _flatten(t: torch.Tensor, batch: Sequence[int], tail: Sequence[int], dtype) 
 
 
 def _mat3(mat: torch.Tensor, batch: Sequence[int]):
+    if mat.dim() == 2 and mat.stride(1) == 1 and mat.data_ptr() % 16 == 0:
+        return mat, 0, mat.stride(0)               # the common case without the general broadcast bookkeeping
     from xitorch_b200._dense import flatten_batch
     m3, bstride, ld = flatten_batch(mat, tuple(batch))
     if m3.data_ptr() % 16 != 0:
@@ -106,9 +108,10 @@ def _mat3(mat: torch.Tensor, batch: Sequence[int]):
     return m3, bstride, ld
 
 
-def _block_callback(fn, ws, nbytes, vdt, shape, opdt, failure):
+def _block_callback(fn, ws, nbytes, vdt, shape, opdt, failure, abort=None):
     """ctypes callback `(user, X, Y, stream)` computing ``Y = fn(X)`` on (nbatch, n, ncols) blocks that live inside the
-    workspace tensor `ws`; exceptions cannot cross the C frame and are collected in `failure`."""
+    workspace tensor `ws`; exceptions cannot cross the C frame: they are collected in `failure` and raise the `abort`
+    cell (`xt_solve_args.abort`), on which the engine returns at once instead of iterating on garbage."""
     base = ws.data_ptr()
 
     def _cb(user, xptr, yptr, stream):
@@ -120,6 +123,8 @@ def _block_callback(fn, ws, nbytes, vdt, shape, opdt, failure):
         except BaseException as exc:
             if not failure:
                 failure.append(exc)
+            if abort is not None:
+                abort.value = 1
 
     return _lib.APPLY_FN(_cb)
 
@@ -209,13 +214,15 @@ def _run_matrix_free(name: str, A: LinearOperator, B: torch.Tensor, E, M, posdef
     g.stream = _lib.stream_ptr(Bf.device)
     nbytes = nb * n * ncols * ws.new_empty(0, dtype=vdt).element_size()
     failure = []
+    abort = C.c_int32(0)
+    g.abort = C.pointer(abort)
     shape = (*batch, n, ncols)
-    cb = _block_callback(op, ws, nbytes, vdt, shape, opdt, failure)
+    cb = _block_callback(op, ws, nbytes, vdt, shape, opdt, failure, abort)
     g.apply = _lib.fn_address(cb)
     keep = [cb]
     for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
         if pc is not None:
-            pcb = _block_callback(pc.mm, ws, nbytes, vdt, shape, opdt, failure)
+            pcb = _block_callback(pc.mm, ws, nbytes, vdt, shape, opdt, failure, abort)
             setattr(g, field, _lib.fn_address(pcb))
             keep.append(pcb)
     with torch.cuda.device(Bf.device):
@@ -405,9 +412,12 @@ def _call(name, Amat, Mmat, E, B, batch, n, ncols, vdt, max_niter, rtol, atol, e
     if precond_l is not None or precond_r is not None:
         # preconditioners reach the library as block callbacks (a dense one is a single xt_block_matvec per call)
         nbytes = nb * n * ncols * X.element_size()
+        abort = C.c_int32(0)
+        g.abort = C.pointer(abort)
+        keep.append(abort)
         for field, pc in (("precond_l", precond_l), ("precond_r", precond_r)):
             if pc is not None:
-                pcb = _block_callback(pc.mm, ws, nbytes, vdt, (*batch, n, ncols), pc.dtype, failure)
+                pcb = _block_callback(pc.mm, ws, nbytes, vdt, (*batch, n, ncols), pc.dtype, failure, abort)
                 setattr(g, field, _lib.fn_address(pcb))
                 keep.append(pcb)
         g.check_every = 1

@@ -201,6 +201,7 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
         return evals, (torch.matmul(LinvT, evecs) if LinvT is not None else evecs)
     V0 = _start(v_init, 1, n, neig, vdt, dev)
     failure = []
+    abort = C.c_int32(0)
 
     def make_apply(ws):
         base, nbytes = ws.data_ptr(), n * neig * V0.element_size()
@@ -214,12 +215,18 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
             except BaseException as exc:
                 if not failure:
                     failure.append(exc)
+                abort.value = 1          # the engine returns right after this callback (xt_symeig_args.abort)
 
         return _lib.APPLY_FN(_cb)
 
     run = {} if info is None else info
-    evals, evecs = _call_engine(None, 0, 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis, check_every,
-                                min_eps, run, name, make_apply=make_apply)
+    try:
+        evals, evecs = _call_engine(None, 0, 0, n, 1, neig, mode, expansion, V0, max_niter, max_basis, check_every,
+                                    min_eps, run, name, make_apply=make_apply, abort=abort)
+    except RuntimeError:
+        if failure:
+            raise failure[0]
+        raise
     if failure:
         raise failure[0]
     if _space_exhausted(run, n, neig, max_niter):
@@ -295,7 +302,7 @@ _WS_CACHE_MAX_BYTES = 64 << 20
 
 
 def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max_basis, check_every, min_eps,
-                 info, name, dist_ctx=None, make_apply=None, out_batch=None):
+                 info, name, dist_ctx=None, make_apply=None, out_batch=None, abort=None):
     """fill `xt_symeig_args` and run `xt_symeig_krylov`.  dist_ctx = (world, rank, group) for the row-partitioned
     operator: A3 is then this rank's (n/world, n) row block and the per-iteration all-gather hook is installed.
     make_apply(workspace) -> APPLY_FN for a matrix-free operator (A3 is then None).
@@ -378,6 +385,8 @@ def _call_engine(A3, lda, a_bs, n, nb, neig, mode, expansion, V0, max_niter, max
         acb = make_apply(ws)
         keep.append(acb)
         g.apply = _lib.fn_address(acb)
+        if abort is not None:
+            g.abort = C.pointer(abort)
     with torch.cuda.device(dev):
         _lib.check(L_.xt_symeig_krylov(g), name)
     if info is not None:

@@ -58,6 +58,7 @@ class SolveArgs(C.Structure):
         ("stream", C.c_void_p),
         ("apply", C.c_void_p), ("apply_user", C.c_void_p),
         ("precond_l", C.c_void_p), ("precond_r", C.c_void_p), ("precond_user", C.c_void_p),
+        ("abort", C.POINTER(C.c_int32)),
     ]
 
 
@@ -83,6 +84,7 @@ class SymeigArgs(C.Structure):
         ("allgather", C.c_void_p), ("allgather_user", C.c_void_p),
         ("apply", C.c_void_p), ("apply_user", C.c_void_p),
         ("peers", C.POINTER(C.c_void_p)), ("epoch", C.c_uint32), ("restart_keep", C.c_int32),
+        ("abort", C.POINTER(C.c_int32)),
     ]
 
 

@@ -288,7 +288,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
     return XT_ERR_WORKSPACE;
   }
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, nullptr, 0, 0, nullptr, 0};
-  op.apply = g->apply; op.apply_user = g->apply_user;
+  op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem_init = (size_t)(2 * g->ncols + 2 * SV_THREADS + 64) * sizeof(double);
   const size_t smem_step =

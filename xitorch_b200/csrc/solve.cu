@@ -439,6 +439,7 @@ template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>&
     // x = P_r xt for the best iterate
     solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, S.ex[1], g->ncols, (int64_t)g->n * g->ncols); XT_LAUNCHED();
     reinterpret_cast<xt_apply_fn>(pre)(g->precond_user, S.ex[1], S.ex[2], st);
+    XT_CHECK_ABORT(g->abort);
     copy_out_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S.ex[2], g->n, g->ncols, static_cast<TV*>(g->X), g->ldx,
                                                           g->x_bstride); XT_LAUNCHED();
   } else {
@@ -464,7 +465,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
-  op.apply = g->apply; op.apply_user = g->apply_user;
+  op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0); XT_LAUNCHED();
@@ -475,7 +476,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   const int* done_flag = &S.ctl->done;
   // preconditioner z = P r (solve.py:136,171): one more operator application per iteration, r.z fused into it
   OpDesc pc{g->dtype, g->n, g->nbatch, g->ncols, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0};
-  pc.apply = g->precond_l; pc.apply_user = g->precond_user;
+  pc.apply = g->precond_l; pc.apply_user = g->precond_user; pc.abort = g->abort;
   S.precond = g->precond_l != nullptr ? 1 : 0;
   TV* zbuf = S.s;                         // unused by plain cg
   auto precond_step = [&](int first) -> int {
@@ -525,13 +526,13 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   if (rc != XT_OK) return rc;
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
-  op.apply = g->apply; op.apply_user = g->apply_user;
+  op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
   // right preconditioner (solve.py:276,282): y = P_r p, z = P_r s and x = h + omega z are the plain recurrences of the
   // composed operator A o P_r on the iterate xt with x = P_r xt (applied once at the end); the residual is untouched
   op.pre = g->precond_r; op.pre_user = g->precond_user; op.pre_tmp = S.ex[0];
   // left preconditioner (solve.py:285-286): only omega = <K t, K s> / <K t, K t>
   OpDesc pl{g->dtype, g->n, g->nbatch, g->ncols, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0};
-  pl.apply = g->precond_l; pl.apply_user = g->precond_user;
+  pl.apply = g->precond_l; pl.apply_user = g->precond_user; pl.abort = g->abort;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1); XT_LAUNCHED();

@@ -95,7 +95,16 @@ struct OpDesc {
   void* pre = nullptr;          // right preconditioner callback: the operator applied is A o pre
   void* pre_user = nullptr;
   void* pre_tmp = nullptr;      // (nbatch, n, ncols) scratch for pre(X)
+  const volatile int* abort = nullptr;   // host flag a callback sets to stop the solve (xt_solve_args.abort)
 };
+
+#define XT_CHECK_ABORT(flag)                                                           \
+  do {                                                                                 \
+    if ((flag) != nullptr && *(flag) != 0) {                                           \
+      xt::set_last_error("stopped by a callback (the operator's code failed)");         \
+      return XT_ERR_ABORTED;                                                           \
+    }                                                                                  \
+  } while (0)
 
 typedef void (*xt_apply_fn)(void* user, const void* X, void* Y, void* stream);
 
@@ -141,6 +150,7 @@ static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const T
   if (op.pre != nullptr) {
     // composed operator A o pre: the preconditioned block goes through scratch, then the operator proper
     reinterpret_cast<xt_apply_fn>(op.pre)(op.pre_user, X, op.pre_tmp, st);
+    XT_CHECK_ABORT(op.abort);
     OpDesc inner = op;
     inner.pre = nullptr;
     return apply_op<TV>(inner, static_cast<const TV*>(op.pre_tmp), Y, mx, U, dots, dots_gstride, done_flag, st, napply);
@@ -149,6 +159,7 @@ static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const T
     // matrix-free operator: the caller applies it, the dot products the dense path fuses into the matvec epilogue
     // come from one small kernel with the same per-tile layout
     reinterpret_cast<xt_apply_fn>(op.apply)(op.apply_user, X, Y, st);
+    XT_CHECK_ABORT(op.abort);
     if (dots != nullptr) {
       const MvTiling til = mv_tiling(op.nbatch, op.n);
       tile_dots_kernel<TV><<<til.ntiles, 256, 0, st>>>(U, Y, op.n, op.ncols, til.tile_rows, til.tiles_per_batch, dots,

@@ -48,7 +48,8 @@ struct EigCtl {
   unsigned int counter;
   unsigned int resmax_bits;   // max |R| of the current iteration (float bits, atomicMax)
   float best_resid;
-  unsigned int bar_count, bar_gen;   // grid barrier of the fused expansion kernel
+  unsigned int bar_count, bar_gen;   // grid barrier of the fused expansion kernel (monotone arrival counter; bar_gen unused)
+  unsigned int bar_done;             // grid barriers completed by earlier launches of this solve
   int bar_abort;        // latched at a grid barrier: some CTA saw `done` (raised asynchronously by a side-stream check)
   int done_latched;     // set by the fused kernel that left through `bar_abort`: stream-ordered copy of `done`, uniform
                         // for every later kernel of the main stream (which then returns at once instead of meeting at
@@ -507,25 +508,25 @@ struct PostArgs {
 // side stream at any moment, so the CTAs must not read it on their own (some would leave, the others would wait for
 // them).  Every CTA that has seen the flag when it arrives latches `bar_abort`; all arrivals precede the release, so
 // after it every CTA reads the same value and the grid leaves together (returns false).
-__device__ __forceinline__ bool grid_barrier(EigCtl* ctl, unsigned int nblocks, unsigned long long* tin = nullptr,
-                                             unsigned long long* tout = nullptr, bool async_stop = false) {
+__device__ __forceinline__ bool grid_barrier(EigCtl* ctl, unsigned int nblocks, unsigned int index,
+                                             unsigned long long* tin = nullptr, unsigned long long* tout = nullptr,
+                                             bool async_stop = false) {
+  // Monotone arrival counter: barrier number `index` of this kernel is number ctl->bar_done + index of the solve
+  // (ctl->bar_done counts the barriers completed by earlier launches; CTA 0 advances it after the LAST barrier of a
+  // kernel, when every CTA has long read it) and is passed once the counter reaches (that number + 1) * nblocks.  One fire-and-forget atomic per CTA and a polled read -- no "last arriver" hop (the
+  // sense-reversing form cost one more L2 round trip per barrier, ~1 us, twice per iteration).
   __shared__ int ok_s;
   __syncthreads();
   if (threadIdx.x == 0) {
     int ok = 1;
     if (tin) tin[blockIdx.x] = gtimer();
     if (async_stop && *reinterpret_cast<volatile int*>(&ctl->done) != 0) atomicExch(&ctl->bar_abort, 1);
-    const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&ctl->bar_gen);
+    const unsigned int target = (ctl->bar_done + index + 1u) * nblocks;
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    if (atomicAdd(&ctl->bar_count, 1u) == nblocks - 1) {
-      ctl->bar_count = 0;
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      atomicAdd(&ctl->bar_gen, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(&ctl->bar_gen) == gen) {
-        if (clock64() - t0 > 1500000000LL) { ok = 0; break; }      // ~0.8 s: never hang the device
-      }
+    atomicAdd(&ctl->bar_count, 1u);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(&ctl->bar_count) < target) {
+      if (clock64() - t0 > 1500000000LL) { ok = 0; break; }      // ~0.8 s: never hang the device
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     if (tout) tout[blockIdx.x] = gtimer();
@@ -807,7 +808,7 @@ expand_fused_kernel(const PostArgs p) {
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, false, part, accC);
   if (tr) ctl->ptrace[p.iter][3] = gtimer();
   const bool btr = (p.iter == 8 && gridDim.x <= 160);
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr, p.async_stop != 0)) {
+  if (!grid_barrier(ctl, gridDim.x, 0u, btr ? ctl->barr[0] : nullptr, btr ? ctl->barr[1] : nullptr, p.async_stop != 0)) {
     if (p.async_stop && blockIdx.x == 0 && tid == 0) ctl->done_latched = 1;
     return;
   }
@@ -858,10 +859,11 @@ expand_fused_kernel(const PostArgs p) {
   if (tr) ctl->ptrace[p.iter][5] = gtimer();
   po_project<TV, KP>(Vb, Zs, rows, vbs, k, m, true, part, accC2);
   if (tr) ctl->ptrace[p.iter][6] = gtimer();
-  if (!grid_barrier(ctl, gridDim.x, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr, p.async_stop != 0)) {
+  if (!grid_barrier(ctl, gridDim.x, 1u, btr ? ctl->barr[2] : nullptr, btr ? ctl->barr[3] : nullptr, p.async_stop != 0)) {
     if (p.async_stop && blockIdx.x == 0 && tid == 0) ctl->done_latched = 1;
     return;
   }
+  if (blockIdx.x == 0 && tid == 0) ctl->bar_done += 2u;          // every CTA has read it (it arrived at both barriers)
   if (tr) ctl->ptrace[p.iter][7] = gtimer();
 
   // ---- P3: Q = (W' - V C2) Rinv
@@ -2094,7 +2096,7 @@ __global__ void init_ctl_kernel(EigCtl* ctl, int collective, int* host_done, int
   ctl->local_done = 0; ctl->collective = collective;
   ctl->done = 0; ctl->converged = 0; ctl->breakdown = 0; ctl->niter = 0; ctl->best_slot = 0;
   ctl->counter = 0; ctl->resmax_bits = 0; ctl->best_resid = INFINITY;
-  ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_abort = 0; ctl->done_latched = 0;
+  ctl->bar_count = 0; ctl->bar_gen = 0; ctl->bar_done = 0; ctl->bar_abort = 0; ctl->done_latched = 0;
   ctl->best_in_S = 0; ctl->best_m = 0; ctl->check_done = 0; ctl->stop_iter = 0;
   ctl->trace[0][0] = gtimer();
 }
@@ -2595,6 +2597,12 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
         // matrix-free operator: the caller computes Y = A X on the stream (the rest of the iteration is unchanged)
         typedef void (*apply_fn)(void*, const void*, void*, void*);
         reinterpret_cast<apply_fn>(g->apply)(g->apply_user, a.X, a.Y, g->stream);
+        if (g->abort != nullptr && *reinterpret_cast<const volatile int32_t*>(g->abort) != 0) {
+          // the operator's code failed: quiesce the side streams, then report
+          for (int q = 0; q < 2; ++q) cudaStreamSynchronize(side[q]);
+          set_last_error("symeig: stopped by the operator callback");
+          return XT_ERR_ABORTED;
+        }
       } else {
         rc = mv_launch(a, st);
       }
