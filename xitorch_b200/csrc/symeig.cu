@@ -3294,6 +3294,16 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
   bool ev_used[NSLOT] = {false, false, false};
   int check_seq = 0;
   int latched_upto = 0;
+  // How many iterations later a check's verdict is consumed.  One, while a Rayleigh-Ritz kernel (~5 us per basis vector
+  // at the cap, next to a running matvec) fits under the local matvec; two beyond (8 GPUs at C5: 0.5 ms of matvec
+  // against 0.6 ms), where waiting for it every iteration would make the replicated kernel the critical path -- at the
+  // price of one more matvec after convergence.  (Two is also the most the double-buffered Q copies allow.)
+  int lag = 1;
+  {
+    const double t_mv = (double)n_loc * n * sizeof(TV) / (k > 8 ? 4.2e12 : 6.0e12);
+    if (5.0e-6 * mb > t_mv) lag = 2;
+    if (const char* lv = getenv("XT_SHARDED_LAG")) lag = atoi(lv) >= 2 ? 2 : 1;
+  }
   const int nbk = mb / k;                 // block index of the spare slot of V / AV
   // thick restart, deferred by one matvec: the iteration that fills the basis only requests `keep` Ritz pairs from its
   // Rayleigh-Ritz kernel (side stream); the next iteration's matvec -- it needs nothing but the new block -- runs
@@ -3336,13 +3346,13 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     int rc = mv_launch(a, st);
     if (rc != XT_OK) return rc;
     ++napply;
-    // 2. the verdict of the previous iteration's check, consumed here on every rank (its Rayleigh-Ritz ran next to
-    //    the matvec above)
-    if (iter > 1) {
-      const int pp = (iter - 1) % NSLOT;
+    // 2. the verdict of the check of iteration iter - lag, consumed here on every rank (its Rayleigh-Ritz ran next to
+    //    the matvec(s) above)
+    if (iter > lag) {
+      const int pp = (iter - lag) % NSLOT;
       if (ev_used[pp]) XT_CUDA_OK(cudaStreamWaitEvent(st, evR[pp], 0));
-      latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter - 1); XT_LAUNCHED();
-      latched_upto = iter - 1;
+      latch_kernel<<<1, 32, 0, st>>>(W.ctl, iter - lag); XT_LAUNCHED();
+      latched_upto = iter - lag;
     }
     if (restart_m) {
       // 2b. the pending thick restart (local rows only; every kernel returns at once if the solve has just stopped)
