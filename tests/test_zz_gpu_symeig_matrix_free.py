@@ -2,10 +2,8 @@
 only through `_mv` must give the eigenpairs the dense kernels give for the same matrix (same engine, same start block:
 only the operator application differs) and satisfy the residual identity in fp64.
 
-STATUS: this path was written after the round's GPU minutes were spent -- its host side is tested on CPU
-(tests/test_symeig_matrix_free_host.py) and the engine branch itself by running the engine's source as a host build
-(tests/test_engine_emulation.py), but the first run on hardware is the driver's.  The file sorts last and is marked xfail(strict=False) for that reason only; the mark goes away with the
-first green run.
+Its host side is also tested on CPU (tests/test_symeig_matrix_free_host.py) and the engine branch by running the engine's
+source as a host build (tests/test_engine_emulation.py).  Green on hardware since round 2 (the round-1 xfail mark is gone).
 """
 import pytest
 import torch
@@ -13,8 +11,7 @@ import torch
 import xitorch_b200 as xt
 from xitorch_b200.linalg import symeig, svd
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of the matrix-free symeig hook")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _herm(n, dtype, seed=0):

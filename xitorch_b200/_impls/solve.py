@@ -39,35 +39,67 @@ def get_batchdims(A, B, E, M):
 
 # ----------------------------------------------------------------------------- exact (dense) path
 def exactsolve(A: LinearOperator, B: torch.Tensor, E: Optional[torch.Tensor], M: Optional[LinearOperator]):
-    """Direct dense solve (row f2 of SURVEY.md 8f; reference solve.py:481-537): LU of the full matrix, one
-    shifted matrix per column when E is given, Cholesky whitening when M is given."""
+    """Direct dense solve (row f2 of SURVEY.md 8f; reference solve.py:481-537).  Without E: LU of the full matrix.  With
+    E the reference materialises one shifted N x N matrix PER COLUMN (`_solve_ABE`, solve.py:514-537: ncols x N x N --
+    unusable at N = 16384); here a Hermitian operator is diagonalised ONCE and every column is a diagonal
+    solve in its eigenbasis, a non-Hermitian one is solved column chunk by column chunk within a fixed memory budget.
+    Cholesky whitening when M is given."""
     Amat = A.fullmatrix()
     if E is None:
         return torch.linalg.solve(Amat, B)
+    hermit = bool(A.is_hermitian) and (M is None or bool(M.is_hermitian))
     if M is None:
-        return _solve_shifted(Amat, B, E)
+        return _solve_shifted(Amat, B, E, hermit)
     L = torch.linalg.cholesky(M.fullmatrix())
     Linv = torch.inverse(L)
     LinvT = Linv.transpose(-2, -1).conj()
     A2 = torch.matmul(Linv, A.mm(LinvT))
-    X2 = _solve_shifted(A2, torch.matmul(Linv, B), E)
+    X2 = _solve_shifted(A2, torch.matmul(Linv, B), E, hermit)
     return torch.matmul(LinvT, X2)
 
 
-def _solve_shifted(Amat, B, E):
+_SHIFT_CHUNK_BYTES = 1 << 30        # memory budget of the shifted matrices formed at once (non-Hermitian path)
+
+
+def _solve_shifted(Amat, B, E, hermitian: bool = False):
+    """columns x_j of (A - e_j I) x_j = b_j"""
     n = Amat.shape[-1]
     BA, BB, BE = normalize_bcast_dims(Amat.shape[:-2], B.shape[:-2], E.shape[:-1])
-    Ec = E.reshape(1, *BE, E.shape[-1]).transpose(0, -1)                  # (ncols, *BE, 1)
-    Bc = B.reshape(1, *BB, *B.shape[-2:]).transpose(0, -1)                # (ncols, *BB, n, 1)
+    eps = torch.finfo(Amat.dtype).eps
+    if hermitian:
+        # A = Q diag(lam) Q^H once:  x_j = Q ((Q^H b_j) / (lam - e_j)).  An (almost) singular shift -- the symeig
+        # backward solves at its own eigenvalues -- gets the same remedy as the reference's fallback (a diagonal bump
+        # of 10 eps max|A|, solve.py:531-536), applied to the offending denominators only.
+        As = 0.5 * (Amat + Amat.transpose(-2, -1).conj())
+        lam, Q = torch.linalg.eigh(As.reshape(*BA, n, n))
+        Qh = Q.transpose(-2, -1).conj()
+        Y = torch.matmul(Qh, B.reshape(*BB, *B.shape[-2:]).to(Q.dtype))              # (*B, n, ncols)
+        den = lam.unsqueeze(-1) - E.reshape(*BE, 1, E.shape[-1]).to(lam.dtype)       # (*B, n, ncols)
+        bump = 10 * eps * Amat.abs().reshape(*BA, -1).max(dim=-1)[0][..., None, None]
+        small = den.abs() < bump
+        den = torch.where(small, torch.where(den < 0, -bump, bump).expand_as(den), den)
+        return torch.matmul(Q, Y / den)
+    ncols = B.shape[-1]
+    nbatch = 1
+    for d in bcast_dims(BA, BB, BE):
+        nbatch *= d
+    per_col = max(1, nbatch) * n * n * Amat.element_size()
+    chunk = max(1, min(ncols, _SHIFT_CHUNK_BYTES // max(per_col, 1)))
     eye = torch.eye(n, dtype=Amat.dtype, device=Amat.device)
-    AE = Amat.reshape(*BA, n, n) - Ec.unsqueeze(-1) * eye                 # (ncols, *BAE, n, n)
-    try:
-        r = torch.linalg.solve(AE, Bc)
-    except torch._C._LinAlgError:
-        eps = torch.finfo(Amat.dtype).eps
-        bump = 10 * eps * AE.reshape(*AE.shape[:-2], -1).max(dim=-1)[0][..., None, None]
-        r = torch.linalg.solve(AE + eye * bump, Bc)
-    return r.transpose(0, -1).squeeze(0)
+    outs = []
+    for c0 in range(0, ncols, chunk):
+        c1 = min(ncols, c0 + chunk)
+        Ec = E[..., c0:c1].reshape(1, *BE, c1 - c0).transpose(0, -1)               # (cols, *BE, 1)
+        Bc = B[..., c0:c1].reshape(1, *BB, n, c1 - c0).transpose(0, -1)            # (cols, *BB, n, 1)
+        AE = Amat.reshape(*BA, n, n) - Ec.unsqueeze(-1) * eye                       # (cols, *BAE, n, n)
+        try:
+            r = torch.linalg.solve(AE, Bc)
+        except torch._C._LinAlgError:
+            bump = 10 * eps * AE.reshape(*AE.shape[:-2], -1).max(dim=-1)[0][..., None, None]
+            r = torch.linalg.solve(AE + eye * bump, Bc)
+        outs.append(r.transpose(0, -1).squeeze(0))
+        del AE
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)
 
 
 def custom_exactsolve(A, B, E=None, M=None, **options):

@@ -19,7 +19,8 @@ from xitorch_b200.debug import is_debug_enabled
 from xitorch_b200.linop import LinearOperator, MatrixLinearOperator
 from xitorch_b200._impls.solve import _dense_of, _mat3
 
-_MATERIALISE_MAX_N = 16384      # composite / matrix-free operators up to this size are materialised by default
+_MATERIALISE_MAX_N = 2048       # composite / matrix-free operators up to this size are materialised by default; beyond,
+                                # the engine's `apply` hook runs them matrix-free (verified on hardware in round 2)
 
 __all__ = ["exacteig", "custom_exacteig", "davidson", "lanczos"]
 
@@ -540,7 +541,7 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
     matrix_free: bool or None
         How an operator that is not a dense matrix (user ``_mv``, ``A.H.matmul(A)``, Jacobians ...) is applied.
         ``True``: through ``A.mm`` once per iteration, nothing is materialised.  ``False``: ``A.fullmatrix()`` is built
-        once and the dense kernels are used.  ``None``: materialise up to n = 16384, matrix-free beyond.
+        once and the dense kernels are used.  ``None``: materialise up to n = 2048, matrix-free beyond.
     """
     if expansion not in ("krylov", "residual"):
         raise RuntimeError("Unknown expansion: %s" % expansion)

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["matvec.cu", "solve.cu", "gmres.cu", "symeig.cu", "linop.cu", "peer.cu"]
+SOURCES = ["matvec.cu", "solve.cu", "gmres.cu", "symeig.cu", "linop.cu", "peer.cu", "small_solve.cu"]
 HEADERS = ["common.cuh", "matvec.cuh", "solve_common.cuh", os.path.join(ROOT, "include", "xitorch_b200.h")]
 LIB = os.path.join(HERE, "libxitorch_b200.so")
 

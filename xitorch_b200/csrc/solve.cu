@@ -579,6 +579,13 @@ size_t gmres_ws_bytes(size_t vs, int n, int nbatch, int ncols, int max_niter);  
 
 }  // namespace xt
 
+#ifdef __CUDACC__
+namespace xt {
+bool small_cg_applies(const xt_solve_args* g);
+int run_small_cg(const xt_solve_args* g);
+}  // namespace xt
+#endif
+
 extern "C" {
 
 size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, int32_t nbatch, int32_t ncols,
@@ -595,6 +602,10 @@ size_t xt_solve_workspace_bytes(const char* method, int32_t dtype, int32_t n, in
 int xt_cg(const xt_solve_args* g) {
   int rc = xt::check_solve_args(g);
   if (rc != XT_OK) return rc;
+#ifdef __CUDACC__
+  // problems that fit the shared memory of one thread-block cluster: the whole solve in one launch (small_solve.cu)
+  if (xt::small_cg_applies(g)) return xt::run_small_cg(g);
+#endif
   return g->dtype == XT_F64 ? xt::run_cg<double>(g) : xt::run_cg<float>(g);
 }
 

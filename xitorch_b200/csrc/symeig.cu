@@ -3294,16 +3294,11 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
   bool ev_used[NSLOT] = {false, false, false};
   int check_seq = 0;
   int latched_upto = 0;
-  // How many iterations later a check's verdict is consumed.  One, while a Rayleigh-Ritz kernel (~5 us per basis vector
-  // at the cap, next to a running matvec) fits under the local matvec; two beyond (8 GPUs at C5: 0.5 ms of matvec
-  // against 0.6 ms), where waiting for it every iteration would make the replicated kernel the critical path -- at the
-  // price of one more matvec after convergence.  (Two is also the most the double-buffered Q copies allow.)
+  // How many iterations later a check's verdict is consumed: one.  (Two -- XT_SHARDED_LAG=2, the most the double-buffered Q
+  // copies allow -- takes the replicated Rayleigh-Ritz kernel off the critical path but spends one more matvec after
+  // convergence; measured at C5 on 8 GPUs it loses: 11.7 against 10.96 ms.)
   int lag = 1;
-  {
-    const double t_mv = (double)n_loc * n * sizeof(TV) / (k > 8 ? 4.2e12 : 6.0e12);
-    if (5.0e-6 * mb > t_mv) lag = 2;
-    if (const char* lv = getenv("XT_SHARDED_LAG")) lag = atoi(lv) >= 2 ? 2 : 1;
-  }
+  if (const char* lv = getenv("XT_SHARDED_LAG")) lag = atoi(lv) >= 2 ? 2 : 1;
   const int nbk = mb / k;                 // block index of the spare slot of V / AV
   // thick restart, deferred by one matvec: the iteration that fills the basis only requests `keep` Ritz pairs from its
   // Rayleigh-Ritz kernel (side stream); the next iteration's matvec -- it needs nothing but the new block -- runs
