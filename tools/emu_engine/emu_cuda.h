@@ -303,7 +303,7 @@ struct MvArgs {
   const void* E; int64_t e_bstride;
   const void* Z; int64_t ldz, z_bstride;
   const void* U; int64_t ldu, u_bstride;
-  double* dot_out; int impl; const int* done_flag; const int* abort_flag; int reserve_sms; int reverse; int l2_keep_mb; int pdl;
+  double* dot_out; int impl; const int* done_flag; const int* abort_flag; int* latch_out; int reserve_sms; int reverse; int l2_keep_mb; int pdl;
 };
 struct emu_bf16 {
   uint16_t bits;

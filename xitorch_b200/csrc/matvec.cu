@@ -175,6 +175,7 @@ struct MvDev {
   double* dot_out;
   const int* done_flag;
   const int* abort_flag;   // may be raised by another stream while the kernel runs (see MvArgs)
+  int* latch_out;          // set by a CTA that abandons its tile (see MvArgs)
   int reverse;      // traverse the column chunks of A from the last to the first
   int keep_from;    // chunks (in traversal order) >= keep_from are loaded with an L2 evict-last hint: the next,
                     // oppositely ordered pass finds the tail of this one in L2
@@ -330,6 +331,7 @@ __device__ __forceinline__ void mv_producer(const CUtensorMap* tmA, const MvDev&
           mbar_wait(&full[q], 0u);
         }
         *reinterpret_cast<volatile int*>(abort_at) = seq;
+        if (p.latch_out != nullptr) *reinterpret_cast<volatile int*>(p.latch_out) = 1;
         return;
       }
       const bool pre = seq < npre;
@@ -526,6 +528,7 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
     __syncthreads();
     const bool skip = skip_s != 0 || (abort_at != nullptr && abort_at_s == 0);
     if (skip) {
+      if (threadIdx.x == 0 && p.latch_out != nullptr && skip_s == 0) *reinterpret_cast<volatile int*>(p.latch_out) = 1;
       if (warp == 0 && lane == 0) {
         for (int q = 0; q < npre; ++q) {          // the pre-issued A boxes must land before the CTA may leave
           mbar_arrive_expect_tx(&full[q], 0u);
@@ -539,6 +542,8 @@ mv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const MvDev p) {
   if (warp == 0) {
     if (lane == 0 && (abort_at == nullptr || abort_at_s != 0))
       mv_producer<TA, TV, K, STAGE_BYTES>(&tmA, p, stage_base, full, empty, NS, nchunks, abort_at, npre);
+    else if (lane == 0 && p.latch_out != nullptr)
+      *reinterpret_cast<volatile int*>(p.latch_out) = 1;            // the flag was up at launch: nothing is produced
   } else if (warp == 1) {
     if (!p.x_bulk) mv_xstager<TA, TV, K, STAGE_BYTES, NBX>(p, stage_base, full, empty, NS, nchunks, lane, abort_at);
   } else {
@@ -1999,6 +2004,7 @@ int mv_launch(const MvArgs& a0, cudaStream_t st) {
   d.dot_out = a.dot_out;
   d.done_flag = a.done_flag;
   d.abort_flag = a.abort_flag;
+  d.latch_out = a.latch_out;
   d.pdl = 0;
   d.dbg = 0;
   d.y_atomic = y_atomic;

@@ -44,6 +44,8 @@ struct MvArgs {
   const int* abort_flag;                       // optional device flag that may be raised ASYNCHRONOUSLY (another stream)
                                                // while the kernel runs: the TMA producer polls it every few chunks, stops
                                                // producing and the CTA drains and exits without storing its tile
+  int* latch_out;                              // optional: set to 1 by a CTA that abandons its tile because of abort_flag
+                                               // (a stream-ordered 'this pass is incomplete' mark for the kernels behind it)
   int reserve_sms;                             // leave this many SMs free (for kernels overlapped on another stream)
   int reverse;                                 // traverse A's column chunks last-to-first (alternate per call, see l2_keep_mb)
   int l2_keep_mb;                              // MB of the end of this pass to keep in L2 for the next, reversed pass

@@ -2023,19 +2023,40 @@ __global__ void output_kernel(const TV* __restrict__ V, const TV* Xslots, const 
   const int64_t ldo = to_slot ? (int64_t)k : ldv;
   const TV* X = Xslots + (int64_t)slot * n * k;
   const int nblk = in_S ? ctl->best_m / k : 0;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n * k;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = e / k;
-    const int j = (int)(e - row * k);
-    if (in_S) {
-      double acc = 0.0;
+  if (in_S) {
+    // X = V[:, :best_m] Sbest, a thread per row: the coefficients are staged in shared memory (<= 128 x 16 doubles) and
+    // read as broadcasts, every basis row is loaded once (this kernel is the last thing between two solves)
+    __shared__ double Ss[128 * SE_MAXK];
+    const int msz = nblk * k * k;
+    const bool staged = msz <= 128 * SE_MAXK;
+    if (staged) {
+      for (int e = threadIdx.x; e < msz; e += blockDim.x) Ss[e] = Sbest[e];
+      __syncthreads();
+    }
+    const double* Sm = staged ? Ss : Sbest;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+      double acc[SE_MAXK];
+#pragma unroll
+      for (int j = 0; j < SE_MAXK; ++j) acc[j] = 0.0;
       for (int b = 0; b < nblk; ++b) {
         const TV* vr = V + ((int64_t)b * n + row) * k;
-        const double* sr = Sbest + (size_t)b * k * k + j;
-        for (int i = 0; i < k; ++i) acc = fma((double)vr[i], sr[i * k], acc);
+        const double* sb = Sm + (size_t)b * k * k;
+        for (int i = 0; i < k; ++i) {
+          const double v = (double)vr[i];
+#pragma unroll
+          for (int j = 0; j < SE_MAXK; ++j)
+            if (j < k) acc[j] = fma(v, sb[i * k + j], acc[j]);
+        }
       }
-      out[row * ldo + j] = (TV)acc;
-    } else {
+#pragma unroll
+      for (int j = 0; j < SE_MAXK; ++j)
+        if (j < k) out[row * ldo + j] = (TV)acc[j];
+    }
+  } else {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n * k;
+         e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t row = e / k;
+      const int j = (int)(e - row * k);
       out[row * ldo + j] = X[e];
     }
   }
@@ -2584,6 +2605,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
       a.ldy = k; a.y_bstride = 0;
       a.done_flag = async_check ? &W.ctl->done_latched : &W.ctl->done;
       a.abort_flag = async_check ? &W.ctl->done : nullptr;
+      a.latch_out = async_check ? &W.ctl->done_latched : nullptr;   // an abandoned pass makes every later kernel return at once
       // two free SMs, one per Rayleigh-Ritz kernel in flight (alternating side streams), so that no matvec CTA ever
       // waits for an SM.  Free: with two rows per consumer thread the k = 8 matvec runs at the same 6.26 TB/s for
       // any tile height 112..128 (tests/gpu_tile_sweep.py), i.e. on 145 SMs as well as on 147.
