@@ -3502,9 +3502,20 @@ int xt_symeig_krylov(const xt_symeig_args* g) {
   XT_REQUIRE((g->A || g->apply) && g->V0 && g->evals && g->evecs && g->workspace, "symeig: null pointer");
   XT_REQUIRE(g->mode == 0 || g->mode == 1, "symeig: mode must be 0 (lowest) or 1 (uppest)");
   XT_REQUIRE(g->max_basis <= 1024, "symeig: max_basis=%d exceeds 1024", g->max_basis);
+  int rc;
   if (g->peers != nullptr)
-    return g->dtype == XT_F64 ? xt::run_symeig_sharded<double>(g) : xt::run_symeig_sharded<float>(g);
-  return g->dtype == XT_F64 ? xt::run_symeig<double>(g) : xt::run_symeig<float>(g);
+    rc = g->dtype == XT_F64 ? xt::run_symeig_sharded<double>(g) : xt::run_symeig_sharded<float>(g);
+  else
+    rc = g->dtype == XT_F64 ? xt::run_symeig<double>(g) : xt::run_symeig<float>(g);
+  if (rc != XT_OK) {
+    // an error exit may leave Rayleigh-Ritz kernels in flight on the side streams: they read the caller's workspace, which
+    // the caller is about to free -- quiesce them first
+    xt::SidePool* pool = nullptr;
+    if (xt::side_pool_get(&pool) == XT_OK && pool != nullptr)
+      for (int q = 0; q < 2; ++q)
+        if (pool->s[q] != nullptr) cudaStreamSynchronize(pool->s[q]);
+  }
+  return rc;
 }
 
 static bool sharded_dims(int32_t dtype, int32_t n, int32_t neig, int32_t max_basis, int32_t world, int* mb_out) {
