@@ -1744,6 +1744,7 @@ struct CheckArgs {
   double* evals_best;       // [k]
   float min_eps;
   int seq;                  // checks apply their bookkeeping in launch order: this one waits for ticket seq - 1
+  unsigned int dyn_smem_bytes;  // dynamic shared memory of this launch (the staged check carves its buffers out of it)
   int* host_res;            // optional host-mapped result mirror (see output_kernel): filled by the check that converges,
   int res_seq;              // so that the host has niter / best_resid the moment it sees the stop flag
   // row-sharded engine: Q / n are this rank's rows only and the maximum is completed over the ranks through the
@@ -1812,6 +1813,63 @@ __device__ __forceinline__ float lanczos_resid_max_k(const TV* __restrict__ Q, i
   }
   return lmax;
 }
+#ifdef __CUDACC__
+// The same maximum with Q streamed through shared memory by the TMA unit (cp.async.bulk, two buffers): the loop above is
+// bound by the latency of one CTA's global loads next to a running matvec (~29 us for 512 KB), the bulk copies keep many
+// more bytes in flight.  `buf`: two buffers of `chunk_rows` rows (16-byte aligned), `bars`: two mbarriers.
+template <typename TV, int K>
+__device__ __forceinline__ float lanczos_resid_max_staged(const TV* __restrict__ Q, int n, const double* Ms, TV* buf,
+                                                          int chunk_rows, uint64_t* bars) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  TV mreg[K][K <= 8 ? K : 8];
+  float lmax = 0.f;
+  const int nch = (n + chunk_rows - 1) / chunk_rows;
+  constexpr int LH = K <= 8 ? K : 8;
+  uint32_t gen = 0;                            // chunks issued before this pass (two passes for K = 16 re-arm the barriers)
+#pragma unroll 1
+  for (int l0 = 0; l0 < K; l0 += LH) {
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int l = 0; l < LH; ++l) mreg[c][l] = (TV)Ms[c * K + l0 + l];
+    if (tid == 0) {
+      const int rows0 = min(chunk_rows, n);
+      mbar_arrive_expect_tx(&bars[gen & 1], (uint32_t)(rows0 * K * sizeof(TV)));
+      bulk_load_1d(buf + (size_t)(gen & 1) * chunk_rows * K, Q, (uint32_t)(rows0 * K * sizeof(TV)), &bars[gen & 1]);
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+      const uint32_t cur = gen + (uint32_t)ch;
+      if (tid == 0 && ch + 1 < nch) {
+        const int r0 = (ch + 1) * chunk_rows;
+        const int rws = min(chunk_rows, n - r0);
+        mbar_arrive_expect_tx(&bars[(cur + 1) & 1], (uint32_t)(rws * K * sizeof(TV)));
+        bulk_load_1d(buf + (size_t)((cur + 1) & 1) * chunk_rows * K, Q + (int64_t)r0 * K, (uint32_t)(rws * K * sizeof(TV)),
+                     &bars[(cur + 1) & 1]);
+      }
+      mbar_wait(&bars[cur & 1], (cur >> 1) & 1u);
+      const TV* qb = buf + (size_t)(cur & 1) * chunk_rows * K;
+      const int rws = min(chunk_rows, n - ch * chunk_rows);
+      for (int r = tid; r < rws; r += nt) {
+        TV q[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) q[c] = qb[(size_t)r * K + c];
+#pragma unroll
+        for (int l = 0; l < LH; ++l) {
+          TV acc = TV(0);
+#pragma unroll
+          for (int c = 0; c < K; ++c) acc = fma(q[c], mreg[c][l], acc);
+          lmax = fmaxf(lmax, fabsf((float)acc));
+          if (!(acc == acc)) lmax = INFINITY;
+        }
+      }
+      __syncthreads();                         // the buffer is free for the copy issued two chunks later
+    }
+    gen += (uint32_t)nch;
+  }
+  return lmax;
+}
+#endif
+
 template <typename TV>
 __device__ float lanczos_resid_max(const TV* __restrict__ Q, int n, int k, const double* Ms) {
   constexpr bool F64 = sizeof(TV) == 8;
@@ -1895,8 +1953,39 @@ rr_kernel(double* T, int ldt, const double* C, int m, int k, int nev, double* Tw
       Ms[e] = acc;
     }
     __syncthreads();
-    const float lmax = chk.is_f64 ? lanczos_resid_max<double>(static_cast<const double*>(chk.Q), chk.n, k, Ms)
-                                  : lanczos_resid_max<float>(static_cast<const float*>(chk.Q), chk.n, k, Ms);
+    float lmax;
+    bool staged_done = false;
+#ifdef __CUDACC__
+    {
+      // Q through shared memory (TMA bulk copies) when the eigensolver's work area -- free by now -- can take two
+      // buffers of at least 8 KB; fp32 blocks with k = 8 / 16 (the configurations on the measured paths)
+      const size_t rest_off = ((size_t)nev + (nev & 1) + (y_in_smem ? (size_t)m * nev : 0)) * sizeof(double);
+      const size_t avail = chk.dyn_smem_bytes > rest_off + 512 ? chk.dyn_smem_bytes - rest_off - 512 : 0;
+      const size_t row_bytes = (size_t)k * 4;
+      int chunk_rows = (int)((avail / 2) / row_bytes) & ~31;
+      if (chunk_rows > 2048) chunk_rows = 2048;
+      if (!chk.is_f64 && (k == 8 || k == 16) && chunk_rows >= 256 && chk.n >= 4 * chunk_rows &&
+          (reinterpret_cast<uintptr_t>(chk.Q) & 15) == 0) {
+        char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(reinterpret_cast<char*>(dyn) + rest_off) + 127) &
+                                             ~uintptr_t(127));
+        uint64_t* qbars = reinterpret_cast<uint64_t*>(base);          // two mbarriers, then the two buffers
+        float* buf = reinterpret_cast<float*>(base + 128);
+        if (tid == 0) {
+          mbar_init(&qbars[0], 1);
+          mbar_init(&qbars[1], 1);
+          fence_mbar_init();
+        }
+        fence_proxy_async();                   // the buffers were written with ordinary stores by the eigensolver
+        __syncthreads();
+        lmax = k == 8 ? lanczos_resid_max_staged<float, 8>(static_cast<const float*>(chk.Q), chk.n, Ms, buf, chunk_rows, qbars)
+                      : lanczos_resid_max_staged<float, 16>(static_cast<const float*>(chk.Q), chk.n, Ms, buf, chunk_rows, qbars);
+        staged_done = true;
+      }
+    }
+#endif
+    if (!staged_done)
+      lmax = chk.is_f64 ? lanczos_resid_max<double>(static_cast<const double*>(chk.Q), chk.n, k, Ms)
+                        : lanczos_resid_max<float>(static_cast<const float*>(chk.Q), chk.n, k, Ms);
     rmax = block_max(lmax, redmax);
     if (chk.world > 1) {
       // every rank runs this kernel for the same iterations in the same state (the row-sharded driver consumes
@@ -2291,6 +2380,15 @@ static bool carve(Arena& ar, EigWs& W, size_t vs, int n, int k, int mb, int worl
 constexpr int LOOKAHEAD = 3; // the host enqueues at most this many iterations beyond the last one known complete
 constexpr int NSLOT = 3;     // Rayleigh-Ritz results are consumed two iterations after they are requested
 // side streams / events are host-side handles: created once per device and thread, reused by every call
+// XT_NO_STAGED_CHECK=1 keeps the Ritz check on plain loads (A/B switch for the TMA-staged residual pass)
+static bool staged_check_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XT_NO_STAGED_CHECK");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 struct SidePool {
   cudaStream_t s[2] = {nullptr, nullptr};
   cudaEvent_t c[NSLOT] = {nullptr, nullptr, nullptr}, r[NSLOT] = {nullptr, nullptr, nullptr};
@@ -2698,6 +2796,7 @@ template <typename TV> static int run_symeig(const xt_symeig_args* g) {
               chk.Sbest = W.Sbest; chk.evals_best = W.evals_best; chk.min_eps = (float)g->min_eps;
               chk.seq = ++check_seq;
               chk.host_res = pool.hflag_dev + 8; chk.res_seq = my_seq;
+              chk.dyn_smem_bytes = staged_check_enabled() ? (unsigned int)plf.smem_bytes : 0u;
               async_inflight = true;
             }
             rr_kernel<<<1, EIG_THREADS, plf.smem_bytes, rsf>>>(W.T, mb, nullptr, m, k, k, Twpar[iter & 1], Skpar[par],
@@ -3421,6 +3520,7 @@ template <typename TV> static int run_symeig_sharded(const xt_symeig_args* g) {
     chk.seq = ++check_seq;
     chk.world = world; chk.rank = rank;
     for (int q = 0; q < world; ++q) chk.vbuf[q] = reinterpret_cast<unsigned long long*>(base.peer[q] + base.lay.vbuf);
+    chk.dyn_smem_bytes = staged_check_enabled() ? (unsigned int)pl.smem_bytes : 0u;
     chk.tag = ((g->epoch & 0xffffu) << 16) | ((unsigned int)check_seq & 0xffffu);
     if (chk.tag == 0u) chk.tag = 0x10000u;
     rr_kernel<<<1, EIG_THREADS, pl.smem_bytes, rs>>>(W.T, mb, nullptr, m, k, nev, W.Tw[iter & 1], W.Sk[par], W.theta[par],
