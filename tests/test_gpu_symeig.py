@@ -61,6 +61,70 @@ def test_generalized_problem(golden):
     assert (c["A"] @ X - c["M"] @ X * evals.cpu().unsqueeze(-2)).abs().max().item() <= 1e-6
 
 
+def _gen_exact(A, M, k, mode="lowest"):
+    Li = torch.inverse(torch.linalg.cholesky(M.double()))
+    w = torch.linalg.eigvalsh(Li @ A.double() @ Li.transpose(-2, -1))
+    return w[..., :k] if mode == "lowest" else w[..., -k:]
+
+
+def _spd_metric(n, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(n, 64, generator=g, dtype=torch.float64)
+    return (a @ a.T / 64 * 0.2 + torch.eye(n, dtype=torch.float64)).to(dtype)
+
+
+@pytest.mark.parametrize("n,dtype,min_eps", [(4096, torch.float32, 1e-5), (1536, torch.float64, 1e-9)])
+def test_generalized_problem_through_the_matvec_kernel(n, dtype, min_eps):
+    """A x = lambda M x with dense A and M: both are applied with the block-matvec kernel, one launch each per iteration,
+    and nothing of order n^3 (no Cholesky whitening, no n x n temporaries) is formed -- checked on the allocator's
+    high-water mark -- against fp64 generalized eigh (reference: symeig.py:182-185, 212-214)."""
+    neig = 8
+    A = oracle.make_herm(n, neig, dtype)
+    M = _spd_metric(n, dtype, 5)
+    Ad, Md = A.to(DEV), M.to(DEV)
+    Aop, Mop = xt.LinearOperator.m(Ad, True), xt.LinearOperator.m(Md, True)
+    xt.linalg.symeig(Aop, neig=2, M=Mop, method="davidson", min_eps=1e-2)      # library handles etc. allocated
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    _lib.profile_reset(True)
+    info = {}
+    evals, evecs = xt.linalg.symeig(Aop, neig=neig, M=Mop, method="davidson", min_eps=min_eps, info=info)
+    torch.cuda.synchronize()
+    _, mv_launches, _ = _lib.profile_read()
+    _lib.profile_reset(False)
+    extra = torch.cuda.max_memory_allocated() - base
+    assert info["converged"] and info["engine"] == "host-composed", info
+    assert extra < 0.5 * n * n * A.element_size(), (extra, n * n * A.element_size())
+    assert mv_launches >= info["napply"] + info["napply_M"] > 0, (mv_launches, info)   # A and M through OUR kernel
+    ref = _gen_exact(A, M, neig)
+    assert ((evals.double().cpu() - ref).abs() / ref.abs()).max().item() <= EIG_RTOL
+    X = evecs.double().cpu()
+    assert (A.double() @ X - M.double() @ X * evals.double().cpu().unsqueeze(-2)).abs().max().item() <= 20 * min_eps
+    assert (X.T @ M.double() @ X - torch.eye(neig, dtype=torch.float64)).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("with_m", [False, True])
+def test_wide_start_block_and_preconditioner(with_m):
+    """nguess > neig (reference symeig.py:137-138) and Davidson's diagonal preconditioner"""
+    n, neig = 2048, 6
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = (0.5 * (a + a.T) * 0.05 + torch.diag(torch.arange(n, dtype=torch.float64) * 2.0 + 1.0))
+    M = _spd_metric(n, torch.float64, 6) if with_m else None
+    Aop = xt.LinearOperator.m(A.to(DEV), True)
+    Mop = xt.LinearOperator.m(M.to(DEV), True) if with_m else None
+    ref = _gen_exact(A, M, neig) if with_m else torch.linalg.eigvalsh(A)[:neig]
+    runs = {}
+    for tag, kw in (("wide", dict(nguess=10)), ("plain", dict(nguess=neig + 1)), ("diag", dict(nguess=neig + 1, precond="diag"))):
+        info = {}
+        evals, evecs = xt.linalg.symeig(Aop, neig=neig, M=Mop, method="davidson", min_eps=1e-8, info=info, **kw)
+        assert info["converged"] and info["engine"] == "host-composed", (tag, info)
+        assert ((evals.cpu() - ref).abs() / ref.abs()).max().item() <= 1e-9, tag
+        runs[tag] = info["niter"]
+    assert runs["diag"] < runs["plain"], runs
+
+
 @pytest.mark.parametrize("method", ["davidson", "lanczos"])
 def test_fp32_2048_vs_oracle_fp64(method):
     """fp32 operator at N=2048: the reference's own fp32 davidson only survives min_eps >= 1e-4

@@ -252,7 +252,7 @@ def test_symeig_generalized_and_strided(eng):
 def test_symeig_options_and_errors(eng):
     A = xt.LinearOperator.m(_spd(8, seed=37), is_hermitian=True)
     with pytest.raises(RuntimeError, match="nguess"):
-        symeig(A, neig=2, method="davidson", nguess=3)
+        symeig(A, neig=3, method="davidson", nguess=2)
     with pytest.raises(ValueError, match="v_init"):
         symeig(A, neig=2, method="davidson", v_init="nope")
     with pytest.raises(RuntimeError, match="expansion"):

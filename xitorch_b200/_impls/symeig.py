@@ -166,29 +166,19 @@ def _full_space_pairs(Amat: torch.Tensor, neig: int, mode: str, run: dict):
     return w.contiguous(), S.contiguous()
 
 
-def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps, max_basis, check_every, info, name):
+def _krylov_matrix_free(A, neig, mode, expansion, max_niter, v_init, min_eps, max_basis, check_every, info, name):
     """Krylov eigensolver on an operator that is only known through `A.mm` (user `_mv`, composite operators such as
     ``A^H A`` of `svd`, autograd Hessians): the whole iteration stays in the engine's kernels, each block application
     ``Y = A X`` comes back to Python through the `apply` hook of `xt_symeig_args` (one call per iteration, on the current
-    stream), as the reference calls `A.mm` on whatever operator it gets (symeig.py:155,165).  A generalized problem is
-    whitened with the dense Cholesky factor of M: the operator becomes ``X -> L^-1 A (L^-T X)``."""
+    stream), as the reference calls `A.mm` on whatever operator it gets (symeig.py:155,165).  Generalized problems go
+    through `_davidson_host`."""
     n = A.shape[-1]
     probe = torch.empty(0, dtype=A.dtype, device=A.device)
     _lib.require_cuda(probe, "linalg.symeig(method=%r)" % name)
     if A.dtype not in (torch.float32, torch.float64):
         raise RuntimeError("xitorch_b200.%s: matrix-free operators must be float32 or float64 (got %s)" % (name, A.dtype))
     vdt, dev = A.dtype, A.device
-    LinvT = None
     op = A.mm
-    if M is not None:
-        with torch.no_grad():
-            L = torch.linalg.cholesky(_dense_of(M, "M").to(vdt).reshape(n, n))
-            Linv = torch.inverse(L)
-        LinvT = Linv.transpose(-2, -1)
-
-        def op(x):
-            return torch.matmul(Linv, A.mm(torch.matmul(LinvT, x)))
-
     if n < 2 * neig:
         # not even two blocks fit: the reference's first expansion already fills the whole space (symeig.py:209-211);
         # same shortcut as the dense path (a tiny operator, e.g. the A^H A of `svd` of a thin matrix)
@@ -198,8 +188,7 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
             full = op(torch.eye(n, dtype=vdt, device=dev))
         evals, evecs = _full_space_pairs(full.reshape(1, n, n), neig, mode, run)
         batch = tuple(A.shape[:-2])
-        evals, evecs = evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
-        return evals, (torch.matmul(LinvT, evecs) if LinvT is not None else evecs)
+        return evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
     V0 = _start(v_init, 1, n, neig, vdt, dev)
     failure = []
     abort = C.c_int32(0)
@@ -237,21 +226,209 @@ def _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps,
     batch = tuple(A.shape[:-2])
     evals = evals.reshape(*batch, neig)
     evecs = evecs.reshape(*batch, n, neig)
-    if LinvT is not None:
-        evecs = torch.matmul(LinvT, evecs)
     return evals, evecs
+
+
+def _m_orthonormalise(W, MW, rtol):
+    """M-orthonormal basis of span(W), given ``MW = M W`` (``MW is W`` for the standard problem): with the Gram matrix
+    ``W^T M W = U diag(d) U^T`` the result is ``W U d^-1/2`` (and the same transformation of MW).  Directions with
+    ``d <= rtol * max(d)`` are dropped -- the Ritz residuals of converged pairs are numerically dependent, which is
+    where a Cholesky factor of the Gram matrix (the reference's `tallqr`, _utils/tensor.py:8-19) breaks down.  The number
+    of columns kept is the smallest numerical rank over the batch."""
+    G = torch.matmul(W.transpose(-2, -1), MW)
+    d, U = torch.linalg.eigh(0.5 * (G + G.transpose(-2, -1)))          # ascending
+    dmax = d[..., -1:].clamp_min(torch.finfo(d.dtype).tiny)
+    keep = int((d > rtol * dmax).sum(-1).min().item())
+    if keep == 0:
+        return W[..., :0], MW[..., :0]
+    U = U[..., -keep:] * d[..., -keep:].clamp_min(torch.finfo(d.dtype).tiny).rsqrt().unsqueeze(-2)
+    Wn = torch.matmul(W, U)
+    return Wn, (Wn if MW is W else torch.matmul(MW, U))
+
+
+def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_basis, precond, info, name):
+    """Davidson for the cases the one-kernel engine does not take: a generalized problem ``A x = lambda M x``, a start
+    block wider than ``neig`` (`nguess`), a preconditioned expansion.  Follows the reference loop
+    (/root/reference/xitorch/_impls/linalg/symeig.py:164-223): Rayleigh-Ritz on an M-orthonormal basis, residual
+    ``A V s - lambda M V s``, expansion with the residuals -- but incrementally: the basis keeps ``V``, ``A V`` and
+    ``M V``, so one iteration applies A once and M once to the NEW block only (the reference re-applies M to the whole
+    basis and once more in the residual, symeig.py:184,212), and nothing of order n^3 is ever formed (no Cholesky
+    whitening of M).  The two O(n^2 k) applications go through `A.mm` / `M.mm`, i.e. the block-matvec kernel for dense
+    operators; the O(n m k) tall-skinny algebra and the m x m eigenproblem are library calls on the same stream.
+    Thick restart on ``max(2 * neig, nguess)`` Ritz vectors when the basis is full.
+
+    precond: None | "diag" | callable(resid (*B, n, k), eigvals (*B, k)) -> (*B, n, k).  "diag" is Davidson's
+    ``t = r / (diag(A) - lambda diag(M))`` for dense operators."""
+    n = A.shape[-1]
+    vdt, dev = A.dtype, A.device
+    _lib.require_cuda(torch.empty(0, dtype=vdt, device=dev), "linalg.symeig(method=%r)" % name)
+    if vdt not in (torch.float32, torch.float64):
+        raise RuntimeError("xitorch_b200.%s: generalized / wide-start / preconditioned problems need float32 or "
+                           "float64 operators (got %s)" % (name, vdt))
+    batch = tuple(A.shape[:-2]) if M is None else tuple(bcast_dims(A.shape[:-2], M.shape[:-2]))
+    nb = 1
+    for s_ in batch:
+        nb *= s_
+    nguess = neig if nguess is None else int(nguess)
+    if nguess < neig:
+        raise RuntimeError("xitorch_b200.%s: nguess must be at least neig (got %d vs %d)" % (name, nguess, neig))
+    nguess = min(nguess, n)
+    if max_basis is None:
+        max_basis = _default_max_basis(n, neig)
+    nkeep = max(2 * neig, nguess)
+    max_basis = min(max(int(max_basis), nkeep + neig), n)
+    if max_basis + neig >= n:
+        max_basis = n                  # small problems run to the full space, where the pairs are exact (symeig.py:203)
+    nkeep = min(nkeep, max_basis)
+    eps = torch.finfo(vdt).eps
+    small_on_host = dev.type == "cuda" and nb <= 4 and max_basis <= 512
+
+    dA = dM = None
+    if precond == "diag":
+        if not isinstance(A, MatrixLinearOperator) or (M is not None and not isinstance(M, MatrixLinearOperator)):
+            raise RuntimeError("xitorch_b200.%s: precond='diag' needs dense operators" % name)
+        dA = _dense_of(A, "A").diagonal(dim1=-2, dim2=-1).to(vdt).unsqueeze(-1)
+        dM = None if M is None else _dense_of(M, "M").diagonal(dim1=-2, dim2=-1).to(vdt).unsqueeze(-1)
+    elif precond is not None and not callable(precond):
+        raise RuntimeError("Unknown precond: %s" % (precond,))
+
+    def a_mm(X):
+        return A.mm(X.contiguous())
+
+    def m_mm(X):
+        return X if M is None else M.mm(X.contiguous())
+
+    with torch.no_grad():
+        Vb = torch.empty((*batch, n, max_basis), dtype=vdt, device=dev)
+        AVb = torch.empty_like(Vb)
+        MVb = Vb if M is None else torch.empty_like(Vb)
+        T = torch.zeros((*batch, max_basis, max_basis), dtype=vdt, device=dev)
+
+        W = _start(v_init, nb, n, nguess, vdt, dev).reshape(*batch, n, nguess)
+        MW = m_mm(W)
+        for _ in range(2):
+            W, MW = _m_orthonormalise(W, MW, 64 * eps)
+        m = W.shape[-1]
+        if m < neig:
+            raise RuntimeError("xitorch_b200.%s: the start block has numerical rank %d < neig" % (name, m))
+        AW = a_mm(W)
+        napply, napply_m = 1, (0 if M is None else 1)
+        Vb[..., :m], AVb[..., :m] = W, AW
+        if M is not None:
+            MVb[..., :m] = MW
+        T[..., :m, :m] = torch.matmul(W.transpose(-2, -1), AW)
+
+        best = (float("inf"), None, None, None, None)
+        converged = False
+        niter = 0
+        for niter in range(1, max_niter + 1):
+            V, AV, MV = Vb[..., :m], AVb[..., :m], MVb[..., :m]
+            Tm = T[..., :m, :m]
+            Tsym = 0.5 * (Tm + Tm.transpose(-2, -1))
+            if small_on_host:
+                # an m x m problem with m <= 128: LAPACK on the host beats the device library's launch chain several
+                # times over, and the loop synchronises once per iteration for the stop test anyway
+                theta, S = torch.linalg.eigh(Tsym.cpu())
+                theta, S = theta.to(dev), S.to(dev)
+            else:
+                theta, S = torch.linalg.eigh(Tsym)
+            lam, Sk = _take(theta, S, neig, mode)
+            X = torch.matmul(V, Sk)
+            AX = torch.matmul(AV, Sk)
+            MX = X if M is None else torch.matmul(MV, Sk)
+            R = AX - MX * lam.unsqueeze(-2)
+            resid = R.abs().max().item()                   # the reference's stop test, global over the batch (:188,201)
+            if resid < best[0]:
+                best = (resid, lam, X, AX, MX)
+            if resid < min_eps:
+                converged = True
+                break
+            if m == n:                                     # the basis is the whole space: the pairs are exact (:203)
+                converged = True
+                break
+            if niter == max_niter:
+                break
+            if m + 1 > max_basis:
+                # thick restart: the basis becomes the nkeep extreme Ritz vectors (still M-orthonormal, T diagonal)
+                thk, Skp = _take(theta, S, nkeep, mode)
+                Vk, AVk = torch.matmul(V, Skp), torch.matmul(AV, Skp)
+                MVk = None if M is None else torch.matmul(MV, Skp)
+                m = nkeep
+                Vb[..., :m], AVb[..., :m] = Vk, AVk
+                if M is not None:
+                    MVb[..., :m] = MVk
+                T.zero_()
+                T[..., :m, :m] = torch.diag_embed(thk)
+                V, AV, MV = Vb[..., :m], AVb[..., :m], MVb[..., :m]
+            # expansion block: the (preconditioned) residuals, at most what still fits
+            if dA is not None:
+                den = dA - lam.unsqueeze(-2) * (1.0 if dM is None else dM)
+                floor = 1e-3 * dA.abs().amax(dim=(-2, -1), keepdim=True).clamp_min(torch.finfo(vdt).tiny)
+                den = torch.where(den.abs() < floor, torch.where(den < 0, -floor, floor), den)
+                W = R / den
+            elif precond is not None:
+                W = precond(R, lam)
+            else:
+                W = R
+            nadd = min(neig, n - m, max_basis - m)
+            W = W[..., :nadd]
+            W = W / W.norm(dim=-2, keepdim=True).clamp_min(torch.finfo(vdt).tiny)
+            MVt = MV.transpose(-2, -1)
+            for _ in range(2):                             # block Gram-Schmidt against the basis in the M inner product
+                W = W - torch.matmul(V, torch.matmul(MVt, W))
+            MW = m_mm(W)
+            napply_m += 0 if M is None else 1
+            W, MW = _m_orthonormalise(W, MW, 64 * eps)
+            if W.shape[-1] > 0:
+                c = torch.matmul(MVt, W)                   # what normalising amplified
+                W = W - torch.matmul(V, c)
+                MW = W if M is None else MW - torch.matmul(MV, c)
+                W, MW = _m_orthonormalise(W, MW, 64 * eps)
+            k = W.shape[-1]
+            if k == 0:
+                break                                      # the residuals add nothing to the basis: stagnation
+            AW = a_mm(W)
+            napply += 1
+            Vb[..., m:m + k], AVb[..., m:m + k] = W, AW
+            if M is not None:
+                MVb[..., m:m + k] = MW
+            C1 = torch.matmul(V.transpose(-2, -1), AW)
+            T[..., :m, m:m + k] = C1
+            T[..., m:m + k, :m] = C1.transpose(-2, -1)
+            T[..., m:m + k, m:m + k] = torch.matmul(W.transpose(-2, -1), AW)
+            m += k
+        resid, evals, evecs, AX, MX = best
+        if vdt == torch.float32:
+            # final Rayleigh-Ritz on the neig Ritz vectors with fp64 accumulation: removes what fp32 sums of length n
+            # put into T and into the M-orthonormality of the basis (a few 1e-6 relative at n = 4096)
+            Xd = evecs.double()
+            AXd, MXd = AX.double(), (Xd if M is None else MX.double())
+            Xt = Xd.transpose(-2, -1)
+            Tk, Gk = torch.matmul(Xt, AXd), torch.matmul(Xt, MXd)
+            Li = torch.inverse(torch.linalg.cholesky(0.5 * (Gk + Gk.transpose(-2, -1))))
+            Tw = torch.matmul(Li, torch.matmul(0.5 * (Tk + Tk.transpose(-2, -1)), Li.transpose(-2, -1)))
+            w, Q = torch.linalg.eigh(Tw)
+            evals = w.to(vdt)
+            evecs = torch.matmul(Xd, torch.matmul(Li.transpose(-2, -1), Q)).to(vdt)
+    if info is not None:
+        info.update(niter=niter, converged=converged, best_resid=resid, napply=napply, napply_M=napply_m,
+                    max_basis=int(max_basis), engine="host-composed")
+    return evals.contiguous(), evecs.contiguous()
 
 
 def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator], expansion: int,
             max_niter: int, nguess: Optional[int], v_init: str, min_eps: float, max_basis: Optional[int],
-            check_every: Optional[int], info: Optional[dict], name: str, matrix_free: Optional[bool] = None):
-    if nguess is not None and nguess != neig:
-        raise RuntimeError("xitorch_b200.%s: nguess must equal neig (got %d vs %d)" % (name, nguess, neig))
+            check_every: Optional[int], info: Optional[dict], name: str, matrix_free: Optional[bool] = None,
+            precond=None):
     if mode not in ("lowest", "uppest"):
         raise RuntimeError("Unknown mode: %s" % mode)
     n = A.shape[-1]
+    if M is not None or precond is not None or (nguess is not None and nguess != neig):
+        # generalized problem, wide start block or preconditioned expansion: host-composed loop over the block-matvec
+        # kernel (the one-kernel engine is the standard problem with a start block of neig vectors)
+        return _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_basis, precond, info, name)
     if _use_callback(A, M, matrix_free):
-        return _krylov_matrix_free(A, neig, mode, M, expansion, max_niter, v_init, min_eps, max_basis, check_every,
+        return _krylov_matrix_free(A, neig, mode, expansion, max_niter, v_init, min_eps, max_basis, check_every,
                                    info, name)
     Amat = _dense_of(A, "A")
     _lib.require_cuda(Amat, "linalg.symeig(method=%r)" % name)
@@ -261,15 +438,6 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     if Amat.dtype == torch.bfloat16:
         raise RuntimeError("xitorch_b200.%s: bf16 operators are not supported for eigenproblems" % name)
     dev = Amat.device
-    LinvT = None
-    if M is not None:
-        # generalized problem A x = lambda M x  ->  (L^-1 A L^-T) y = lambda y,  x = L^-T y   (library GEMMs)
-        Mmat = _dense_of(M, "M").to(Amat.dtype)
-        L = torch.linalg.cholesky(Mmat)
-        Linv = torch.inverse(L)
-        LinvT = Linv.transpose(-2, -1)
-        Amat = torch.matmul(Linv, torch.matmul(Amat, LinvT))
-        Amat = 0.5 * (Amat + Amat.transpose(-2, -1))
     batch = tuple(Amat.shape[:-2])
     nb = 1
     for s in batch:
@@ -284,16 +452,13 @@ def _krylov(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
         # not even two blocks fit: the reference's first expansion already fills the whole space (symeig.py:209-211)
         run.update(niter=0, converged=False, napply=0, max_basis=n)
         evals, evecs = _full_space_pairs(Amat.reshape(nb, n, n).to(vdt), neig, mode, run)
-        evals, evecs = evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
-        return evals, (torch.matmul(LinvT, evecs) if LinvT is not None else evecs)
+        return evals.reshape(*batch, neig), evecs.reshape(*batch, n, neig)
     evals, evecs = _call_engine(A3, lda, (a_bs if nb > 1 else 0), n, nb, neig, mode, expansion, V0, max_niter,
                                 max_basis, check_every, min_eps, run, name, out_batch=batch)
     if _space_exhausted(run, n, neig, max_niter):
         evals, evecs = _full_space_pairs(Amat.reshape(nb, n, n), neig, mode, run)
         evals = evals.reshape(*batch, neig)
         evecs = evecs.reshape(*batch, n, neig)
-    if LinvT is not None:
-        evecs = torch.matmul(LinvT, evecs)
     return evals, evecs
 
 
@@ -507,7 +672,8 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
              max_niter: int = 1000, nguess: Optional[int] = None, v_init: str = "randn",
              max_addition: Optional[int] = None, min_eps: float = 1e-6, verbose: bool = False,
              max_basis: Optional[int] = None, check_every: Optional[int] = None,
-             info: Optional[dict] = None, expansion: str = "krylov", matrix_free: Optional[bool] = None, **unused):
+             info: Optional[dict] = None, expansion: str = "krylov", matrix_free: Optional[bool] = None,
+             precond=None, **unused):
     """
     Block Davidson (Rayleigh-Ritz on span{V0, r0, r1, ...}) on the B200.
 
@@ -516,7 +682,8 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
     max_niter: int
         Maximum number of iterations (subspace expansions)
     nguess: int or None
-        Size of the start block; must be ``neig`` (or None)
+        Size of the start block (None: ``neig``).  A block wider than ``neig`` runs the host-composed loop
+        (`_davidson_host`), as do generalized problems (``M``) and ``precond``
     v_init: str
         Mode of the initial guess (``"randn"``, ``"rand"``, ``"eye"``)
     max_addition: int or None
@@ -542,11 +709,15 @@ def davidson(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator
         How an operator that is not a dense matrix (user ``_mv``, ``A.H.matmul(A)``, Jacobians ...) is applied.
         ``True``: through ``A.mm`` once per iteration, nothing is materialised.  ``False``: ``A.fullmatrix()`` is built
         once and the dense kernels are used.  ``None``: materialise up to n = 2048, matrix-free beyond.
+    precond: None, "diag" or callable
+        Preconditioner of the expansion block (the reference has the hook but no preconditioner, symeig.py:206-207).
+        ``"diag"``: Davidson's ``r / (diag(A) - lambda diag(M))`` for dense operators; a callable gets
+        ``(resid, eigvals)`` and returns the block to add.
     """
     if expansion not in ("krylov", "residual"):
         raise RuntimeError("Unknown expansion: %s" % expansion)
     return _krylov(A, neig, mode, M, 1 if expansion == "krylov" else 0, max_niter, nguess, v_init, min_eps,
-                   max_basis, check_every, info, "davidson", matrix_free)
+                   max_basis, check_every, info, "davidson", matrix_free, precond)
 
 
 def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator] = None,
@@ -564,7 +735,8 @@ def lanczos(A: LinearOperator, neig: int, mode: str, M: Optional[LinearOperator]
     max_niter: int
         Maximum number of iterations (subspace expansions)
     nguess: int or None
-        Size of the start block; must be ``neig`` (or None)
+        Size of the start block (None: ``neig``); as in :func:`davidson`.  Generalized problems (``M``) and wide start
+        blocks are expanded with the Ritz residuals (there is no ``M^-1`` to build a Krylov space of ``M^-1 A`` with)
     v_init: str
         Mode of the initial guess (``"randn"``, ``"rand"``, ``"eye"``)
     min_eps: float

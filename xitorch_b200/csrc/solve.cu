@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(SV_THREADS) solve_init_kernel(SolveState<TV> S
 // phase 2: r = B - q; norms; beta; p = r + beta p
 template <typename TV>
 __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, int iter, int phase) {
+  pdl_wait();        // may have been scheduled while the matvec before it drains
+  pdl_trigger();     // the matvec after it may start streaming A now (it waits for this grid before reading vectors)
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const Geo g = geo(S.ncols);
@@ -194,6 +196,8 @@ __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, i
 // beta = rz_new / safedenom(rz), p = z + beta p  (first call: p = z)
 template <typename TV>
 __global__ void __launch_bounds__(SV_THREADS) cg_precond_kernel(SolveState<TV> S, const TV* __restrict__ z, int first) {
+  pdl_wait();        // may have been scheduled while the matvec before it drains
+  pdl_trigger();     // the matvec after it may start streaming A now (it waits for this grid before reading vectors)
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const Geo g = geo(S.ncols);
@@ -228,6 +232,8 @@ __global__ void __launch_bounds__(SV_THREADS) cg_precond_kernel(SolveState<TV> S
 // stage 5 (true residual, after):        r = B - t; norms; rho = rho_new
 template <typename TV>
 __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S, int iter, int stage) {
+  pdl_wait();        // may have been scheduled while the matvec before it drains
+  pdl_trigger();     // the matvec after it may start streaming A now (it waits for this grid before reading vectors)
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const Geo g = geo(S.ncols);
@@ -456,6 +462,23 @@ template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>&
   return XT_OK;
 }
 
+// step kernels go out as programmatic dependents of the matvec before them (and the matvec after them as theirs):
+// launch latency and CTA scheduling of every kernel of an iteration overlap the tail of the one before
+template <typename TV>
+static inline void launch_cg_step(const SolveState<TV>& S, int nbatch, size_t smem, cudaStream_t st, int k, int phase) {
+#ifdef __CUDACC__
+  if (dep_launch(cg_step_kernel<TV>, nbatch, SV_THREADS, smem, st, S, k, phase)) return;
+#endif
+  cg_step_kernel<TV><<<nbatch, SV_THREADS, smem, st>>>(S, k, phase);
+}
+template <typename TV>
+static inline void launch_bicg_step(const SolveState<TV>& S, int nbatch, size_t smem, cudaStream_t st, int k, int stage) {
+#ifdef __CUDACC__
+  if (dep_launch(bicg_step_kernel<TV>, nbatch, SV_THREADS, smem, st, S, k, stage)) return;
+#endif
+  bicg_step_kernel<TV><<<nbatch, SV_THREADS, smem, st>>>(S, k, stage);
+}
+
 template <typename TV> static int run_cg(const xt_solve_args* g) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
   Arena ar(g->workspace, g->workspace_bytes);
@@ -466,6 +489,7 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
   op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
+  op.pdl = solve_pdl_enabled() ? 1 : 0;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
   const size_t smem = step_smem<TV>(g->ncols);
   solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0); XT_LAUNCHED();
@@ -494,12 +518,12 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
     if (rc != XT_OK) return rc;
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 0); XT_LAUNCHED();
+      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 0); XT_LAUNCHED();
     } else {
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1); XT_LAUNCHED();
+      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 1); XT_LAUNCHED();
       rc = apply_op<TV>(op, S.x, S.q, mx, nullptr, nullptr, 0, done_flag, st, &napply);
       if (rc != XT_OK) return rc;
-      cg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
+      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 2); XT_LAUNCHED();
     }
     if (S.precond) {
       rc = precond_step(0);
@@ -527,6 +551,7 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   OpDesc op{g->dtype, g->n, g->nbatch, g->ncols, g->A, g->lda, g->a_bstride, g->M, g->ldm, g->m_bstride,
             g->E, g->e_bstride};
   op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
+  op.pdl = solve_pdl_enabled() ? 1 : 0;
   // right preconditioner (solve.py:276,282): y = P_r p, z = P_r s and x = h + omega z are the plain recurrences of the
   // composed operator A o P_r on the iterate xt with x = P_r xt (applied once at the end); the residual is untouched
   op.pre = g->precond_r; op.pre_user = g->precond_user; op.pre_tmp = S.ex[0];
@@ -542,10 +567,10 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
   for (int k = 1; k <= g->max_niter; ++k) {
-    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 1); XT_LAUNCHED();
+    launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 1); XT_LAUNCHED();
     rc = apply_op<TV>(op, S.p, S.q, mx, S.rhat, S.dots, S.dots_gstride, done_flag, st, &napply);   // v = A p, rhat.v
     if (rc != XT_OK) return rc;
-    bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 2); XT_LAUNCHED();
+    launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 2); XT_LAUNCHED();
     rc = apply_op<TV>(op, S.s, S.t, mx, S.s, S.dots, S.dots_gstride, done_flag, st, &napply);      // t = A s, t.s, t.t
     if (rc != XT_OK) return rc;
     if (pl.apply != nullptr) {            // K s, then K t with <K s, K t> and <K t, K t> in place of t.s and t.t
@@ -556,12 +581,12 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
     }
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 3); XT_LAUNCHED();
+      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 3); XT_LAUNCHED();
     } else {
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 4); XT_LAUNCHED();
+      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 4); XT_LAUNCHED();
       rc = apply_op<TV>(op, S.x, S.t, mx, nullptr, nullptr, 0, done_flag, st, &napply);
       if (rc != XT_OK) return rc;
-      bicg_step_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, k, 5); XT_LAUNCHED();
+      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 5); XT_LAUNCHED();
     }
     XT_CUDA_OK(cudaGetLastError());
     if (k == next_check || k == g->max_niter) {

@@ -96,7 +96,38 @@ struct OpDesc {
   void* pre_user = nullptr;
   void* pre_tmp = nullptr;      // (nbatch, n, ncols) scratch for pre(X)
   const volatile int* abort = nullptr;   // host flag a callback sets to stop the solve (xt_solve_args.abort)
+  int pdl = 0;                  // launch the dense matvecs as programmatic dependents of the step kernels (MvArgs.pdl)
 };
+
+// XT_NO_SOLVE_PDL=1: plain stream-ordered launches in cg / bicgstab (A/B switch)
+static inline bool solve_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XT_NO_SOLVE_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
+#ifdef __CUDACC__
+// launch `kern` as a programmatic dependent of the kernel before it on `st`: its CTAs may be scheduled while the
+// predecessor drains, and it must call pdl_wait() before touching anything the predecessor wrote.  false: not launched.
+template <typename... KArgs, typename... Args>
+static inline bool dep_launch(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args&&... args) {
+  static std::atomic<int> ok{1};
+  if (!ok.load(std::memory_order_relaxed) || !solve_pdl_enabled()) return false;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...) == cudaSuccess) return true;
+  (void)cudaGetLastError();
+  ok.store(0);
+  return false;
+}
+#endif
 
 #define XT_CHECK_ABORT(flag)                                                           \
   do {                                                                                 \
@@ -177,6 +208,7 @@ static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const T
     a.nbatch = op.nbatch; a.nrows = op.n; a.ncolsA = op.n; a.k = kg;
     a.X = X + c0; a.ldx = op.ncols; a.x_bstride = len;
     a.done_flag = done_flag;
+    a.pdl = op.pdl;
     if (op.E != nullptr && op.M != nullptr) {
       a.A = op.M; a.lda = op.ldm; a.a_bstride = op.m_bstride;
       a.Y = mx + c0; a.ldy = op.ncols; a.y_bstride = len;
