@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 400 > gpurun_out/P_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/P_pytest.log; tail -3 gpurun_out/P_pytest.log
-timeout 500 python bench.py --steps 30 --warmup 3 > gpurun_out/P_bench.log 2>&1; tail -1 gpurun_out/P_bench.log | cut -c1-200
-timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/P_bench_ref.log 2>&1; tail -1 gpurun_out/P_bench_ref.log | cut -c1-200
-XT_TRACE=1 timeout 100 python tools/trace_c2.py > gpurun_out/P_trace.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/P_launches.csv python tools/trace_c2.py > gpurun_out/P_ncu1.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_solve.py tests/test_gpu_rootfinder.py tests/test_gpu_baseline_sizes.py -m gpu -x -q --timeout 300 > gpurun_out/P_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/P_pytest.log; tail -5 gpurun_out/P_pytest.log
+XT_NO_SOLVE_SLICES=1 timeout 300 python tests/gpu_bench_solve_pdl.py 2>&1 | sed 's/^pdl  /1slice/' > gpurun_out/P_one.log
+timeout 300 python tests/gpu_bench_solve_pdl.py 2>&1 | sed 's/^pdl  /sliced/' > gpurun_out/P_sliced.log
+paste -d'\n' gpurun_out/P_one.log gpurun_out/P_sliced.log

@@ -63,6 +63,7 @@ template <typename K> static inline cudaError_t set_max_dyn_smem(K kern, int tot
 
 // launch accounting / in-situ kernel timing (xt_profile_* in the C ABI)
 void note_launch(int n = 1);                        // every kernel launch site calls this
+bool prof_on();                                     // event profiling of the matvec launches is enabled (xt_profile_reset)
 void prof_mv_begin(cudaStream_t st);                // CUDA events around each block-matvec launch when enabled
 void prof_mv_end(cudaStream_t st);
 #define XT_LAUNCHED() xt::note_launch(1)

@@ -48,6 +48,7 @@ struct ProfState {
 };
 static ProfState g_prof;
 void note_launch(int n) { g_prof.launches.fetch_add(n, std::memory_order_relaxed); }
+bool prof_on() { return g_prof.on.load(std::memory_order_relaxed); }
 static void prof_record(cudaStream_t st) {          // caller holds g_prof.mu
   if (g_prof.used == g_prof.ev.size()) {
     cudaEvent_t e;

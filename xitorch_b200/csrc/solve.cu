@@ -17,12 +17,12 @@ namespace xt {
 
 // deferred copy of the best iterate (decided by the last CTA of the previous norm evaluation)
 template <typename TV>
-__device__ __forceinline__ void deferred_best_copy(const SolveState<TV>& S, int b, int prev_iter) {
+__device__ __forceinline__ void deferred_best_copy(const SolveState<TV>& S, int b, int prev_iter, RowRange rr) {
   if (S.ctl->improved_iter == prev_iter) {
     const int64_t len = (int64_t)S.n * S.ncols;
     const TV* src = S.x + (int64_t)b * len;
     TV* dst = S.bestx + (int64_t)b * len;
-    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+    for (int64_t i = (int64_t)rr.lo * S.ncols + threadIdx.x; i < (int64_t)rr.hi * S.ncols; i += blockDim.x) dst[i] = src[i];
   }
 }
 
@@ -77,7 +77,8 @@ __device__ __forceinline__ void norm_bookkeeping(const SolveState<TV>& S, int b,
 template <typename TV>
 __global__ void __launch_bounds__(SV_THREADS) solve_init_kernel(SolveState<TV> S, double rtol, double atol, int bicg) {
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / S.nslices, sl = blockIdx.x - b * S.nslices;
+  const RowRange rr = slice_rows(S, sl);
   const Geo g = geo(S.ncols);
   double* res = sm;                       // [1][ncols]
   double* scr = sm + S.ncols;             // [TY][1][TX]
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(SV_THREADS) solve_init_kernel(SolveState<TV> S
   for (int cs = 0; cs * g.TX < S.ncols; ++cs) {
     const int c = cs * g.TX + g.tx;
     if (c < S.ncols) {
-      for (int row = g.ty; row < S.n; row += g.TY) {
+      for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
         const TV v = Bb[(int64_t)row * S.ldb + c];
         const int64_t o = (int64_t)b * len + (int64_t)row * S.ncols + c;
         S.r[o] = v;
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(SV_THREADS) solve_init_kernel(SolveState<TV> S
     }
   }
   col_reduce<1>(part, S.ncols, g.tx, g.ty, g.TX, g.TY, scr, res);
-  if (threadIdx.x == 0) {
+  slice_allreduce(S, b, sl, res, S.ncols, 0u);            // the solve's reduction number 0
+  if (sl == 0 && threadIdx.x == 0) {
     double mx = 0.0;
     for (int c = 0; c < S.ncols; ++c) {
       const double bn = sqrt(res[c]);
@@ -130,26 +132,33 @@ __global__ void __launch_bounds__(SV_THREADS) solve_init_kernel(SolveState<TV> S
 // phase 1: alpha; x += alpha p                                   (then the driver computes q = A x)
 // phase 2: r = B - q; norms; beta; p = r + beta p
 template <typename TV>
-__global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, int iter, int phase) {
+__global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, int iter, int phase, unsigned int epoch, int rel) {
   pdl_wait();        // may have been scheduled while the matvec before it drains
   pdl_trigger();     // the matvec after it may start streaming A now (it waits for this grid before reading vectors)
+  if (rel) {         // replayed from a graph: numbers relative to the period's base
+    iter += S.ctl->graph_base;
+    epoch += S.ctl->epoch_base;
+  }
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / S.nslices, sl = blockIdx.x - b * S.nslices;
+  const RowRange rr = slice_rows(S, sl);
   const Geo g = geo(S.ncols);
   double* res = sm;                       // [ncols]   (r.r)
   double* alp = sm + S.ncols;             // [ncols]
-  double* scr = sm + 2 * S.ncols;
+  double* rzo = sm + 2 * S.ncols;         // [ncols]   r.z of the previous iteration (slice 0 overwrites it at the end)
+  double* scr = sm + 3 * S.ncols;
   const int64_t len = (int64_t)S.n * S.ncols;
   const int64_t base = (int64_t)b * len;
 
-  if (phase != 2) deferred_best_copy(S, b, iter - 1);
+  if (phase != 2) deferred_best_copy(S, b, iter - 1, rr);
   if (S.ctl->done) return;
 
-  if (phase != 2) {
-    for (int c = threadIdx.x; c < S.ncols; c += blockDim.x)
-      alp[c] = S.rz[b * S.ncols + c] / safedenom(tile_dot(S, b, c, 0), S.eps);
-    __syncthreads();
+  if (phase != 2) tile_dots_all(S, b, false, alp);        // p.Ap per column
+  for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) {
+    rzo[c] = S.rz[b * S.ncols + c];
+    if (phase != 2) alp[c] = rzo[c] / safedenom(alp[c], S.eps);
   }
+  __syncthreads();
   double part[1][SV_MAXCS];
 #pragma unroll
   for (int i = 0; i < SV_MAXCS; ++i) part[0][i] = 0.0;
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, i
     const int c = cs * g.TX + g.tx;
     if (c < S.ncols) {
       const TV a = (phase != 2) ? (TV)alp[c] : TV(0);
-      for (int row = g.ty; row < S.n; row += g.TY) {
+      for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
         const int64_t o = base + (int64_t)row * S.ncols + c;
         if (phase != 2) S.x[o] = S.x[o] + a * S.p[o];
         if (phase == 0) {
@@ -175,21 +184,22 @@ __global__ void __launch_bounds__(SV_THREADS) cg_step_kernel(SolveState<TV> S, i
   }
   if (phase == 1) return;
   col_reduce<1>(part, S.ncols, g.tx, g.ty, g.TX, g.TY, scr, res);
-  norm_bookkeeping(S, b, res, iter, scr);
+  slice_allreduce(S, b, sl, res, S.ncols, epoch);
+  if (sl == 0) norm_bookkeeping(S, b, res, iter, scr);
   if (S.precond) return;          // z = P r, beta and p follow in cg_precond_kernel
   // beta = rz_new / safedenom(rz);  p = r + beta p
   for (int cs = 0; cs * g.TX < S.ncols; ++cs) {
     const int c = cs * g.TX + g.tx;
     if (c < S.ncols) {
-      const TV beta = (TV)(res[c] / safedenom(S.rz[b * S.ncols + c], S.eps));
-      for (int row = g.ty; row < S.n; row += g.TY) {
+      const TV beta = (TV)(res[c] / safedenom(rzo[c], S.eps));
+      for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
         const int64_t o = base + (int64_t)row * S.ncols + c;
         S.p[o] = S.r[o] + beta * S.p[o];
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) S.rz[b * S.ncols + c] = res[c];
+  if (sl == 0)
+    for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) S.rz[b * S.ncols + c] = res[c];
 }
 
 // preconditioned CG tail (solve.py:170-180): rz_new = r.z (fused into the application of the preconditioner),
@@ -205,8 +215,9 @@ __global__ void __launch_bounds__(SV_THREADS) cg_precond_kernel(SolveState<TV> S
   if (S.ctl->done) return;
   const int64_t len = (int64_t)S.n * S.ncols;
   const int64_t base = (int64_t)b * len;
+  tile_dots_all(S, b, false, bet);
   for (int c = threadIdx.x; c < S.ncols; c += blockDim.x) {
-    const double rzn = tile_dot(S, b, c, 0);
+    const double rzn = bet[c];
     bet[c] = first ? 0.0 : rzn / safedenom(S.rz[b * S.ncols + c], S.eps);
     S.rz[b * S.ncols + c] = rzn;
   }
@@ -231,20 +242,25 @@ __global__ void __launch_bounds__(SV_THREADS) cg_precond_kernel(SolveState<TV> S
 // stage 4 (true residual, before q=A x): omega...; x += omega s        (then the driver computes t = A x)
 // stage 5 (true residual, after):        r = B - t; norms; rho = rho_new
 template <typename TV>
-__global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S, int iter, int stage) {
+__global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S, int iter, int stage, unsigned int epoch, int rel) {
   pdl_wait();        // may have been scheduled while the matvec before it drains
   pdl_trigger();     // the matvec after it may start streaming A now (it waits for this grid before reading vectors)
+  if (rel) {         // replayed from a graph: numbers relative to the period's base
+    iter += S.ctl->graph_base;
+    epoch += S.ctl->epoch_base;
+  }
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / S.nslices, sl = blockIdx.x - b * S.nslices;
+  const RowRange rr = slice_rows(S, sl);
   const Geo g = geo(S.ncols);
   double* res = sm;                       // [2][ncols]
-  double* sc = sm + 2 * S.ncols;          // [ncols] scalar scratch
-  double* scr = sm + 3 * S.ncols;
+  double* sc = sm + 2 * S.ncols;          // [2][ncols] scalar scratch
+  double* scr = sm + 4 * S.ncols;
   const int64_t len = (int64_t)S.n * S.ncols;
   const int64_t base = (int64_t)b * len;
   const int nc = S.ncols;
 
-  if (stage == 1) deferred_best_copy(S, b, iter - 1);
+  if (stage == 1) deferred_best_copy(S, b, iter - 1, rr);
   if (S.ctl->done) return;
 
   double part[1][SV_MAXCS];
@@ -255,29 +271,32 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
     for (int cs = 0; cs * g.TX < nc; ++cs) {
       const int c = cs * g.TX + g.tx;
       if (c < nc)
-        for (int row = g.ty; row < S.n; row += g.TY) {
+        for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
           const int64_t o = base + (int64_t)row * nc + c;
           part[0][cs] += (double)S.rhat[o] * (double)S.r[o];
         }
     }
     col_reduce<1>(part, nc, g.tx, g.ty, g.TX, g.TY, scr, res);
+    slice_allreduce(S, b, sl, res, nc, epoch);
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const int i = b * nc + c;
-      // reference order (solve.py:273-275): omega and rho are "safed" in place before use
+      // reference order (solve.py:273-275): omega and rho are "safed" in place before use (every slice computes the
+      // same values; an exact zero is replaced by eps whichever slice's store lands first)
       double om = S.omega[i];
       if (om == 0.0) { om = S.eps; S.omega[i] = om; }
       double rho = S.rz[i];
       if (rho == 0.0) { rho = S.eps; S.rz[i] = rho; }
-      S.rhonew[i] = res[c];
+      if (sl == 0) S.rhonew[i] = res[c];
       sc[c] = res[c] / rho * (S.alpha[i] / om);
+      sc[nc + c] = om;
     }
     __syncthreads();
     for (int cs = 0; cs * g.TX < nc; ++cs) {
       const int c = cs * g.TX + g.tx;
       if (c < nc) {
         const TV beta = (TV)sc[c];
-        const TV om = (TV)S.omega[b * nc + c];
-        for (int row = g.ty; row < S.n; row += g.TY) {
+        const TV om = (TV)sc[nc + c];
+        for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
           const int64_t o = base + (int64_t)row * nc + c;
           S.p[o] = S.r[o] + beta * (S.p[o] - om * S.q[o]);
         }
@@ -286,10 +305,11 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
     return;
   }
   if (stage == 2) {
+    tile_dots_all(S, b, false, sc);                     // rhat.v per column
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const int i = b * nc + c;
-      const double a = S.rhonew[i] / safedenom(tile_dot(S, b, c, 0), S.eps);
-      S.alpha[i] = a;
+      const double a = S.rhonew[i] / safedenom(sc[c], S.eps);
+      if (sl == 0) S.alpha[i] = a;
       sc[c] = a;
     }
     __syncthreads();
@@ -297,7 +317,7 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
       const int c = cs * g.TX + g.tx;
       if (c < nc) {
         const TV a = (TV)sc[c];
-        for (int row = g.ty; row < S.n; row += g.TY) {
+        for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
           const int64_t o = base + (int64_t)row * nc + c;
           S.x[o] = S.x[o] + a * S.p[o];
           S.s[o] = S.r[o] - a * S.q[o];
@@ -307,10 +327,11 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
     return;
   }
   if (stage == 3 || stage == 4) {
+    tile_dots_all(S, b, true, sc);                      // t.s and t.t per column
     for (int c = threadIdx.x; c < nc; c += blockDim.x) {
       const int i = b * nc + c;
-      const double om = tile_dot(S, b, c, 0) / safedenom(tile_dot(S, b, c, 1), S.eps);
-      S.omega[i] = om;
+      const double om = sc[c] / safedenom(sc[nc + c], S.eps);
+      if (sl == 0) S.omega[i] = om;
       sc[c] = om;
     }
     __syncthreads();
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
       const int c = cs * g.TX + g.tx;
       if (c < nc) {
         const TV om = (TV)sc[c];
-        for (int row = g.ty; row < S.n; row += g.TY) {
+        for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
           const int64_t o = base + (int64_t)row * nc + c;
           S.x[o] = S.x[o] + om * S.s[o];
           if (stage == 3) {
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
     for (int cs = 0; cs * g.TX < nc; ++cs) {
       const int c = cs * g.TX + g.tx;
       if (c < nc)
-        for (int row = g.ty; row < S.n; row += g.TY) {
+        for (int row = rr.lo + g.ty; row < rr.hi; row += g.TY) {
           const int64_t o = base + (int64_t)row * nc + c;
           const TV rn = Bb[(int64_t)row * S.ldb + c] - S.t[o];
           S.r[o] = rn;
@@ -344,6 +365,8 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
     }
   }
   col_reduce<1>(part, nc, g.tx, g.ty, g.TX, g.TY, scr, res);
+  slice_allreduce(S, b, sl, res, nc, epoch);
+  if (sl != 0) return;
   norm_bookkeeping(S, b, res, iter, scr);
   __syncthreads();
   for (int c = threadIdx.x; c < nc; c += blockDim.x) S.rz[b * nc + c] = S.rhonew[b * nc + c];
@@ -353,18 +376,36 @@ __global__ void __launch_bounds__(SV_THREADS) bicg_step_kernel(SolveState<TV> S,
 template <typename TV>
 __global__ void __launch_bounds__(SV_THREADS) solve_final_kernel(SolveState<TV> S, TV* X, int64_t ldx,
                                                                 int64_t x_bstride) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / S.nslices, sl = blockIdx.x - b * S.nslices;
+  const RowRange rr = slice_rows(S, sl);
   const int64_t len = (int64_t)S.n * S.ncols;
   const bool pending = (S.ctl->improved_iter == S.ctl->last_iter) && (S.ctl->last_iter > 0);
   const TV* src = (pending ? S.x : S.bestx) + (int64_t)b * len;
   TV* Xb = X + (int64_t)b * x_bstride;
-  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+  for (int64_t i = (int64_t)rr.lo * S.ncols + threadIdx.x; i < (int64_t)rr.hi * S.ncols; i += blockDim.x) {
     const int64_t row = i / S.ncols, c = i - row * S.ncols;
     Xb[row * ldx + c] = src[i];
   }
 }
 
 // ============================================================================ host drivers
+// CTAs per batch item of the step kernels: one wave of at most num_sms() co-resident CTAs, at least 128 rows each.
+// One slice on the host build (its launches run the CTAs of a grid one after another) and with XT_NO_SOLVE_SLICES=1.
+static int step_slices(int n, int nbatch) {
+#ifdef __CUDACC__
+  const char* e = getenv("XT_NO_SOLVE_SLICES");        // read per solve: the tests switch it
+  if (e && e[0] == '1') return 1;
+  int cap = num_sms();
+  if (cap > SV_MAX_SLICED_CTAS) cap = SV_MAX_SLICED_CTAS;
+  int ns = cap / nbatch;
+  if (ns > n / 128) ns = n / 128;
+  return ns < 1 ? 1 : ns;
+#else
+  (void)n; (void)nbatch;
+  return 1;
+#endif
+}
+
 static size_t solve_ws_bytes(int nvecs, size_t vs, int n, int nbatch, int ncols) {
   const MvTiling til = mv_tiling(nbatch, n);
   const int ngroups = (ncols + MV_MAXK - 1) / MV_MAXK;
@@ -373,6 +414,8 @@ static size_t solve_ws_bytes(int nvecs, size_t vs, int n, int nbatch, int ncols)
   bytes += align_up((size_t)ngroups * til.ntiles * 2 * MV_MAXK * sizeof(double), 256) + 256;
   bytes += 6 * (align_up((size_t)nbatch * ncols * sizeof(double), 256) + 256);
   bytes += 2 * (align_up((size_t)nbatch * sizeof(double), 256) + 256);
+  bytes += align_up((size_t)(nbatch + SV_MAX_SLICED_CTAS) * ncols * sizeof(double), 256) + 256;   // slice_part
+  bytes += align_up((size_t)nbatch * sizeof(unsigned int), 256) + 256;                           // slice_bar
   bytes += 1024;
   return bytes;
 }
@@ -402,6 +445,9 @@ static int setup_state(const xt_solve_args* g, int nvecs, Arena& ar, SolveState<
   S.cta_max = ar.take<double>(g->nbatch);
   S.cta_bad = ar.take<int>(g->nbatch);
   S.ctl = ar.take<SolveCtl>(1);
+  S.nslices = step_slices(g->n, g->nbatch);
+  S.slice_part = ar.take<double>((size_t)g->nbatch * S.nslices * g->ncols);
+  S.slice_bar = ar.take<unsigned int>(g->nbatch);
   S.B = static_cast<const TV*>(g->B); S.ldb = g->ldb; S.b_bstride = g->b_bstride;
   S.eps = g->eps;
   if (!ar.ok()) {
@@ -424,7 +470,7 @@ static int check_solve_args(const xt_solve_args* g) {
 template <typename TV> static size_t step_smem(int ncols) {
   int TX = 1;
   while (TX < ncols && TX < 32) TX <<= 1;
-  return (size_t)(3 * ncols + 2 * SV_THREADS + 64) * sizeof(double);
+  return (size_t)(4 * ncols + 2 * SV_THREADS + 64) * sizeof(double);
 }
 
 template <typename TV>
@@ -443,13 +489,13 @@ template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>&
                                          void* pre = nullptr) {
   if (pre != nullptr) {
     // x = P_r xt for the best iterate
-    solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, S.ex[1], g->ncols, (int64_t)g->n * g->ncols); XT_LAUNCHED();
+    solve_final_kernel<TV><<<g->nbatch * S.nslices, SV_THREADS, 0, st>>>(S, S.ex[1], g->ncols, (int64_t)g->n * g->ncols); XT_LAUNCHED();
     reinterpret_cast<xt_apply_fn>(pre)(g->precond_user, S.ex[1], S.ex[2], st);
     XT_CHECK_ABORT(g->abort);
     copy_out_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S.ex[2], g->n, g->ncols, static_cast<TV*>(g->X), g->ldx,
                                                           g->x_bstride); XT_LAUNCHED();
   } else {
-    solve_final_kernel<TV><<<g->nbatch, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
+    solve_final_kernel<TV><<<g->nbatch * S.nslices, SV_THREADS, 0, st>>>(S, static_cast<TV*>(g->X), g->ldx, g->x_bstride); XT_LAUNCHED();
   }
   XT_CUDA_OK(cudaGetLastError());
   SolveCtl h;
@@ -465,19 +511,186 @@ template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>&
 // step kernels go out as programmatic dependents of the matvec before them (and the matvec after them as theirs):
 // launch latency and CTA scheduling of every kernel of an iteration overlap the tail of the one before
 template <typename TV>
-static inline void launch_cg_step(const SolveState<TV>& S, int nbatch, size_t smem, cudaStream_t st, int k, int phase) {
+static inline void launch_init(SolveState<TV>& S, size_t smem, cudaStream_t st, double rtol, double atol, int bicg) {
 #ifdef __CUDACC__
-  if (dep_launch(cg_step_kernel<TV>, nbatch, SV_THREADS, smem, st, S, k, phase)) return;
+  if (S.nslices > 1) {
+    if (coop_launch(solve_init_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, rtol, atol, bicg)) return;
+    S.nslices = 1;
+  }
 #endif
-  cg_step_kernel<TV><<<nbatch, SV_THREADS, smem, st>>>(S, k, phase);
+  solve_init_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, rtol, atol, bicg);
 }
 template <typename TV>
-static inline void launch_bicg_step(const SolveState<TV>& S, int nbatch, size_t smem, cudaStream_t st, int k, int stage) {
+static inline void launch_cg_step(SolveState<TV>& S, size_t smem, cudaStream_t st, int k, int phase, unsigned int& epoch,
+                                  int rel = 0) {
+  const unsigned int e = epoch;     // cross-slice reductions of the solve so far (every reducing launch is one)
+  if (phase != 1) ++epoch;
 #ifdef __CUDACC__
-  if (dep_launch(bicg_step_kernel<TV>, nbatch, SV_THREADS, smem, st, S, k, stage)) return;
+  if (S.nslices > 1) {
+    if (coop_launch(cg_step_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, k, phase, e, rel)) return;
+    S.nslices = 1;          // slices only partition the rows: from here on one CTA per batch item, no spinning
+  }
+  if (dep_launch(cg_step_kernel<TV>, S.nbatch, SV_THREADS, smem, st, S, k, phase, e, rel)) return;
 #endif
-  bicg_step_kernel<TV><<<nbatch, SV_THREADS, smem, st>>>(S, k, stage);
+  cg_step_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, k, phase, e, rel);
 }
+template <typename TV>
+static inline void launch_bicg_step(SolveState<TV>& S, size_t smem, cudaStream_t st, int k, int stage, unsigned int& epoch,
+                                    int rel = 0) {
+  const unsigned int e = epoch;
+  if (stage == 1 || stage == 3 || stage == 5) ++epoch;
+#ifdef __CUDACC__
+  if (S.nslices > 1) {
+    if (coop_launch(bicg_step_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, k, stage, e, rel)) return;
+    S.nslices = 1;
+  }
+  if (dep_launch(bicg_step_kernel<TV>, S.nbatch, SV_THREADS, smem, st, S, k, stage, e, rel)) return;
+#endif
+  bicg_step_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, k, stage, e, rel);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------- launch-bound solves: CUDA graphs
+// Below a few thousand rows one iteration is a handful of microseconds of GPU work behind 2-5 launches that cost the
+// host more than that.  After the first `P` iterations (plain launches: short solves never pay for a graph) the next
+// iterations are replayed from a graph of one PERIOD -- P iterations, the true-residual iteration (solve.py:160) last --
+// whose step kernels number themselves relative to `SolveCtl::graph_base / epoch_base`, advanced by the last node.
+// The device `done` flag of period g is read back while period g + 1 runs.  Instantiated graphs are kept per thread,
+// keyed by everything the captured launches contain (state pointers = workspace, operator, sizes).
+__global__ void graph_base_kernel(SolveCtl* ctl, int set, int diter, unsigned int depoch) {
+  if (set) {
+    ctl->graph_base = diter;
+    ctl->epoch_base = depoch;
+  } else {
+    ctl->graph_base += diter;
+    ctl->epoch_base += depoch;
+  }
+}
+
+struct GraphEntry {
+  std::string key;
+  cudaGraphExec_t exec;
+  uint64_t stamp;
+  int64_t napply;      // operator applications in one period
+};
+struct GraphTools {          // per thread and device
+  int dev = -1;
+  cudaStream_t capture = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int* pinned = nullptr;     // [2]
+  std::vector<GraphEntry> cache;
+  uint64_t clock = 0;
+};
+static GraphTools* graph_tools() {
+  static thread_local std::vector<GraphTools*> all;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (GraphTools* t : all)
+    if (t->dev == dev) return t;
+  GraphTools* t = new GraphTools();
+  t->dev = dev;
+  if (cudaStreamCreateWithFlags(&t->capture, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&t->ev[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void**>(&t->pinned), 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete t;
+    return nullptr;
+  }
+  all.push_back(t);
+  return t;
+}
+
+// iterations per graph period (0: no graph for this solve)
+static int graph_period(const xt_solve_args* g) {
+  const char* e = getenv("XT_NO_SOLVE_GRAPH");         // read per solve: the tests switch it
+  if ((e && e[0] == '1') || prof_on()) return 0;
+  if (g->apply != nullptr || g->precond_l != nullptr || g->precond_r != nullptr) return 0;   // host code in the loop
+  const double esize = g->dtype == XT_F64 ? 8.0 : (g->dtype == XT_BF16 ? 2.0 : 4.0);
+  if ((double)g->nbatch * g->n * g->n * esize / 6.0e12 > 60e-6) return 0;     // not launch-bound
+  const int rce = g->resid_calc_every;
+  const int P = rce <= 0 ? 8 : (rce >= 8 ? rce : rce * ((8 + rce - 1) / rce));
+  if (P > 32 || g->max_niter < 3 * P) return 0;
+  return P;
+}
+
+template <typename T> static void key_add(std::string& k, const T& v) {
+  k.append(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+template <typename TV>
+static std::string graph_key(const char* method, const xt_solve_args* g, const SolveState<TV>& S, const OpDesc& op, int P) {
+  std::string k(method);
+  key_add(k, S);                 // zero-filled before it was set up: no stray padding bytes
+  key_add(k, op.A); key_add(k, op.lda); key_add(k, op.a_bstride);
+  key_add(k, op.M); key_add(k, op.ldm); key_add(k, op.m_bstride);
+  key_add(k, op.E); key_add(k, op.e_bstride); key_add(k, op.pdl); key_add(k, op.dtype);
+  key_add(k, g->resid_calc_every); key_add(k, P);
+  return k;
+}
+
+// replays up to `nper` periods on `st`; enq(stream) enqueues one period (relative numbering) and returns its status.
+// *launched = periods put on the stream, *done = 1 when the stop flag was seen.  XT_NO_GRAPH means that nothing was
+// launched and the caller carries on with plain launches; negative values are errors.
+constexpr int XT_NO_GRAPH = 1;
+template <typename EnqFn>
+static int graph_phase(const std::string& key, EnqFn&& enq, SolveCtl* ctl, int P, unsigned int E, unsigned int epoch_now,
+                       int nper, cudaStream_t st, int* launched, int* done, int64_t* napply) {
+  *launched = 0;
+  GraphTools* t = graph_tools();
+  if (t == nullptr) return XT_NO_GRAPH;
+  GraphEntry* ge = nullptr;
+  for (GraphEntry& e : t->cache)
+    if (e.key == key) ge = &e;
+  if (ge == nullptr) {
+    if (cudaStreamBeginCapture(t->capture, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return XT_NO_GRAPH;
+    }
+    const int64_t before = *napply;
+    const int rc = enq(t->capture);
+    graph_base_kernel<<<1, 1, 0, t->capture>>>(ctl, 0, P, E);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(t->capture, &graph);
+    const int64_t per = *napply - before;
+    *napply = before;
+    cudaGraphExec_t exec = nullptr;
+    if (rc != XT_OK || err != cudaSuccess || graph == nullptr ||
+        cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      return XT_NO_GRAPH;
+    }
+    cudaGraphDestroy(graph);
+    if (t->cache.size() >= 8) {          // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < t->cache.size(); ++i)
+        if (t->cache[i].stamp < t->cache[lru].stamp) lru = i;
+      cudaGraphExecDestroy(t->cache[lru].exec);
+      t->cache.erase(t->cache.begin() + lru);
+    }
+    t->cache.push_back(GraphEntry{key, exec, 0, per});
+    ge = &t->cache.back();
+  }
+  ge->stamp = ++t->clock;
+  graph_base_kernel<<<1, 1, 0, st>>>(ctl, 1, P, epoch_now);      // the first P iterations went out as plain launches
+  XT_CUDA_OK(cudaGetLastError());
+  for (int gi = 0; gi < nper; ++gi) {
+    XT_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+    XT_CUDA_OK(cudaMemcpyAsync(&t->pinned[gi & 1], &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    XT_CUDA_OK(cudaEventRecord(t->ev[gi & 1], st));
+    ++*launched;
+    *napply += ge->napply;
+    if (gi >= 1) {                                       // the flag of the period before, while this one runs
+      XT_CUDA_OK(cudaEventSynchronize(t->ev[(gi - 1) & 1]));
+      if (t->pinned[(gi - 1) & 1] != 0) {
+        *done = 1;
+        break;
+      }
+    }
+  }
+  return XT_OK;
+}
+#endif
 
 template <typename TV> static int run_cg(const xt_solve_args* g) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(g->stream);
@@ -491,10 +704,12 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
   op.apply = g->apply; op.apply_user = g->apply_user; op.abort = g->abort;
   op.pdl = solve_pdl_enabled() ? 1 : 0;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
+  XT_CUDA_OK(cudaMemsetAsync(S.slice_bar, 0, (size_t)g->nbatch * sizeof(unsigned int), st));
   const size_t smem = step_smem<TV>(g->ncols);
-  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 0); XT_LAUNCHED();
+  launch_init<TV>(S, smem, st, g->rtol, g->atol, 0); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
+  unsigned int epoch = 1;     // cross-slice reductions launched so far (number 0 was the init kernel's)
   const int ce = g->check_every > 0 ? g->check_every : 1;
   int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
@@ -513,18 +728,53 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
     rc = precond_step(1);
     if (rc != XT_OK) return rc;
   }
-  for (int k = 1; k <= g->max_niter; ++k) {
-    rc = apply_op<TV>(op, S.p, S.q, mx, S.p, S.dots, S.dots_gstride, done_flag, st, &napply);
-    if (rc != XT_OK) return rc;
+  // one iteration on stream `s`; rel = 1: k and the epoch are relative to the graph period (see graph_phase)
+  auto iteration = [&](int k, int rel, cudaStream_t s, unsigned int& ep) -> int {
+    int rc_ = apply_op<TV>(op, S.p, S.q, mx, S.p, S.dots, S.dots_gstride, done_flag, s, &napply);
+    if (rc_ != XT_OK) return rc_;
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 0); XT_LAUNCHED();
+      launch_cg_step<TV>(S, smem, s, k, 0, ep, rel); XT_LAUNCHED();
     } else {
-      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 1); XT_LAUNCHED();
-      rc = apply_op<TV>(op, S.x, S.q, mx, nullptr, nullptr, 0, done_flag, st, &napply);
-      if (rc != XT_OK) return rc;
-      launch_cg_step<TV>(S, g->nbatch, smem, st, k, 2); XT_LAUNCHED();
+      launch_cg_step<TV>(S, smem, s, k, 1, ep, rel); XT_LAUNCHED();
+      rc_ = apply_op<TV>(op, S.x, S.q, mx, nullptr, nullptr, 0, done_flag, s, &napply);
+      if (rc_ != XT_OK) return rc_;
+      launch_cg_step<TV>(S, smem, s, k, 2, ep, rel); XT_LAUNCHED();
     }
+    return XT_OK;
+  };
+#ifdef __CUDACC__
+  const int P = graph_period(g);
+#endif
+  for (int k = 1; k <= g->max_niter; ++k) {
+#ifdef __CUDACC__
+    if (P > 0 && k == P + 1) {
+      // launch-bound solve still running after its first period: the following whole periods come from a graph
+      int done = 0;
+      rc = poll_done(S.ctl, st, &done);
+      if (rc != XT_OK) return rc;
+      if (done) break;
+      const unsigned int E = epoch - 1u;                  // reductions per period (the first one just ran)
+      int launched = 0;
+      rc = graph_phase(graph_key<TV>("cg", g, S, op, P), [&](cudaStream_t cs) -> int {
+        unsigned int ep = 0;
+        for (int j = 1; j <= P; ++j) {
+          const int rc_ = iteration(j, 1, cs, ep);
+          if (rc_ != XT_OK) return rc_;
+        }
+        return XT_OK;
+      }, S.ctl, P, E, epoch, (g->max_niter - P) / P, st, &launched, &done, &napply);
+      if (rc < 0) return rc;
+      if (rc == XT_OK) {
+        k += launched * P;
+        epoch += (unsigned int)launched * E;
+        if (done || k > g->max_niter) break;
+        next_check = g->max_niter;                        // fewer than P iterations left: one poll at the end
+      }
+    }
+#endif
+    rc = iteration(k, 0, st, epoch);
+    if (rc != XT_OK) return rc;
     if (S.precond) {
       rc = precond_step(0);
       if (rc != XT_OK) return rc;
@@ -559,35 +809,71 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
   OpDesc pl{g->dtype, g->n, g->nbatch, g->ncols, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0};
   pl.apply = g->precond_l; pl.apply_user = g->precond_user; pl.abort = g->abort;
   XT_CUDA_OK(cudaMemsetAsync(S.ctl, 0, sizeof(SolveCtl), st));
+  XT_CUDA_OK(cudaMemsetAsync(S.slice_bar, 0, (size_t)g->nbatch * sizeof(unsigned int), st));
   const size_t smem = step_smem<TV>(g->ncols);
-  solve_init_kernel<TV><<<g->nbatch, SV_THREADS, smem, st>>>(S, g->rtol, g->atol, 1); XT_LAUNCHED();
+  launch_init<TV>(S, smem, st, g->rtol, g->atol, 1); XT_LAUNCHED();
   XT_CUDA_OK(cudaGetLastError());
   int64_t napply = 0;
+  unsigned int epoch = 1;     // cross-slice reductions launched so far (number 0 was the init kernel's)
   const int ce = g->check_every > 0 ? g->check_every : 1;
   int next_check = ce < 4 ? ce : 4;      // poll the device flag at 4, 8, 16, ... iterations, then every `ce`
   const int* done_flag = &S.ctl->done;
-  for (int k = 1; k <= g->max_niter; ++k) {
-    launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 1); XT_LAUNCHED();
-    rc = apply_op<TV>(op, S.p, S.q, mx, S.rhat, S.dots, S.dots_gstride, done_flag, st, &napply);   // v = A p, rhat.v
-    if (rc != XT_OK) return rc;
-    launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 2); XT_LAUNCHED();
-    rc = apply_op<TV>(op, S.s, S.t, mx, S.s, S.dots, S.dots_gstride, done_flag, st, &napply);      // t = A s, t.s, t.t
-    if (rc != XT_OK) return rc;
+  // one iteration on stream `s`; rel = 1: k and the epoch are relative to the graph period (see graph_phase)
+  auto iteration = [&](int k, int rel, cudaStream_t s, unsigned int& ep) -> int {
+    launch_bicg_step<TV>(S, smem, s, k, 1, ep, rel); XT_LAUNCHED();
+    int rc_ = apply_op<TV>(op, S.p, S.q, mx, S.rhat, S.dots, S.dots_gstride, done_flag, s, &napply);   // v = A p, rhat.v
+    if (rc_ != XT_OK) return rc_;
+    launch_bicg_step<TV>(S, smem, s, k, 2, ep, rel); XT_LAUNCHED();
+    rc_ = apply_op<TV>(op, S.s, S.t, mx, S.s, S.dots, S.dots_gstride, done_flag, s, &napply);      // t = A s, t.s, t.t
+    if (rc_ != XT_OK) return rc_;
     if (pl.apply != nullptr) {            // K s, then K t with <K s, K t> and <K t, K t> in place of t.s and t.t
-      rc = apply_op<TV>(pl, S.s, S.ex[1], mx, nullptr, nullptr, 0, done_flag, st, nullptr);
-      if (rc != XT_OK) return rc;
-      rc = apply_op<TV>(pl, S.t, S.ex[2], mx, S.ex[1], S.dots, S.dots_gstride, done_flag, st, nullptr);
-      if (rc != XT_OK) return rc;
+      rc_ = apply_op<TV>(pl, S.s, S.ex[1], mx, nullptr, nullptr, 0, done_flag, s, nullptr);
+      if (rc_ != XT_OK) return rc_;
+      rc_ = apply_op<TV>(pl, S.t, S.ex[2], mx, S.ex[1], S.dots, S.dots_gstride, done_flag, s, nullptr);
+      if (rc_ != XT_OK) return rc_;
     }
     const bool true_resid = g->resid_calc_every != 0 && (k % g->resid_calc_every == 0);
     if (!true_resid) {
-      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 3); XT_LAUNCHED();
+      launch_bicg_step<TV>(S, smem, s, k, 3, ep, rel); XT_LAUNCHED();
     } else {
-      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 4); XT_LAUNCHED();
-      rc = apply_op<TV>(op, S.x, S.t, mx, nullptr, nullptr, 0, done_flag, st, &napply);
-      if (rc != XT_OK) return rc;
-      launch_bicg_step<TV>(S, g->nbatch, smem, st, k, 5); XT_LAUNCHED();
+      launch_bicg_step<TV>(S, smem, s, k, 4, ep, rel); XT_LAUNCHED();
+      rc_ = apply_op<TV>(op, S.x, S.t, mx, nullptr, nullptr, 0, done_flag, s, &napply);
+      if (rc_ != XT_OK) return rc_;
+      launch_bicg_step<TV>(S, smem, s, k, 5, ep, rel); XT_LAUNCHED();
     }
+    return XT_OK;
+  };
+#ifdef __CUDACC__
+  const int P = graph_period(g);
+#endif
+  for (int k = 1; k <= g->max_niter; ++k) {
+#ifdef __CUDACC__
+    if (P > 0 && k == P + 1) {
+      int done = 0;
+      rc = poll_done(S.ctl, st, &done);
+      if (rc != XT_OK) return rc;
+      if (done) break;
+      const unsigned int E = epoch - 1u;
+      int launched = 0;
+      rc = graph_phase(graph_key<TV>("bicgstab", g, S, op, P), [&](cudaStream_t cs) -> int {
+        unsigned int ep = 0;
+        for (int j = 1; j <= P; ++j) {
+          const int rc_ = iteration(j, 1, cs, ep);
+          if (rc_ != XT_OK) return rc_;
+        }
+        return XT_OK;
+      }, S.ctl, P, E, epoch, (g->max_niter - P) / P, st, &launched, &done, &napply);
+      if (rc < 0) return rc;
+      if (rc == XT_OK) {
+        k += launched * P;
+        epoch += (unsigned int)launched * E;
+        if (done || k > g->max_niter) break;
+        next_check = g->max_niter;
+      }
+    }
+#endif
+    rc = iteration(k, 0, st, epoch);
+    if (rc != XT_OK) return rc;
     XT_CUDA_OK(cudaGetLastError());
     if (k == next_check || k == g->max_niter) {
       next_check += (next_check < ce) ? next_check : ce;

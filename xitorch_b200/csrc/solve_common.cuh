@@ -3,11 +3,14 @@
 #include "matvec.cuh"
 
 #include <cstring>
+#include <vector>
+#include <string>
 #include <cmath>
 
 namespace xt {
 
 constexpr int SV_THREADS = 512;
+constexpr int SV_MAX_SLICED_CTAS = 160;   // nbatch * nslices of a sliced step launch never exceeds this (one wave)
 constexpr int SV_MAXCS = 8;     // column slots per thread  => ncols <= 32 * 8
 
 // device-resident control block of one solve
@@ -19,6 +22,9 @@ struct SolveCtl {
   int last_iter;       // last iteration whose residual norms were evaluated
   unsigned int counter;
   double best_resid;
+  // launches replayed from a CUDA graph carry iteration numbers / reduction epochs relative to these (solve.cu)
+  int graph_base;
+  unsigned int epoch_base;
 };
 
 template <typename TV> struct SolveState {
@@ -38,7 +44,52 @@ template <typename TV> struct SolveState {
   double eps;
   TV* ex[3];             // bicgstab scratch: pre(X) | K s | K t   (preconditioners)
   int precond;           // cg: z = P r comes from a separate operator application (the step kernel stops after the norms)
+  // sliced step kernels: the rows of one batch item are split over `nslices` CTAs (grid = nbatch * nslices, all
+  // co-resident: cooperative launch); column sums cross the slices through slice_part / slice_bar
+  int nslices;
+  double* slice_part;        // [nbatch * nslices][ncols]
+  unsigned int* slice_bar;   // [nbatch] arrivals, monotone over the solve (zeroed with the control block)
 };
+
+struct RowRange { int lo, hi; };
+template <typename TV> __device__ __forceinline__ RowRange slice_rows(const SolveState<TV>& S, int sl) {
+  const int per = (S.n + S.nslices - 1) / S.nslices;
+  RowRange r;
+  r.lo = sl * per < S.n ? sl * per : S.n;
+  r.hi = r.lo + per < S.n ? r.lo + per : S.n;
+  return r;
+}
+
+// res[0..nc) holds this CTA's column sums over its rows; on return it holds the sums over all slices of batch item b,
+// added in slice order (the same bits in every slice).  `epoch` = number of such reductions in earlier launches of
+// this solve.  One reduction per launch: the partials of the previous one are no longer read when these are written.
+template <typename TV>
+__device__ __forceinline__ void slice_allreduce(const SolveState<TV>& S, int b, int sl, double* res, int nc,
+                                                unsigned int epoch) {
+  if (S.nslices == 1) return;
+  double* mine = S.slice_part + ((size_t)b * S.nslices + sl) * nc;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) mine[c] = res[c];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&S.slice_bar[b], 1u);
+    const unsigned int target = (epoch + 1u) * (unsigned int)S.nslices;
+    while (*reinterpret_cast<volatile unsigned int*>(&S.slice_bar[b]) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  {   // one warp per column, lanes over the slices, butterfly: the same order (the same bits) in every slice
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = warp; c < nc; c += nw) {
+      double sum = 0.0;
+      for (int j = lane; j < S.nslices; j += 32) sum += __ldcg(&S.slice_part[((size_t)b * S.nslices + j) * nc + c]);
+      sum = warp_sum(sum);
+      if (lane == 0) res[c] = sum;
+    }
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ double safedenom(double v, double eps) { return v == 0.0 ? eps : v; }
 
@@ -69,6 +120,25 @@ __device__ __forceinline__ double tile_dot(const SolveState<TV>& S, int b, int c
   for (int t = 0; t < S.tiles_per_batch; ++t)
     sum += base[((size_t)(b * S.tiles_per_batch + t) * 2 + which) * MV_MAXK + (c % MV_MAXK)];
   return sum;
+}
+
+// the same sums for every column at once, one warp per column (lanes stride over the tiles, butterfly at the end: a
+// fixed order): out[c] for which = 0, out[ncols + c] for which = 1 when `both`.  All threads of the CTA call it; ends
+// with a barrier.  The one-thread loop above is a chain of tiles_per_batch dependent-latency loads (~10 us at 148 tiles).
+template <typename TV>
+__device__ __forceinline__ void tile_dots_all(const SolveState<TV>& S, int b, bool both, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nq = both ? 2 * S.ncols : S.ncols;
+  for (int q = warp; q < nq; q += nw) {
+    const int which = q / S.ncols, c = q - which * S.ncols;
+    const double* base = S.dots + (int64_t)(c / MV_MAXK) * S.dots_gstride;
+    double sum = 0.0;
+    for (int t = lane; t < S.tiles_per_batch; t += 32)
+      sum += base[((size_t)(b * S.tiles_per_batch + t) * 2 + which) * MV_MAXK + (c % MV_MAXK)];
+    sum = warp_sum(sum);
+    if (lane == 0) out[q] = sum;
+  }
+  __syncthreads();
 }
 
 struct Geo {
@@ -125,6 +195,24 @@ static inline bool dep_launch(void (*kern)(KArgs...), int grid, int threads, siz
   if (cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...) == cudaSuccess) return true;
   (void)cudaGetLastError();
   ok.store(0);
+  return false;
+}
+
+// cooperative launch (all CTAs co-resident: the sliced step kernels spin on each other), as a programmatic dependent
+// when that is enabled.  false: not launched (the caller falls back to one slice per batch item).
+template <typename... KArgs, typename... Args>
+static inline bool coop_launch(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = solve_pdl_enabled() ? 2 : 1;
+  if (cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...) == cudaSuccess) return true;
+  (void)cudaGetLastError();
   return false;
 }
 #endif
