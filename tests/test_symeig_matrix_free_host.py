@@ -172,7 +172,7 @@ def test_default_materialises_small_composites(engine, monkeypatch):
     assert torch.allclose(evals, torch.linalg.eigvalsh(mat)[:2], atol=1e-9)
 
 
-def test_generalized_problem_is_whitened_in_the_callback(engine):
+def test_generalized_problem_with_a_matrix_free_operator(engine):
     n, k = 42, 3
     A = _sym(n, torch.float64, seed=5)
     Mm = _sym(n, torch.float64, seed=6)

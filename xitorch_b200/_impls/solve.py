@@ -119,8 +119,10 @@ def _dense_of(op: LinearOperator, what: str) -> torch.Tensor:
 
 
 def _default_check_every(n: int, nbatch: int, esize: int) -> int:
+    # every poll drains the launch pipeline (~30 us of idle GPU), an iteration enqueued after convergence costs a few
+    # microseconds (its kernels exit at once): never poll more often than every 8 iterations
     t_iter = max(nbatch * n * n * esize / 6.0e12, 8e-6)     # one pass over A at ~6 TB/s, >= launch floor
-    return max(1, min(64, int(4e-4 / t_iter)))
+    return max(8, min(64, int(4e-4 / t_iter)))
 
 
 def _flatten(t: torch.Tensor, batch: Sequence[int], tail: Sequence[int], dtype) -> torch.Tensor:
