@@ -389,23 +389,6 @@ __global__ void __launch_bounds__(SV_THREADS) solve_final_kernel(SolveState<TV> 
 }
 
 // ============================================================================ host drivers
-// CTAs per batch item of the step kernels: one wave of at most num_sms() co-resident CTAs, at least 128 rows each.
-// One slice on the host build (its launches run the CTAs of a grid one after another) and with XT_NO_SOLVE_SLICES=1.
-static int step_slices(int n, int nbatch) {
-#ifdef __CUDACC__
-  const char* e = getenv("XT_NO_SOLVE_SLICES");        // read per solve: the tests switch it
-  if (e && e[0] == '1') return 1;
-  int cap = num_sms();
-  if (cap > SV_MAX_SLICED_CTAS) cap = SV_MAX_SLICED_CTAS;
-  int ns = cap / nbatch;
-  if (ns > n / 128) ns = n / 128;
-  return ns < 1 ? 1 : ns;
-#else
-  (void)n; (void)nbatch;
-  return 1;
-#endif
-}
-
 static size_t solve_ws_bytes(int nvecs, size_t vs, int n, int nbatch, int ncols) {
   const MvTiling til = mv_tiling(nbatch, n);
   const int ngroups = (ncols + MV_MAXK - 1) / MV_MAXK;

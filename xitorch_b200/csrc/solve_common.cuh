@@ -320,6 +320,23 @@ static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const T
   return XT_OK;
 }
 
+// CTAs per batch item of the step kernels: one wave of at most num_sms() co-resident CTAs, at least 128 rows each.
+// One slice on the host build (its launches run the CTAs of a grid one after another) and with XT_NO_SOLVE_SLICES=1.
+static inline int step_slices(int n, int nbatch) {
+#ifdef __CUDACC__
+  const char* e = getenv("XT_NO_SOLVE_SLICES");        // read per solve: the tests switch it
+  if (e && e[0] == '1') return 1;
+  int cap = num_sms();
+  if (cap > SV_MAX_SLICED_CTAS) cap = SV_MAX_SLICED_CTAS;
+  int ns = cap / nbatch;
+  if (ns > n / 128) ns = n / 128;
+  return ns < 1 ? 1 : ns;
+#else
+  (void)n; (void)nbatch;
+  return 1;
+#endif
+}
+
 static inline int poll_done(SolveCtl* ctl, cudaStream_t st, int* done) {
   int h = 0;
   XT_CUDA_OK(cudaMemcpyAsync(&h, &ctl->done, sizeof(int), cudaMemcpyDeviceToHost, st));
