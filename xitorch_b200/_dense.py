@@ -73,7 +73,17 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
         m3 = m3.contiguous()
         lda = m3.stride(-2)
         a_bstride = m3.stride(0) if (m3.dim() == 3 and a_bstride != 0) else a_bstride
-    xx = x.to(vdt).expand(*batch, nin, k).reshape(nb, nin, k).contiguous()
+    # block widths between the kernel's instantiations (1, 2, 4, 8, 16): the operand is padded with zero columns so that
+    # it stays on the bulk-copy path of its slot (a k = 9..15 block ran at 3.2 TB/s against 4.3 for k = 16: the ragged
+    # rows of X went through the plain-load staging warp); the copy is n x 16 elements, the pass over A is n x n
+    k_user = k
+    if E is None and not trans and k < 16 and (k & (k - 1)) != 0:
+        kp = 1 << k.bit_length()
+        xx = torch.zeros((nb, nin, kp), dtype=vdt, device=x.device)
+        xx[:, :, :k] = x.to(vdt).expand(*batch, nin, k).reshape(nb, nin, k)
+        k = kp
+    else:
+        xx = x.to(vdt).expand(*batch, nin, k).reshape(nb, nin, k).contiguous()
     y = torch.empty((nb, nout, k), dtype=vdt, device=x.device)
     a = _lib.MatvecArgs()
     a.dtype = _lib.dtype_code(mat.dtype)
@@ -95,7 +105,9 @@ def block_matvec(mat: torch.Tensor, x: torch.Tensor, adjoint: bool = False,
     a.stream = _lib.stream_ptr(x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().xt_block_matvec(a), "block_matvec")
-    y = y.reshape(*batch, nout, k)
+    if k != k_user:
+        y = y[:, :, :k_user]
+    y = y.reshape(*batch, nout, k_user)
     return y if out_dtype == vdt else y.to(out_dtype)
 
 
