@@ -229,6 +229,21 @@ def _krylov_matrix_free(A, neig, mode, expansion, max_niter, v_init, min_eps, ma
     return evals, evecs
 
 
+def _small_eigh_device(Tsym: torch.Tensor, nev: int, mode: str):
+    """`nev` extreme eigenpairs (ascending) of a symmetric m x m device matrix with the engine's one-CTA eigensolver
+    (`xt_small_eigh`, csrc/symeig.cu; replaces torch.linalg.eigh at reference symeig.py:174).  fp64 in and out."""
+    m = Tsym.shape[-1]
+    dev = Tsym.device
+    T64 = Tsym.to(torch.float64).contiguous()
+    w = torch.empty(nev, dtype=torch.float64, device=dev)
+    S = torch.empty((m, nev), dtype=torch.float64, device=dev)
+    scratch = torch.empty(m * (m | 1) + 16, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().xt_small_eigh(T64.data_ptr(), m, nev, 0 if mode == "lowest" else 1, w.data_ptr(),
+                                            S.data_ptr(), scratch.data_ptr(), _lib.stream_ptr(dev)), "small_eigh")
+    return w, S
+
+
 def _m_orthonormalise(W, MW, rtol):
     """M-orthonormal basis of span(W), given ``MW = M W`` (``MW is W`` for the standard problem): with the Gram matrix
     ``W^T M W = U diag(d) U^T`` the result is ``W U d^-1/2`` (and the same transformation of MW).  Directions with
@@ -236,12 +251,18 @@ def _m_orthonormalise(W, MW, rtol):
     where a Cholesky factor of the Gram matrix (the reference's `tallqr`, _utils/tensor.py:8-19) breaks down.  The number
     of columns kept is the smallest numerical rank over the batch."""
     G = torch.matmul(W.transpose(-2, -1), MW)
-    d, U = torch.linalg.eigh(0.5 * (G + G.transpose(-2, -1)))          # ascending
+    G = 0.5 * (G + G.transpose(-2, -1))
+    dev = G.device
+    if dev.type == "cuda" and G.numel() <= 65536:
+        G = G.cpu()            # k x k with k <= 16: LAPACK on the host, one round trip instead of the device library's
+                               # launch chain plus a second synchronisation for `keep`
+    d, U = torch.linalg.eigh(G)                                         # ascending
     dmax = d[..., -1:].clamp_min(torch.finfo(d.dtype).tiny)
     keep = int((d > rtol * dmax).sum(-1).min().item())
     if keep == 0:
         return W[..., :0], MW[..., :0]
     U = U[..., -keep:] * d[..., -keep:].clamp_min(torch.finfo(d.dtype).tiny).rsqrt().unsqueeze(-2)
+    U = U.to(dev)
     Wn = torch.matmul(W, U)
     return Wn, (Wn if MW is W else torch.matmul(MW, U))
 
@@ -281,7 +302,7 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
         max_basis = n                  # small problems run to the full space, where the pairs are exact (symeig.py:203)
     nkeep = min(nkeep, max_basis)
     eps = torch.finfo(vdt).eps
-    small_on_host = dev.type == "cuda" and nb <= 4 and max_basis <= 512
+    on_chip_eigh = dev.type == "cuda" and nb == 1 and max_basis <= 512 and max(nkeep, neig) <= 128
 
     dA = dM = None
     if precond == "diag":
@@ -325,14 +346,15 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
             V, AV, MV = Vb[..., :m], AVb[..., :m], MVb[..., :m]
             Tm = T[..., :m, :m]
             Tsym = 0.5 * (Tm + Tm.transpose(-2, -1))
-            if small_on_host:
-                # an m x m problem with m <= 128: LAPACK on the host beats the device library's launch chain several
-                # times over, and the loop synchronises once per iteration for the stop test anyway
-                theta, S = torch.linalg.eigh(Tsym.cpu())
-                theta, S = theta.to(dev), S.to(dev)
+            theta = S = None
+            if on_chip_eigh:
+                # the engine's one-CTA eigensolver (`xt_small_eigh`: 0.2 ms at m = 88, no synchronisation) for the neig
+                # wanted pairs; the device library's `eigh` is a chain of ~ms launches for a matrix this small
+                lam, Sk = _small_eigh_device(Tsym.reshape(m, m), neig, mode)
+                lam, Sk = lam.to(vdt).reshape(*batch, neig), Sk.to(vdt).reshape(*batch, m, neig)
             else:
                 theta, S = torch.linalg.eigh(Tsym)
-            lam, Sk = _take(theta, S, neig, mode)
+                lam, Sk = _take(theta, S, neig, mode)
             X = torch.matmul(V, Sk)
             AX = torch.matmul(AV, Sk)
             MX = X if M is None else torch.matmul(MV, Sk)
@@ -350,7 +372,11 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
                 break
             if m + 1 > max_basis:
                 # thick restart: the basis becomes the nkeep extreme Ritz vectors (still M-orthonormal, T diagonal)
-                thk, Skp = _take(theta, S, nkeep, mode)
+                if theta is None:
+                    thk, Skp = _small_eigh_device(Tsym.reshape(m, m), nkeep, mode)
+                    thk, Skp = thk.to(vdt).reshape(*batch, nkeep), Skp.to(vdt).reshape(*batch, m, nkeep)
+                else:
+                    thk, Skp = _take(theta, S, nkeep, mode)
                 Vk, AVk = torch.matmul(V, Skp), torch.matmul(AV, Skp)
                 MVk = None if M is None else torch.matmul(MV, Skp)
                 m = nkeep
