@@ -232,7 +232,6 @@ __global__ void __launch_bounds__(SV_THREADS) gm_step_kernel(GmState<TV> S, int 
   gm_bookkeeping(S, b, resn, k + 1);
 }
 
-#ifdef __CUDACC__
 // ---------------------------------------------------------------------------- sliced Arnoldi step
 // One CTA per system pushes 2 x 2 x (k + 1) basis vectors through one SM per step (330 us at n = 16384, k = 128: twice
 // the matvec).  Here the rows of a system are split over `nslices` co-resident CTAs (cooperative launch).  Each keeps its
@@ -253,6 +252,7 @@ __device__ __forceinline__ void gm_slice_allreduce(const GmState<TV>& S, int b, 
     atomicAdd(&S.slice_bar[b], 1u);
     const unsigned int target = (arrival + 1u) * (unsigned int)S.nslices;
     while (*reinterpret_cast<volatile unsigned int*>(&S.slice_bar[b]) < target) {
+      XT_SPIN_PAUSE();
     }
     __threadfence();
   }
@@ -380,7 +380,6 @@ template <typename TV> static size_t gm_sliced_smem(const GmState<TV>& S) {
   const int per = (S.n + S.nslices - 1) / S.nslices;
   return ((size_t)2 * (S.maxk + 1) * S.ncols + 2 * S.ncols + SV_THREADS + (size_t)per * S.ncols + 64) * sizeof(double);
 }
-#endif
 
 // x = sum_j y_j q_j with R y = g (back substitution over the first `kk` Arnoldi vectors, kk = ctl->niter)
 template <typename TV>
@@ -439,9 +438,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   S.cta_bad = ar.take<int>(g->nbatch);
   S.ctl = ar.take<SolveCtl>(1);
   S.nslices = step_slices(g->n, g->nbatch);
-#ifdef __CUDACC__
   if (S.nslices > 1 && gm_sliced_smem(S) > 200 * 1024) S.nslices = 1;
-#endif
   if (S.nslices > 1) {
     S.slice_part = ar.take<double>((size_t)3 * g->nbatch * S.nslices * (maxk + 1) * g->ncols);
     S.slice_bar = ar.take<unsigned int>(g->nbatch);
@@ -465,9 +462,7 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
   if (attr_once.pending()) {
     XT_CUDA_OK(cudaFuncSetAttribute(gm_step_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     XT_CUDA_OK(cudaFuncSetAttribute(gm_final_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-#ifdef __CUDACC__
     XT_CUDA_OK(cudaFuncSetAttribute(gm_step_sliced_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-#endif
     attr_once.mark();
   }
   XT_REQUIRE(smem_step <= 200 * 1024 && smem_fin <= 200 * 1024,
@@ -482,14 +477,12 @@ template <typename TV> static int run_gmres(const xt_solve_args* g) {
     int rc = apply_op<TV>(op, S.Q + (int64_t)k * len, S.w, mx, nullptr, nullptr, 0, done_flag, st, &napply);
     if (rc != XT_OK) return rc;
     bool stepped = false;
-#ifdef __CUDACC__
     if (S.nslices > 1) {
       stepped = coop_launch(gm_step_sliced_kernel<TV>, g->nbatch * S.nslices, SV_THREADS, gm_sliced_smem(S), st, S, k);
       // a refused cooperative launch: one CTA per system from here on.  The arrivals counted so far stay consistent
       // because the sliced kernel is never launched again in this solve.
       if (!stepped) S.nslices = 1;
     }
-#endif
     if (!stepped) gm_step_kernel<TV><<<g->nbatch, SV_THREADS, smem_step, st>>>(S, k);
     XT_LAUNCHED();
     XT_CUDA_OK(cudaGetLastError());

@@ -495,12 +495,10 @@ template <typename TV> static int finish(const xt_solve_args* g, SolveState<TV>&
 // launch latency and CTA scheduling of every kernel of an iteration overlap the tail of the one before
 template <typename TV>
 static inline void launch_init(SolveState<TV>& S, size_t smem, cudaStream_t st, double rtol, double atol, int bicg) {
-#ifdef __CUDACC__
   if (S.nslices > 1) {
     if (coop_launch(solve_init_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, rtol, atol, bicg)) return;
     S.nslices = 1;
   }
-#endif
   solve_init_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, rtol, atol, bicg);
 }
 template <typename TV>
@@ -508,11 +506,11 @@ static inline void launch_cg_step(SolveState<TV>& S, size_t smem, cudaStream_t s
                                   int rel = 0) {
   const unsigned int e = epoch;     // cross-slice reductions of the solve so far (every reducing launch is one)
   if (phase != 1) ++epoch;
-#ifdef __CUDACC__
   if (S.nslices > 1) {
     if (coop_launch(cg_step_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, k, phase, e, rel)) return;
     S.nslices = 1;          // slices only partition the rows: from here on one CTA per batch item, no spinning
   }
+#ifdef __CUDACC__
   if (dep_launch(cg_step_kernel<TV>, S.nbatch, SV_THREADS, smem, st, S, k, phase, e, rel)) return;
 #endif
   cg_step_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, k, phase, e, rel);
@@ -522,11 +520,11 @@ static inline void launch_bicg_step(SolveState<TV>& S, size_t smem, cudaStream_t
                                     int rel = 0) {
   const unsigned int e = epoch;
   if (stage == 1 || stage == 3 || stage == 5) ++epoch;
-#ifdef __CUDACC__
   if (S.nslices > 1) {
     if (coop_launch(bicg_step_kernel<TV>, S.nbatch * S.nslices, SV_THREADS, smem, st, S, k, stage, e, rel)) return;
     S.nslices = 1;
   }
+#ifdef __CUDACC__
   if (dep_launch(bicg_step_kernel<TV>, S.nbatch, SV_THREADS, smem, st, S, k, stage, e, rel)) return;
 #endif
   bicg_step_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, k, stage, e, rel);

@@ -3,6 +3,12 @@
 #include "matvec.cuh"
 
 #include <cstring>
+#ifdef __CUDACC__
+#define XT_SPIN_PAUSE() ((void)0)
+#else
+#include <thread>
+#define XT_SPIN_PAUSE() std::this_thread::yield()      // host build: one host thread per CUDA thread
+#endif
 #include <vector>
 #include <string>
 #include <cmath>
@@ -75,6 +81,7 @@ __device__ __forceinline__ void slice_allreduce(const SolveState<TV>& S, int b, 
     atomicAdd(&S.slice_bar[b], 1u);
     const unsigned int target = (epoch + 1u) * (unsigned int)S.nslices;
     while (*reinterpret_cast<volatile unsigned int*>(&S.slice_bar[b]) < target) {
+      XT_SPIN_PAUSE();
     }
     __threadfence();
   }
@@ -215,6 +222,13 @@ static inline bool coop_launch(void (*kern)(KArgs...), int grid, int threads, si
   (void)cudaGetLastError();
   return false;
 }
+#else
+// host build (tools/emu_engine): all CTAs of the grid at once, one host thread per CUDA thread
+template <typename F, typename... Args>
+static inline bool coop_launch(F kern, int grid, int threads, size_t smem, cudaStream_t, Args... args) {
+  emu_launch_coop(dim3(grid), dim3(threads), smem, [=]() { kern(args...); });
+  return true;
+}
 #endif
 
 #define XT_CHECK_ABORT(flag)                                                           \
@@ -321,7 +335,8 @@ static inline int apply_op(const OpDesc& op, const TV* X, TV* Y, TV* mx, const T
 }
 
 // CTAs per batch item of the step kernels: one wave of at most num_sms() co-resident CTAs, at least 128 rows each.
-// One slice on the host build (its launches run the CTAs of a grid one after another) and with XT_NO_SOLVE_SLICES=1.
+// XT_NO_SOLVE_SLICES=1: one slice.  Host build: one slice unless XT_EMU_SLICES asks for more (cooperative launches
+// run all CTAs of the grid at once there, ordinary ones one after another).
 static inline int step_slices(int n, int nbatch) {
 #ifdef __CUDACC__
   const char* e = getenv("XT_NO_SOLVE_SLICES");        // read per solve: the tests switch it
@@ -332,8 +347,11 @@ static inline int step_slices(int n, int nbatch) {
   if (ns > n / 128) ns = n / 128;
   return ns < 1 ? 1 : ns;
 #else
-  (void)n; (void)nbatch;
-  return 1;
+  (void)nbatch;
+  const char* e = getenv("XT_EMU_SLICES");             // the CPU tests run the sliced kernels with a few slices
+  int ns = e ? atoi(e) : 1;
+  if (ns > n / 8) ns = n / 8;
+  return ns < 1 ? 1 : ns;
 #endif
 }
 
