@@ -282,6 +282,64 @@ def multi_gpu_records(args, rank, world, dev, dist, oracle, xt):
     return out
 
 
+def solver_records(args, dev, oracle, xt):
+    """device-timed per-iteration cost of the linear solvers next to the headline (N = 1 only): cg / bicgstab / gmres on
+    one dense SPD operator of the headline's order, fixed iteration counts (rtol = 0), and the C1 configuration
+    (BASELINE configs[0]: cg, 256 x 256 fp64, 3 right-hand sides).  Informational: the headline metric is unchanged."""
+    import warnings
+    import torch
+    peak, _ = _peaks()
+    n = args.n
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    a = torch.randn(n, n, device=dev, generator=g)
+    A = torch.matmul(a, a.t()) / n + torch.eye(n, device=dev)          # SPD, cond ~ 5
+    del a
+    op = xt.LinearOperator.m(A, is_hermitian=True)
+    out = {"workload": "dense SPD operator N=%d fp32 (A A^T / N + I), rtol=0: fixed iteration counts" % n}
+
+    def timed(method, ncols, niter, passes_over_a):
+        B = torch.randn(n, ncols, device=dev, generator=g)
+        best = None
+        info = {}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                xt.linalg.solve(op, B, method=method, posdef=True, rtol=1e-30, atol=0.0, max_niter=niter, info=info)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+        it = max(int(info.get("niter", niter)), 1)
+        us = best * 1e3 / it
+        gbs = passes_over_a * 4.0 * n * n / (us * 1e-6) / 1e9
+        return {"ncols": ncols, "iters": it, "us_per_iter": us, "a_passes_per_iter": passes_over_a,
+                "hbm_gbs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None}
+
+    out["cg"] = timed("cg", 8, 100, 1.1)                 # + the true residual every 10th iteration (solve.py:160)
+    out["bicgstab"] = timed("bicgstab", 8, 60, 2.1)
+    out["gmres"] = timed("gmres", 1, 64, 1.0)
+    A1 = oracle.make_spd_c1(256).to(dev)
+    B1 = torch.matmul(A1, torch.randn(256, 3, dtype=torch.float64, device=dev, generator=g))
+    op1 = xt.LinearOperator.m(A1, is_hermitian=True)
+    info = {}
+    best = None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        xt.linalg.solve(op1, B1, method="cg", posdef=True, info=info)
+        e1.record()
+        torch.cuda.synchronize()
+        best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+    out["c1_cg_256_fp64"] = {"ms_per_solve": best, "iters": int(info.get("niter", 0)),
+                             "converged": bool(info.get("converged", False))}
+    return out
+
+
 def run_reference(args, rank, world):
     """the reference's own CPU implementation of the path (the oracle is a bit-identical restatement of
     xitorch/_impls/linalg/symeig.py:100-227 on the same ATen calls), all host threads."""
@@ -338,6 +396,7 @@ def main():
     ap.add_argument("--seed", type=int, default=7, help="make_herm seed (7: the reference's own fp32 davidson survives on it)")
     ap.add_argument("--c5-n", dest="c5_n", type=int, default=65536, help="order of the row-partitioned operator of the multi_gpu record")
     ap.add_argument("--no-multi-gpu", action="store_true", help="skip the C5 / C3 partitioned records")
+    ap.add_argument("--no-solvers", action="store_true", help="skip the linear-solver records (N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -559,6 +618,12 @@ def main():
         }
         if multi is not None:
             out["multi_gpu"] = multi
+        if world == 1 and not args.no_solvers:
+            try:
+                out["solvers"] = solver_records(args, dev, oracle, xt)
+            except Exception as exc:                                      # noqa: BLE001 -- never lose the headline line
+                out["solvers"] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
