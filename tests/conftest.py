@@ -28,6 +28,13 @@ def golden():
     return torch.load(path, weights_only=False)
 
 
+@pytest.fixture(scope="session")
+def golden_generalized():
+    """the reference's davidson on generalized problems and wide start blocks (oracle/gen_golden_generalized.py)"""
+    path = os.path.join(ROOT, "tests", "golden", "generalized_golden.pt")
+    return torch.load(path, weights_only=False)["davidson_generalized"]
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_extension():
     # the product fails loudly without its CUDA extension; build it (nvcc cross-compiles on CPU boxes)

@@ -72,6 +72,26 @@ def test_reference_generalized_case(eng, golden):
     assert (c["A"] @ evecs - c["M"] @ evecs * evals).abs().max().item() <= c["min_eps"]
 
 
+def test_reference_generalized_and_wide_start_fixture(eng, golden_generalized):
+    """every case of tests/golden/generalized_golden.pt (outputs of the unmodified reference: generalized problems in
+    both modes, batched, the full-space exit, nguess > neig with and without M): same eigenvalues, same eigenvectors up
+    to sign, M-orthonormal, and no more operator applications than the reference needed iterations"""
+    for c in golden_generalized:
+        A, Mm = c["A"], c["M"]
+        info = {}
+        evals, evecs = symeig(xt.LinearOperator.m(A, True), neig=c["neig"], mode=c["mode"],
+                              M=None if Mm is None else xt.LinearOperator.m(Mm, True), method="davidson",
+                              nguess=c["nguess"], min_eps=c["min_eps"], info=info)
+        assert info["engine"] == "host-composed" and info["converged"], c["tag"]
+        assert ((evals - c["evals"]).abs() / c["evals"].abs()).max().item() <= 1e-9, c["tag"]
+        assert (evecs.abs() - c["evecs_abs"]).abs().max().item() <= 1e-5, c["tag"]
+        Md = torch.eye(A.shape[-1], dtype=DT) if Mm is None else Mm
+        gram = evecs.transpose(-2, -1) @ Md @ evecs
+        assert (gram - torch.eye(c["neig"], dtype=DT)).abs().max().item() <= 1e-9, c["tag"]
+        assert (A @ evecs - Md @ evecs * evals.unsqueeze(-2)).abs().max().item() <= c["min_eps"], c["tag"]
+        assert info["napply"] <= c["oracle_niter"] + 3, (c["tag"], info, c["oracle_niter"])
+
+
 @pytest.mark.parametrize("mode", ["lowest", "uppest"])
 @pytest.mark.parametrize("with_m", [True, False])
 @pytest.mark.parametrize("n,neig,nguess", [(200, 4, None), (200, 4, 7), (300, 8, 12), (9, 2, None), (9, 2, 5)])

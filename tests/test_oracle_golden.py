@@ -40,6 +40,19 @@ def test_davidson_generalized_matches_reference(golden):
     assert torch.allclose(vec.abs(), c["evecs_abs"], rtol=0, atol=1e-8)
 
 
+def test_davidson_generalized_and_wide_start_match_reference(golden_generalized):
+    """generalized problems (both modes, batched, the full-space exit) and nguess > neig: the oracle reproduces the
+    reference's eigenvalues to the last bits and its iteration count"""
+    for c in golden_generalized:
+        Mop = None if c["M"] is None else oracle.DenseOp(c["M"], True)
+        kw = {} if c["nguess"] is None else {"nguess": c["nguess"]}
+        ev, vec, info = oracle.davidson(c["A"], c["neig"], c["mode"], M=Mop, min_eps=c["min_eps"], return_info=True, **kw)
+        assert torch.allclose(ev, c["evals"], rtol=1e-12, atol=1e-13), c["tag"]
+        assert torch.allclose(vec.abs(), c["evecs_abs"], rtol=0, atol=1e-8), c["tag"]
+        assert info["niter"] == c["oracle_niter"], c["tag"]
+        assert c["ref_resid"] <= 20 * c["min_eps"], c["tag"]          # the reference's answer solves the pencil
+
+
 def test_solvers_match_reference(golden):
     for case in golden["solve"]:
         fn = getattr(oracle, case["method"])

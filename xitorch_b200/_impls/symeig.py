@@ -295,7 +295,9 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
         raise RuntimeError("xitorch_b200.%s: nguess must be at least neig (got %d vs %d)" % (name, nguess, neig))
     nguess = min(nguess, n)
     if max_basis is None:
-        max_basis = _default_max_basis(n, neig)
+        # small problems never restart, like the reference (its basis grows until it is the whole space, symeig.py:203);
+        # beyond, the engine's cap
+        max_basis = n if n <= 512 else _default_max_basis(n, neig)
     nkeep = max(2 * neig, nguess)
     max_basis = min(max(int(max_basis), nkeep + neig), n)
     if max_basis + neig >= n:
@@ -347,7 +349,7 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
             Tm = T[..., :m, :m]
             Tsym = 0.5 * (Tm + Tm.transpose(-2, -1))
             theta = S = None
-            if on_chip_eigh:
+            if on_chip_eigh and m <= 256:          # sizes the kernel's hardware tests cover
                 # the engine's one-CTA eigensolver (`xt_small_eigh`: 0.2 ms at m = 88, no synchronisation) for the neig
                 # wanted pairs; the device library's `eigh` is a chain of ~ms launches for a matrix this small
                 lam, Sk = _small_eigh_device(Tsym.reshape(m, m), neig, mode)
