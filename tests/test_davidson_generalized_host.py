@@ -196,3 +196,23 @@ def test_cpu_tensors_still_raise_without_the_standin():
     A, Mm = _herm(16, seed=17), _spd(16, seed=18)
     with pytest.raises(RuntimeError, match="CUDA"):
         symeig(xt.LinearOperator.m(A, True), neig=2, M=xt.LinearOperator.m(Mm, True), method="davidson")
+
+
+def test_start_block_kinds_iteration_cap_and_metric_batch(eng):
+    n, neig = 80, 3
+    A, Mm = _herm(n, seed=19), _spd(n, 2, seed=20)                  # M (2, n, n), A (n, n) broadcast
+    Aop, Mop = xt.LinearOperator.m(A, True), xt.LinearOperator.m(Mm, True)
+    ref = torch.stack([_exact(A, Mm[i], neig, "lowest") for i in range(2)])
+    for v_init in ("randn", "rand", "eye"):
+        evals, evecs = symeig(Aop, neig=neig, M=Mop, method="davidson", v_init=v_init, min_eps=1e-8)
+        assert evals.shape == (2, neig) and evecs.shape == (2, n, neig)
+        assert (evals - ref).abs().max().item() <= 1e-9, v_init
+    with pytest.raises(ValueError, match="v_init"):
+        symeig(Aop, neig=neig, M=Mop, method="davidson", v_init="nope")
+    # out of iterations: the best pair so far comes back, flagged as not converged (the reference returns it silently)
+    info = {}
+    evals, evecs = symeig(Aop, neig=neig, M=Mop, method="davidson", max_niter=3, min_eps=1e-12, info=info)
+    assert not info["converged"] and info["niter"] == 3 and info["best_resid"] > 1e-12
+    assert evals.shape == (2, neig) and torch.isfinite(evecs).all()
+    # info is optional
+    symeig(Aop, neig=neig, M=Mop, method="davidson", min_eps=1e-6)
