@@ -275,8 +275,9 @@ def _davidson_host(A, neig, mode, M, max_niter, nguess, v_init, min_eps, max_bas
     ``M V``, so one iteration applies A once and M once to the NEW block only (the reference re-applies M to the whole
     basis and once more in the residual, symeig.py:184,212), and nothing of order n^3 is ever formed (no Cholesky
     whitening of M).  The two O(n^2 k) applications go through `A.mm` / `M.mm`, i.e. the block-matvec kernel for dense
-    operators; the O(n m k) tall-skinny algebra and the m x m eigenproblem are library calls on the same stream.
-    Thick restart on ``max(2 * neig, nguess)`` Ritz vectors when the basis is full.
+    operators; the O(n m k) tall-skinny algebra is library calls on the same stream, the m x m eigenproblem goes to the
+    engine's one-CTA eigensolver (`xt_small_eigh`; torch.linalg.eigh for batches and m > 256).  Problems up to n = 512
+    never restart (as the reference); beyond, thick restart on ``max(2 * neig, nguess)`` Ritz vectors.
 
     precond: None | "diag" | callable(resid (*B, n, k), eigvals (*B, k)) -> (*B, n, k).  "diag" is Davidson's
     ``t = r / (diag(A) - lambda diag(M))`` for dense operators."""
