@@ -27,8 +27,10 @@
  *   - dtype = storage type of A (and M); vectors, scalars and results are
  *     float for XT_F32 / XT_BF16 and double for XT_F64
  *   - re-entrant.  Process-wide state: the per-device SM-count cache, per-device "kernel attributes set" bits, a
- *     thread-local pool of side streams / events per device for the eigensolver, and the xt_profile_* diagnostics
- *     (two atomic launch counters; the event list is mutex-protected and only filled while profiling is enabled)
+ *     thread-local pool of side streams / events per device for the eigensolver, a thread-local cache of instantiated
+ *     CUDA graphs (with its capture stream, two events and two pinned words) per device for launch-bound cg / bicgstab
+ *     solves, and the xt_profile_* diagnostics (two atomic launch counters; the event list is mutex-protected and only
+ *     filled while profiling is enabled)
  */
 #ifndef XITORCH_B200_H
 #define XITORCH_B200_H
