@@ -41,16 +41,19 @@ def _indent(s: str, n: int) -> str:
 
 
 def _equals_adjoint(mat: torch.Tensor) -> bool:
-    """``allclose(mat, mat^H)`` (reference linop.py:96-103).  Real CUDA matrices take the one-pass kernel; a verdict of
-    "not Hermitian" -- and any failure of that path -- is settled by the library test, so the kernel can only ever make
-    the check cheaper, never change its outcome for a matrix the library test accepts."""
-    if mat.is_cuda and mat.dim() >= 2 and mat.dtype in (torch.float32, torch.float64) and mat.numel() > 0:
+    """``allclose(mat, mat^H)`` (reference linop.py:96-103).  Real square CUDA matrices take the one-pass kernel; a
+    verdict of "not Hermitian" is settled by the library test, so the kernel can only ever make the check cheaper, never
+    change its outcome for a matrix the library test accepts.  A FAILURE of the kernel path is not swallowed: it is
+    reported (RuntimeWarning) before the library test takes over, so a broken build cannot hide behind the fallback."""
+    if (mat.is_cuda and mat.dim() >= 2 and mat.shape[-1] == mat.shape[-2]
+            and mat.dtype in (torch.float32, torch.float64) and mat.numel() > 0):
         try:
             from xitorch_b200 import _dense
             if _dense.hermitian_check(mat):
                 return True
-        except Exception:                                        # noqa: BLE001 -- fall through to the library test
-            pass
+        except Exception as exc:                                 # noqa: BLE001 -- reported, then the library test
+            warnings.warn(RuntimeWarning("xitorch_b200: the one-pass Hermiticity check failed (%r); falling back to "
+                                         "torch.allclose on the matrix and its transpose" % (exc,)))
     return bool(torch.allclose(mat, mat.transpose(-2, -1).conj()))
 
 
