@@ -266,3 +266,30 @@ def test_debug_mode_runs_checks():
         assert xt.is_debug_enabled()
         xt.linalg.symeig(LinearOperator.m(sym, True), 1)
     assert not xt.is_debug_enabled()
+
+
+def test_failing_hermiticity_kernel_is_reported_not_hidden(monkeypatch):
+    """`LinearOperator.m` checks the Hermitian flag with the one-pass CUDA kernel; if that path FAILS the library test
+    still decides, but the failure is reported (round-1 review: the fallback used to swallow every exception)"""
+    import warnings
+    from xitorch_b200 import linop, _dense
+
+    class LooksLikeCuda(torch.Tensor):
+        is_cuda = property(lambda self: True)
+
+    a = torch.randn(5, 5, dtype=torch.float64)
+    sym = (a + a.T).as_subclass(LooksLikeCuda)
+
+    def broken(mat, *args, **kwargs):
+        raise RuntimeError("kernel launch failed")
+
+    monkeypatch.setattr(_dense, "hermitian_check", broken)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert linop._equals_adjoint(sym) is True                      # the library test still settles it
+    assert any(issubclass(i.category, RuntimeWarning) and "Hermiticity check failed" in str(i.message) for i in w)
+    monkeypatch.setattr(_dense, "hermitian_check", lambda mat, *a_, **k_: False)   # a "not Hermitian" verdict is silent
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert linop._equals_adjoint(sym) is True
+    assert not [i for i in w if issubclass(i.category, RuntimeWarning)]
