@@ -10,6 +10,8 @@ TEST INFRASTRUCTURE: the emulated library is built in a temporary directory and 
 box loads libxitorch_b200.so only."""
 import os
 
+import warnings
+
 import pytest
 import torch
 
@@ -259,6 +261,43 @@ def test_sliced_step_kernels_against_one_cta(engine, method, monkeypatch):
     assert abs(i6["niter"] - i1["niter"]) <= 1, (i1, i6)
     assert ((x6 - x1).norm() / ref.norm()).item() <= 1e-8
     assert not torch.equal(x6, x1)
+
+
+@pytest.mark.parametrize("method", ["cg", "bicgstab"])
+@pytest.mark.parametrize("rce,slices", [(10, 1), (3, 1), (0, 4)])
+def test_replayed_periods_number_their_iterations_relatively(engine, method, rce, slices, monkeypatch):
+    """launch-bound solves replay whole periods of iterations (on the GPU from an instantiated CUDA graph): the step
+    kernels of a replayed period get iteration numbers and reduction epochs RELATIVE to `SolveCtl::graph_base /
+    epoch_base`, which a one-thread kernel advances after every period; the true-residual iteration closes a period; the
+    stop flag is looked at one period late; the last iterations go out as plain launches again.  The host build replays
+    a period by enqueueing it again (XT_EMU_GRAPH=1), everything else is the shipped code: same iterates, to the bit, as
+    the plain loop -- iteration count, best iterate, solution -- with and without sliced step kernels."""
+    n, nc = 90, 2
+    g = torch.Generator().manual_seed(41)
+    a = torch.randn(n, n, generator=g, dtype=torch.float64)
+    A = a @ a.T / n + 0.02 * torch.eye(n, dtype=torch.float64)              # ~70-110 iterations at rtol = 1e-10
+    B = torch.randn(n, nc, generator=g, dtype=torch.float64)
+    op = xt.LinearOperator.m(A, is_hermitian=True)
+    kw = dict(rtol=1e-10, atol=1e-14, resid_calc_every=rce)
+    monkeypatch.setenv("XT_EMU_SLICES", str(slices))
+    i0, i1, i2 = {}, {}, {}
+    x0 = solve(op, B, method=method, info=i0, **kw)
+    monkeypatch.setenv("XT_EMU_GRAPH", "1")
+    x1 = solve(op, B, method=method, info=i1, **kw)
+    assert i0["converged"] and i0["niter"] > 40, i0                        # several replayed periods
+    assert i1["niter"] == i0["niter"] and i1["converged"]
+    assert torch.equal(x1, x0)
+    # an iteration cap that leaves a tail of plain launches after the last whole period, without convergence
+    cap = 47
+    monkeypatch.delenv("XT_EMU_GRAPH")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xa = solve(op, B, method=method, info=i2, max_niter=cap, **kw)
+        monkeypatch.setenv("XT_EMU_GRAPH", "1")
+        i3 = {}
+        xb = solve(op, B, method=method, info=i3, max_niter=cap, **kw)
+    assert i2["niter"] == i3["niter"] == cap and not i3["converged"]
+    assert torch.equal(xa, xb)
 
 
 def test_golden_preconditioned_cases(engine, golden):

@@ -530,7 +530,6 @@ static inline void launch_bicg_step(SolveState<TV>& S, size_t smem, cudaStream_t
   bicg_step_kernel<TV><<<S.nbatch, SV_THREADS, smem, st>>>(S, k, stage, e, rel);
 }
 
-#ifdef __CUDACC__
 // ---------------------------------------------------------------------------- launch-bound solves: CUDA graphs
 // Below a few thousand rows one iteration is a handful of microseconds of GPU work behind 2-5 launches that cost the
 // host more than that.  After the first `P` iterations (plain launches: short solves never pay for a graph) the next
@@ -548,6 +547,18 @@ __global__ void graph_base_kernel(SolveCtl* ctl, int set, int diter, unsigned in
   }
 }
 
+constexpr int XT_NO_GRAPH = 1;
+
+// iterations per graph period for this solve's `resid_calc_every` (0: none): the true-residual iteration closes a period
+static int graph_period_len(const xt_solve_args* g) {
+  if (g->apply != nullptr || g->precond_l != nullptr || g->precond_r != nullptr) return 0;   // host code in the loop
+  const int rce = g->resid_calc_every;
+  const int P = rce <= 0 ? 8 : (rce >= 8 ? rce : rce * ((8 + rce - 1) / rce));
+  if (P > 32 || g->max_niter < 3 * P) return 0;
+  return P;
+}
+
+#ifdef __CUDACC__
 struct GraphEntry {
   std::string key;
   cudaGraphExec_t exec;
@@ -586,13 +597,9 @@ static GraphTools* graph_tools() {
 static int graph_period(const xt_solve_args* g) {
   const char* e = getenv("XT_NO_SOLVE_GRAPH");         // read per solve: the tests switch it
   if ((e && e[0] == '1') || prof_on()) return 0;
-  if (g->apply != nullptr || g->precond_l != nullptr || g->precond_r != nullptr) return 0;   // host code in the loop
   const double esize = g->dtype == XT_F64 ? 8.0 : (g->dtype == XT_BF16 ? 2.0 : 4.0);
   if ((double)g->nbatch * g->n * g->n * esize / 6.0e12 > 60e-6) return 0;     // not launch-bound
-  const int rce = g->resid_calc_every;
-  const int P = rce <= 0 ? 8 : (rce >= 8 ? rce : rce * ((8 + rce - 1) / rce));
-  if (P > 32 || g->max_niter < 3 * P) return 0;
-  return P;
+  return graph_period_len(g);
 }
 
 template <typename T> static void key_add(std::string& k, const T& v) {
@@ -612,7 +619,6 @@ static std::string graph_key(const char* method, const xt_solve_args* g, const S
 // replays up to `nper` periods on `st`; enq(stream) enqueues one period (relative numbering) and returns its status.
 // *launched = periods put on the stream, *done = 1 when the stop flag was seen.  XT_NO_GRAPH means that nothing was
 // launched and the caller carries on with plain launches; negative values are errors.
-constexpr int XT_NO_GRAPH = 1;
 template <typename EnqFn>
 static int graph_phase(const std::string& key, EnqFn&& enq, SolveCtl* ctl, int P, unsigned int E, unsigned int epoch_now,
                        int nper, cudaStream_t st, int* launched, int* done, int64_t* napply) {
@@ -671,6 +677,37 @@ static int graph_phase(const std::string& key, EnqFn&& enq, SolveCtl* ctl, int P
   }
   return XT_OK;
 }
+#else
+// host build (tools/emu_engine): with XT_EMU_GRAPH=1 a "replay" enqueues the period again with relative numbering, so the
+// numbering, the base kernel, the lagged stop flag and the bookkeeping around the replay run on the CPU; capture and
+// instantiation are the part only the hardware tests cover
+static int graph_period(const xt_solve_args* g) {
+  const char* e = getenv("XT_EMU_GRAPH");
+  return (e && e[0] == '1') ? graph_period_len(g) : 0;
+}
+template <typename TV>
+static std::string graph_key(const char*, const xt_solve_args*, const SolveState<TV>&, const OpDesc&, int) {
+  return std::string();
+}
+template <typename EnqFn>
+static int graph_phase(const std::string&, EnqFn&& enq, SolveCtl* ctl, int P, unsigned int E, unsigned int epoch_now,
+                       int nper, cudaStream_t st, int* launched, int* done, int64_t*) {
+  *launched = 0;
+  int flag[2] = {0, 0};
+  graph_base_kernel<<<1, 1, 0, st>>>(ctl, 1, P, epoch_now);
+  for (int gi = 0; gi < nper; ++gi) {
+    const int rc = enq(st);
+    if (rc != XT_OK) return rc;
+    graph_base_kernel<<<1, 1, 0, st>>>(ctl, 0, P, E);
+    flag[gi & 1] = ctl->done;
+    ++*launched;
+    if (gi >= 1 && flag[(gi - 1) & 1] != 0) {
+      *done = 1;
+      break;
+    }
+  }
+  return XT_OK;
+}
 #endif
 
 template <typename TV> static int run_cg(const xt_solve_args* g) {
@@ -724,11 +761,8 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
     }
     return XT_OK;
   };
-#ifdef __CUDACC__
   const int P = graph_period(g);
-#endif
   for (int k = 1; k <= g->max_niter; ++k) {
-#ifdef __CUDACC__
     if (P > 0 && k == P + 1) {
       // launch-bound solve still running after its first period: the following whole periods come from a graph
       int done = 0;
@@ -753,7 +787,6 @@ template <typename TV> static int run_cg(const xt_solve_args* g) {
         next_check = g->max_niter;                        // fewer than P iterations left: one poll at the end
       }
     }
-#endif
     rc = iteration(k, 0, st, epoch);
     if (rc != XT_OK) return rc;
     if (S.precond) {
@@ -824,11 +857,8 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
     }
     return XT_OK;
   };
-#ifdef __CUDACC__
   const int P = graph_period(g);
-#endif
   for (int k = 1; k <= g->max_niter; ++k) {
-#ifdef __CUDACC__
     if (P > 0 && k == P + 1) {
       int done = 0;
       rc = poll_done(S.ctl, st, &done);
@@ -852,7 +882,6 @@ template <typename TV> static int run_bicgstab(const xt_solve_args* g) {
         next_check = g->max_niter;
       }
     }
-#endif
     rc = iteration(k, 0, st, epoch);
     if (rc != XT_OK) return rc;
     XT_CUDA_OK(cudaGetLastError());
