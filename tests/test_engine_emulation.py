@@ -263,8 +263,7 @@ def test_sliced_step_kernels_against_one_cta(engine, method, monkeypatch):
     assert not torch.equal(x6, x1)
 
 
-@pytest.mark.parametrize("method", ["cg", "bicgstab"])
-@pytest.mark.parametrize("rce,slices", [(10, 1), (3, 1), (0, 4)])
+@pytest.mark.parametrize("method,rce,slices", [("cg", 10, 1), ("cg", 0, 4), ("bicgstab", 3, 1)])
 def test_replayed_periods_number_their_iterations_relatively(engine, method, rce, slices, monkeypatch):
     """launch-bound solves replay whole periods of iterations (on the GPU from an instantiated CUDA graph): the step
     kernels of a replayed period get iteration numbers and reduction epochs RELATIVE to `SolveCtl::graph_base /
