@@ -56,7 +56,10 @@ def test_sharded_engine_world1(emu_lib, monkeypatch, n, k, mb, dtype, eps):
         if first is None:
             first = (ev.clone(), info["niter"])
         else:
-            assert torch.equal(first[0], ev) and first[1] == info["niter"]
+            # run to run the fp64 atomics of the projections land in another order: same answer to rounding (what is
+            # bit-identical is the result ACROSS the ranks of one solve, checked by the world-2 test below)
+            assert ((first[0].double() - ev.double()).abs() / ref.abs()).max().item() <= tol
+            assert abs(first[1] - info["niter"]) <= 1
     assert reg.epoch == 2
 
 
